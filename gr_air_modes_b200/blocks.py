@@ -1,0 +1,285 @@
+"""Host-side mirror of the reference block surface for the Mode S receive hot path.
+
+  air_modes.preamble(channel_rate, threshold_db)   include/gr_air_modes/preamble.h:36-45, lib/preamble_impl.cc:37-76
+  air_modes.slicer(queue)                          include/gr_air_modes/slicer.h:37-42,  lib/slicer_impl.cc:46-63
+  air_modes.rx_path(rate, threshold, queue, use_pmf=False, use_dcblock=False)   python/rx_path.py:25-87
+  modes_check_crc(data, length)                    include/gr_air_modes/modes_crc.h:26
+
+Same names, argument meaning and defaults. The GNU Radio scheduler is replaced by explicit
+`process()` calls (a GNU Radio adapter that forwards work() to them lives in gr_adapter.py and is only
+importable where gnuradio is). All arithmetic happens in libairmodes_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import collections
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Frame, Stats, check
+
+
+# ---------------------------------------------------------------------------------------------
+# gr.msg_queue / gr.message stand-ins (radio.py:43,84-87 only uses handle/insert_tail/delete_head
+# and msg.to_string()); a real gr.msg_queue can be passed instead wherever `queue` is accepted.
+# ---------------------------------------------------------------------------------------------
+class message:
+    def __init__(self, s: str):
+        self._s = s
+
+    def to_string(self) -> str:
+        return self._s
+
+
+def message_from_string(s: str) -> message:
+    return message(s)
+
+
+class msg_queue:
+    def __init__(self, limit: int = 0):
+        self._q = collections.deque()
+        self._limit = limit
+
+    def handle(self, msg) -> None:
+        self._q.append(msg)
+
+    insert_tail = handle
+
+    def delete_head_nowait(self):
+        return self._q.popleft() if self._q else None
+
+    def delete_head(self):
+        return self.delete_head_nowait()
+
+    def empty_p(self) -> bool:
+        return not self._q
+
+    def count(self) -> int:
+        return len(self._q)
+
+    def flush(self) -> None:
+        self._q.clear()
+
+    def strings(self):
+        return [m.to_string() for m in self._q]
+
+
+def _make_gr_message(queue, text: str):
+    """Wrap `text` in whatever message type `queue` expects."""
+    if isinstance(queue, msg_queue):
+        return message(text)
+    try:  # a real gnuradio msg_queue
+        from gnuradio import gr  # type: ignore
+        return gr.message_from_string(text)
+    except Exception:
+        return message(text)
+
+
+def modes_check_crc(data, length: int | None = None) -> int:
+    """modes_check_crc(unsigned char data[], int length) (lib/modes_crc.cc:55-63): CRC of the first
+    `length` bytes. Host table routine exported by the library (the slicer kernel has its own device CRC)."""
+    data = bytes(data)
+    if length is None:
+        length = len(data)
+    return int(_lib.load().amb_modes_check_crc(data, length))
+
+
+modes_crc = modes_check_crc
+
+
+def _as_iq(iq):
+    """Return (pointer, n_complex, mem_kind, keepalive) for numpy (host) or torch CUDA (device) input."""
+    try:
+        import torch
+        if isinstance(iq, torch.Tensor):
+            t = iq
+            if t.is_complex():
+                t = torch.view_as_real(t)
+            if t.dtype != torch.float32:
+                raise TypeError("IQ tensor must be complex64 or float32")
+            t = t.contiguous()
+            n = t.numel() // 2
+            kind = _lib.MEM_DEVICE if t.is_cuda else _lib.MEM_HOST
+            return C.c_void_p(t.data_ptr()), n, kind, t
+    except ImportError:
+        pass
+    a = np.asarray(iq)
+    if a.dtype == np.complex64:
+        a = a.view(np.float32)
+    a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+    return C.c_void_p(a.ctypes.data), a.size // 2, _lib.MEM_HOST, a
+
+
+class _Context:
+    """Owner of one amb_ctx (one IQ stream on one GPU)."""
+
+    def __init__(self, rate, threshold_db, use_pmf, use_dcblock, device=0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        check(self._lib.amb_create(int(device), float(rate), float(threshold_db), int(bool(use_pmf)),
+                                   int(bool(use_dcblock)), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.amb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def call(self, name, *args):
+        return check(getattr(self._lib, name)(self._h, *args), self._h)
+
+    def poll(self):
+        n = self.call("amb_pending_frames")
+        if n == 0:
+            return []
+        buf = (Frame * n)()
+        got = self.call("amb_poll_frames", buf, n)
+        return list(buf)[:got]
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self.call("amb_get_stats", C.byref(s))
+        return s
+
+
+def format_message(frame: Frame, first: bool) -> str:
+    buf = C.create_string_buffer(200)
+    check(_lib.load().amb_format_message(C.byref(frame), int(first), buf, 200))
+    return buf.value.decode()
+
+
+class slicer:
+    """air_modes.slicer(queue): turns 240-chip packets into queue messages (slicer_impl.cc:102-198)."""
+
+    def __init__(self, queue, device: int = 0, _ctx: _Context | None = None):
+        self._queue = queue
+        self._ctx = _ctx or _Context(4e6, 7.0, False, False, device)
+        self._first = True          # d_payload precision: 6 until the first message (slicer_impl.cc:192)
+
+    def emit(self, frames) -> int:
+        """Queue one message per frame that passed the slicer rules. Returns how many."""
+        k = 0
+        for f in frames:
+            if f.passed:
+                self._queue.handle(_make_gr_message(self._queue, format_message(f, self._first)))
+                self._first = False
+                k += 1
+        return k
+
+    def process(self, chips, tags) -> list:
+        """chips: (ndet, 240) float32 packets; tags: per packet (secs, frac) = the preamble_found tag value.
+        Returns the frames (all packets; see .passed) after queueing the messages."""
+        chips = np.ascontiguousarray(chips, dtype=np.float32).reshape(-1, 240)
+        ndet = chips.shape[0]
+        secs = np.ascontiguousarray([t[0] for t in tags], dtype=np.uint64)
+        frac = np.ascontiguousarray([t[1] for t in tags], dtype=np.float64)
+        out = (Frame * max(ndet, 1))()
+        self._ctx.call("amb_slicer_process", chips.ctypes.data_as(C.POINTER(C.c_float)), ndet,
+                       secs.ctypes.data_as(C.POINTER(C.c_uint64)), frac.ctypes.data_as(C.POINTER(C.c_double)), out)
+        frames = list(out)[:ndet]
+        self.emit(frames)
+        return frames
+
+
+class preamble:
+    """air_modes.preamble(channel_rate, threshold_db) (preamble.h:39-45)."""
+
+    def __init__(self, channel_rate, threshold_db, device: int = 0):
+        self._ctx = _Context(channel_rate, threshold_db, False, False, device)
+
+    def set_rate(self, channel_rate):
+        self._ctx.call("amb_set_rate", float(channel_rate))
+
+    def set_threshold(self, threshold_db):
+        self._ctx.call("amb_set_threshold", float(threshold_db))
+
+    def get_rate(self):
+        return float(self._ctx._lib.amb_get_rate(self._ctx._h))
+
+    def get_threshold(self):
+        return float(self._ctx._lib.amb_get_threshold(self._ctx._h))
+
+    def process(self, in0, in1, flush: bool = True, max_det: int | None = None):
+        """Whole streams in0 (signal) / in1 (moving-average reference) -> (chips[ndet,240], tags) with
+        tags = [(sample_index, secs, frac)], i.e. the 240-item packets and preamble_found tags of
+        preamble_impl.cc:219-232."""
+        in0 = np.ascontiguousarray(in0, dtype=np.float32)
+        in1 = np.ascontiguousarray(in1, dtype=np.float32)
+        n = min(in0.size, in1.size)
+        if max_det is None:
+            max_det = n // 200 + 16
+        chips = np.empty((max_det, 240), np.float32)
+        idx = np.empty(max_det, np.uint64)
+        nd = self._ctx.call("amb_preamble_process", in0.ctypes.data_as(C.POINTER(C.c_float)),
+                            in1.ctypes.data_as(C.POINTER(C.c_float)), n, int(flush),
+                            chips.ctypes.data_as(C.POINTER(C.c_float)), idx.ctypes.data_as(C.POINTER(C.c_uint64)), max_det)
+        rate = int(self.get_rate())
+        tags = [(int(i), int(i) // rate, (int(i) % rate) / float(rate)) for i in idx[:nd]]
+        return chips[:nd].copy(), tags
+
+
+class rx_path:
+    """air_modes.rx_path(rate, threshold, queue, use_pmf=False, use_dcblock=False) (rx_path.py:27).
+
+    A sink of gr_complex: feed it with process(iq) (numpy complex64 / interleaved float32 on the host, or a
+    torch CUDA tensor that is read in place). Decoded frames are pushed to `queue` as the reference's
+    ASCII messages."""
+
+    def __init__(self, rate, threshold, queue, use_pmf=False, use_dcblock=False, device: int = 0):
+        self._rate = int(rate)                      # rx_path.py:32
+        self._threshold = threshold
+        self._queue = queue
+        self._spc = int(rate / 2e6)                 # rx_path.py:35
+        self._use_pmf = bool(use_pmf)
+        self._ctx = _Context(rate, threshold, use_pmf, use_dcblock, device)
+        self._slicer = slicer(queue, device, _ctx=self._ctx)
+        self.frames = []                            # every detection of the last process() call
+
+    # -- the reference's methods (rx_path.py:67-87)
+    def set_rate(self, rate):
+        self._ctx.call("amb_set_rate", float(int(rate)))    # rx_path.py:68 passes int(rate)
+        self._rate = int(rate)
+        self._spc = int(rate / 2e6)
+
+    def set_threshold(self, threshold):
+        self._ctx.call("amb_set_threshold", float(threshold))
+        self._threshold = threshold
+
+    def set_pmf(self, pmf):
+        pass                                        # rx_path.py:79-81: "must be done when top block is stopped"
+
+    def get_pmf(self, pmf=None):
+        return bool(self._ctx._lib.amb_get_pmf(self._ctx._h))
+
+    def get_threshold(self):
+        return float(self._ctx._lib.amb_get_threshold(self._ctx._h))
+
+    # -- data path
+    def process(self, iq, flush: bool = False, collect: bool = True) -> int:
+        """Consume a stretch of the stream; returns the number of messages queued (0 if collect=False:
+        results then stay on the device until drain())."""
+        ptr, n, kind, keep = _as_iq(iq)
+        self._ctx.call("amb_process", ptr, n, kind, int(flush))
+        self._keep = keep
+        return self.drain() if collect else 0
+
+    def drain(self) -> int:
+        self.frames = self._ctx.poll()
+        self._keep = None
+        return self._slicer.emit(self.frames)
+
+    def reset(self):
+        self._ctx.call("amb_reset")
+
+    def stats(self) -> Stats:
+        return self._ctx.stats()
+
+    def close(self):
+        self._ctx.close()

@@ -1,0 +1,611 @@
+// Host side of libairmodes_b200.so: stream context, per-call orchestration and the C ABI declared in
+// include/airmodes_b200.h. No CPU implementation of the hot path lives here: every compute entry point
+// launches the kernels in amb_kernels.cu or fails. Citations are file:line under gr-air-modes.
+#include "amb_internal.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#define AMB_VERSION "gr-air-modes_b200 0.1 (sm_100a)"
+
+struct amb_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    float rate_arg = 0.f, thr_db = 0.f;
+    int use_pmf = 0;
+    AmbParams P{};
+    int chip_off[240];
+    int kc = 0, guard = 0;
+    float2* carry[2] = {nullptr, nullptr};
+    int cur = 0;
+    float2* tail = nullptr; int tail_cap = 0;
+    float2* staging = nullptr; size_t staging_cap = 0;
+    uint32_t* coarse = nullptr; uint32_t* fine = nullptr; uint32_t* span_count = nullptr;
+    size_t rows_cap = 0; int spans_cap = 0;
+    int* cand_j = nullptr; uint32_t* cand_info = nullptr; float* cand_avg = nullptr; unsigned cand_cap = 0;
+    amb_frame* frames = nullptr; unsigned frame_cap = 0; unsigned frames_ub = 0;
+    float* chips = nullptr; bool keep_chips = false;
+    AmbCounters* ctr = nullptr; AmbWalkState* st = nullptr;
+    // stream state
+    uint64_t n_in = 0; long long r_done = 0; bool flushed = false;
+    long long last_org = 0; bool have_last = false;
+    std::vector<amb_frame> pending;
+    // stats / timing
+    amb_stats stats{};
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    int resolver = 0;
+    std::string err;
+};
+
+static int fail(amb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        char buf[256];
+        if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+        else snprintf(buf, sizeof buf, "%s", what);
+        c->err = buf;
+    }
+    return code;
+}
+#define CK(call)                                                                  \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, AMB_ERR_CUDA, #call, e_); } while (0)
+
+// ---- parameters: preamble_impl.cc:56-68,158-162,192,205-208,212,237; rx_path.py:35,49,54 -------------------
+static int compute_params(float channel_rate, float threshold_db, int use_pmf, AmbParams* P, int* chip_off)
+{
+    const int chip_rate = 2000000;                       // preamble_impl.cc:46
+    memset(P, 0, sizeof *P);
+    P->spc_f = channel_rate / chip_rate;                 // :57
+    P->sps_f = P->spc_f * 2;                             // :58
+    if (!(P->spc_f >= 1.0f) || P->spc_f > (float)AMB_MAX_SPC) return AMB_ERR_RATE;
+    P->spc_i = (int)P->spc_f;
+    const int spc_rx = (int)((double)channel_rate / 2e6);   // rx_path.py:35
+    if (spc_rx != P->spc_i) return AMB_ERR_RATE;
+    P->rate_int = (int)channel_rate;                     // :60
+    P->L = 48 * spc_rx;                                  // rx_path.py:54
+    P->H = (int)(unsigned)P->sps_f - 1;                  // :62 set_history
+    P->po1 = (int)(2 * P->spc_f); P->po2 = (int)(7 * P->spc_f); P->po3 = (int)(9 * P->spc_f);   // :158-162
+    {   // loop bounds exactly as the for statements evaluate them (:205, :207)
+        int j = 1.5 * P->sps_f; P->qa0 = j; P->qa1 = j - 1;
+        for (; j <= 3 * P->sps_f; j++) P->qa1 = j;
+        j = 5 * P->sps_f; P->qb0 = j; P->qb1 = j - 1;
+        for (; j <= 7.5 * P->sps_f; j++) P->qb1 = j;
+    }
+    {   // do { ...; if (late) how_late++; } while (late && how_late < spc)  (:184-192) with late always true
+        int how_late = 0;
+        do { how_late++; } while (how_late < P->spc_f);
+        P->maxlate = how_late;
+    }
+    P->skip_f = 240 * P->spc_f;                          // :212, :237
+    P->skip0 = (int)P->skip_f;
+    P->thr = powf(10., threshold_db / 20.);              // :67
+    P->scale_p = (float)(1.0 / spc_rx);                  // rx_path.py:49
+    P->scale_a = (float)(1.0 / (48 * spc_rx));           // rx_path.py:54
+    P->use_pmf = use_pmf ? 1 : 0;
+    for (int j = 0; j < 240; j++) chip_off[j] = (int)(j * P->spc_f);   // :220
+    const double eps = 1.0 / 32768.0;
+    float cT = (float)((double)P->thr * (double)P->scale_a * (1.0 - eps) * (1.0 - eps));
+    P->cT = nextafterf(cT, 0.0f);
+    P->one_eps = 1.0f + (float)eps;
+    P->gfac = 1.0f / 524288.0f;                          // 2^-19
+    int fwd = 10 * P->spc_i;
+    if (P->qb1 > fwd) fwd = P->qb1;
+    if (P->po3 > fwd) fwd = P->po3;
+    P->fwd = fwd + 2;
+    P->i_exact = 0;
+    if (P->maxlate > 14) return AMB_ERR_RATE;
+    return AMB_OK;
+}
+
+static void free_dev(amb_ctx* c)
+{
+    cudaFree(c->carry[0]); cudaFree(c->carry[1]); cudaFree(c->tail); cudaFree(c->staging);
+    cudaFree(c->coarse); cudaFree(c->fine); cudaFree(c->span_count);
+    cudaFree(c->cand_j); cudaFree(c->cand_info); cudaFree(c->cand_avg);
+    cudaFree(c->frames); cudaFree(c->chips); cudaFree(c->ctr); cudaFree(c->st);
+    c->carry[0] = c->carry[1] = c->tail = c->staging = nullptr;
+    c->coarse = c->fine = c->span_count = nullptr;
+    c->cand_j = nullptr; c->cand_info = nullptr; c->cand_avg = nullptr;
+    c->frames = nullptr; c->chips = nullptr; c->ctr = nullptr; c->st = nullptr;
+    c->rows_cap = 0; c->spans_cap = 0; c->cand_cap = 0; c->frame_cap = 0; c->staging_cap = 0;
+}
+
+static int setup_rate(amb_ctx* ctx)
+{
+    AmbParams P; int off[240];
+    int rc = compute_params(ctx->rate_arg, ctx->thr_db, ctx->use_pmf, &P, off);
+    if (rc != AMB_OK) return fail(ctx, rc, "unsupported rate (need 2e6 <= rate <= 20e6 and int(rate/2e6) consistent)");
+    ctx->P = P;
+    memcpy(ctx->chip_off, off, sizeof off);
+    CK(amb_upload_tables(off));
+    ctx->guard = P.maxlate + (int)ceilf(P.skip_f) + 4;
+    int need = ctx->guard + P.L + 2 * P.spc_i + 64;
+    ctx->kc = (need + AMB_STAGE - 1) / AMB_STAGE * AMB_STAGE;
+    cudaFree(ctx->carry[0]); cudaFree(ctx->carry[1]); cudaFree(ctx->tail);
+    CK(cudaMalloc(&ctx->carry[0], (size_t)ctx->kc * sizeof(float2)));
+    CK(cudaMalloc(&ctx->carry[1], (size_t)ctx->kc * sizeof(float2)));
+    ctx->tail_cap = 4 * AMB_STAGE;
+    CK(cudaMalloc(&ctx->tail, (size_t)ctx->tail_cap * sizeof(float2)));
+    return AMB_OK;
+}
+
+static int reset_stream(amb_ctx* ctx)
+{
+    CK(cudaMemsetAsync(ctx->carry[0], 0, (size_t)ctx->kc * sizeof(float2), ctx->stream));
+    CK(cudaMemsetAsync(ctx->carry[1], 0, (size_t)ctx->kc * sizeof(float2), ctx->stream));
+    CK(cudaMemsetAsync(ctx->ctr, 0, sizeof(AmbCounters), ctx->stream));
+    CK(cudaMemsetAsync(ctx->st, 0, sizeof(AmbWalkState), ctx->stream));
+    ctx->cur = 0; ctx->n_in = 0; ctx->r_done = 0; ctx->flushed = false; ctx->have_last = false;
+    ctx->frames_ub = 0;
+    ctx->pending.clear();
+    return AMB_OK;
+}
+
+extern "C" {
+
+const char* amb_version(void) { return AMB_VERSION; }
+
+const char* amb_strerror(int code)
+{
+    switch (code) {
+        case AMB_OK: return "ok";
+        case AMB_ERR_INVALID: return "invalid argument";
+        case AMB_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (there is no CPU path)";
+        case AMB_ERR_CUDA: return "CUDA runtime error";
+        case AMB_ERR_RATE: return "unsupported sample rate";
+        case AMB_ERR_OVERFLOW: return "internal buffer overflow";
+        case AMB_ERR_UNSUPPORTED: return "feature not supported";
+        case AMB_ERR_ALIGN: return "device pointer not 16-byte aligned";
+        case AMB_ERR_STATE: return "invalid state for this call";
+    }
+    return "unknown error";
+}
+
+const char* amb_last_error(const amb_ctx* ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+int amb_create(int device, float rate, float threshold_db, int use_pmf, int use_dcblock, amb_ctx** out)
+{
+    if (!out) return AMB_ERR_INVALID;
+    *out = nullptr;
+    if (use_dcblock) return AMB_ERR_UNSUPPORTED;     // filter.dc_blocker_cc (rx_path.py:39-41): not built yet
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return AMB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return AMB_ERR_NO_DEVICE;
+    if (prop.major != 10) return AMB_ERR_NO_DEVICE;  // sm_100a cubin only
+    amb_ctx* ctx = new amb_ctx();
+    ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
+    ctx->rate_arg = rate; ctx->thr_db = threshold_db; ctx->use_pmf = use_pmf ? 1 : 0;
+    int rc = AMB_OK;
+    do {
+        if (cudaSetDevice(device) != cudaSuccess) { rc = AMB_ERR_NO_DEVICE; break; }
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
+        ctx->own_stream = true;
+        if (cudaMalloc(&ctx->ctr, sizeof(AmbCounters)) != cudaSuccess || cudaMalloc(&ctx->st, sizeof(AmbWalkState)) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
+        for (int k = 0; k < 4; k++) if (cudaEventCreate(&ctx->ev[k]) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
+        if (rc != AMB_OK) break;
+        rc = setup_rate(ctx);
+        if (rc != AMB_OK) break;
+        rc = reset_stream(ctx);
+    } while (0);
+    if (rc != AMB_OK) { amb_destroy(ctx); return rc; }
+    *out = ctx;
+    return AMB_OK;
+}
+
+void amb_destroy(amb_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_dev(ctx);
+    for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int amb_reset(amb_ctx* ctx)
+{
+    if (!ctx) return AMB_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    return reset_stream(ctx);
+}
+
+int amb_set_rate(amb_ctx* ctx, float channel_rate)
+{
+    if (!ctx) return AMB_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const float old = ctx->rate_arg;
+    ctx->rate_arg = channel_rate;
+    int rc = setup_rate(ctx);
+    if (rc != AMB_OK) { ctx->rate_arg = old; setup_rate(ctx); reset_stream(ctx); return rc; }
+    return reset_stream(ctx);
+}
+
+int amb_set_threshold(amb_ctx* ctx, float threshold_db)
+{
+    if (!ctx) return AMB_ERR_INVALID;
+    ctx->thr_db = threshold_db;                          // preamble_impl.cc:65-68
+    AmbParams P; int off[240];
+    int rc = compute_params(ctx->rate_arg, threshold_db, ctx->use_pmf, &P, off);
+    if (rc != AMB_OK) return rc;
+    ctx->P = P;
+    return AMB_OK;
+}
+
+float amb_get_rate(const amb_ctx* ctx) { return ctx ? (float)ctx->P.rate_int : 0.f; }   // preamble_impl.cc:74-76
+float amb_get_threshold(const amb_ctx* ctx) { return ctx ? ctx->thr_db : 0.f; }         // :70-72
+int amb_get_pmf(const amb_ctx* ctx) { return ctx ? ctx->use_pmf : 0; }
+
+int amb_set_stream(amb_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return AMB_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return AMB_OK;
+}
+
+int amb_enable_timing(amb_ctx* ctx, int on) { if (!ctx) return AMB_ERR_INVALID; ctx->timing = on != 0; return AMB_OK; }
+
+int amb_set_option(amb_ctx* ctx, const char* name, int value)
+{
+    if (!ctx || !name) return AMB_ERR_INVALID;
+    if (!strcmp(name, "resolver")) { ctx->resolver = value; return AMB_OK; }
+    if (!strcmp(name, "keep_chips")) { ctx->keep_chips = value != 0; return AMB_OK; }
+    return AMB_ERR_INVALID;
+}
+
+int amb_synchronize(amb_ctx* ctx)
+{
+    if (!ctx) return AMB_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AMB_OK;
+}
+
+static int ensure(amb_ctx* ctx, void** p, size_t* cap_field, size_t need_elems, size_t elem, size_t* /*unused*/)
+{
+    if (*cap_field >= need_elems) return AMB_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(*p); *p = nullptr;
+    size_t ncap = need_elems + need_elems / 4 + 64;
+    CK(cudaMalloc(p, ncap * elem));
+    *cap_field = ncap;
+    return AMB_OK;
+}
+
+int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, int flush)
+{
+    if (!ctx || (!iq && n_complex)) return AMB_ERR_INVALID;
+    if (ctx->flushed) return fail(ctx, AMB_ERR_STATE, "stream already flushed; amb_reset first");
+    if (n_complex > 0x60000000ull) return fail(ctx, AMB_ERR_INVALID, "at most 1.5 Gi samples per call");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const AmbParams& P = ctx->P;
+    const int kc = ctx->kc;
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[2], s));
+
+    // ---- input placement: device pointers are used in place, host data goes through a staging buffer
+    const float2* src = reinterpret_cast<const float2*>(iq);
+    if (mem_kind == AMB_MEM_HOST || ((uintptr_t)iq & 15u)) {
+        if (ctx->staging_cap < n_complex) {
+            CK(cudaStreamSynchronize(s));
+            cudaFree(ctx->staging); ctx->staging = nullptr;
+            size_t ncap = n_complex + 1024;
+            CK(cudaMalloc(&ctx->staging, ncap * sizeof(float2)));
+            ctx->staging_cap = ncap;
+        }
+        if (n_complex)
+            CK(cudaMemcpyAsync(ctx->staging, iq, n_complex * sizeof(float2),
+                               mem_kind == AMB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+        src = ctx->staging;
+    }
+    const int n_new = (int)n_complex;
+    const int n_main = n_new & ~(AMB_STAGE - 1);
+    const int n_tv = n_new - n_main;
+    const int n_tail = (n_tv + 512 + AMB_STAGE - 1) / AMB_STAGE * AMB_STAGE;   // <= 4 stages
+    CK(cudaMemsetAsync(ctx->tail, 0, (size_t)ctx->tail_cap * sizeof(float2), s));
+    if (n_tv) CK(cudaMemcpyAsync(ctx->tail, src + n_main, (size_t)n_tv * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+
+    AmbSegs S;
+    S.carry = ctx->carry[ctx->cur]; S.main_ = src; S.tail = ctx->tail;
+    S.n_carry = kc; S.n_main = n_main; S.n_tail = n_tail; S.n_valid = kc + n_new;
+
+    const long long org = (long long)ctx->n_in - kc + P.H;        // reported index of j = 0
+    const long long n_after = (long long)ctx->n_in + n_new;
+    long long j_lo = ctx->r_done - org;
+    long long j_hi, r_safe = 0, ntot = 0;
+    if (flush) { ntot = n_after + P.H; j_hi = S.n_valid; }
+    else { r_safe = n_after + P.H - ctx->guard; if (r_safe < ctx->r_done) r_safe = ctx->r_done; j_hi = r_safe - org; }
+    ctx->last_org = org; ctx->have_last = true;
+
+    // per-call counters
+    CK(cudaMemsetAsync(&ctx->ctr->ncand, 0, sizeof(unsigned), s));
+    CK(cudaMemsetAsync(&ctx->ctr->ndet_call, 0, 3 * sizeof(unsigned), s));
+
+    AmbWalkArgs wa{};
+    wa.P = P; wa.org = org; wa.ntot = ntot; wa.r_safe = r_safe; wa.flush = flush ? 1 : 0;
+    wa.ctr = ctx->ctr; wa.st = ctx->st;
+
+    if (j_hi > j_lo) {
+        AmbScanArgs a{};
+        a.P = P; a.S = S; a.j_lo = (int)j_lo; a.j_hi = (int)j_hi;
+        a.row_lo = (int)(j_lo / AMB_ROW) & ~(AMB_SPAN_ROWS_ALIGN - 1);
+        a.row_hi = (int)((j_hi + AMB_ROW - 1) / AMB_ROW);
+        const int rows = a.row_hi - a.row_lo;
+        const int target = ctx->sm_count * 16;
+        int rps = (rows + target - 1) / target;
+        rps = (rps + AMB_SPAN_ROWS_ALIGN - 1) / AMB_SPAN_ROWS_ALIGN * AMB_SPAN_ROWS_ALIGN;
+        if (rps < AMB_SPAN_ROWS_ALIGN) rps = AMB_SPAN_ROWS_ALIGN;
+        a.rows_per_span = rps;
+        a.n_spans = (rows + rps - 1) / rps;
+        // buffers
+        const size_t rows_need = (size_t)a.row_hi + 64;
+        if (ctx->rows_cap < rows_need) {
+            CK(cudaStreamSynchronize(s));
+            cudaFree(ctx->fine); cudaFree(ctx->coarse); ctx->fine = ctx->coarse = nullptr;
+            const size_t rc = rows_need + rows_need / 8;
+            CK(cudaMalloc(&ctx->fine, rc * 4 * sizeof(uint32_t)));
+            CK(cudaMalloc(&ctx->coarse, (rc / 32 + 2) * sizeof(uint32_t)));
+            ctx->rows_cap = rc;
+        }
+        if (ctx->spans_cap < a.n_spans) {
+            CK(cudaStreamSynchronize(s));
+            cudaFree(ctx->span_count); ctx->span_count = nullptr;
+            CK(cudaMalloc(&ctx->span_count, (size_t)(a.n_spans + 64) * sizeof(uint32_t)));
+            ctx->spans_cap = a.n_spans + 64;
+        }
+        unsigned cap_need = (unsigned)std::max<long long>(1 << 16, (j_hi - j_lo) / 8 + 1024);
+        if (ctx->cand_cap < cap_need) {
+            CK(cudaStreamSynchronize(s));
+            cudaFree(ctx->cand_j); cudaFree(ctx->cand_info); cudaFree(ctx->cand_avg);
+            ctx->cand_j = nullptr; ctx->cand_info = nullptr; ctx->cand_avg = nullptr;
+            CK(cudaMalloc(&ctx->cand_j, (size_t)cap_need * sizeof(int)));
+            CK(cudaMalloc(&ctx->cand_info, (size_t)cap_need * sizeof(uint32_t)));
+            CK(cudaMalloc(&ctx->cand_avg, (size_t)cap_need * sizeof(float)));
+            ctx->cand_cap = cap_need;
+        }
+        // a detection consumes >= skip0 samples (preamble_impl.cc:237): bound on frames of this call
+        const unsigned fr_ub = (unsigned)((j_hi - j_lo) / std::max(P.skip0, 1) + 2);
+        if (ctx->frame_cap < ctx->frames_ub + fr_ub) {
+            CK(cudaStreamSynchronize(s));
+            const unsigned ncap = (ctx->frames_ub + fr_ub) * 2 + 1024;
+            amb_frame* nf = nullptr; float* nc = nullptr;
+            CK(cudaMalloc(&nf, (size_t)ncap * sizeof(amb_frame)));
+            if (ctx->frames && ctx->frames_ub) CK(cudaMemcpy(nf, ctx->frames, (size_t)std::min(ctx->frames_ub, ctx->frame_cap) * sizeof(amb_frame), cudaMemcpyDeviceToDevice));
+            if (ctx->keep_chips) {
+                CK(cudaMalloc(&nc, (size_t)ncap * 240 * sizeof(float)));
+                if (ctx->chips && ctx->frames_ub) CK(cudaMemcpy(nc, ctx->chips, (size_t)std::min(ctx->frames_ub, ctx->frame_cap) * 240 * sizeof(float), cudaMemcpyDeviceToDevice));
+            }
+            cudaFree(ctx->frames); cudaFree(ctx->chips);
+            ctx->frames = nf; ctx->chips = nc; ctx->frame_cap = ncap;
+        }
+        if (ctx->keep_chips && !ctx->chips) CK(cudaMalloc(&ctx->chips, (size_t)ctx->frame_cap * 240 * sizeof(float)));
+        ctx->frames_ub += fr_ub;
+        a.coarse = ctx->coarse; a.fine = ctx->fine; a.span_count = ctx->span_count;
+
+        if (ctx->timing) CK(cudaEventRecord(ctx->ev[0], s));
+        CK(amb_launch_scan(a, ctx->sm_count, s));
+        if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], s));
+        CK(amb_launch_compact(a, ctx->cand_j, ctx->cand_cap, ctx->ctr, s));
+        AmbExactArgs ea{};
+        ea.P = P; ea.S = S; ea.cand_j = ctx->cand_j; ea.cand_info = ctx->cand_info; ea.cand_avg = ctx->cand_avg; ea.ctr = ctx->ctr;
+        CK(amb_launch_exact(ea, ctx->sm_count, s));
+        wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info;
+        CK(amb_launch_walk_seq(wa, s));
+        AmbSliceArgs sa{};
+        sa.P = P; sa.S = S; sa.cand_j = ctx->cand_j; sa.cand_info = ctx->cand_info; sa.cand_avg = ctx->cand_avg;
+        sa.ctr = ctx->ctr; sa.frames = ctx->frames; sa.frame_cap = ctx->frame_cap;
+        sa.chips_out = ctx->keep_chips ? ctx->chips : nullptr; sa.org = org;
+        CK(amb_launch_slice(sa, ctx->sm_count, s));
+        ctx->stats.kernel_launches += 5;
+        ctx->ev_valid = ctx->timing;
+    } else {
+        // nothing can be decided yet; on flush the resolver still has to close the stream
+        if (flush) {
+            if (!ctx->cand_j) {
+                CK(cudaMalloc(&ctx->cand_j, 64 * sizeof(int)));
+                CK(cudaMalloc(&ctx->cand_info, 64 * sizeof(uint32_t)));
+                CK(cudaMalloc(&ctx->cand_avg, 64 * sizeof(float)));
+                ctx->cand_cap = 64;
+            }
+            wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info;
+            CK(amb_launch_walk_seq(wa, s));
+            ctx->stats.kernel_launches += 1;
+        }
+        ctx->ev_valid = false;
+    }
+    // ---- carry the tail of the stream into the next call
+    CK(amb_launch_carry(S, ctx->carry[ctx->cur ^ 1], kc, s));
+    ctx->stats.kernel_launches += 1;
+    ctx->cur ^= 1;
+    ctx->n_in = (uint64_t)n_after;
+    if (flush) ctx->flushed = true;
+    else if (j_hi > j_lo) ctx->r_done = r_safe;
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[3], s));
+    return AMB_OK;
+}
+
+// tag_to_timestamp with no rx_time tag (preamble_impl.cc:100-137)
+static void stamp(amb_frame* f, int rate_int)
+{
+    const uint64_t cnt = f->sample_index;
+    f->secs = cnt / (uint64_t)rate_int;
+    f->frac = (double)(cnt % (uint64_t)rate_int) / (double)rate_int;
+    if (f->frac > 1.0f) { f->frac -= 1.0f; f->secs += 1; }
+}
+
+static int collect(amb_ctx* ctx)
+{
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    AmbCounters h;
+    CK(cudaMemcpy(&h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost));
+    ctx->stats.candidates = h.ncand;
+    ctx->stats.candidates_real = h.nreal_call;
+    ctx->stats.detections = h.ndet_call;
+    ctx->stats.frames_passed = h.npassed_call;
+    if (h.overflow) return fail(ctx, AMB_ERR_OVERFLOW, "candidate buffer overflow");
+    if (h.frame_overflow) return fail(ctx, AMB_ERR_OVERFLOW, "frame buffer overflow");
+    if (h.nframes) {
+        const size_t base = ctx->pending.size();
+        ctx->pending.resize(base + h.nframes);
+        CK(cudaMemcpy(ctx->pending.data() + base, ctx->frames, (size_t)h.nframes * sizeof(amb_frame), cudaMemcpyDeviceToHost));
+        std::sort(ctx->pending.begin() + base, ctx->pending.end(),
+                  [](const amb_frame& x, const amb_frame& y) { return x.sample_index < y.sample_index; });
+        for (size_t k = base; k < ctx->pending.size(); k++) stamp(&ctx->pending[k], ctx->P.rate_int);
+        CK(cudaMemset(&ctx->ctr->nframes, 0, sizeof(unsigned)));
+    }
+    ctx->frames_ub = 0;
+    return AMB_OK;
+}
+
+int amb_pending_frames(amb_ctx* ctx)
+{
+    if (!ctx) return AMB_ERR_INVALID;
+    int rc = collect(ctx);
+    if (rc != AMB_OK) return rc;
+    return (int)ctx->pending.size();
+}
+
+int amb_poll_frames(amb_ctx* ctx, amb_frame* out, int max)
+{
+    if (!ctx || (!out && max > 0)) return AMB_ERR_INVALID;
+    int rc = collect(ctx);
+    if (rc != AMB_OK) return rc;
+    const int n = (int)std::min<size_t>(ctx->pending.size(), (size_t)std::max(max, 0));
+    if (n) memcpy(out, ctx->pending.data(), (size_t)n * sizeof(amb_frame));
+    ctx->pending.erase(ctx->pending.begin(), ctx->pending.begin() + n);
+    return n;
+}
+
+int amb_get_stats(amb_ctx* ctx, amb_stats* out)
+{
+    if (!ctx || !out) return AMB_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    AmbCounters h; AmbWalkState st;
+    CK(cudaMemcpy(&h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&st, ctx->st, sizeof st, cudaMemcpyDeviceToHost));
+    ctx->stats.samples_in = ctx->n_in;
+    ctx->stats.candidates = h.ncand;
+    ctx->stats.candidates_real = h.nreal_call;
+    ctx->stats.detections = h.ndet_call;
+    ctx->stats.frames_passed = h.npassed_call;
+    ctx->stats.resolver_fallback = st.fallback;
+    if (ctx->timing) {
+        float ms = 0.f;
+        if (ctx->ev_valid && cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->stats.ms_scan = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->stats.ms_total = ms;
+    }
+    *out = ctx->stats;
+    return AMB_OK;
+}
+
+int amb_debug_candidates(amb_ctx* ctx, uint64_t* index, uint32_t* info, int max)
+{
+    if (!ctx) return AMB_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->have_last || !ctx->cand_j) return 0;
+    AmbCounters h;
+    CK(cudaMemcpy(&h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost));
+    const int n = (int)std::min<unsigned>(h.ncand, (unsigned)std::max(max, 0));
+    if (n <= 0) return 0;
+    std::vector<int> j(n);
+    CK(cudaMemcpy(j.data(), ctx->cand_j, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (info) CK(cudaMemcpy(info, ctx->cand_info, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (index) for (int k = 0; k < n; k++) index[k] = (uint64_t)(ctx->last_org + j[k]);
+    return n;
+}
+
+// slicer_impl.cc:186-192
+int amb_format_message(const amb_frame* f, int first, char* buf, size_t buflen)
+{
+    if (!f || !buf) return AMB_ERR_INVALID;
+    char tmp[192];
+    int o = 0;
+    for (int m = 0; m < f->nbits / 8 && m < 14; m++) o += snprintf(tmp + o, sizeof tmp - o, "%02x", (unsigned)f->data[m]);
+    o += snprintf(tmp + o, sizeof tmp - o, " %06lx %.*g %llu %.10g", (unsigned long)f->crc, first ? 6 : 10,
+                  (double)f->ref_level, (unsigned long long)f->secs, f->frac);
+    if ((size_t)o + 1 > buflen) return AMB_ERR_INVALID;
+    memcpy(buf, tmp, (size_t)o + 1);
+    return o;
+}
+
+// modes_crc.cc:33-63
+uint32_t amb_modes_check_crc(const uint8_t* data, int length)
+{
+    static uint32_t table[256];
+    static bool ready = false;
+    if (!ready) {
+        for (int n = 0; n < 256; n++) {
+            uint32_t crc = (uint32_t)n << 16;
+            for (int k = 0; k < 8; k++) crc = (crc & 0x800000u) ? (((crc << 1) ^ 0xFFF409u) & 0xFFFFFFu) : ((crc << 1) & 0xFFFFFFu);
+            table[n] = crc;
+        }
+        ready = true;
+    }
+    uint32_t crc = 0;
+    for (int i = 0; i < length; i++) crc = table[((crc >> 16) ^ data[i]) & 0xff] ^ (crc << 8);
+    return crc & 0xFFFFFFu;
+}
+
+int amb_device_crc(amb_ctx* ctx, const uint8_t* data, int n, int length, uint32_t* out)
+{
+    if (!ctx || !data || !out || n < 0 || length < 1 || length > 11) return AMB_ERR_INVALID;
+    if (n == 0) return AMB_OK;
+    CK(cudaSetDevice(ctx->device));
+    uint8_t* d = nullptr; uint32_t* o = nullptr;
+    CK(cudaMalloc(&d, (size_t)n * length));
+    CK(cudaMalloc(&o, (size_t)n * sizeof(uint32_t)));
+    cudaError_t e = cudaMemcpyAsync(d, data, (size_t)n * length, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = amb_launch_crc(d, n, length, o, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, o, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d); cudaFree(o);
+    ctx->stats.kernel_launches += 1;
+    if (e != cudaSuccess) return fail(ctx, AMB_ERR_CUDA, "amb_device_crc", e);
+    return AMB_OK;
+}
+
+int amb_slicer_process(amb_ctx* ctx, const float* chips, int ndet, const uint64_t* secs, const double* frac, amb_frame* out)
+{
+    if (!ctx || ndet < 0 || (ndet && (!chips || !out))) return AMB_ERR_INVALID;
+    if (ndet == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    float* d = nullptr; amb_frame* f = nullptr;
+    CK(cudaMalloc(&d, (size_t)ndet * 240 * sizeof(float)));
+    CK(cudaMalloc(&f, (size_t)ndet * sizeof(amb_frame)));
+    cudaError_t e = cudaMemsetAsync(f, 0, (size_t)ndet * sizeof(amb_frame), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d, chips, (size_t)ndet * 240 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = amb_launch_slice_chips(d, ndet, f, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, f, (size_t)ndet * sizeof(amb_frame), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d); cudaFree(f);
+    ctx->stats.kernel_launches += 1;
+    if (e != cudaSuccess) return fail(ctx, AMB_ERR_CUDA, "amb_slicer_process", e);
+    for (int k = 0; k < ndet; k++) {
+        out[k].secs = secs ? secs[k] : 0;
+        out[k].frac = frac ? frac[k] : 0.0;
+        out[k].sample_index = secs ? (uint64_t)(secs[k] * (uint64_t)ctx->P.rate_int + (uint64_t)llround((frac ? frac[k] : 0.0) * ctx->P.rate_int)) : 0;
+    }
+    return ndet;
+}
+
+int amb_preamble_process(amb_ctx* ctx, const float*, const float*, size_t, int, float*, uint64_t*, int)
+{
+    return fail(ctx, AMB_ERR_UNSUPPORTED, "split-form preamble not built yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+// Internal definitions shared by the kernels (amb_kernels.cu) and the host API (amb_api.cu).
+// Reference citations are file:line under the gr-air-modes tree.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/airmodes_b200.h"
+
+#define AMB_STAGE 256          // samples per TMA bulk stage (2 KiB of float2)
+#define AMB_ROW 128            // samples per warp row (4 per lane)
+#define AMB_MAX_SPC 10         // samples per chip supported (20 Msps)
+#define AMB_SPAN_ROWS_ALIGN 32 // spans are multiples of 32 rows = one coarse bitmap word
+
+// Everything the kernels need that the reference derives from (rate, threshold):
+// preamble_impl.cc:56-68 (set_rate/set_threshold), :158-162 (pulse offsets), :205-208 (quiet zones),
+// :192 (late-gate budget), :212,:237 (240*spc), rx_path.py:35,49,54 (window lengths and scales).
+struct AmbParams {
+    float spc_f, sps_f;   // d_samples_per_chip, d_samples_per_symbol (float!)
+    int spc_i;            // int(d_samples_per_chip): PMF length, correlator samples/chip, ninputs rounding
+    int L;                // 48*spc_i noise-floor window
+    int H;                // history()-1
+    int po1, po2, po3;    // int(2*spc), int(7*spc), int(9*spc)
+    int qa0, qa1, qb0, qb1; // inclusive j ranges of the two quiet-zone loops
+    int maxlate;          // number of late shifts the do/while allows
+    int skip0;            // (int)(240*spc_f)
+    float skip_f;         // 240*spc_f as the reference computes it
+    float thr;            // d_threshold = powf(10, dB/20)
+    float scale_p, scale_a; // (float)(1/spc_i), (float)(1/(48*spc_i))
+    int use_pmf;
+    int rate_int;
+    // conservative pre-filter constants (see amb_kernels.cu, scan kernel)
+    float cT;             // thr*scale_a*(1-eps)^2   (threshold side, slightly lowered)
+    float one_eps;        // 1+eps                    (peak test slack)
+    float gfac;           // absolute guard factor on the window sum
+    int fwd;              // forward reach of the exact stage from a candidate start (bb samples)
+    int64_t i_exact;      // for i_rel < i_exact: (int)((float)i_rel + skip_f) == i_rel + skip0
+};
+
+// Logical input of one call = carry ++ main ++ tail, each a multiple of AMB_STAGE samples.
+struct AmbSegs {
+    const float2* carry; const float2* main_; const float2* tail;
+    int n_carry, n_main, n_tail;   // samples
+    int n_valid;                   // samples of real data (carry + new); beyond it the tail is zeros
+};
+
+// Resolver state carried across calls (absolute reported coordinates r = sample + H).
+struct AmbWalkState {
+    long long pos;   // nitems_read at the start of the current general_work() call (preamble_impl.cc:164)
+    long long p;     // next index the scan loop will look at
+    int done;        // stream finished (flush processed)
+    int fallback;    // parallel resolver handed over to the sequential one
+    unsigned long long ncand_real, ndet;
+};
+
+struct AmbCounters {
+    unsigned int ncand;        // candidates produced by the compaction
+    unsigned int overflow;     // 1 = candidate capacity exceeded
+    unsigned int nframes;      // frames appended (all calls since last poll)
+    unsigned int frame_overflow;
+    unsigned int ndet_call;    // detections in this call
+    unsigned int npassed_call;
+    unsigned int nreal_call;
+    unsigned int pad;
+};
+
+struct AmbScanArgs {
+    AmbParams P; AmbSegs S;
+    int j_lo, j_hi;            // predicate evaluated for j in [j_lo, j_hi)
+    int row_lo, row_hi;        // rows covering that range (row_lo multiple of 32)
+    int rows_per_span, n_spans;
+    uint32_t* coarse; uint32_t* fine; uint32_t* span_count;
+};
+
+struct AmbExactArgs {
+    AmbParams P; AmbSegs S;
+    const int* cand_j; uint32_t* cand_info; float* cand_avg;
+    const AmbCounters* ctr;
+    // split-form (float streams instead of IQ): if in0 != nullptr the exact stage reads these
+    const float* in0; const float* in1; long long n_streams;
+};
+
+struct AmbWalkArgs {
+    AmbParams P;
+    const int* cand_j; uint32_t* cand_info;
+    AmbCounters* ctr; AmbWalkState* st;
+    long long org;        // absolute reported index of j = 0
+    long long ntot;       // flush: total items incl. history (N + H); else unused
+    long long r_safe;     // !flush: first reported index that may not be decided yet
+    int flush;
+};
+
+struct AmbSliceArgs {
+    AmbParams P; AmbSegs S;
+    const int* cand_j; const uint32_t* cand_info; const float* cand_avg;
+    AmbCounters* ctr;
+    amb_frame* frames; unsigned int frame_cap;
+    float* chips_out;     // optional 240 floats per detection (same slot as the frame)
+    long long org;
+    const float* in0; const float* in1; long long n_streams;
+};
+
+// kernel launchers (amb_kernels.cu)
+cudaError_t amb_launch_scan(const AmbScanArgs& a, int sm_count, cudaStream_t s);
+cudaError_t amb_launch_compact(const AmbScanArgs& a, int* cand_j, unsigned int cand_cap, AmbCounters* ctr, cudaStream_t s);
+cudaError_t amb_launch_exact(const AmbExactArgs& a, int sm_count, cudaStream_t s);
+cudaError_t amb_launch_walk_seq(const AmbWalkArgs& a, cudaStream_t s);
+cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, unsigned int cand_cap, int* scratch, cudaStream_t s);
+cudaError_t amb_launch_slice(const AmbSliceArgs& a, int sm_count, cudaStream_t s);
+cudaError_t amb_launch_carry(const AmbSegs& S, float2* dst, int kc, cudaStream_t s);
+cudaError_t amb_launch_stream_candidates(const AmbParams& P, const float* in0, const float* in1, long long n,
+                                         long long j_lo, long long j_hi, int* cand_j, unsigned int cand_cap,
+                                         AmbCounters* ctr, cudaStream_t s);
+cudaError_t amb_launch_slice_chips(const float* chips, int ndet, amb_frame* frames, cudaStream_t s);
+cudaError_t amb_launch_crc(const uint8_t* data, int n, int length, uint32_t* out, cudaStream_t s);
+cudaError_t amb_upload_tables(const int* chip_off);
+size_t amb_scan_smem_bytes(int spc_i);

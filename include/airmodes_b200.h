@@ -1,0 +1,152 @@
+/* airmodes_b200.h - C ABI of libairmodes_b200.so: the Mode S / ADS-B receive hot path of
+ * gr-air-modes (|x|^2 -> pulse matched filter -> noise floor -> preamble detect -> PPM slice with
+ * confidence -> 24-bit CRC) as hand-written sm_100a CUDA.
+ *
+ * This is the drop-in boundary for that path. The reference exposes it as GNU Radio C++ blocks
+ * behind SWIG (swig/air_modes_swig.i:15-16); each entry point below names the reference interface
+ * it replaces (file:line relative to the gr-air-modes tree). Plain pointers and sizes only.
+ * There is NO CPU fallback: every compute entry point fails with AMB_ERR_NO_DEVICE / a CUDA error
+ * when no sm_100 device is usable.
+ *
+ * Conventions
+ *   IQ input    : interleaved float32 I,Q = gr_complex (python/rx_path.py:29), host or device memory.
+ *   sample_index: the value the reference stamps, nitems_read(0)+i (lib/preamble_impl.cc:164,224),
+ *                 i.e. stream sample number of the preamble peak + history()-1.
+ *   Threading   : one amb_ctx per IQ stream, one producer thread (like one GNU Radio block thread).
+ */
+#ifndef AIRMODES_B200_H
+#define AIRMODES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define AMB_API __attribute__((visibility("default")))
+#else
+#define AMB_API
+#endif
+
+#define AMB_OK 0
+#define AMB_ERR_INVALID (-1)      /* bad argument */
+#define AMB_ERR_NO_DEVICE (-2)    /* no CUDA device / not sm_100: there is no CPU path */
+#define AMB_ERR_CUDA (-3)         /* CUDA runtime error, see amb_last_error() */
+#define AMB_ERR_RATE (-4)         /* rate < 2 Msps or samples/chip > 10 (unsupported geometry) */
+#define AMB_ERR_OVERFLOW (-5)     /* internal candidate/frame buffers exhausted even after growth */
+#define AMB_ERR_UNSUPPORTED (-6)  /* feature not built (use_dcblock) */
+#define AMB_ERR_ALIGN (-7)        /* device IQ pointer not 16-byte aligned */
+#define AMB_ERR_STATE (-8)        /* call not valid in this state (e.g. process after flush without reset) */
+
+#define AMB_MEM_HOST 0
+#define AMB_MEM_DEVICE 1
+
+typedef struct amb_ctx amb_ctx;
+
+/* One detected preamble after slicing. Mirrors struct modes_packet (include/gr_air_modes/types.h:29-41)
+ * plus the tag the preamble block attaches (lib/preamble_impl.cc:224-232). `passed` != 0 means the
+ * frame survived every drop rule of slicer_impl::work (lib/slicer_impl.cc:162-182) and the reference
+ * would have queued a message for it. */
+typedef struct amb_frame {
+    uint64_t sample_index;   /* abs_sample_cnt + i (preamble_impl.cc:224) */
+    uint64_t secs;           /* tag_to_timestamp (preamble_impl.cc:100-137) */
+    double frac;
+    float ref_level;         /* reference_level (slicer_impl.cc:128-131) */
+    uint32_t crc;            /* modes_check_crc ^ last 3 bytes (slicer_impl.cc:173-177) */
+    uint8_t nbits;           /* 56 or 112 (slicer_impl.cc:140-142) */
+    uint8_t df;              /* message_type (slicer_impl.cc:168) */
+    uint8_t numlowconf;      /* saturates at 24 (slicer_impl.cc:157) */
+    uint8_t passed;
+    uint8_t lowconfbits[24];
+    uint8_t data[14];
+    uint8_t pad_[6];
+} amb_frame;                 /* 80 bytes */
+
+typedef struct amb_stats {
+    uint64_t samples_in;     /* complex samples accepted so far on this stream */
+    uint64_t candidates;     /* first-four-test candidates handed to the exact stage (last call) */
+    uint64_t candidates_real;/* ... of which pass the exact tests (preamble_impl.cc:174-179) */
+    uint64_t detections;     /* accepted preambles = 240-chip packets (last call) */
+    uint64_t frames_passed;  /* ... of which pass the slicer rules (last call) */
+    uint64_t kernel_launches;/* kernels launched by this ctx since creation */
+    float ms_scan;           /* device time of the streaming scan kernel, last call (timing on) */
+    float ms_total;          /* device time of the whole call incl. copies on the ctx stream */
+    int resolver_fallback;   /* 1 if the exact sequential resolver had to replace the parallel one */
+    int reserved_;
+} amb_stats;
+
+/* ---- lifetime -------------------------------------------------------------------------------
+ * Replaces air_modes.rx_path(rate, threshold, queue, use_pmf, use_dcblock) (python/rx_path.py:27)
+ * = preamble::make(channel_rate, threshold_db) (include/gr_air_modes/preamble.h:40,
+ * lib/preamble_impl.cc:37-54) + slicer::make(queue) (include/gr_air_modes/slicer.h:41) + the
+ * GNU Radio front end wired in rx_path.py:38-65. */
+AMB_API int amb_create(int device, float rate, float threshold_db, int use_pmf, int use_dcblock, amb_ctx** out);
+AMB_API void amb_destroy(amb_ctx* ctx);
+/* Forget all stream state (history, scan position, pending frames): next sample is sample 0. */
+AMB_API int amb_reset(amb_ctx* ctx);
+
+/* ---- preamble accessors: preamble.h:42-45, preamble_impl.cc:56-76 --------------------------- */
+AMB_API int amb_set_rate(amb_ctx* ctx, float channel_rate);     /* also rx_path.set_rate (rx_path.py:67-72); resets the stream */
+AMB_API int amb_set_threshold(amb_ctx* ctx, float threshold_db);/* takes effect at the next amb_process */
+AMB_API float amb_get_rate(const amb_ctx* ctx);                 /* (float)(int)rate, as preamble_impl.cc:74-76 */
+AMB_API float amb_get_threshold(const amb_ctx* ctx);            /* dB, as preamble_impl.cc:70-72 */
+AMB_API int amb_get_pmf(const amb_ctx* ctx);                    /* rx_path.get_pmf (rx_path.py:83-84) */
+
+/* ---- the hot path -----------------------------------------------------------------------------
+ * Feed n_complex samples (2*n_complex floats). Replaces the scheduler calling
+ * complex_to_mag_squared/moving_average_ff work() (rx_path.py:38-54),
+ * preamble_impl::general_work (preamble_impl.cc:139-246) and slicer_impl::work
+ * (slicer_impl.cc:102-198) on this stretch of the stream. flush != 0 marks end of stream: the
+ * reference's end-of-input rules are applied and the stream must be reset before more input.
+ * Work is enqueued on the ctx's CUDA stream; results are collected by amb_poll_frames. */
+AMB_API int amb_process(amb_ctx* ctx, const float* iq_interleaved, size_t n_complex, int mem_kind, int flush);
+
+/* Wait for enqueued work and copy out up to `max` frames in stream order (all detections; test
+ * .passed for what slicer_impl.cc:193-194 would queue). Returns the count, or <0 on error.
+ * amb_pending_frames() tells how many are waiting (also synchronises). */
+AMB_API int amb_poll_frames(amb_ctx* ctx, amb_frame* out, int max);
+AMB_API int amb_pending_frames(amb_ctx* ctx);
+
+/* Message text exactly as slicer_impl.cc:186-192 builds it: "<hex payload> <crc %06x> <ref> <secs> <frac>".
+ * `first` != 0 formats ref with the stream's default precision 6 (the first message a slicer instance
+ * emits; setprecision(10) at :192 is sticky afterwards). Returns strlen, <0 if buflen too small. */
+AMB_API int amb_format_message(const amb_frame* f, int first, char* buf, size_t buflen);
+
+/* unsigned int modes_check_crc(unsigned char data[], int length) (include/gr_air_modes/modes_crc.h:26,
+ * lib/modes_crc.cc:55-63). Host helper with the same table; the device CRC is a separate kernel path. */
+AMB_API uint32_t amb_modes_check_crc(const uint8_t* data, int length);
+/* Same CRC computed by the device routine used inside the slicer kernel (parity hook). `n` messages of
+ * `length` bytes each, packed; out[n]. */
+AMB_API int amb_device_crc(amb_ctx* ctx, const uint8_t* data, int n, int length, uint32_t* out);
+
+/* ---- split-form blocks (stream contract of the two reference blocks) ---------------------------
+ * preamble: in0 = signal, in1 = moving-average reference (preamble_impl.cc:43), whole streams of n
+ * floats in host memory; out = 240 chips per detection + reported index (tag offset). Returns the
+ * number of detections (<= max_det) or <0. */
+AMB_API int amb_preamble_process(amb_ctx* ctx, const float* in0, const float* in1, size_t n, int flush,
+                         float* chips_out, uint64_t* index_out, int max_det);
+/* slicer: ndet packets of 240 chips (slicer_impl.cc:117-182) -> frames (sample_index/secs/frac are
+ * taken from the arrays, as the slicer takes them from the tag value, slicer_impl.cc:184). */
+AMB_API int amb_slicer_process(amb_ctx* ctx, const float* chips, int ndet, const uint64_t* secs,
+                       const double* frac, amb_frame* out);
+
+/* ---- plumbing ---------------------------------------------------------------------------------- */
+AMB_API int amb_set_stream(amb_ctx* ctx, void* cuda_stream);   /* run on a caller-owned cudaStream_t */
+AMB_API int amb_enable_timing(amb_ctx* ctx, int on);           /* CUDA events around the scan kernel / the call */
+AMB_API int amb_get_stats(amb_ctx* ctx, amb_stats* out);       /* synchronises */
+AMB_API int amb_synchronize(amb_ctx* ctx);
+/* Parity dumps of the last amb_process call: candidate start indices (reported coordinates) and their
+ * exact-stage verdict: bits 0-7 late shift, bit 8 passes preamble_impl.cc:174-179, bit 9 valid preamble
+ * (:205-209), bit 10 visited-and-accepted. Returns count. */
+AMB_API int amb_debug_candidates(amb_ctx* ctx, uint64_t* index, uint32_t* info, int max);
+AMB_API int amb_set_option(amb_ctx* ctx, const char* name, int value); /* "resolver": 0 auto, 1 sequential, 2 parallel */
+AMB_API const char* amb_strerror(int code);
+AMB_API const char* amb_last_error(const amb_ctx* ctx);
+AMB_API const char* amb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIRMODES_B200_H */
