@@ -352,7 +352,7 @@ cudaError_t amb_launch_compact(const AmbScanArgs& a, int* cand_j, unsigned int c
 }
 
 // ------------------------------------------------------------------------------------------------
-// canonical arithmetic (identical to oracle/modes_oracle.c, which is pinned against the reference):
+// canonical arithmetic (the definition DESIGN.md gives; the CPU checker used by tests/ states the same):
 //   m2  = fl(fl(re*re) + fl(im*im))                         complex_to_mag_squared, no FMA
 //   bb  = fl( (float)(fp64 ascending sum of spc_i m2) * scale_p )   moving_average_ff(spc, 1/spc)   rx_path.py:49
 //   avg = fl( (float)(fp64 ascending sum of L bb)   * scale_a )     moving_average_ff(48 spc, ...)  rx_path.py:54

@@ -1,0 +1,105 @@
+"""CPU-side checks of the product's host logic and of the C-ABI surface (no compute without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gr_air_modes_b200 as am
+from gr_air_modes_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build_native()
+    return _lib.load()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "airmodes_b200.h")).read()
+    return sorted(set(re.findall(r"AMB_API\s+[\w\s\*]+?\b(amb_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = header_symbols()
+    assert len(names) >= 25
+    bound = {n for n, _, _ in _lib.SYMBOLS}
+    assert set(names) == bound
+    for n in names:
+        assert getattr(lib, n) is not None
+
+
+def test_frame_layout_matches_header():
+    assert C.sizeof(_lib.Frame) == 80
+    assert _lib.Frame.data.offset == 60 and _lib.Frame.lowconfbits.offset == 36
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    assert lib.amb_create(0, 4e6, 7.0, 1, 0, C.byref(h)) == -2      # AMB_ERR_NO_DEVICE
+    with pytest.raises(RuntimeError):
+        am.rx_path(4e6, 7.0, am.msg_queue(), use_pmf=True)
+    with pytest.raises(RuntimeError):
+        am.preamble(4e6, 7.0)
+
+
+def test_host_crc_known_answers(lib):
+    assert am.modes_check_crc(bytes.fromhex("8D4840D6202CC371C32CE0576098"), 11) == 0x576098
+    assert am.modes_check_crc(bytes.fromhex("8D40621D58C382D690C8AC2863A7"), 11) == 0x2863A7
+    assert am.modes_check_crc(bytes([0, 0, 1]), 3) == 0xFFF409
+
+
+def test_host_crc_matches_oracle(lib, port):
+    rng = np.random.default_rng(3)
+    for length in (4, 11):
+        for _ in range(300):
+            b = rng.integers(0, 256, length, dtype=np.uint8).tobytes()
+            assert am.modes_check_crc(b, length) == port.crc24(b)
+
+
+def test_message_format_matches_oracle(lib, port):
+    from oracle import cpu_oracle as co
+    rng = np.random.default_rng(4)
+    for k in range(200):
+        f = _lib.Frame()
+        g = co.Frame()
+        nb = 112 if k % 2 else 56
+        data = rng.integers(0, 256, 14, dtype=np.uint8)
+        for m in range(14):
+            f.data[m] = g.data[m] = int(data[m])
+        f.nbits = g.nbits = nb
+        f.crc = g.crc = int(rng.integers(0, 1 << 24))
+        ref = np.float32(10.0 ** rng.uniform(-6, 1))
+        f.ref_level = g.ref_level = float(ref)
+        f.secs = g.secs = int(rng.integers(0, 1000))
+        f.frac = g.frac = float(rng.random())
+        for first in (True, False):
+            assert am.format_message(f, first) == port.format_message(g, first)
+
+
+def test_msg_queue_stand_in():
+    q = am.msg_queue()
+    assert q.empty_p()
+    q.handle(am.message_from_string("abc"))
+    q.insert_tail(am.message("def"))
+    assert q.count() == 2 and q.delete_head().to_string() == "abc"
+    assert q.strings() == ["def"]
+    q.flush()
+    assert q.empty_p() and q.delete_head_nowait() is None
+
+
+def test_product_does_not_touch_oracle():
+    """The shipped package must not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "gr_air_modes_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert "cpu_oracle" not in txt and "liboracle" not in txt and "modes_oracle" not in txt, fn
+    assert "oracle" not in open(os.path.join(ROOT, "include", "airmodes_b200.h")).read().lower()

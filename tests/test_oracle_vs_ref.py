@@ -1,0 +1,121 @@
+"""Pins the plain-C oracle port (oracle/modes_oracle.c) against the UNMODIFIED reference objects
+(oracle/_ref = /root/reference/lib/*.cc compiled against oracle/shim). CPU only."""
+import numpy as np
+import pytest
+
+from gr_air_modes_b200 import synth
+from oracle import cpu_oracle as co
+
+from helpers import load_golden, parse_msg
+
+KNOWN = [("8D4840D6202CC371C32CE0576098", 0x576098), ("8D40621D58C382D690C8AC2863A7", 0x2863A7)]
+
+
+def test_crc_known_answers(port):
+    for hexs, want in KNOWN:
+        b = bytes.fromhex(hexs)
+        assert port.crc24(b[:11]) == want
+        assert synth.crc24(b[:11]) == want
+
+
+def test_crc_port_equals_reference(port, ref):
+    rng = np.random.default_rng(0)
+    for length in (4, 11):
+        for _ in range(200):
+            b = rng.integers(0, 256, length, dtype=np.uint8).tobytes()
+            assert port.crc24(b) == ref.crc24(b)
+    assert ref.crc24(bytes([0, 0, 1])) == 0xFFF409  # crc_table[1] == POLY (modes_crc.cc:57)
+
+
+@pytest.mark.parametrize("rate,thr", [(2e6, 7.0), (4e6, 7.0), (10e6, 3.5), (20e6, 7.0), (3e6, 7.0), (5e6, 9.0), (2.4e6, 7.0)])
+def test_params_match_reference(port, ref, rate, thr):
+    p = port.params(rate, thr)
+    r, t, h = ref.preamble_params(rate, thr)
+    assert (float(p.rate_int), p.threshold_db, p.history) == (r, t, h)
+
+
+@pytest.mark.parametrize("rate,n,nb,pmf,thr,seed", [
+    (2e6, 400_000, 30, True, 7.0, 1), (4e6, 400_000, 30, True, 7.0, 2), (4e6, 400_000, 30, False, 7.0, 3),
+    (10e6, 600_000, 20, True, 7.0, 4), (20e6, 1_000_000, 16, True, 7.0, 5), (4e6, 400_000, 30, True, 4.0, 6),
+    (5e6, 300_000, 20, True, 7.0, 7), (3e6, 300_000, 20, True, 7.0, 8), (2.4e6, 300_000, 20, True, 6.0, 9),
+    (4e6, 300_000, 300, True, 6.0, 10),
+])
+def test_port_matches_reference_on_scenes(port, ref, rate, n, nb, pmf, thr, seed):
+    sc = synth.make_scene(rate, n, nb, seed, garble_frac=0.2 if nb > 100 else 0.0, fruit=50 if nb > 100 else 0)
+    bb, avg = port.frontend(sc.iq, rate, pmf, co.MA_CANONICAL)
+    r = ref.run_streams(bb, avg, rate, thr)
+    p = port.run_streams(bb, avg, rate, thr)
+    assert len(r.index) > 0
+    assert np.array_equal(r.index, p.index)
+    assert np.array_equal(r.secs, p.secs) and np.array_equal(r.frac, p.frac)
+    assert np.array_equal(r.chips, p.chips)          # bit-exact 240-chip packets
+    assert r.msgs == p.msgs                           # incl. the sticky-precision quirk
+    assert r.calls == p.calls
+    q = port.run_iq(sc.iq, rate, thr, pmf, co.MA_CANONICAL)
+    assert q.msgs == r.msgs
+
+
+def test_end_of_stream_rules(port, ref):
+    """Bursts cut off by the end of the file exercise the 'no room' path (preamble_impl.cc:212-216)."""
+    rate = 4e6
+    for cut in range(0, 700, 37):
+        sc = synth.make_scene(rate, 60_000, 0, 11, starts=[20_000.3, 59_200.0 - cut], amplitude=0.3)
+        bb, avg = port.frontend(sc.iq, rate, True, co.MA_CANONICAL)
+        r = ref.run_streams(bb, avg, rate, 7.0)
+        p = port.run_streams(bb, avg, rate, 7.0)
+        assert np.array_equal(r.index, p.index) and r.msgs == p.msgs and r.calls == p.calls
+
+
+def test_empty_and_tiny_streams(port, ref):
+    for n in (0, 1, 2, 3, 5, 17, 239, 481):
+        z = np.zeros(n, np.float32)
+        r = ref.run_streams(z, z, 4e6, 7.0)
+        p = port.run_streams(z, z, 4e6, 7.0)
+        assert len(r.index) == len(p.index) == 0 and r.calls == p.calls
+
+
+def test_slicer_only_matches_reference(port, ref):
+    rng = np.random.default_rng(5)
+    chips = rng.normal(0.0, 0.3, (300, 240)).astype(np.float32)
+    chips[:, [0, 2, 7, 9]] += 1.0
+    chips[::3, 16:240:2] += 1.0     # plenty of ones
+    secs = np.arange(300, dtype=np.uint64)
+    frac = rng.random(300)
+    r = ref.run_slicer(chips, secs, frac)
+    p = port.run_slicer(chips, secs, frac)
+    assert r.msgs == p.msgs and len(r.msgs) > 0
+
+
+def test_moving_average_schedules_do_not_change_frames(port, ref):
+    """GR's fp32 running sum (chunk dependent) vs the canonical fp64 window."""
+    sc = synth.make_scene(4e6, 500_000, 60, 21)
+    base = port.run_iq(sc.iq, 4e6, 7.0, True, co.MA_CANONICAL).msgs
+    for mode, chunk in ((co.MA_GR_FLOAT, 4096), (co.MA_GR_FLOAT, 1024), (co.MA_SLIDING64, 0)):
+        other = port.run_iq(sc.iq, 4e6, 7.0, True, mode, chunk).msgs
+        assert [m.split()[:2] for m in other] == [m.split()[:2] for m in base]
+        for a, b in zip(other, base):
+            assert abs(10 * np.log10(parse_msg(a)[2]) - 10 * np.log10(parse_msg(b)[2])) < 1e-3
+
+
+def test_golden_fixtures_reproduce(port):
+    """The committed reference-generated goldens (tests/golden) are what the port computes."""
+    meta, scenes = load_golden()
+    for e in meta["crc"]:
+        b = bytes.fromhex(e["frame"])
+        assert "%06x" % port.crc24(b[:11]) == e["crc_first_11"] and e["syndrome"] == "000000"
+    for s, iq in scenes:
+        r = port.run_iq(iq, s["rate"], s["threshold_db"], s["use_pmf"], co.MA_CANONICAL)
+        assert [int(x) for x in r.index] == s["det_index"], s["name"]
+        assert r.msgs == s["msgs"], s["name"]
+        sent = set(s["sent"])
+        assert len(sent & {m.split()[0] for m in r.msgs}) >= 1
+
+
+def test_golden_fixtures_against_live_reference(port, ref):
+    import hashlib
+    meta, scenes = load_golden()
+    for s, iq in scenes:
+        bb, avg = port.frontend(iq, s["rate"], s["use_pmf"], co.MA_CANONICAL)
+        r = ref.run_streams(bb, avg, s["rate"], s["threshold_db"])
+        assert r.msgs == s["msgs"]
+        assert hashlib.sha256(np.ascontiguousarray(r.chips).tobytes()).hexdigest() == s["chips_sha256"]
