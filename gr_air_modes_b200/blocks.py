@@ -148,6 +148,14 @@ class _Context:
         self.call("amb_get_stats", C.byref(s))
         return s
 
+    def scan_times_ms(self, max_n: int = 64):
+        buf = (C.c_float * max_n)()
+        n = self.call("amb_get_scan_times", buf, max_n)
+        return [buf[i] for i in range(n)]
+
+    def use_stream(self, cuda_stream_ptr: int):
+        self.call("amb_set_stream", C.c_void_p(cuda_stream_ptr))
+
 
 def format_message(frame: Frame, first: bool) -> str:
     buf = C.create_string_buffer(200)

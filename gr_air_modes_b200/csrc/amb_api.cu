@@ -13,8 +13,14 @@
 
 #define AMB_VERSION "gr-air-modes_b200 0.1 (sm_100a)"
 
+typedef CUresult (*amb_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
 struct amb_ctx {
     int device = 0, sm_count = 0;
+    amb_encode_fn encode = nullptr;
+    CUtensorMap tm_carry[2], tm_tail;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     float rate_arg = 0.f, thr_db = 0.f;
@@ -29,6 +35,7 @@ struct amb_ctx {
     uint32_t* coarse = nullptr; uint32_t* fine = nullptr; uint32_t* span_count = nullptr;
     size_t rows_cap = 0; int spans_cap = 0;
     int* cand_j = nullptr; uint32_t* cand_info = nullptr; float* cand_avg = nullptr; unsigned cand_cap = 0;
+    void* walk_scratch = nullptr;
     amb_frame* frames = nullptr; unsigned frame_cap = 0; unsigned frames_ub = 0;
     float* chips = nullptr; bool keep_chips = false;
     AmbCounters* ctr = nullptr; AmbWalkState* st = nullptr;
@@ -41,6 +48,8 @@ struct amb_ctx {
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
+    cudaEvent_t ring[128] = {};          // 64 (start, stop) pairs around the scan kernel of the last calls
+    unsigned ring_n = 0;
     int resolver = 0;
     std::string err;
 };
@@ -57,6 +66,24 @@ static int fail(amb_ctx* c, int code, const char* what, cudaError_t e = cudaSucc
 }
 #define CK(call)                                                                  \
     do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, AMB_ERR_CUDA, #call, e_); } while (0)
+
+// IQ as a 2-D tensor of 128-byte lines (16 complex samples each); tiles of 16 lines = 256 samples land in
+// shared memory with the 128B swizzle the scan kernel reads through.
+static int make_tmap(amb_ctx* ctx, CUtensorMap* m, const void* base, size_t n_samples)
+{
+    const cuuint64_t dims[2] = {32, (cuuint64_t)(n_samples / 16)};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {32, 16};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[96]; snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+        ctx->err = buf; return AMB_ERR_CUDA;
+    }
+    return AMB_OK;
+}
 
 // ---- parameters: preamble_impl.cc:56-68,158-162,192,205-208,212,237; rx_path.py:35,49,54 -------------------
 static int compute_params(float channel_rate, float threshold_db, int use_pmf, AmbParams* P, int* chip_off)
@@ -100,7 +127,13 @@ static int compute_params(float channel_rate, float threshold_db, int use_pmf, A
     if (P->qb1 > fwd) fwd = P->qb1;
     if (P->po3 > fwd) fwd = P->po3;
     P->fwd = fwd + 2;
-    P->i_exact = 0;
+    if (P->skip_f == floorf(P->skip_f)) {
+        P->i_exact = (1ll << 24) + 1 - P->skip0;         // first i with i+skip odd above 2^24 rounds away
+    } else {                                             // fractional 240*spc: find the first i where :237 rounds up
+        long long i = 0;
+        for (; i < (1ll << 25); i++) if ((int)((float)i + P->skip_f) != (int)i + P->skip0) break;
+        P->i_exact = i;
+    }
     if (P->maxlate > 14) return AMB_ERR_RATE;
     return AMB_OK;
 }
@@ -109,7 +142,7 @@ static void free_dev(amb_ctx* c)
 {
     cudaFree(c->carry[0]); cudaFree(c->carry[1]); cudaFree(c->tail); cudaFree(c->staging);
     cudaFree(c->coarse); cudaFree(c->fine); cudaFree(c->span_count);
-    cudaFree(c->cand_j); cudaFree(c->cand_info); cudaFree(c->cand_avg);
+    cudaFree(c->cand_j); cudaFree(c->cand_info); cudaFree(c->cand_avg); cudaFree(c->walk_scratch); c->walk_scratch = nullptr;
     cudaFree(c->frames); cudaFree(c->chips); cudaFree(c->ctr); cudaFree(c->st);
     c->carry[0] = c->carry[1] = c->tail = c->staging = nullptr;
     c->coarse = c->fine = c->span_count = nullptr;
@@ -134,6 +167,8 @@ static int setup_rate(amb_ctx* ctx)
     CK(cudaMalloc(&ctx->carry[1], (size_t)ctx->kc * sizeof(float2)));
     ctx->tail_cap = 4 * AMB_STAGE;
     CK(cudaMalloc(&ctx->tail, (size_t)ctx->tail_cap * sizeof(float2)));
+    for (int k = 0; k < 2; k++) { int rc2 = make_tmap(ctx, &ctx->tm_carry[k], ctx->carry[k], (size_t)ctx->kc); if (rc2) return rc2; }
+    { int rc2 = make_tmap(ctx, &ctx->tm_tail, ctx->tail, (size_t)ctx->tail_cap); if (rc2) return rc2; }
     return AMB_OK;
 }
 
@@ -191,7 +226,13 @@ int amb_create(int device, float rate, float threshold_db, int use_pmf, int use_
         ctx->own_stream = true;
         if (cudaMalloc(&ctx->ctr, sizeof(AmbCounters)) != cudaSuccess || cudaMalloc(&ctx->st, sizeof(AmbWalkState)) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
         for (int k = 0; k < 4; k++) if (cudaEventCreate(&ctx->ev[k]) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
+        for (int k = 0; k < 128 && rc == AMB_OK; k++) if (cudaEventCreate(&ctx->ring[k]) != cudaSuccess) rc = AMB_ERR_CUDA;
         if (rc != AMB_OK) break;
+        {   // driver entry point for tensor-map encoding (no link-time dependency on libcuda)
+            void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) { rc = AMB_ERR_CUDA; break; }
+            ctx->encode = (amb_encode_fn)fn;
+        }
         rc = setup_rate(ctx);
         if (rc != AMB_OK) break;
         rc = reset_stream(ctx);
@@ -208,6 +249,7 @@ void amb_destroy(amb_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_dev(ctx);
     for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    for (int k = 0; k < 128; k++) if (ctx->ring[k]) cudaEventDestroy(ctx->ring[k]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -270,17 +312,6 @@ int amb_synchronize(amb_ctx* ctx)
     if (!ctx) return AMB_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    return AMB_OK;
-}
-
-static int ensure(amb_ctx* ctx, void** p, size_t* cap_field, size_t need_elems, size_t elem, size_t* /*unused*/)
-{
-    if (*cap_field >= need_elems) return AMB_OK;
-    CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(*p); *p = nullptr;
-    size_t ncap = need_elems + need_elems / 4 + 64;
-    CK(cudaMalloc(p, ncap * elem));
-    *cap_field = ncap;
     return AMB_OK;
 }
 
@@ -355,7 +386,7 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
             CK(cudaStreamSynchronize(s));
             cudaFree(ctx->fine); cudaFree(ctx->coarse); ctx->fine = ctx->coarse = nullptr;
             const size_t rc = rows_need + rows_need / 8;
-            CK(cudaMalloc(&ctx->fine, rc * 4 * sizeof(uint32_t)));
+            CK(cudaMalloc(&ctx->fine, rc * 8 * sizeof(uint32_t)));
             CK(cudaMalloc(&ctx->coarse, (rc / 32 + 2) * sizeof(uint32_t)));
             ctx->rows_cap = rc;
         }
@@ -368,8 +399,9 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         unsigned cap_need = (unsigned)std::max<long long>(1 << 16, (j_hi - j_lo) / 8 + 1024);
         if (ctx->cand_cap < cap_need) {
             CK(cudaStreamSynchronize(s));
-            cudaFree(ctx->cand_j); cudaFree(ctx->cand_info); cudaFree(ctx->cand_avg);
-            ctx->cand_j = nullptr; ctx->cand_info = nullptr; ctx->cand_avg = nullptr;
+            cudaFree(ctx->cand_j); cudaFree(ctx->cand_info); cudaFree(ctx->cand_avg); cudaFree(ctx->walk_scratch);
+            ctx->cand_j = nullptr; ctx->cand_info = nullptr; ctx->cand_avg = nullptr; ctx->walk_scratch = nullptr;
+            CK(cudaMalloc(&ctx->walk_scratch, amb_walk_scratch_bytes(cap_need)));
             CK(cudaMalloc(&ctx->cand_j, (size_t)cap_need * sizeof(int)));
             CK(cudaMalloc(&ctx->cand_info, (size_t)cap_need * sizeof(uint32_t)));
             CK(cudaMalloc(&ctx->cand_avg, (size_t)cap_need * sizeof(float)));
@@ -393,22 +425,27 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         if (ctx->keep_chips && !ctx->chips) CK(cudaMalloc(&ctx->chips, (size_t)ctx->frame_cap * 240 * sizeof(float)));
         ctx->frames_ub += fr_ub;
         a.coarse = ctx->coarse; a.fine = ctx->fine; a.span_count = ctx->span_count;
+        a.tm_carry = ctx->tm_carry[ctx->cur]; a.tm_tail = ctx->tm_tail;
+        if (n_main) { int rc2 = make_tmap(ctx, &a.tm_main, src, (size_t)n_main); if (rc2) return rc2; }
+        else a.tm_main = ctx->tm_tail;
 
-        if (ctx->timing) CK(cudaEventRecord(ctx->ev[0], s));
+        const unsigned slot = (ctx->ring_n & 63u) * 2;
+        if (ctx->timing) { CK(cudaEventRecord(ctx->ev[0], s)); CK(cudaEventRecord(ctx->ring[slot], s)); }
         CK(amb_launch_scan(a, ctx->sm_count, s));
-        if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], s));
+        if (ctx->timing) { CK(cudaEventRecord(ctx->ev[1], s)); CK(cudaEventRecord(ctx->ring[slot + 1], s)); ctx->ring_n++; }
         CK(amb_launch_compact(a, ctx->cand_j, ctx->cand_cap, ctx->ctr, s));
         AmbExactArgs ea{};
         ea.P = P; ea.S = S; ea.cand_j = ctx->cand_j; ea.cand_info = ctx->cand_info; ea.cand_avg = ctx->cand_avg; ea.ctr = ctx->ctr;
         CK(amb_launch_exact(ea, ctx->sm_count, s));
         wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info;
-        CK(amb_launch_walk_seq(wa, s));
+        if (ctx->resolver == 1) { CK(amb_launch_walk_seq(wa, s)); ctx->stats.kernel_launches += 1; }
+        else { CK(amb_launch_walk_par(wa, ctx->walk_scratch, s)); ctx->stats.kernel_launches += 3; }
         AmbSliceArgs sa{};
         sa.P = P; sa.S = S; sa.cand_j = ctx->cand_j; sa.cand_info = ctx->cand_info; sa.cand_avg = ctx->cand_avg;
         sa.ctr = ctx->ctr; sa.frames = ctx->frames; sa.frame_cap = ctx->frame_cap;
         sa.chips_out = ctx->keep_chips ? ctx->chips : nullptr; sa.org = org;
         CK(amb_launch_slice(sa, ctx->sm_count, s));
-        ctx->stats.kernel_launches += 5;
+        ctx->stats.kernel_launches += 4;
         ctx->ev_valid = ctx->timing;
     } else {
         // nothing can be decided yet; on flush the resolver still has to close the stream
@@ -510,6 +547,22 @@ int amb_get_stats(amb_ctx* ctx, amb_stats* out)
     }
     *out = ctx->stats;
     return AMB_OK;
+}
+
+int amb_get_scan_times(amb_ctx* ctx, float* ms_out, int max)
+{
+    if (!ctx || (!ms_out && max > 0)) return AMB_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const unsigned have = ctx->ring_n < 64u ? ctx->ring_n : 64u;
+    const unsigned n = have < (unsigned)(max > 0 ? max : 0) ? have : (unsigned)(max > 0 ? max : 0);
+    for (unsigned k = 0; k < n; k++) {
+        const unsigned call = ctx->ring_n - n + k;
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ring[(call & 63u) * 2], ctx->ring[(call & 63u) * 2 + 1]));
+        ms_out[k] = ms;
+    }
+    return (int)n;
 }
 
 int amb_debug_candidates(amb_ctx* ctx, uint64_t* index, uint32_t* info, int max)

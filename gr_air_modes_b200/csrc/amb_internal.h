@@ -1,12 +1,13 @@
 // Internal definitions shared by the kernels (amb_kernels.cu) and the host API (amb_api.cu).
 // Reference citations are file:line under the gr-air-modes tree.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/airmodes_b200.h"
 
 #define AMB_STAGE 256          // samples per TMA bulk stage (2 KiB of float2)
-#define AMB_ROW 128            // samples per warp row (4 per lane)
+#define AMB_ROW 256            // samples per warp row (8 per lane) = one TMA tile
 #define AMB_MAX_SPC 10         // samples per chip supported (20 Msps)
 #define AMB_SPAN_ROWS_ALIGN 32 // spans are multiples of 32 rows = one coarse bitmap word
 
@@ -67,7 +68,10 @@ struct AmbScanArgs {
     int j_lo, j_hi;            // predicate evaluated for j in [j_lo, j_hi)
     int row_lo, row_hi;        // rows covering that range (row_lo multiple of 32)
     int rows_per_span, n_spans;
-    uint32_t* coarse; uint32_t* fine; uint32_t* span_count;
+    uint32_t* coarse; uint32_t* fine; uint32_t* span_count;   // fine: 8 words per row, coarse: 1 bit per row
+    alignas(64) CUtensorMap tm_carry;   // 2-D {32 floats, rows of 128 B}, box {32,16}, SWIZZLE_128B
+    alignas(64) CUtensorMap tm_main;
+    alignas(64) CUtensorMap tm_tail;
 };
 
 struct AmbExactArgs {
@@ -103,7 +107,8 @@ cudaError_t amb_launch_scan(const AmbScanArgs& a, int sm_count, cudaStream_t s);
 cudaError_t amb_launch_compact(const AmbScanArgs& a, int* cand_j, unsigned int cand_cap, AmbCounters* ctr, cudaStream_t s);
 cudaError_t amb_launch_exact(const AmbExactArgs& a, int sm_count, cudaStream_t s);
 cudaError_t amb_launch_walk_seq(const AmbWalkArgs& a, cudaStream_t s);
-cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, unsigned int cand_cap, int* scratch, cudaStream_t s);
+cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, cudaStream_t s);
+size_t amb_walk_scratch_bytes(unsigned int cand_cap);
 cudaError_t amb_launch_slice(const AmbSliceArgs& a, int sm_count, cudaStream_t s);
 cudaError_t amb_launch_carry(const AmbSegs& S, float2* dst, int kc, cudaStream_t s);
 cudaError_t amb_launch_stream_candidates(const AmbParams& P, const float* in0, const float* in1, long long n,

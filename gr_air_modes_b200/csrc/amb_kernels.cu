@@ -5,7 +5,7 @@
 //                                 matched filter, noise-floor window and the first four pulse tests of
 //                                 preamble_impl.cc:173-179 as a CONSERVATIVE fp32 pre-filter -> candidate bitmap
 //   compact  amb_compact_kernel   bitmap -> ordered candidate list
-//   exact    amb_exact_kernel     one warp per candidate: canonical arithmetic (bit-for-bit the oracle's),
+//   exact    amb_exact_kernel     one warp per candidate: canonical arithmetic (bit-for-bit the checker's),
 //                                 re-checks :173-179, late-gate :182-192, quiet zones :198-209
 //   resolve  amb_walk_*           reproduces the visit order of the sequential scan loop (:172, :190, :209,
 //                                 :212-216, :237) over the sparse candidate list
@@ -19,7 +19,7 @@ __constant__ int c_chip_off[240];        // int(j*spc) (preamble_impl.cc:220)
 __constant__ unsigned int c_crc_rem[96]; // x^(t+24) mod 0xFFF409, t = distance of a message bit from the parity field
 
 // ------------------------------------------------------------------------------------------------
-// small PTX helpers: mbarrier + TMA 1-D bulk copy (SASS: UBLKCP / SYNCS)
+// small PTX helpers: mbarrier + TMA tensor copy (SASS: UTMALDG / SYNCS)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -36,9 +36,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+// 2-D tiled TMA load: box {32 floats, 16 rows} = 2 KiB = 256 complex samples, 128B-swizzled in shared memory
+__device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -53,217 +54,281 @@ __device__ __forceinline__ const float2* seg_ptr(const AmbSegs& S, int j) {
 // ------------------------------------------------------------------------------------------------
 // scan kernel
 // ------------------------------------------------------------------------------------------------
-// Work decomposition: the evaluated range is cut into contiguous spans of rows_per_span rows (a row =
-// 128 samples, 4 per lane); ONE WARP owns a span and streams through it on its own, with a private
-// 4-stage TMA ring (lane 0 issues cp.async.bulk of 2 KiB stages, all lanes wait on the stage mbarrier).
-// No block-level barrier exists in this kernel; a CTA is just four independent warps.
+// Work decomposition: the evaluated range is cut into contiguous spans of rows_per_span rows; a row is
+// 256 samples = one 2 KiB TMA tile, EIGHT consecutive samples per lane. ONE WARP owns a span and streams
+// through it on its own with a private 4-deep tile ring (lane 0 issues cp.async.bulk.tensor, all lanes wait
+// on the tile's mbarrier). There is no block-level barrier; a CTA is four independent warps.
+//
+// Shared-memory layouts are all bank-conflict free for 32 B-per-lane accesses:
+//   * IQ tiles are written by TMA with the 128B swizzle (16 B chunk index ^= 128 B line index mod 8); a lane
+//     reads its 64 B (8 samples) as 4 LDS.128 from pre-computed swizzled offsets.
+//   * the warp's own arrays (filtered samples `bb`, row-local prefix `pr`) store 16 B chunk c at c ^ ((c>>3)&1).
 //
 // Arithmetic (deliberately NOT the canonical one - this is a filter, the exact stage decides):
-//   m2 = re*re + im*im (fma), bbs = sum of the last SPC m2 (all-positive adds, unscaled PMF),
-//   Pr = row-local inclusive prefix of bbs (warp scan), Rt = row total,
-//   W[n] = sum of the last L bbs = (A - Pr_kd[posd]) + Pr_k[pos] with A = totals of the rows in between.
+//   m2 = re*re + im*im (fma); bbs = sum of the last FL m2 (all-positive adds, unscaled PMF);
+//   Pr = row-local inclusive prefix of bbs (warp scan), Rt = row total;
+//   W[n] = sum of the last L bbs = (A - Pr_kd[posd]) + Pr_k[pos], A = totals of the rows in between.
 //   Exact test (preamble_impl.cc:173-174) is  bb > fl(avg*T)  with bb = fl(S1)*sp, avg = fl(sum bb)*sa;
-//   since sp cancels, it is implied by  bbs >= cT*W - G  with cT = T*sa*(1-eps)^2 and the absolute guard
-//   G = cT*gfac*(Rt+A) >= cT * (accumulated rounding of W)  (every operand of W is <= Rt+A, <= 24 roundings
-//   of 2^-24 each; gfac = 2^-19).  The other tests use the same lowered threshold; the peak test
-//   in[i+1] > in[i] (:175) is relaxed by (1+eps). eps = 2^-15 dwarfs the <= 2^-20 relative error of bbs.
-//   Result: a superset of the reference's candidates; typically < 0.01 % extra.
+//   sp cancels, so it is implied by  bbs >= cT*W - G  with cT = T*sa*(1-eps)^2 and the absolute guard
+//   G = cT*gfac*(Rt+A) >= cT * (accumulated rounding of W): every operand of W is <= Rt+A and fewer than
+//   32 roundings of 2^-24 enter it, gfac = 2^-19. Tests :177-179 use the same lowered threshold; the
+//   peak test in[i+1] > in[i] (:175) is relaxed by (1+eps); eps = 2^-15 dwarfs the <= 2^-19 relative error
+//   of bbs. Result: a superset of the reference's candidates, typically < 0.01 % larger.
 template <int SPC, bool PMF> struct ScanCfg {
     static constexpr int FL = PMF ? SPC : 1;       // pulse-matched-filter length (rx_path.py:48-51)
     static constexpr int L = 48 * SPC;             // noise-floor window (rx_path.py:54)
+    static constexpr int LW = L / 8;               // ... in lanes
     static constexpr int RB = L / AMB_ROW;
     static constexpr int LMOD = L % AMB_ROW;
-    static constexpr int PRR = (RB + 2 <= 2) ? 2 : ((RB + 2 <= 4) ? 4 : 8);
+    static constexpr int PRR = (RB + 2 <= 2) ? 2 : 4;
     static constexpr int NST = 4;
-    static constexpr int WARM = (RB + 2 + 1) & ~1;
-    static constexpr int WARP_BYTES = NST * 2048 + 1024 + 1024 + PRR * 512 + 64;
+    static constexpr int WARM = RB + 2;
+    static constexpr int IQ_BYTES = NST * 2048;                    // per warp, 1 KiB aligned
+    static constexpr int WORK_BYTES = 2 * 1024 + PRR * 1024 + 64;  // bb ring, pr ring, mbarriers
+    static constexpr int CTA_BYTES = 4 * (IQ_BYTES + WORK_BYTES);
 };
 
-__device__ __forceinline__ uint32_t spread8(uint32_t x) {  // 8 bits -> bit positions 0,4,...,28
-    x = (x | (x << 12)) & 0x000F000Fu;
-    x = (x | (x << 6)) & 0x03030303u;
-    x = (x | (x << 3)) & 0x11111111u;
-    return x;
-}
+// float index p (0..255 within a row slot) -> swizzled float index
+__device__ __forceinline__ int swz(int p) { return p ^ ((p >> 3) & 4); }
+
+struct RowRegs { float b[8]; float t[8]; };
+
+template <int SPC, bool PMF>
+struct ScanWarp {
+    using C = ScanCfg<SPC, PMF>;
+    // per-lane constants
+    int lane;
+    const AmbScanArgs* a;
+    unsigned char* iq;      // tile ring
+    float* bbr;             // 2 rows x 256 floats
+    float* prr;             // PRR rows x 256 floats
+    uint32_t iq_s, bar0;
+    int off[4];             // swizzled byte offsets of this lane's 4 IQ chunks within a tile
+    int own;                // swizzled float offset of this lane's first own chunk (chunks own, own^4)
+    int ownd;               // same for the lane LW lanes back (window tail)
+    bool hi; int rows_back;
+    float rth[C::RB + 1];
+    float lastm[8];         // previous row's m2 of this lane (PMF look-back across the row boundary)
+    uint32_t cw, cnt;
+    int ra, rb;
+
+    __device__ __forceinline__ void issue(int k, int slot) const {
+        const AmbSegs& S = a->S;
+        int j = k * AMB_ROW;
+        const void* map; int c1;
+        if (j < S.n_carry) { map = &a->tm_carry; c1 = j >> 4; }
+        else if (j < S.n_carry + S.n_main) { map = &a->tm_main; c1 = (j - S.n_carry) >> 4; }
+        else { map = &a->tm_tail; c1 = (j - S.n_carry - S.n_main) >> 4; }
+        mbar_expect_tx(bar0 + 8 * slot, 2048);
+        tma_tile_g2s(iq_s + 2048 * slot, map, 0, c1, bar0 + 8 * slot);
+    }
+
+    // one row: compute cur, evaluate prev (row k-1)
+    __device__ __forceinline__ void step(int k, int gl, RowRegs& cur, const RowRegs& prev) {
+        const int slot = gl & (C::NST - 1);
+        const uint32_t parity = (gl / C::NST) & 1;
+        while (!mbar_try_wait(bar0 + 8 * slot, parity)) {}
+        const unsigned char* st = iq + slot * 2048;
+        float m[8];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4 v = *reinterpret_cast<const float4*>(st + off[q]);
+            m[2 * q] = fmaf(v.x, v.x, v.y * v.y);
+            m[2 * q + 1] = fmaf(v.z, v.z, v.w * v.w);
+        }
+        // ---- pulse matched filter: unscaled sum of the last FL samples, all-positive adds
+        float* b = cur.b;
+        if (C::FL > 1) {
+            float v[C::FL - 1 + 8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) v[C::FL - 1 + r] = m[r];
+#pragma unroll
+            for (int t = 1; t < C::FL; t++) {
+                const int d = (t + 7) / 8;                 // lanes back
+                const int ridx = (8 * d - t);              // register of that lane
+                const float src = (lane > 31 - d) ? lastm[ridx] : m[ridx];
+                v[C::FL - 1 - t] = __shfl_sync(FULL, src, (lane - d) & 31);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                float s = v[C::FL - 1 + r];
+#pragma unroll
+                for (int t = 1; t < C::FL; t++) s += v[C::FL - 1 + r - t];
+                b[r] = s;
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++) lastm[r] = m[r];
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; r++) b[r] = m[r];
+        }
+        // ---- row-local inclusive prefix
+        float p[8];
+        p[0] = b[0];
+#pragma unroll
+        for (int r = 1; r < 8; r++) p[r] = p[r - 1] + b[r];
+        float inc = p[7];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float y = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc += y;
+        }
+        float exc = __shfl_up_sync(FULL, inc, 1);
+        if (lane == 0) exc = 0.f;
+        const float Rt = __shfl_sync(FULL, inc, 31);
+#pragma unroll
+        for (int r = 0; r < 8; r++) p[r] += exc;
+        float* bslot = bbr + (k & 1) * 256;
+        float* pslot = prr + (k & (C::PRR - 1)) * 256;
+        *reinterpret_cast<float4*>(bslot + own) = make_float4(b[0], b[1], b[2], b[3]);
+        *reinterpret_cast<float4*>(bslot + (own ^ 4)) = make_float4(b[4], b[5], b[6], b[7]);
+        *reinterpret_cast<float4*>(pslot + own) = make_float4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<float4*>(pslot + (own ^ 4)) = make_float4(p[4], p[5], p[6], p[7]);
+        __syncwarp();
+        // ---- noise-floor window sums and lowered thresholds of row k
+        float A = 0.f;
+#pragma unroll
+        for (int mm = 0; mm < C::RB; mm++) A += rth[mm];
+        if (hi) A += rth[C::RB];
+        const float* dslot = prr + ((k - rows_back) & (C::PRR - 1)) * 256;
+        const float4 d0 = *reinterpret_cast<const float4*>(dslot + ownd);
+        const float4 d1 = *reinterpret_cast<const float4*>(dslot + (ownd ^ 4));
+        const float cT = a->P.cT;
+        const float g = cT * a->P.gfac * (Rt + A);
+        cur.t[0] = fmaf(cT, (A - d0.x) + p[0], -g); cur.t[1] = fmaf(cT, (A - d0.y) + p[1], -g);
+        cur.t[2] = fmaf(cT, (A - d0.z) + p[2], -g); cur.t[3] = fmaf(cT, (A - d0.w) + p[3], -g);
+        cur.t[4] = fmaf(cT, (A - d1.x) + p[4], -g); cur.t[5] = fmaf(cT, (A - d1.y) + p[5], -g);
+        cur.t[6] = fmaf(cT, (A - d1.z) + p[6], -g); cur.t[7] = fmaf(cT, (A - d1.w) + p[7], -g);
+        // ---- evaluate row k-1 (its look-ahead reaches into row k, now in the ring)
+        const int ke = k - 1;
+        if (ke >= ra) {
+            const float oe = a->P.one_eps;
+            float nx = __shfl_down_sync(FULL, prev.b[0], 1);
+            const float c0 = __shfl_sync(FULL, b[0], 0);
+            if (lane == 31) nx = c0;
+            uint32_t msk = 0;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const float nxt = (r < 7) ? prev.b[r + 1] : nx;
+                if (prev.b[r] >= prev.t[r] && nxt <= prev.b[r] * oe) msk |= 1u << r;
+            }
+            const int jb = ke * AMB_ROW + 8 * lane;
+            if (jb < a->j_lo || jb + 8 > a->j_hi) {           // only the first / last row of a call
+#pragma unroll
+                for (int r = 0; r < 8; r++) if (jb + r < a->j_lo || jb + r >= a->j_hi) msk &= ~(1u << r);
+            }
+            if (msk) {
+                const int rbase = (ke & 1) * 256 + 8 * lane;
+                const int po1 = a->P.po1, po2 = a->P.po2, po3 = a->P.po3;
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    if (msk & (1u << r)) {
+                        const int q = rbase + r;
+                        const float x1 = bbr[swz((q + po1) & 511)];
+                        const float x2 = bbr[swz((q + po2) & 511)];
+                        const float x3 = bbr[swz((q + po3) & 511)];
+                        if (!(fminf(fminf(x1, x2), x3) >= prev.t[r])) msk &= ~(1u << r);
+                    }
+                }
+            }
+            if (__any_sync(FULL, msk != 0)) {
+                // natural bit order: word w covers samples 32w..32w+31 of the row = lanes 4w..4w+3
+                uint32_t e[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++) e[r] = __ballot_sync(FULL, (msk >> r) & 1u);
+                if (lane < 8) {
+                    uint32_t w = 0;
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        const uint32_t x = (e[r] >> (4 * lane)) & 0xFu;
+                        w |= ((x & 1u) | ((x & 2u) << 7) | ((x & 4u) << 14) | ((x & 8u) << 21)) << r;
+                    }
+                    a->fine[(size_t)ke * 8 + lane] = w;
+                }
+#pragma unroll
+                for (int r = 0; r < 8; r++) cnt += __popc(e[r]);
+                cw |= 1u << (ke & 31);
+            }
+            if ((ke & 31) == 31 || ke == rb - 1) {
+                if (lane == 0) a->coarse[ke >> 5] = cw;
+                cw = 0;
+            }
+        }
+#pragma unroll
+        for (int mm = C::RB; mm > 0; mm--) rth[mm] = rth[mm - 1];
+        rth[0] = Rt;
+        __syncwarp();
+        // ---- refill this slot with row k+NST
+        if (lane == 0 && k + C::NST <= rb) {
+            fence_proxy_async();
+            issue(k + C::NST, slot);
+        }
+    }
+};
 
 template <int SPC, bool PMF>
 __global__ void __launch_bounds__(128) amb_scan_kernel(const __grid_constant__ AmbScanArgs a)
 {
     using C = ScanCfg<SPC, PMF>;
-    constexpr int FL = C::FL;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int span = blockIdx.x * 4 + warp;
     if (span >= a.n_spans) return;
 
-    unsigned char* ws = smem + warp * C::WARP_BYTES;
-    float* m2r = reinterpret_cast<float*>(ws + C::NST * 2048);
-    float* bbr = m2r + 256;
-    float* prr = bbr + 256;
-    const uint32_t iq_s = smem_u32(ws);
-    const uint32_t bar0 = smem_u32(prr + C::PRR * 128);
+    ScanWarp<SPC, PMF> w;
+    w.lane = lane; w.a = &a;
+    w.iq = smem + warp * C::IQ_BYTES;
+    unsigned char* work = smem + 4 * C::IQ_BYTES + warp * C::WORK_BYTES;
+    w.bbr = reinterpret_cast<float*>(work);
+    w.prr = w.bbr + 512;
+    w.iq_s = smem_u32(w.iq);
+    w.bar0 = smem_u32(w.prr + C::PRR * 256);
+    {   // TMA 128B swizzle: 16 B chunk index (bits 4-6) ^= 128 B line index (bits 7-9)
+        const int line = lane >> 1, c0 = 4 * (lane & 1);
+#pragma unroll
+        for (int q = 0; q < 4; q++) w.off[q] = line * 128 + (((c0 + q) ^ (line & 7)) << 4);
+    }
+    w.own = swz(8 * lane);
+    w.ownd = swz(8 * ((lane - C::LW) & 31));
+    w.hi = (C::LMOD != 0) && (8 * lane < C::LMOD);
+    w.rows_back = C::RB + (w.hi ? 1 : 0);
+#pragma unroll
+    for (int m = 0; m <= C::RB; m++) w.rth[m] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; r++) w.lastm[r] = 0.f;
+    w.cw = 0; w.cnt = 0;
+    w.ra = a.row_lo + span * a.rows_per_span;              // evaluate rows [ra, rb)
+    w.rb = min(w.ra + a.rows_per_span, a.row_hi);
+    const int rs = max(w.ra - C::WARM, 0);                 // first row computed (window warm-up)
+    const int nrows = w.rb - rs + 1;                       // row rb is computed as look-ahead only
 
-    const int ra = a.row_lo + span * a.rows_per_span;      // evaluate rows [ra, rb)
-    const int rb = min(ra + a.rows_per_span, a.row_hi);
-    const int rs = max(ra - C::WARM, 0);                   // first row computed (warm-up of the windows)
-    const int g0 = rs >> 1;
-    const int nstages = (rb >> 1) - g0 + 1;                // row rb is computed as look-ahead only
-
-    // zero the rings the warm-up may read before writing
-    for (int i = lane; i < 256; i += 32) { m2r[i] = 0.f; bbr[i] = 0.f; }
-    for (int i = lane; i < C::PRR * 128; i += 32) prr[i] = 0.f;
+    for (int i = lane; i < 512; i += 32) w.bbr[i] = 0.f;
+    for (int i = lane; i < C::PRR * 256; i += 32) w.prr[i] = 0.f;
     if (lane == 0) {
-        for (int s = 0; s < C::NST; s++) mbar_init(bar0 + 8 * s, 1);
+        for (int s = 0; s < C::NST; s++) mbar_init(w.bar0 + 8 * s, 1);
         fence_mbar_init();
     }
     __syncwarp();
     if (lane == 0) {
-        const int pre = nstages < C::NST ? nstages : C::NST;
-        for (int s = 0; s < pre; s++) {
-            mbar_expect_tx(bar0 + 8 * s, 2048);
-            tma_bulk_g2s(iq_s + 2048 * s, seg_ptr(a.S, (g0 + s) * AMB_STAGE), 2048, bar0 + 8 * s);
-        }
+        const int pre = nrows < C::NST ? nrows : C::NST;
+        for (int s = 0; s < pre; s++) w.issue(rs + s, s);
     }
-
-    const float cT = a.P.cT, oe = a.P.one_eps, cTg = a.P.cT * a.P.gfac;
-    const int po1 = a.P.po1, po2 = a.P.po2, po3 = a.P.po3;
-    const int j_lo = a.j_lo, j_hi = a.j_hi;
-    constexpr bool kHasHi = (C::LMOD != 0);
-    const bool hi = kHasHi && (4 * lane < C::LMOD);
-    const int rows_back = C::RB + (hi ? 1 : 0);
-    const int lq = (lane - (C::L / 4)) & 31;
-
-    float rth[C::RB + 1];
+    RowRegs ra_, rb_;
 #pragma unroll
-    for (int m = 0; m <= C::RB; m++) rth[m] = 0.f;
-    float pb0 = 0.f, pb1 = 0.f, pb2 = 0.f, pb3 = 0.f;      // previous row: bbs quad
-    float pt0 = 0.f, pt1 = 0.f, pt2 = 0.f, pt3 = 0.f;      // previous row: lowered thresholds
-    uint32_t cw = 0, cnt = 0;
-
-    for (int gl = 0; gl < nstages; gl++) {
-        const int slot = gl & (C::NST - 1);
-        const uint32_t parity = (gl / C::NST) & 1;
-        while (!mbar_try_wait(bar0 + 8 * slot, parity)) {}
-        const unsigned char* st = ws + slot * 2048;
-#pragma unroll 1
-        for (int half = 0; half < 2; half++) {
-            const int k = ((g0 + gl) << 1) + half;
-            if (k > rb) break;
-            // ---- |x|^2 of this lane's 4 consecutive samples
-            const float4 v0 = *reinterpret_cast<const float4*>(st + half * 1024 + lane * 32);
-            const float4 v1 = *reinterpret_cast<const float4*>(st + half * 1024 + lane * 32 + 16);
-            float m0 = fmaf(v0.x, v0.x, v0.y * v0.y);
-            float m1 = fmaf(v0.z, v0.z, v0.w * v0.w);
-            float m2 = fmaf(v1.x, v1.x, v1.y * v1.y);
-            float m3 = fmaf(v1.z, v1.z, v1.w * v1.w);
-            // ---- pulse matched filter: unscaled sum of the last SPC samples, all-positive adds
-            float b0, b1, b2, b3;
-            if (FL > 1) {
-                const int mb = (k & 1) * 128 + 4 * lane;
-                *reinterpret_cast<float4*>(m2r + mb) = make_float4(m0, m1, m2, m3);
-                __syncwarp();
-                float v[FL + 3];
-                v[FL - 1] = m0; v[FL] = m1; v[FL + 1] = m2; v[FL + 2] = m3;
-#pragma unroll
-                for (int t = 1; t < FL; t++) v[FL - 1 - t] = m2r[(mb - t) & 255];
-                b0 = v[FL - 1]; b1 = v[FL]; b2 = v[FL + 1]; b3 = v[FL + 2];
-#pragma unroll
-                for (int t = 1; t < FL; t++) {
-                    b0 += v[FL - 1 - t]; b1 += v[FL - t]; b2 += v[FL + 1 - t]; b3 += v[FL + 2 - t];
-                }
-            } else {
-                b0 = m0; b1 = m1; b2 = m2; b3 = m3;
-            }
-            // ---- row-local inclusive prefix (warp scan of quad totals)
-            const float q1 = b0 + b1, q2 = q1 + b2, q3 = q2 + b3;
-            float inc = q3;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const float y = __shfl_up_sync(FULL, inc, d);
-                if (lane >= d) inc += y;
-            }
-            float exc = __shfl_up_sync(FULL, inc, 1);
-            if (lane == 0) exc = 0.f;
-            const float Rt = __shfl_sync(FULL, inc, 31);
-            const float p0 = exc + b0, p1 = exc + q1, p2 = exc + q2, p3 = exc + q3;
-            *reinterpret_cast<float4*>(bbr + (k & 1) * 128 + 4 * lane) = make_float4(b0, b1, b2, b3);
-            *reinterpret_cast<float4*>(prr + (k & (C::PRR - 1)) * 128 + 4 * lane) = make_float4(p0, p1, p2, p3);
-            __syncwarp();
-            // ---- noise-floor window and lowered thresholds of row k
-            float A_lo = 0.f;
-#pragma unroll
-            for (int m = 0; m < C::RB; m++) A_lo += rth[m];
-            const float A = hi ? (A_lo + rth[C::RB]) : A_lo;
-            const float4 pd = *reinterpret_cast<const float4*>(prr + ((k - rows_back) & (C::PRR - 1)) * 128 + 4 * lq);
-            const float g = cTg * (Rt + A);
-            const float t0 = fmaf(cT, (A - pd.x) + p0, -g);
-            const float t1 = fmaf(cT, (A - pd.y) + p1, -g);
-            const float t2 = fmaf(cT, (A - pd.z) + p2, -g);
-            const float t3 = fmaf(cT, (A - pd.w) + p3, -g);
-            // ---- evaluate row k-1 (its look-ahead reaches into row k, now in the ring)
-            const int ke = k - 1;
-            if (ke >= ra) {
-                float nx3 = __shfl_down_sync(FULL, pb0, 1);
-                const float c0 = __shfl_sync(FULL, b0, 0);
-                if (lane == 31) nx3 = c0;
-                const int jb = ke * AMB_ROW + 4 * lane;
-                uint32_t m = 0;
-                if (pb0 >= pt0 && pb1 <= pb0 * oe && jb >= j_lo && jb < j_hi) m |= 1u;
-                if (pb1 >= pt1 && pb2 <= pb1 * oe && jb + 1 >= j_lo && jb + 1 < j_hi) m |= 2u;
-                if (pb2 >= pt2 && pb3 <= pb2 * oe && jb + 2 >= j_lo && jb + 2 < j_hi) m |= 4u;
-                if (pb3 >= pt3 && nx3 <= pb3 * oe && jb + 3 >= j_lo && jb + 3 < j_hi) m |= 8u;
-                if (m) {
-                    const int rbase = (ke & 1) * 128 + 4 * lane;
-                    const float th[4] = {pt0, pt1, pt2, pt3};
-#pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        if (m & (1u << r)) {
-                            const float x1 = bbr[(rbase + r + po1) & 255];
-                            const float x2 = bbr[(rbase + r + po2) & 255];
-                            const float x3 = bbr[(rbase + r + po3) & 255];
-                            if (!(fminf(fminf(x1, x2), x3) >= th[r])) m &= ~(1u << r);
-                        }
-                    }
-                }
-                const uint32_t e0 = __ballot_sync(FULL, m & 1u), e1 = __ballot_sync(FULL, m & 2u);
-                const uint32_t e2 = __ballot_sync(FULL, m & 4u), e3 = __ballot_sync(FULL, m & 8u);
-                if (e0 | e1 | e2 | e3) {
-                    if (lane < 4) {   // natural bit order: word q covers samples 32q..32q+31 of the row
-                        const int sh = 8 * lane;
-                        const uint32_t w = spread8((e0 >> sh) & 0xffu) | (spread8((e1 >> sh) & 0xffu) << 1) |
-                                           (spread8((e2 >> sh) & 0xffu) << 2) | (spread8((e3 >> sh) & 0xffu) << 3);
-                        a.fine[(size_t)ke * 4 + lane] = w;
-                    }
-                    cnt += __popc(e0) + __popc(e1) + __popc(e2) + __popc(e3);
-                    cw |= 1u << (ke & 31);
-                }
-                if ((ke & 31) == 31 || ke == rb - 1) {
-                    if (lane == 0) a.coarse[ke >> 5] = cw;
-                    cw = 0;
-                }
-            }
-            // ---- rotate
-#pragma unroll
-            for (int m = C::RB; m > 0; m--) rth[m] = rth[m - 1];
-            rth[0] = Rt;
-            pb0 = b0; pb1 = b1; pb2 = b2; pb3 = b3;
-            pt0 = t0; pt1 = t1; pt2 = t2; pt3 = t3;
-            __syncwarp();
-        }
-        // ---- refill this slot with stage gl+NST
-        if (lane == 0 && gl + C::NST < nstages) {
-            fence_proxy_async();
-            mbar_expect_tx(bar0 + 8 * slot, 2048);
-            tma_bulk_g2s(iq_s + 2048 * slot, seg_ptr(a.S, (g0 + gl + C::NST) * AMB_STAGE), 2048, bar0 + 8 * slot);
-        }
+    for (int r = 0; r < 8; r++) { ra_.b[r] = ra_.t[r] = rb_.b[r] = rb_.t[r] = 0.f; }
+    int gl = 0;
+    for (; gl + 1 < nrows; gl += 2) {
+        w.step(rs + gl, gl, ra_, rb_);
+        w.step(rs + gl + 1, gl + 1, rb_, ra_);
     }
-    if (lane == 0) a.span_count[span] = cnt;
+    if (gl < nrows) w.step(rs + gl, gl, ra_, rb_);
+    if (lane == 0) a.span_count[span] = w.cnt;
 }
 
 size_t amb_scan_smem_bytes(int spc_i)
 {
     switch (spc_i) {
-#define CASE(n) case n: return 4 * (size_t)ScanCfg<n, true>::WARP_BYTES;
+#define CASE(n) case n: return (size_t)ScanCfg<n, true>::CTA_BYTES;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
 #undef CASE
     }
@@ -273,7 +338,7 @@ size_t amb_scan_smem_bytes(int spc_i)
 template <int SPC, bool PMF>
 static cudaError_t launch_scan_t(const AmbScanArgs& a, cudaStream_t s)
 {
-    const size_t smem = 4 * (size_t)ScanCfg<SPC, PMF>::WARP_BYTES;
+    const size_t smem = (size_t)ScanCfg<SPC, PMF>::CTA_BYTES;
     cudaError_t e = cudaFuncSetAttribute(amb_scan_kernel<SPC, PMF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int blocks = (a.n_spans + 3) / 4;
@@ -296,7 +361,7 @@ cudaError_t amb_launch_scan(const AmbScanArgs& a, int, cudaStream_t s)
 // compaction: (coarse, fine) bitmap -> ordered candidate list. One warp per scan span, so the order is
 // span order x row order x bit order = ascending sample index. Offsets come from the per-span counts.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) amb_compact_kernel(const AmbScanArgs a, int* __restrict__ cand_j,
+__global__ void __launch_bounds__(128) amb_compact_kernel(const __grid_constant__ AmbScanArgs a, int* __restrict__ cand_j,
                                                           unsigned int cap, AmbCounters* ctr)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -316,8 +381,10 @@ __global__ void __launch_bounds__(128) amb_compact_kernel(const AmbScanArgs a, i
         unsigned int cnt = 0;
         for (uint32_t m = cw; m; m &= m - 1) {
             const int row = idx * 32 + (__ffs(m) - 1);
-            const uint4 f = *reinterpret_cast<const uint4*>(a.fine + (size_t)row * 4);
-            cnt += __popc(f.x) + __popc(f.y) + __popc(f.z) + __popc(f.w);
+            const uint4 f0 = *reinterpret_cast<const uint4*>(a.fine + (size_t)row * 8);
+            const uint4 f1 = *reinterpret_cast<const uint4*>(a.fine + (size_t)row * 8 + 4);
+            cnt += __popc(f0.x) + __popc(f0.y) + __popc(f0.z) + __popc(f0.w) +
+                   __popc(f1.x) + __popc(f1.y) + __popc(f1.z) + __popc(f1.w);
         }
         unsigned int inc = cnt;
 #pragma unroll
@@ -328,11 +395,8 @@ __global__ void __launch_bounds__(128) amb_compact_kernel(const AmbScanArgs a, i
         unsigned int o = running + inc - cnt;
         for (uint32_t m = cw; m; m &= m - 1) {
             const int row = idx * 32 + (__ffs(m) - 1);
-            const uint4 f = *reinterpret_cast<const uint4*>(a.fine + (size_t)row * 4);
-            const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                for (uint32_t w = fw[q]; w; w &= w - 1) {
+            for (int q = 0; q < 8; q++)
+                for (uint32_t w = a.fine[(size_t)row * 8 + q]; w; w &= w - 1) {
                     if (o < cap) cand_j[o] = row * AMB_ROW + q * 32 + (__ffs(w) - 1);
                     o++;
                 }
@@ -482,15 +546,11 @@ __device__ __forceinline__ long long ninputs_of(long long ntot, long long pos, i
     return n > 0 ? n : 0;
 }
 
-__global__ void amb_walk_seq_kernel(const AmbWalkArgs a)
+// Exact sequential walk from candidate cursor `idx` with state `st`; returns detections flagged.
+__device__ unsigned int seq_walk(const AmbWalkArgs& a, AmbWalkState& st, int idx, int n)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const AmbParams& P = a.P;
-    AmbWalkState st = *a.st;
-    const int n = (int)a.ctr->ncand;
-    unsigned int ndet = 0, nreal = 0;
-    for (int k = 0; k < n; k++) if (a.cand_info[k] & (1u << 8)) nreal++;
-    int idx = 0;
+    unsigned int ndet = 0;
     while (!st.done) {
         long long ninputs = 0, limit;
         if (a.flush) {
@@ -524,6 +584,25 @@ __global__ void amb_walk_seq_kernel(const AmbWalkArgs a)
         st.pos += consumed; st.p = st.pos;
         idx++;
     }
+    return ndet;
+}
+
+// Sequential resolver. mode 0: always run; mode 1: run only if the parallel resolver raised st->fallback == 2
+// (it then restarts from the state saved in scratch and clears the parallel resolver's marks).
+__global__ void amb_walk_seq_kernel(const AmbWalkArgs a, int mode, const AmbWalkState* saved)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    AmbWalkState st = *a.st;
+    const int n = (int)a.ctr->ncand;
+    if (mode == 1) {
+        if (st.fallback != 2) return;
+        st = *saved;
+        st.fallback = 1;
+        for (int k = 0; k < n; k++) a.cand_info[k] &= ~(1u << 10);
+    }
+    unsigned int nreal = 0;
+    for (int k = 0; k < n; k++) if (a.cand_info[k] & (1u << 8)) nreal++;
+    const unsigned int ndet = seq_walk(a, st, 0, n);
     st.ncand_real += nreal; st.ndet += ndet;
     *a.st = st;
     a.ctr->ndet_call = ndet;
@@ -532,7 +611,143 @@ __global__ void amb_walk_seq_kernel(const AmbWalkArgs a)
 
 cudaError_t amb_launch_walk_seq(const AmbWalkArgs& a, cudaStream_t s)
 {
-    amb_walk_seq_kernel<<<1, 32, 0, s>>>(a);
+    amb_walk_seq_kernel<<<1, 32, 0, s>>>(a, 0, nullptr);
+    return cudaGetLastError();
+}
+
+// ---- parallel resolver ----------------------------------------------------------------------------
+// Two candidates further apart than GAP = maxlate + skip0 + 4 samples cannot influence each other through the
+// scan position p: whatever happens at the earlier one, the loop index is back to plain i++ before it reaches
+// the later one (an accepted packet skips at most fin + skip0 + 1, :237). So the candidate list splits into
+// independent CLUSTERS at such gaps, and every cluster can be walked sequentially by its own thread.
+// The one thing that crosses clusters is `pos` (nitems_read at the start of the current general_work call):
+// :237 adds 240*spc to i in FLOAT, which is exact only while i = fin - pos < P.i_exact (about 2^24). Pass 2
+// checks that with a prefix-max of the clusters' consume points; if it ever fails (a gap of > 16.7 M samples
+// between packets), the exact sequential kernel redoes the call. Pass 2 also applies the end-of-stream rules
+// (:150, :212-216) sequentially to the last 240*spc samples when flushing.
+struct AmbClus { long long exit_pos; long long exit_p; long long first_fin; };   // per head, stored at the head's index
+
+__global__ void __launch_bounds__(256) amb_walk_par1_kernel(const AmbWalkArgs a, AmbClus* clus, long long zone)
+{
+    const AmbParams& P = a.P;
+    const int n = (int)a.ctr->ncand;
+    const long long gap = (long long)P.maxlate + P.skip0 + 4;
+    unsigned int ndet = 0, nreal = 0;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        const long long s0 = a.org + a.cand_j[c];
+        if (a.cand_info[c] & (1u << 8)) nreal++;
+        const bool head = (c == 0) || (a.cand_j[c] - a.cand_j[c - 1] >= gap);
+        AmbClus out; out.exit_pos = -1; out.exit_p = -1; out.first_fin = -1;
+        if (head && s0 < zone) {
+            long long pos = -1, p = -1;                     // unknown / "not beyond this cluster's start"
+            if (c == 0) { pos = a.st->pos; p = a.st->p; }   // the first cluster continues the previous call
+            bool pos_known = (c == 0);
+            int k = c;
+            for (;;) {
+                const long long s = a.org + a.cand_j[k];
+                if (s >= zone) break;
+                const uint32_t info = a.cand_info[k];
+                if ((info & (1u << 8)) && s >= p) {
+                    const long long fin = s + (long long)(info & 0xffu);
+                    if (!(info & (1u << 9))) p = fin + 1;
+                    else {
+                        long long consumed;
+                        if (pos_known) consumed = (long long)(int)((float)(fin - pos) + P.skip_f) - (fin - pos);
+                        else { consumed = P.skip0; out.first_fin = fin; }
+                        a.cand_info[k] = info | (1u << 10);
+                        ndet++;
+                        pos = fin + consumed; p = pos; pos_known = true;
+                        out.exit_pos = pos;
+                    }
+                }
+                k++;
+                if (k >= n || a.cand_j[k] - a.cand_j[k - 1] >= gap) break;
+            }
+            out.exit_p = p;
+        }
+        clus[c] = out;
+    }
+    // block-level reduction of the counters
+    for (int d = 16; d > 0; d >>= 1) { ndet += __shfl_xor_sync(FULL, ndet, d); nreal += __shfl_xor_sync(FULL, nreal, d); }
+    if ((threadIdx.x & 31) == 0) { if (ndet) atomicAdd(&a.ctr->ndet_call, ndet); if (nreal) atomicAdd(&a.ctr->nreal_call, nreal); }
+}
+
+__global__ void __launch_bounds__(1024) amb_walk_par2_kernel(const AmbWalkArgs a, const AmbClus* clus, long long zone,
+                                                             AmbWalkState* saved)
+{
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry, s_lastp;
+    __shared__ int s_viol;
+    const AmbParams& P = a.P;
+    const int n = (int)a.ctr->ncand;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    AmbWalkState st0 = *a.st;
+    if (tid == 0) { s_carry = st0.pos; s_lastp = st0.p; s_viol = 0; *saved = st0; }
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int c = base + tid;
+        AmbClus cl; cl.exit_pos = -1; cl.exit_p = -1; cl.first_fin = -1;
+        if (c < n) cl = clus[c];
+        // inclusive prefix max of exit_pos over the block
+        long long v = cl.exit_pos;
+        for (int d = 1; d < 32; d <<= 1) { const long long y = __shfl_up_sync(FULL, v, d); if (lane >= d && y > v) v = y; }
+        if (lane == 31) s_warp[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = s_warp[lane];
+            for (int d = 1; d < 32; d <<= 1) { const long long y = __shfl_up_sync(FULL, w, d); if (lane >= d && y > w) w = y; }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        long long before = s_carry;                                   // max over everything before this thread
+        if (warp > 0 && s_warp[warp - 1] > before) before = s_warp[warp - 1];
+        const long long up = __shfl_up_sync(FULL, v, 1);
+        if (lane > 0 && up > before) before = up;
+        if (cl.first_fin >= 0 && cl.first_fin - before >= P.i_exact) s_viol = 1;   // float rounding at :237 could matter
+        // last cluster's exit p (highest index with a valid exit_p)
+        const unsigned has = __ballot_sync(FULL, cl.exit_p >= 0);
+        __syncthreads();
+        if (has && lane == 31 - __clz(has)) atomicMax((unsigned long long*)&s_lastp, (unsigned long long)cl.exit_p);
+        if (tid == 1023) { if (s_warp[31] > s_carry) s_carry = s_warp[31]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        AmbWalkState st = st0;
+        if (s_viol) { st.fallback = 2; *a.st = st; return; }
+        st.fallback = 0;
+        if (s_carry > st.pos) st.pos = s_carry;
+        if ((long long)s_lastp > st.p) st.p = s_lastp;
+        unsigned int extra = 0;
+        if (a.flush) {
+            // end zone: continue sequentially with the exact end-of-stream rules
+            int idx = 0, lo = 0, hi = n;                 // first candidate with start >= zone
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.org + a.cand_j[mid] < zone) lo = mid + 1; else hi = mid; }
+            idx = lo;
+            extra = seq_walk(a, st, idx, n);
+        } else if (st.p < a.r_safe) {
+            st.p = a.r_safe;
+        }
+        st.ndet += a.ctr->ndet_call + extra; st.ncand_real += a.ctr->nreal_call;
+        a.ctr->ndet_call += extra;
+        *a.st = st;
+    }
+}
+
+size_t amb_walk_scratch_bytes(unsigned int cand_cap) { return sizeof(AmbWalkState) + 8 + (size_t)cand_cap * sizeof(AmbClus); }
+
+cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, cudaStream_t s)
+{
+    AmbWalkState* saved = reinterpret_cast<AmbWalkState*>(scratch);
+    AmbClus* clus = reinterpret_cast<AmbClus*>(reinterpret_cast<unsigned char*>(scratch) + ((sizeof(AmbWalkState) + 7) & ~(size_t)7));
+    const long long guard = (long long)a.P.maxlate + a.P.skip0 + 2 * a.P.spc_i + 8;
+    const long long zone = a.flush ? (a.ntot - guard) : a.r_safe;
+    amb_walk_par1_kernel<<<296, 256, 0, s>>>(a, clus, zone);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    amb_walk_par2_kernel<<<1, 1024, 0, s>>>(a, clus, zone, saved);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    amb_walk_seq_kernel<<<1, 32, 0, s>>>(a, 1, saved);
     return cudaGetLastError();
 }
 

@@ -136,6 +136,9 @@ AMB_API int amb_slicer_process(amb_ctx* ctx, const float* chips, int ndet, const
 AMB_API int amb_set_stream(amb_ctx* ctx, void* cuda_stream);   /* run on a caller-owned cudaStream_t */
 AMB_API int amb_enable_timing(amb_ctx* ctx, int on);           /* CUDA events around the scan kernel / the call */
 AMB_API int amb_get_stats(amb_ctx* ctx, amb_stats* out);       /* synchronises */
+/* Device time (ms) of the streaming scan kernel for the most recent calls made with timing on (oldest
+ * first, at most 64). Returns how many were written. Synchronises. */
+AMB_API int amb_get_scan_times(amb_ctx* ctx, float* ms_out, int max);
 AMB_API int amb_synchronize(amb_ctx* ctx);
 /* Parity dumps of the last amb_process call: candidate start indices (reported coordinates) and their
  * exact-stage verdict: bits 0-7 late shift, bit 8 passes preamble_impl.cc:174-179, bit 9 valid preamble

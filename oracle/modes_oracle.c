@@ -10,6 +10,7 @@
  * (gr-blocks/lib/moving_average_impl.cc, volk_32fc_magnitude_squared_32f generic kernel) and
  * anchored on the call sites python/rx_path.py:38-65.
  */
+#define _POSIX_C_SOURCE 200809L   /* strdup */
 #include "modes_oracle.h"
 
 #include <math.h>

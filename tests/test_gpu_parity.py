@@ -1,0 +1,228 @@
+"""Parity tests proper: the CUDA path through the C ABI vs the CPU oracle / reference goldens. Need a B200."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+import gr_air_modes_b200 as am
+from gr_air_modes_b200 import synth
+from oracle import cpu_oracle as co
+
+from helpers import first_four, load_golden, parse_msg
+
+pytestmark = pytest.mark.gpu
+
+
+def run_cuda(iq, rate, thr, pmf, chunks=None, resolver=0, keep=False):
+    q = am.msg_queue()
+    rx = am.rx_path(rate, thr, q, use_pmf=pmf)
+    rx._ctx.call("amb_set_option", b"resolver", resolver)
+    frames = []
+    if chunks is None:
+        rx.process(iq, flush=True)
+        frames += rx.frames
+    else:
+        pos, n = 0, iq.size // 2
+        for c in chunks:
+            c = int(min(c, n - pos))
+            last = pos + c >= n
+            rx.process(iq[2 * pos: 2 * (pos + c)], flush=last)
+            frames += rx.frames
+            pos += c
+            if last:
+                break
+    return q.strings(), frames, rx
+
+
+@pytest.mark.parametrize("rate,n,nb,pmf,thr,seed", [
+    (2e6, 600_000, 40, True, 7.0, 1), (4e6, 800_000, 50, True, 7.0, 2), (4e6, 800_000, 50, False, 7.0, 3),
+    (10e6, 1_200_000, 40, True, 7.0, 4), (20e6, 2_000_000, 30, True, 7.0, 5), (4e6, 800_000, 50, True, 4.0, 6),
+    (5e6, 600_000, 30, True, 7.0, 7), (3e6, 600_000, 30, True, 7.0, 8), (2.4e6, 600_000, 30, True, 6.0, 9),
+    (6e6, 600_000, 30, True, 7.0, 10), (8e6, 800_000, 30, True, 7.0, 11), (16e6, 1_600_000, 20, True, 7.0, 12),
+    (4e6, 600_000, 700, True, 6.0, 13),
+])
+def test_frames_bit_exact_vs_oracle(port, rate, n, nb, pmf, thr, seed):
+    """Payload, CRC, timestamp, reference level: every queue message identical to the oracle's."""
+    dense = nb > 100
+    sc = synth.make_scene(rate, n, nb, seed, garble_frac=0.2 if dense else 0.0, fruit=80 if dense else 0)
+    want = port.run_iq(sc.iq, rate, thr, pmf, co.MA_CANONICAL)
+    msgs, frames, rx = run_cuda(sc.iq, rate, thr, pmf)
+    assert len(want.index) > 0
+    assert [f.sample_index for f in frames] == [int(x) for x in want.index]      # detected preamble offsets
+    assert msgs == want.msgs
+    for f, g in zip(frames, want.frames):
+        assert bytes(f.data) == bytes(g.data) and f.crc == g.crc and f.nbits == g.nbits
+        assert f.numlowconf == g.numlowconf and bytes(f.lowconfbits) == bytes(g.lowconfbits)
+        assert f.passed == g.passed and f.ref_level == g.ref_level and f.secs == g.secs and f.frac == g.frac
+    # both resolvers agree
+    msgs1, _, _ = run_cuda(sc.iq, rate, thr, pmf, resolver=1)
+    assert msgs1 == want.msgs
+
+
+def test_golden_fixtures_from_unmodified_reference():
+    """tests/golden was produced by the reference's own preamble_impl/slicer_impl/modes_crc objects."""
+    meta, scenes = load_golden()
+    for s, iq in scenes:
+        assert hashlib.sha256(iq.tobytes()).hexdigest() == s["iq_sha256"]
+        msgs, frames, rx = run_cuda(iq, s["rate"], s["threshold_db"], s["use_pmf"])
+        assert [f.sample_index for f in frames] == s["det_index"], s["name"]
+        assert msgs == s["msgs"], s["name"]
+
+
+def test_against_live_reference_if_present(port, ref):
+    sc = synth.make_scene(4e6, 700_000, 60, 31)
+    bb, avg = port.frontend(sc.iq, 4e6, True, co.MA_CANONICAL)
+    r = ref.run_streams(bb, avg, 4e6, 7.0)
+    msgs, frames, _ = run_cuda(sc.iq, 4e6, 7.0, True)
+    assert msgs == r.msgs and [f.sample_index for f in frames] == [int(x) for x in r.index]
+
+
+def test_streaming_equals_one_shot(port):
+    """Ragged chunking (down to 1 sample) must not change a single frame: history, scan position and the
+    'no room' rules carry across calls."""
+    rng = np.random.default_rng(7)
+    for rate, n in ((4e6, 600_000), (10e6, 900_000), (2e6, 400_000)):
+        sc = synth.make_scene(rate, n, 40, int(rate / 1e6) + 40)
+        want = port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL)
+        for chunks in (list(rng.integers(1, 50_000, 2000)), [1, 2, 3, 255, 256, 257, 100_000] * 200, [n // 3] * 4):
+            msgs, frames, _ = run_cuda(sc.iq, rate, 7.0, True, chunks=chunks)
+            assert msgs == want.msgs
+            assert [f.sample_index for f in frames] == [int(x) for x in want.index]
+
+
+def test_end_of_stream_rules(port):
+    """Bursts cut by the end of the stream: preamble_impl.cc:150 and :212-216."""
+    rate = 4e6
+    for cut in range(0, 700, 41):
+        sc = synth.make_scene(rate, 60_000, 0, 11, starts=[20_000.3, 59_200.0 - cut], amplitude=0.3)
+        want = port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL)
+        for resolver in (0, 1):
+            msgs, frames, _ = run_cuda(sc.iq, rate, 7.0, True, resolver=resolver)
+            assert msgs == want.msgs and [f.sample_index for f in frames] == [int(x) for x in want.index]
+
+
+def test_empty_tiny_and_silent_inputs(port):
+    for n in (0, 1, 2, 5, 255, 256, 257, 1000):
+        iq = np.zeros(2 * n, np.float32)
+        msgs, frames, _ = run_cuda(iq, 4e6, 7.0, True)
+        assert msgs == [] and frames == []
+    iq = (np.random.default_rng(0).standard_normal(2 * 3000) * 0.01).astype(np.float32)
+    want = port.run_iq(iq, 4e6, 7.0, True, co.MA_CANONICAL)
+    msgs, _, _ = run_cuda(iq, 4e6, 7.0, True)
+    assert msgs == want.msgs
+
+
+def test_candidate_prefilter_is_a_superset_and_exact_stage_is_exact(port):
+    """The streaming kernel may over-report candidates but never miss one; the exact stage's verdicts are
+    the reference's first four tests (preamble_impl.cc:173-179)."""
+    for rate, pmf in ((4e6, True), (2e6, True), (10e6, True), (4e6, False)):
+        sc = synth.make_scene(rate, 500_000, 60, 77)
+        bb, avg = port.frontend(sc.iq, rate, pmf, co.MA_CANONICAL)
+        want = set(int(x) for x in first_four(bb, avg, rate, 7.0, port))
+        q = am.msg_queue()
+        rx = am.rx_path(rate, 7.0, q, use_pmf=pmf)
+        rx.process(sc.iq, flush=True)
+        idx = (C.c_uint64 * (1 << 20))(); info = (C.c_uint32 * (1 << 20))()
+        n = rx._ctx.call("amb_debug_candidates", idx, info, 1 << 20)
+        cand = {int(idx[k]) for k in range(n)}
+        real = {int(idx[k]) for k in range(n) if info[k] & 0x100}
+        limit = max(want) if want else 0
+        assert {w for w in want if w < limit - 1000} <= cand
+        assert {r for r in real if r < limit - 1000} == {w for w in want if w < limit - 1000}
+        assert len(cand) <= 1.05 * len(real) + 8           # and it is tight
+
+
+def test_long_gap_float_rounding_falls_back_to_sequential(port):
+    """> 2^24 samples between packets: :237 adds 240*spc in float; the parallel resolver must notice."""
+    rate = 10e6
+    sc = synth.make_scene(rate, (1 << 25) + 5_000_001, 0, 3,
+                          starts=[1_000_000.4, 1_000_000.4 + (1 << 24) + 4_000_001, 33_000_000.2], amplitude=0.3)
+    want = port.run_iq(sc.iq, rate, 7.0, True, co.MA_SLIDING64)
+    msgs, frames, rx = run_cuda(sc.iq, rate, 7.0, True)
+    assert [f.sample_index for f in frames] == [int(x) for x in want.index] and len(frames) == 3
+    assert [m.split()[:2] for m in msgs] == [m.split()[:2] for m in want.msgs]
+    assert rx.stats().resolver_fallback == 1
+
+
+def test_device_crc_and_slicer_block(port):
+    rng = np.random.default_rng(9)
+    q = am.msg_queue()
+    rx = am.rx_path(4e6, 7.0, q, use_pmf=True)
+    for length in (4, 11):
+        data = rng.integers(0, 256, (500, length), dtype=np.uint8)
+        out = (C.c_uint32 * 500)()
+        rx._ctx.call("amb_device_crc", data.tobytes(), 500, length, out)
+        assert [out[k] for k in range(500)] == [port.crc24(data[k].tobytes()) for k in range(500)]
+    chips = rng.normal(0.0, 0.3, (400, 240)).astype(np.float32)
+    chips[:, [0, 2, 7, 9]] += 1.0
+    chips[::3, 16:240:2] += 1.0
+    secs = np.arange(400, dtype=np.uint64); frac = rng.random(400)
+    want = port.run_slicer(chips, secs, frac)
+    q2 = am.msg_queue()
+    s = am.slicer(q2)
+    s.process(chips, list(zip(secs, frac)))
+    assert q2.strings() == want.msgs and len(want.msgs) > 10
+
+
+def test_setters_and_errors():
+    q = am.msg_queue()
+    rx = am.rx_path(4e6, 7.0, q, use_pmf=True)
+    assert rx.get_threshold() == 7.0 and rx.get_pmf() is True
+    rx.set_threshold(5.5)
+    assert rx.get_threshold() == 5.5
+    rx.set_rate(10e6)
+    with pytest.raises(RuntimeError):
+        rx.set_rate(1e6)                         # int(spc) == 0 crashes the reference (% 0); we refuse
+    with pytest.raises(RuntimeError):
+        am.rx_path(4e6, 7.0, q, use_pmf=True, use_dcblock=True)
+    rx.process(np.zeros(2000, np.float32), flush=True)
+    with pytest.raises(RuntimeError):
+        rx.process(np.zeros(2000, np.float32))  # flushed stream needs reset()
+    rx.reset()
+    rx.process(np.zeros(2000, np.float32))
+
+
+def test_threshold_change_takes_effect(port):
+    sc = synth.make_scene(4e6, 400_000, 40, 91)
+    q = am.msg_queue()
+    rx = am.rx_path(4e6, 7.0, q, use_pmf=True)
+    for thr in (7.0, 3.0, 10.0):
+        rx.reset(); q.flush(); rx.set_threshold(thr)
+        rx._slicer._first = True
+        rx.process(sc.iq, flush=True)
+        assert q.strings() == port.run_iq(sc.iq, 4e6, thr, True, co.MA_CANONICAL).msgs
+
+
+def test_full_size_properties():
+    """BASELINE size (2^28 samples at 4 Msps) through size-independent properties: idempotence, payloads
+    invariant under a power-of-two gain with levels scaling by its square, and every strong burst decoded."""
+    import torch
+    n = 1 << 28
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    iq = torch.randn(2 * n, device="cuda", generator=g) * 0.01
+    rng = np.random.Generator(np.random.PCG64(5))
+    sent = []
+    for s in np.sort(rng.uniform(1000, n - 2000, 300)):
+        frame = synth.make_frame((11, 17)[int(rng.integers(0, 2))], rng)
+        n0, w = synth.burst_waveform(synth.Burst(float(s), frame, 0.2, float(rng.uniform(0, 6.28))), 2.0)
+        iq[2 * n0: 2 * n0 + 2 * w.size] += torch.from_numpy(np.ascontiguousarray(w).view(np.float32)).cuda()
+        sent.append(frame.hex())
+    q = am.msg_queue()
+    rx = am.rx_path(4e6, 7.0, q, use_pmf=True)
+    rx.process(iq, flush=True)
+    a = q.strings(); q.flush()
+    rx.reset(); rx._slicer._first = True
+    rx.process(iq, flush=True)
+    b = q.strings(); q.flush()
+    assert a == b and len(a) >= 300
+    assert set(sent) <= {m.split()[0] for m in a}
+    assert all(int(m.split()[1], 16) == 0 for m in a if m.split()[0] in set(sent))
+    iq *= 4.0
+    rx.reset(); rx._slicer._first = True
+    rx.process(iq, flush=True)
+    c = q.strings()
+    assert [m.split()[:2] for m in c] == [m.split()[:2] for m in a]
+    assert [m.split()[3:] for m in c] == [m.split()[3:] for m in a]
+    for x, y in zip(a, c):
+        assert abs(parse_msg(y)[2] / parse_msg(x)[2] - 16.0) < 1e-5
