@@ -123,6 +123,15 @@ struct ScanWarp {
         tma_tile_g2s(iq_s + 2048 * slot, map, 0, c1, bar0 + 8 * slot);
     }
 
+    // element (8*lane + r + PO) of the previous row, continuing into the current row: registers + one shuffle
+    template <int PO>
+    __device__ __forceinline__ float ahead(int r, const float* pb, const float* cb) const {
+        const int d = (r + PO) >> 3, reg = (r + PO) & 7;      // compile-time once r is unrolled
+        if (d == 0) return pb[reg];
+        const float src = (lane >= d) ? pb[reg] : cb[reg];
+        return __shfl_sync(FULL, src, (lane + d) & 31);
+    }
+
     // one row: compute cur, evaluate prev (row k-1)
     __device__ __forceinline__ void step(int k, int gl, RowRegs& cur, const RowRegs& prev) {
         const int slot = gl & (C::NST - 1);
@@ -203,32 +212,41 @@ struct ScanWarp {
         const int ke = k - 1;
         if (ke >= ra) {
             const float oe = a->P.one_eps;
-            float nx = __shfl_down_sync(FULL, prev.b[0], 1);
-            const float c0 = __shfl_sync(FULL, b[0], 0);
-            if (lane == 31) nx = c0;
             uint32_t msk = 0;
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                const float nxt = (r < 7) ? prev.b[r + 1] : nx;
+                const float nxt = ahead<1>(r, prev.b, b);
                 if (prev.b[r] >= prev.t[r] && nxt <= prev.b[r] * oe) msk |= 1u << r;
+            }
+            // second pulse (:177) from registers/shuffles when its offset is the compile-time 2*SPC
+            const bool pref = (a->P.po1 == 2 * SPC);
+            if (pref) {
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const float x1 = ahead<2 * SPC>(r, prev.b, b);
+                    if (!(x1 >= prev.t[r])) msk &= ~(1u << r);
+                }
             }
             const int jb = ke * AMB_ROW + 8 * lane;
             if (jb < a->j_lo || jb + 8 > a->j_hi) {           // only the first / last row of a call
 #pragma unroll
                 for (int r = 0; r < 8; r++) if (jb + r < a->j_lo || jb + r >= a->j_hi) msk &= ~(1u << r);
             }
-            if (msk) {
+            if (__any_sync(FULL, msk != 0)) {
                 const int rbase = (ke & 1) * 256 + 8 * lane;
                 const int po1 = a->P.po1, po2 = a->P.po2, po3 = a->P.po3;
+                uint32_t todo = msk;
+                while (todo) {                                 // rare: a few lanes, usually one bit each
+                    const int r = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    float th = prev.t[0];
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    if (msk & (1u << r)) {
-                        const int q = rbase + r;
-                        const float x1 = bbr[swz((q + po1) & 511)];
-                        const float x2 = bbr[swz((q + po2) & 511)];
-                        const float x3 = bbr[swz((q + po3) & 511)];
-                        if (!(fminf(fminf(x1, x2), x3) >= prev.t[r])) msk &= ~(1u << r);
-                    }
+                    for (int rr = 1; rr < 8; rr++) th = (r == rr) ? prev.t[rr] : th;
+                    const int q = rbase + r;
+                    const float x1 = pref ? th : bbr[swz((q + po1) & 511)];
+                    const float x2 = bbr[swz((q + po2) & 511)];
+                    const float x3 = bbr[swz((q + po3) & 511)];
+                    if (!(fminf(fminf(x1, x2), x3) >= th)) msk &= ~(1u << r);
                 }
             }
             if (__any_sync(FULL, msk != 0)) {

@@ -46,6 +46,7 @@ def main():
         i16 = np.rint(sc.iq * 2048.0).astype(np.int16)
         assert np.array_equal(i16.astype(np.float32) / np.float32(2048.0), sc.iq)
         arrays[name] = i16
+        sc.iq = i16.astype(np.float32) / np.float32(2048.0)      # exactly what the tests reconstruct (no -0.0)
         bb, avg = port.frontend(sc.iq, rate, pmf, co.MA_CANONICAL)
         r = ref.run_streams(bb, avg, rate, thr)
         meta["scenes"].append({
