@@ -28,8 +28,9 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build_native(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build_native(force: bool = False, verbose: bool = False, defines=(), out_path: str | None = None) -> str:
+    """defines/out: experiment builds (tools/variants.py); the product build uses neither."""
+    if out_path is None and not force and not needs_build():
         return LIB
     nvcc = _nvcc()
     env = dict(os.environ)
@@ -37,8 +38,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc, "-ccbin", host, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(CSRC, src.replace(".cu", ".o" if out_path is None else "." + os.path.basename(out_path) + ".o"))
+        cmd = [nvcc, "-ccbin", host, *NVCC_FLAGS, *["-D" + d for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -49,9 +50,10 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out.decode()))
         if verbose:
             print(out.decode())
-    cmd = [nvcc, "-ccbin", host, "-shared", "-o", LIB, *objs, "-cudart", "shared"]
+    target = LIB if out_path is None else out_path
+    cmd = [nvcc, "-ccbin", host, "-shared", "-o", target, *objs, "-cudart", "shared"]
     subprocess.run(cmd, check=True, env=env)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

@@ -345,8 +345,6 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
     const int n_main = n_new & ~(AMB_STAGE - 1);
     const int n_tv = n_new - n_main;
     const int n_tail = (n_tv + 512 + AMB_STAGE - 1) / AMB_STAGE * AMB_STAGE;   // <= 4 stages
-    CK(cudaMemsetAsync(ctx->tail, 0, (size_t)ctx->tail_cap * sizeof(float2), s));
-    if (n_tv) CK(cudaMemcpyAsync(ctx->tail, src + n_main, (size_t)n_tv * sizeof(float2), cudaMemcpyDeviceToDevice, s));
 
     AmbSegs S;
     S.carry = ctx->carry[ctx->cur]; S.main_ = src; S.tail = ctx->tail;
@@ -360,9 +358,6 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
     else { r_safe = n_after + P.H - ctx->guard; if (r_safe < ctx->r_done) r_safe = ctx->r_done; j_hi = r_safe - org; }
     ctx->last_org = org; ctx->have_last = true;
 
-    // per-call counters
-    CK(cudaMemsetAsync(&ctx->ctr->ncand, 0, sizeof(unsigned), s));
-    CK(cudaMemsetAsync(&ctx->ctr->ndet_call, 0, 3 * sizeof(unsigned), s));
 
     AmbWalkArgs wa{};
     wa.P = P; wa.org = org; wa.ntot = ntot; wa.r_safe = r_safe; wa.flush = flush ? 1 : 0;
@@ -393,7 +388,7 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         if (ctx->spans_cap < a.n_spans) {
             CK(cudaStreamSynchronize(s));
             cudaFree(ctx->span_count); ctx->span_count = nullptr;
-            CK(cudaMalloc(&ctx->span_count, (size_t)(a.n_spans + 64) * sizeof(uint32_t)));
+            CK(cudaMalloc(&ctx->span_count, (size_t)(a.n_spans + 64 + 128) * sizeof(uint32_t)));
             ctx->spans_cap = a.n_spans + 64;
         }
         unsigned cap_need = (unsigned)std::max<long long>(1 << 16, (j_hi - j_lo) / 8 + 1024);
@@ -401,7 +396,7 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
             CK(cudaStreamSynchronize(s));
             cudaFree(ctx->cand_j); cudaFree(ctx->cand_info); cudaFree(ctx->cand_avg); cudaFree(ctx->walk_scratch);
             ctx->cand_j = nullptr; ctx->cand_info = nullptr; ctx->cand_avg = nullptr; ctx->walk_scratch = nullptr;
-            CK(cudaMalloc(&ctx->walk_scratch, amb_walk_scratch_bytes(cap_need)));
+            CK(cudaMalloc(&ctx->walk_scratch, amb_walk_scratch_bytes(cap_need, (long long)cap_need * 8 + 4096)));
             CK(cudaMalloc(&ctx->cand_j, (size_t)cap_need * sizeof(int)));
             CK(cudaMalloc(&ctx->cand_info, (size_t)cap_need * sizeof(uint32_t)));
             CK(cudaMalloc(&ctx->cand_avg, (size_t)cap_need * sizeof(float)));
@@ -425,6 +420,9 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         if (ctx->keep_chips && !ctx->chips) CK(cudaMalloc(&ctx->chips, (size_t)ctx->frame_cap * 240 * sizeof(float)));
         ctx->frames_ub += fr_ub;
         a.coarse = ctx->coarse; a.fine = ctx->fine; a.span_count = ctx->span_count;
+        a.group_count = ctx->span_count + ctx->spans_cap;          // 128 words behind the span counts
+        CK(amb_launch_prologue(ctx->tail, ctx->tail_cap, src + n_main, n_tv, ctx->ctr, a.group_count, 128,
+                               ctx->resolver == 1 ? nullptr : ctx->walk_scratch, (long long)S.n_carry + S.n_main + S.n_tail, s));
         a.tm_carry = ctx->tm_carry[ctx->cur]; a.tm_tail = ctx->tm_tail;
         if (n_main) { int rc2 = make_tmap(ctx, &a.tm_main, src, (size_t)n_main); if (rc2) return rc2; }
         else a.tm_main = ctx->tm_tail;
@@ -439,16 +437,17 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         CK(amb_launch_exact(ea, ctx->sm_count, s));
         wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info;
         if (ctx->resolver == 1) { CK(amb_launch_walk_seq(wa, s)); ctx->stats.kernel_launches += 1; }
-        else { CK(amb_launch_walk_par(wa, ctx->walk_scratch, s)); ctx->stats.kernel_launches += 3; }
+        else { CK(amb_launch_walk_par(wa, ctx->walk_scratch, ctx->cand_cap, (long long)S.n_carry + S.n_main + S.n_tail, s)); ctx->stats.kernel_launches += 3; }
         AmbSliceArgs sa{};
         sa.P = P; sa.S = S; sa.cand_j = ctx->cand_j; sa.cand_info = ctx->cand_info; sa.cand_avg = ctx->cand_avg;
         sa.ctr = ctx->ctr; sa.frames = ctx->frames; sa.frame_cap = ctx->frame_cap;
         sa.chips_out = ctx->keep_chips ? ctx->chips : nullptr; sa.org = org;
         CK(amb_launch_slice(sa, ctx->sm_count, s));
-        ctx->stats.kernel_launches += 4;
+        ctx->stats.kernel_launches += 5;
         ctx->ev_valid = ctx->timing;
     } else {
         // nothing can be decided yet; on flush the resolver still has to close the stream
+        CK(amb_launch_prologue(ctx->tail, ctx->tail_cap, src + n_main, n_tv, ctx->ctr, nullptr, 0, nullptr, 0, s));
         if (flush) {
             if (!ctx->cand_j) {
                 CK(cudaMalloc(&ctx->cand_j, 64 * sizeof(int)));

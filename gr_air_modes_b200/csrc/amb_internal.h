@@ -69,6 +69,7 @@ struct AmbScanArgs {
     int row_lo, row_hi;        // rows covering that range (row_lo multiple of 32)
     int rows_per_span, n_spans;
     uint32_t* coarse; uint32_t* fine; uint32_t* span_count;   // fine: 8 words per row, coarse: 1 bit per row
+    uint32_t* group_count;     // candidates per group of 64 spans (zeroed by the prologue)
     alignas(64) CUtensorMap tm_carry;   // 2-D {32 floats, rows of 128 B}, box {32,16}, SWIZZLE_128B
     alignas(64) CUtensorMap tm_main;
     alignas(64) CUtensorMap tm_tail;
@@ -107,8 +108,8 @@ cudaError_t amb_launch_scan(const AmbScanArgs& a, int sm_count, cudaStream_t s);
 cudaError_t amb_launch_compact(const AmbScanArgs& a, int* cand_j, unsigned int cand_cap, AmbCounters* ctr, cudaStream_t s);
 cudaError_t amb_launch_exact(const AmbExactArgs& a, int sm_count, cudaStream_t s);
 cudaError_t amb_launch_walk_seq(const AmbWalkArgs& a, cudaStream_t s);
-cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, cudaStream_t s);
-size_t amb_walk_scratch_bytes(unsigned int cand_cap);
+cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, unsigned int cand_cap, long long n_samples, cudaStream_t s);
+size_t amb_walk_scratch_bytes(unsigned int cand_cap, long long n_samples);
 cudaError_t amb_launch_slice(const AmbSliceArgs& a, int sm_count, cudaStream_t s);
 cudaError_t amb_launch_carry(const AmbSegs& S, float2* dst, int kc, cudaStream_t s);
 cudaError_t amb_launch_stream_candidates(const AmbParams& P, const float* in0, const float* in1, long long n,
@@ -117,4 +118,6 @@ cudaError_t amb_launch_stream_candidates(const AmbParams& P, const float* in0, c
 cudaError_t amb_launch_slice_chips(const float* chips, int ndet, amb_frame* frames, cudaStream_t s);
 cudaError_t amb_launch_crc(const uint8_t* data, int n, int length, uint32_t* out, cudaStream_t s);
 cudaError_t amb_upload_tables(const int* chip_off);
+cudaError_t amb_launch_prologue(float2* tail, int tail_cap, const float2* src_rem, int n_rem, AmbCounters* ctr,
+                                uint32_t* group_count, int n_groups, void* scratch, long long n_samples, cudaStream_t s);
 size_t amb_scan_smem_bytes(int spc_i);

@@ -14,6 +14,12 @@
 #include "amb_internal.h"
 
 #define FULL 0xffffffffu
+#ifndef AMB_NST
+#define AMB_NST 3
+#endif
+#ifndef AMB_PROXY_FENCE
+#define AMB_PROXY_FENCE 0
+#endif
 
 __constant__ int c_chip_off[240];        // int(j*spc) (preamble_impl.cc:220)
 __constant__ unsigned int c_crc_rem[96]; // x^(t+24) mod 0xFFF409, t = distance of a message bit from the parity field
@@ -81,7 +87,7 @@ template <int SPC, bool PMF> struct ScanCfg {
     static constexpr int RB = L / AMB_ROW;
     static constexpr int LMOD = L % AMB_ROW;
     static constexpr int PRR = (RB + 2 <= 2) ? 2 : 4;
-    static constexpr int NST = 4;
+    static constexpr int NST = AMB_NST;            // TMA tile ring depth per warp
     static constexpr int WARM = RB + 2;
     static constexpr int IQ_BYTES = NST * 2048;                    // per warp, 1 KiB aligned
     static constexpr int WORK_BYTES = 2 * 1024 + PRR * 1024 + 64;  // bb ring, pr ring, mbarriers
@@ -111,6 +117,7 @@ struct ScanWarp {
     float lastm[8];         // previous row's m2 of this lane (PMF look-back across the row boundary)
     uint32_t cw, cnt;
     int ra, rb;
+    int cur_slot; uint32_t cur_par;   // tile ring position
 
     __device__ __forceinline__ void issue(int k, int slot) const {
         const AmbSegs& S = a->S;
@@ -134,8 +141,9 @@ struct ScanWarp {
 
     // one row: compute cur, evaluate prev (row k-1)
     __device__ __forceinline__ void step(int k, int gl, RowRegs& cur, const RowRegs& prev) {
-        const int slot = gl & (C::NST - 1);
-        const uint32_t parity = (gl / C::NST) & 1;
+        const int slot = cur_slot;
+        const uint32_t parity = cur_par;
+        (void)gl;
         while (!mbar_try_wait(bar0 + 8 * slot, parity)) {}
         const unsigned char* st = iq + slot * 2048;
         float m[8];
@@ -145,6 +153,18 @@ struct ScanWarp {
             m[2 * q] = fmaf(v.x, v.x, v.y * v.y);
             m[2 * q + 1] = fmaf(v.z, v.z, v.w * v.w);
         }
+#ifdef AMB_DBG_LOADONLY
+        {
+            float acc = 0.f;
+#pragma unroll
+            for (int r = 0; r < 8; r++) acc += m[r];
+            if (acc == 12345.678f) cnt++;
+            __syncwarp();
+            if (lane == 0 && k + C::NST <= rb) issue(k + C::NST, slot);
+            if (++cur_slot == C::NST) { cur_slot = 0; cur_par ^= 1u; }
+            return;
+        }
+#endif
         // ---- pulse matched filter: unscaled sum of the last FL samples, all-positive adds
         float* b = cur.b;
         if (C::FL > 1) {
@@ -210,7 +230,11 @@ struct ScanWarp {
         cur.t[6] = fmaf(cT, (A - d1.z) + p[6], -g); cur.t[7] = fmaf(cT, (A - d1.w) + p[7], -g);
         // ---- evaluate row k-1 (its look-ahead reaches into row k, now in the ring)
         const int ke = k - 1;
+#ifdef AMB_DBG_NOEVAL
+        if (ke >= ra && cur.t[0] == 12345.678f) {
+#else
         if (ke >= ra) {
+#endif
             const float oe = a->P.one_eps;
             uint32_t msk = 0;
 #pragma unroll
@@ -278,9 +302,10 @@ struct ScanWarp {
         __syncwarp();
         // ---- refill this slot with row k+NST
         if (lane == 0 && k + C::NST <= rb) {
-            fence_proxy_async();
+            if (AMB_PROXY_FENCE) fence_proxy_async();
             issue(k + C::NST, slot);
         }
+        if (++cur_slot == C::NST) { cur_slot = 0; cur_par ^= 1u; }
     }
 };
 
@@ -314,7 +339,7 @@ __global__ void __launch_bounds__(128) amb_scan_kernel(const __grid_constant__ A
     for (int m = 0; m <= C::RB; m++) w.rth[m] = 0.f;
 #pragma unroll
     for (int r = 0; r < 8; r++) w.lastm[r] = 0.f;
-    w.cw = 0; w.cnt = 0;
+    w.cw = 0; w.cnt = 0; w.cur_slot = 0; w.cur_par = 0;
     w.ra = a.row_lo + span * a.rows_per_span;              // evaluate rows [ra, rb)
     w.rb = min(w.ra + a.rows_per_span, a.row_hi);
     const int rs = max(w.ra - C::WARM, 0);                 // first row computed (window warm-up)
@@ -340,7 +365,10 @@ __global__ void __launch_bounds__(128) amb_scan_kernel(const __grid_constant__ A
         w.step(rs + gl + 1, gl + 1, rb_, ra_);
     }
     if (gl < nrows) w.step(rs + gl, gl, ra_, rb_);
-    if (lane == 0) a.span_count[span] = w.cnt;
+    if (lane == 0) {
+        a.span_count[span] = w.cnt;
+        if (w.cnt) atomicAdd(&a.group_count[span >> 6], w.cnt);
+    }
 }
 
 size_t amb_scan_smem_bytes(int spc_i)
@@ -385,8 +413,9 @@ __global__ void __launch_bounds__(128) amb_compact_kernel(const __grid_constant_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int span = blockIdx.x * 4 + warp;
     if (span >= a.n_spans) return;
-    unsigned int off = 0;
-    for (int w = lane; w < span; w += 32) off += a.span_count[w];
+    unsigned int off = 0;                                   // candidates before this span: whole groups of 64 spans + the rest
+    for (int g = lane; g < (span >> 6); g += 32) off += a.group_count[g];
+    for (int w = (span & ~63) + lane; w < span; w += 32) off += a.span_count[w];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) off += __shfl_xor_sync(FULL, off, d);
     const int ra = a.row_lo + span * a.rows_per_span;
@@ -605,19 +634,12 @@ __device__ unsigned int seq_walk(const AmbWalkArgs& a, AmbWalkState& st, int idx
     return ndet;
 }
 
-// Sequential resolver. mode 0: always run; mode 1: run only if the parallel resolver raised st->fallback == 2
-// (it then restarts from the state saved in scratch and clears the parallel resolver's marks).
-__global__ void amb_walk_seq_kernel(const AmbWalkArgs a, int mode, const AmbWalkState* saved)
+// Sequential resolver (always correct; one thread). Used on request ("resolver" option = 1).
+__global__ void amb_walk_seq_kernel(const AmbWalkArgs a)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     AmbWalkState st = *a.st;
     const int n = (int)a.ctr->ncand;
-    if (mode == 1) {
-        if (st.fallback != 2) return;
-        st = *saved;
-        st.fallback = 1;
-        for (int k = 0; k < n; k++) a.cand_info[k] &= ~(1u << 10);
-    }
     unsigned int nreal = 0;
     for (int k = 0; k < n; k++) if (a.cand_info[k] & (1u << 8)) nreal++;
     const unsigned int ndet = seq_walk(a, st, 0, n);
@@ -629,7 +651,7 @@ __global__ void amb_walk_seq_kernel(const AmbWalkArgs a, int mode, const AmbWalk
 
 cudaError_t amb_launch_walk_seq(const AmbWalkArgs& a, cudaStream_t s)
 {
-    amb_walk_seq_kernel<<<1, 32, 0, s>>>(a, 0, nullptr);
+    amb_walk_seq_kernel<<<1, 32, 0, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -637,15 +659,24 @@ cudaError_t amb_launch_walk_seq(const AmbWalkArgs& a, cudaStream_t s)
 // Two candidates further apart than GAP = maxlate + skip0 + 4 samples cannot influence each other through the
 // scan position p: whatever happens at the earlier one, the loop index is back to plain i++ before it reaches
 // the later one (an accepted packet skips at most fin + skip0 + 1, :237). So the candidate list splits into
-// independent CLUSTERS at such gaps, and every cluster can be walked sequentially by its own thread.
+// independent CLUSTERS at such gaps, and every cluster is walked sequentially by its own thread (pass 1).
 // The one thing that crosses clusters is `pos` (nitems_read at the start of the current general_work call):
-// :237 adds 240*spc to i in FLOAT, which is exact only while i = fin - pos < P.i_exact (about 2^24). Pass 2
-// checks that with a prefix-max of the clusters' consume points; if it ever fails (a gap of > 16.7 M samples
-// between packets), the exact sequential kernel redoes the call. Pass 2 also applies the end-of-stream rules
-// (:150, :212-216) sequentially to the last 240*spc samples when flushing.
-struct AmbClus { long long exit_pos; long long exit_p; long long first_fin; };   // per head, stored at the head's index
+// :237 adds 240*spc to i in FLOAT, which is exact only while i = fin - pos < P.i_exact (about 2^24). Pass 1
+// records every packet's consume point in 2^20-sample time buckets; pass 2 checks, for each cluster whose first
+// packet was walked without knowing pos, that some earlier packet lies less than i_exact samples back (a
+// non-empty bucket among the preceding (i_exact>>20)-1 ones, or the previous call's pos). If that cannot be
+// shown (no packet for > ~15 M samples) the finalize kernel redoes the whole call with the exact sequential walk.
+// Finalize also applies the end-of-stream rules (:150, :212-216) to the last 240*spc samples when flushing.
+#define AMB_BUCKET_SHIFT 20
+struct AmbParScratch {
+    AmbWalkState saved;
+    unsigned long long max_pos_rel1;   // 1 + (largest consume point - org), 0 = none
+    unsigned long long max_p_rel1;     // 1 + (largest exit p - org)
+    unsigned int violation, pad;
+};
 
-__global__ void __launch_bounds__(256) amb_walk_par1_kernel(const AmbWalkArgs a, AmbClus* clus, long long zone)
+__global__ void __launch_bounds__(256) amb_walk_par1_kernel(const AmbWalkArgs a, AmbParScratch* sc, long long* first_fin,
+                                                            unsigned long long* buckets, long long zone)
 {
     const AmbParams& P = a.P;
     const int n = (int)a.ctr->ncand;
@@ -655,11 +686,12 @@ __global__ void __launch_bounds__(256) amb_walk_par1_kernel(const AmbWalkArgs a,
         const long long s0 = a.org + a.cand_j[c];
         if (a.cand_info[c] & (1u << 8)) nreal++;
         const bool head = (c == 0) || (a.cand_j[c] - a.cand_j[c - 1] >= gap);
-        AmbClus out; out.exit_pos = -1; out.exit_p = -1; out.first_fin = -1;
+        long long ff = -1;
         if (head && s0 < zone) {
             long long pos = -1, p = -1;                     // unknown / "not beyond this cluster's start"
             if (c == 0) { pos = a.st->pos; p = a.st->p; }   // the first cluster continues the previous call
-            bool pos_known = (c == 0);
+            bool pos_known = (c == 0), any = false;
+            long long last_pos = -1;
             int k = c;
             for (;;) {
                 const long long s = a.org + a.cand_j[k];
@@ -667,105 +699,103 @@ __global__ void __launch_bounds__(256) amb_walk_par1_kernel(const AmbWalkArgs a,
                 const uint32_t info = a.cand_info[k];
                 if ((info & (1u << 8)) && s >= p) {
                     const long long fin = s + (long long)(info & 0xffu);
+                    any = true;
                     if (!(info & (1u << 9))) p = fin + 1;
                     else {
                         long long consumed;
                         if (pos_known) consumed = (long long)(int)((float)(fin - pos) + P.skip_f) - (fin - pos);
-                        else { consumed = P.skip0; out.first_fin = fin; }
+                        else { consumed = P.skip0; ff = fin; }
                         a.cand_info[k] = info | (1u << 10);
                         ndet++;
                         pos = fin + consumed; p = pos; pos_known = true;
-                        out.exit_pos = pos;
+                        last_pos = pos;
+                        atomicMax(&buckets[(fin - a.org) >> AMB_BUCKET_SHIFT], (unsigned long long)(pos - a.org + 1));
                     }
                 }
                 k++;
                 if (k >= n || a.cand_j[k] - a.cand_j[k - 1] >= gap) break;
             }
-            out.exit_p = p;
+            if (last_pos >= 0) atomicMax(&sc->max_pos_rel1, (unsigned long long)(last_pos - a.org + 1));
+            if (any && p >= a.org) atomicMax(&sc->max_p_rel1, (unsigned long long)(p - a.org + 1));
         }
-        clus[c] = out;
+        first_fin[c] = ff;
     }
-    // block-level reduction of the counters
     for (int d = 16; d > 0; d >>= 1) { ndet += __shfl_xor_sync(FULL, ndet, d); nreal += __shfl_xor_sync(FULL, nreal, d); }
     if ((threadIdx.x & 31) == 0) { if (ndet) atomicAdd(&a.ctr->ndet_call, ndet); if (nreal) atomicAdd(&a.ctr->nreal_call, nreal); }
 }
 
-__global__ void __launch_bounds__(1024) amb_walk_par2_kernel(const AmbWalkArgs a, const AmbClus* clus, long long zone,
-                                                             AmbWalkState* saved)
+__global__ void __launch_bounds__(256) amb_walk_par2_kernel(const AmbWalkArgs a, AmbParScratch* sc, const long long* first_fin,
+                                                            const unsigned long long* buckets)
 {
-    __shared__ long long s_warp[32];
-    __shared__ long long s_carry, s_lastp;
-    __shared__ int s_viol;
     const AmbParams& P = a.P;
     const int n = (int)a.ctr->ncand;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    AmbWalkState st0 = *a.st;
-    if (tid == 0) { s_carry = st0.pos; s_lastp = st0.p; s_viol = 0; *saved = st0; }
-    __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        const int c = base + tid;
-        AmbClus cl; cl.exit_pos = -1; cl.exit_p = -1; cl.first_fin = -1;
-        if (c < n) cl = clus[c];
-        // inclusive prefix max of exit_pos over the block
-        long long v = cl.exit_pos;
-        for (int d = 1; d < 32; d <<= 1) { const long long y = __shfl_up_sync(FULL, v, d); if (lane >= d && y > v) v = y; }
-        if (lane == 31) s_warp[warp] = v;
-        __syncthreads();
-        if (warp == 0) {
-            long long w = s_warp[lane];
-            for (int d = 1; d < 32; d <<= 1) { const long long y = __shfl_up_sync(FULL, w, d); if (lane >= d && y > w) w = y; }
-            s_warp[lane] = w;
-        }
-        __syncthreads();
-        long long before = s_carry;                                   // max over everything before this thread
-        if (warp > 0 && s_warp[warp - 1] > before) before = s_warp[warp - 1];
-        const long long up = __shfl_up_sync(FULL, v, 1);
-        if (lane > 0 && up > before) before = up;
-        if (cl.first_fin >= 0 && cl.first_fin - before >= P.i_exact) s_viol = 1;   // float rounding at :237 could matter
-        // last cluster's exit p (highest index with a valid exit_p)
-        const unsigned has = __ballot_sync(FULL, cl.exit_p >= 0);
-        __syncthreads();
-        if (has && lane == 31 - __clz(has)) atomicMax((unsigned long long*)&s_lastp, (unsigned long long)cl.exit_p);
-        if (tid == 1023) { if (s_warp[31] > s_carry) s_carry = s_warp[31]; }
-        __syncthreads();
+    const int back = (int)(P.i_exact >> AMB_BUCKET_SHIFT) - 1;     // buckets wholly inside the exact range
+    bool viol = false;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        const long long ff = first_fin[c];
+        if (ff < 0) continue;
+        const int b = (int)((ff - a.org) >> AMB_BUCKET_SHIFT);
+        bool safe = false;
+        int lo = b - back; if (lo < 0) lo = 0;
+        for (int q = b - 1; q >= lo && !safe; q--) safe = buckets[q] != 0;
+        if (!safe && b - back <= 0) safe = (ff - a.st->pos) < P.i_exact;   // nothing earlier in this call: pos is the carried one (or later)
+        if (!safe) viol = true;
     }
-    if (tid == 0) {
-        AmbWalkState st = st0;
-        if (s_viol) { st.fallback = 2; *a.st = st; return; }
-        st.fallback = 0;
-        if (s_carry > st.pos) st.pos = s_carry;
-        if ((long long)s_lastp > st.p) st.p = s_lastp;
-        unsigned int extra = 0;
-        if (a.flush) {
-            // end zone: continue sequentially with the exact end-of-stream rules
-            int idx = 0, lo = 0, hi = n;                 // first candidate with start >= zone
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.org + a.cand_j[mid] < zone) lo = mid + 1; else hi = mid; }
-            idx = lo;
-            extra = seq_walk(a, st, idx, n);
-        } else if (st.p < a.r_safe) {
-            st.p = a.r_safe;
-        }
-        st.ndet += a.ctr->ndet_call + extra; st.ncand_real += a.ctr->nreal_call;
-        a.ctr->ndet_call += extra;
-        *a.st = st;
-    }
+    if (__any_sync(FULL, viol) && (threadIdx.x & 31) == 0) sc->violation = 1;
 }
 
-size_t amb_walk_scratch_bytes(unsigned int cand_cap) { return sizeof(AmbWalkState) + 8 + (size_t)cand_cap * sizeof(AmbClus); }
-
-cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, cudaStream_t s)
+__global__ void amb_walk_finalize_kernel(const AmbWalkArgs a, AmbParScratch* sc, long long zone)
 {
-    AmbWalkState* saved = reinterpret_cast<AmbWalkState*>(scratch);
-    AmbClus* clus = reinterpret_cast<AmbClus*>(reinterpret_cast<unsigned char*>(scratch) + ((sizeof(AmbWalkState) + 7) & ~(size_t)7));
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    AmbWalkState st = *a.st;
+    const int n = (int)a.ctr->ncand;
+    if (sc->violation) {                 // float rounding at :237 may matter: exact sequential walk of the whole call
+        for (int k = 0; k < n; k++) a.cand_info[k] &= ~(1u << 10);
+        st.fallback = 1;
+        const unsigned int ndet = seq_walk(a, st, 0, n);
+        st.ndet += ndet; st.ncand_real += a.ctr->nreal_call;
+        a.ctr->ndet_call = ndet;
+        *a.st = st;
+        return;
+    }
+    st.fallback = 0;
+    if (sc->max_pos_rel1) { const long long v = (long long)sc->max_pos_rel1 - 1 + a.org; if (v > st.pos) st.pos = v; }
+    if (sc->max_p_rel1) { const long long v = (long long)sc->max_p_rel1 - 1 + a.org; if (v > st.p) st.p = v; }
+    unsigned int extra = 0;
+    if (a.flush) {
+        int lo = 0, hi = n;                                  // first candidate with start >= zone
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.org + a.cand_j[mid] < zone) lo = mid + 1; else hi = mid; }
+        extra = seq_walk(a, st, lo, n);
+    } else if (st.p < a.r_safe) {
+        st.p = a.r_safe;
+    }
+    st.ndet += a.ctr->ndet_call + extra; st.ncand_real += a.ctr->nreal_call;
+    a.ctr->ndet_call += extra;
+    *a.st = st;
+}
+
+size_t amb_walk_scratch_bytes(unsigned int cand_cap, long long n_samples)
+{
+    return 256 + (size_t)cand_cap * sizeof(long long) + ((size_t)(n_samples >> AMB_BUCKET_SHIFT) + 8) * sizeof(unsigned long long);
+}
+
+cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, unsigned int cand_cap, long long n_samples, cudaStream_t s)
+{
+    AmbParScratch* sc = reinterpret_cast<AmbParScratch*>(scratch);
+    unsigned long long* buckets = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+    const size_t nb = (size_t)(n_samples >> AMB_BUCKET_SHIFT) + 8;
+    long long* first_fin = reinterpret_cast<long long*>(buckets + nb);
+    (void)cand_cap;
+    cudaError_t e;                                          // scratch header + buckets were zeroed by the prologue kernel
     const long long guard = (long long)a.P.maxlate + a.P.skip0 + 2 * a.P.spc_i + 8;
     const long long zone = a.flush ? (a.ntot - guard) : a.r_safe;
-    amb_walk_par1_kernel<<<296, 256, 0, s>>>(a, clus, zone);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    amb_walk_par2_kernel<<<1, 1024, 0, s>>>(a, clus, zone, saved);
+    amb_walk_par1_kernel<<<296, 256, 0, s>>>(a, sc, first_fin, buckets, zone);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    amb_walk_seq_kernel<<<1, 32, 0, s>>>(a, 1, saved);
+    amb_walk_par2_kernel<<<148, 256, 0, s>>>(a, sc, first_fin, buckets);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    amb_walk_finalize_kernel<<<1, 32, 0, s>>>(a, sc, zone);
     return cudaGetLastError();
 }
 
@@ -851,34 +881,45 @@ __device__ void slice_packet_warp(const float* chips, amb_frame* f, int lane)
     }
 }
 
+#define SL_MAXM 2416   // >= int(239*spc) + spc for spc <= 10
+
 template <bool STREAMS>
 __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
 {
     __shared__ float s_chips[4][240];
+    __shared__ float s_m2[STREAMS ? 1 : 4][STREAMS ? 1 : SL_MAXM];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* chips = s_chips[warp];
     const AmbParams& P = a.P;
     const unsigned int ncand = a.ctr->ncand;
     const int nwarps = gridDim.x * 4;
     const int fl = P.use_pmf ? P.spc_i : 1;
+    const int span = c_chip_off[239] + fl;                     // m2 samples a packet touches
     for (unsigned int ci = blockIdx.x * 4 + warp; ci < ncand; ci += nwarps) {
         const uint32_t info = a.cand_info[ci];
         if (!(info & (1u << 10))) continue;                    // warp-uniform
         const int fin = a.cand_j[ci] + (int)(info & 0xffu);
         const float avg_fin = a.cand_avg[ci];
-        for (int j = lane; j < 240; j += 32) {                 // preamble_impl.cc:219-221
-            const int n = fin + c_chip_off[j];
-            float bb;
-            if (STREAMS) {
-                bb = stream_at(a.in0, a.n_streams, P.H, (long long)n);
-            } else if (P.use_pmf) {
-                double acc = 0.0;
-                for (int t = 0; t < fl; t++) acc += (double)canon_m2(a.S, n - fl + 1 + t);
-                bb = __fmul_rn((float)acc, P.scale_p);
-            } else {
-                bb = canon_m2(a.S, n);
+        if (STREAMS) {
+            for (int j = lane; j < 240; j += 32)               // preamble_impl.cc:219-221
+                chips[j] = __fsub_rn(stream_at(a.in0, a.n_streams, P.H, (long long)fin + c_chip_off[j]), avg_fin);
+        } else {
+            float* m2s = s_m2[STREAMS ? 0 : warp];
+            const int b0 = fin - fl + 1;                       // m2s[i] <-> m2[b0 + i]; independent coalesced loads
+            for (int i = lane; i < span; i += 32) m2s[i] = canon_m2(a.S, b0 + i);
+            __syncwarp();
+            for (int j = lane; j < 240; j += 32) {
+                const int o = c_chip_off[j];                   // bb[fin + o] = PMF over m2[fin+o-fl+1 .. fin+o]
+                float bb;
+                if (P.use_pmf) {
+                    double acc = 0.0;
+                    for (int t = 0; t < fl; t++) acc += (double)m2s[o + t];
+                    bb = __fmul_rn((float)acc, P.scale_p);
+                } else {
+                    bb = m2s[o];
+                }
+                chips[j] = __fsub_rn(bb, avg_fin);
             }
-            chips[j] = __fsub_rn(bb, avg_fin);
         }
         __syncwarp();
         unsigned int slot = 0;
@@ -963,6 +1004,29 @@ __global__ void amb_carry_kernel(const AmbSegs S, float2* __restrict__ dst, int 
 cudaError_t amb_launch_carry(const AmbSegs& S, float2* dst, int kc, cudaStream_t s)
 {
     amb_carry_kernel<<<(kc + 255) / 256, 256, 0, s>>>(S, dst, kc);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// prologue: everything that has to be reset / staged before the scan of one call, in one launch
+// ------------------------------------------------------------------------------------------------
+__global__ void amb_prologue_kernel(float2* __restrict__ tail, int tail_cap, const float2* __restrict__ src_rem, int n_rem,
+                                    AmbCounters* ctr, uint32_t* group_count, int n_groups,
+                                    unsigned long long* scratch64, int n_scratch64)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = gridDim.x * blockDim.x;
+    for (int k = i; k < tail_cap; k += stride) tail[k] = k < n_rem ? src_rem[k] : make_float2(0.f, 0.f);
+    for (int k = i; k < n_groups; k += stride) group_count[k] = 0;
+    for (int k = i; k < n_scratch64; k += stride) scratch64[k] = 0ull;
+    if (i == 0) { ctr->ncand = 0; ctr->ndet_call = 0; ctr->npassed_call = 0; ctr->nreal_call = 0; }
+}
+cudaError_t amb_launch_prologue(float2* tail, int tail_cap, const float2* src_rem, int n_rem, AmbCounters* ctr,
+                                uint32_t* group_count, int n_groups, void* scratch, long long n_samples, cudaStream_t s)
+{
+    const int n64 = scratch ? (int)(32 + (n_samples >> AMB_BUCKET_SHIFT) + 8) : 0;
+    amb_prologue_kernel<<<8, 256, 0, s>>>(tail, tail_cap, src_rem, n_rem, ctr, group_count, n_groups,
+                                          reinterpret_cast<unsigned long long*>(scratch), n64);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,25 @@
+"""Timing probe (device-resident): scan-kernel and whole-call time, plus a parity check vs the oracle."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import gr_air_modes_b200 as am
+from gr_air_modes_b200 import synth
+from oracle import cpu_oracle as co
+logn = int(sys.argv[1]) if len(sys.argv) > 1 else 28
+rate = float(sys.argv[2]) if len(sys.argv) > 2 else 4e6
+sc = synth.make_scene(rate, 1 << 20, 60, seed=11)
+want = co.Port().run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL).msgs
+q = am.msg_queue(); rx = am.rx_path(rate, 7.0, q, use_pmf=True); rx.process(sc.iq, flush=True)
+ok = q.strings() == want
+n = 1 << logn
+g = torch.Generator(device="cuda"); g.manual_seed(1)
+iq = torch.randn(2 * n, device="cuda", generator=g) * 0.01
+q = am.msg_queue(); rx = am.rx_path(rate, 7.0, q, use_pmf=True)
+rx._ctx.call("amb_enable_timing", 1)
+sc_ms, tot = [], []
+for it in range(6):
+    rx.reset(); rx.process(iq, flush=True, collect=False)
+    st = rx.stats(); rx.drain()
+    if it >= 2: sc_ms.append(st.ms_scan); tot.append(st.ms_total)
+print("parity %s scan %.3f ms (%.1f GS/s, %.0f GB/s) total %.3f ms (%.1f GS/s)" % (
+    ok, np.mean(sc_ms), n / np.mean(sc_ms) / 1e6, 8 * n / np.mean(sc_ms) / 1e6, np.mean(tot), n / np.mean(tot) / 1e6))
