@@ -67,13 +67,13 @@ static int fail(amb_ctx* c, int code, const char* what, cudaError_t e = cudaSucc
 #define CK(call)                                                                  \
     do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, AMB_ERR_CUDA, #call, e_); } while (0)
 
-// IQ as a 2-D tensor of 128-byte lines (16 complex samples each); tiles of 16 lines = 256 samples land in
+// IQ as a 2-D tensor of 128-byte lines (16 complex samples each); tiles of 32 lines = 512 samples land in
 // shared memory with the 128B swizzle the scan kernel reads through.
 static int make_tmap(amb_ctx* ctx, CUtensorMap* m, const void* base, size_t n_samples)
 {
     const cuuint64_t dims[2] = {32, (cuuint64_t)(n_samples / 16)};
     const cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {32, 16};
+    const cuuint32_t box[2] = {32, 32};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -344,7 +344,7 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
     const int n_new = (int)n_complex;
     const int n_main = n_new & ~(AMB_STAGE - 1);
     const int n_tv = n_new - n_main;
-    const int n_tail = (n_tv + 512 + AMB_STAGE - 1) / AMB_STAGE * AMB_STAGE;   // <= 4 stages
+    const int n_tail = (n_tv + 512 + AMB_STAGE - 1) / AMB_STAGE * AMB_STAGE;   // <= 3 tiles
 
     AmbSegs S;
     S.carry = ctx->carry[ctx->cur]; S.main_ = src; S.tail = ctx->tail;

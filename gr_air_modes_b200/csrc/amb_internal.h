@@ -6,7 +6,8 @@
 #include <stdint.h>
 #include "../../include/airmodes_b200.h"
 
-#define AMB_STAGE 256          // samples per TMA bulk stage (2 KiB of float2)
+#define AMB_TILE 512           // samples per TMA tile (4 KiB of float2) = 2 rows
+#define AMB_STAGE AMB_TILE      // segment granularity: carry/main/tail are whole tiles
 #define AMB_ROW 256            // samples per warp row (8 per lane) = one TMA tile
 #define AMB_MAX_SPC 10         // samples per chip supported (20 Msps)
 #define AMB_SPAN_ROWS_ALIGN 32 // spans are multiples of 32 rows = one coarse bitmap word
@@ -70,7 +71,7 @@ struct AmbScanArgs {
     int rows_per_span, n_spans;
     uint32_t* coarse; uint32_t* fine; uint32_t* span_count;   // fine: 8 words per row, coarse: 1 bit per row
     uint32_t* group_count;     // candidates per group of 64 spans (zeroed by the prologue)
-    alignas(64) CUtensorMap tm_carry;   // 2-D {32 floats, rows of 128 B}, box {32,16}, SWIZZLE_128B
+    alignas(64) CUtensorMap tm_carry;   // 2-D {32 floats, rows of 128 B}, box {32,32}, SWIZZLE_128B
     alignas(64) CUtensorMap tm_main;
     alignas(64) CUtensorMap tm_tail;
 };

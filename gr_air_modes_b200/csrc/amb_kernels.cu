@@ -15,7 +15,7 @@
 
 #define FULL 0xffffffffu
 #ifndef AMB_NST
-#define AMB_NST 3
+#define AMB_NST 2
 #endif
 #ifndef AMB_PROXY_FENCE
 #define AMB_PROXY_FENCE 0
@@ -42,7 +42,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// 2-D tiled TMA load: box {32 floats, 16 rows} = 2 KiB = 256 complex samples, 128B-swizzled in shared memory
+// 2-D tiled TMA load: box {32 floats, 32 lines} = 4 KiB = 512 complex samples, 128B-swizzled in shared memory
 __device__ __forceinline__ void tma_tile_g2s(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
@@ -87,9 +87,9 @@ template <int SPC, bool PMF> struct ScanCfg {
     static constexpr int RB = L / AMB_ROW;
     static constexpr int LMOD = L % AMB_ROW;
     static constexpr int PRR = (RB + 2 <= 2) ? 2 : 4;
-    static constexpr int NST = AMB_NST;            // TMA tile ring depth per warp
-    static constexpr int WARM = RB + 2;
-    static constexpr int IQ_BYTES = NST * 2048;                    // per warp, 1 KiB aligned
+    static constexpr int NST = AMB_NST;            // TMA tile ring depth per warp (tile = 2 rows = 4 KiB)
+    static constexpr int WARM = (RB + 2 + 1) & ~1;
+    static constexpr int IQ_BYTES = NST * 4096;                    // per warp, 1 KiB aligned
     static constexpr int WORK_BYTES = 2 * 1024 + PRR * 1024 + 64;  // bb ring, pr ring, mbarriers
     static constexpr int CTA_BYTES = 4 * (IQ_BYTES + WORK_BYTES);
 };
@@ -102,14 +102,13 @@ struct RowRegs { float b[8]; float t[8]; };
 template <int SPC, bool PMF>
 struct ScanWarp {
     using C = ScanCfg<SPC, PMF>;
-    // per-lane constants
     int lane;
     const AmbScanArgs* a;
     unsigned char* iq;      // tile ring
     float* bbr;             // 2 rows x 256 floats
     float* prr;             // PRR rows x 256 floats
     uint32_t iq_s, bar0;
-    int off[4];             // swizzled byte offsets of this lane's 4 IQ chunks within a tile
+    int off[4];             // swizzled byte offsets of this lane's 4 IQ chunks within a row of a tile
     int own;                // swizzled float offset of this lane's first own chunk (chunks own, own^4)
     int ownd;               // same for the lane LW lanes back (window tail)
     bool hi; int rows_back;
@@ -117,17 +116,17 @@ struct ScanWarp {
     float lastm[8];         // previous row's m2 of this lane (PMF look-back across the row boundary)
     uint32_t cw, cnt;
     int ra, rb;
-    int cur_slot; uint32_t cur_par;   // tile ring position
 
-    __device__ __forceinline__ void issue(int k, int slot) const {
+    // tile t = rows 2t, 2t+1 = 512 samples = 32 lines of 128 B
+    __device__ __forceinline__ void issue(int t, int slot) const {
         const AmbSegs& S = a->S;
-        int j = k * AMB_ROW;
+        const int j = t * AMB_TILE;
         const void* map; int c1;
         if (j < S.n_carry) { map = &a->tm_carry; c1 = j >> 4; }
         else if (j < S.n_carry + S.n_main) { map = &a->tm_main; c1 = (j - S.n_carry) >> 4; }
         else { map = &a->tm_tail; c1 = (j - S.n_carry - S.n_main) >> 4; }
-        mbar_expect_tx(bar0 + 8 * slot, 2048);
-        tma_tile_g2s(iq_s + 2048 * slot, map, 0, c1, bar0 + 8 * slot);
+        mbar_expect_tx(bar0 + 8 * slot, 4096);
+        tma_tile_g2s(iq_s + 4096 * slot, map, 0, c1, bar0 + 8 * slot);
     }
 
     // element (8*lane + r + PO) of the previous row, continuing into the current row: registers + one shuffle
@@ -139,13 +138,8 @@ struct ScanWarp {
         return __shfl_sync(FULL, src, (lane + d) & 31);
     }
 
-    // one row: compute cur, evaluate prev (row k-1)
-    __device__ __forceinline__ void step(int k, int gl, RowRegs& cur, const RowRegs& prev) {
-        const int slot = cur_slot;
-        const uint32_t parity = cur_par;
-        (void)gl;
-        while (!mbar_try_wait(bar0 + 8 * slot, parity)) {}
-        const unsigned char* st = iq + slot * 2048;
+    // one row: compute cur from the tile half at `st`, evaluate prev (row k-1)
+    __device__ __forceinline__ void step(int k, const unsigned char* st, RowRegs& cur, const RowRegs& prev) {
         float m[8];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -153,18 +147,6 @@ struct ScanWarp {
             m[2 * q] = fmaf(v.x, v.x, v.y * v.y);
             m[2 * q + 1] = fmaf(v.z, v.z, v.w * v.w);
         }
-#ifdef AMB_DBG_LOADONLY
-        {
-            float acc = 0.f;
-#pragma unroll
-            for (int r = 0; r < 8; r++) acc += m[r];
-            if (acc == 12345.678f) cnt++;
-            __syncwarp();
-            if (lane == 0 && k + C::NST <= rb) issue(k + C::NST, slot);
-            if (++cur_slot == C::NST) { cur_slot = 0; cur_par ^= 1u; }
-            return;
-        }
-#endif
         // ---- pulse matched filter: unscaled sum of the last FL samples, all-positive adds
         float* b = cur.b;
         if (C::FL > 1) {
@@ -228,68 +210,76 @@ struct ScanWarp {
         cur.t[2] = fmaf(cT, (A - d0.z) + p[2], -g); cur.t[3] = fmaf(cT, (A - d0.w) + p[3], -g);
         cur.t[4] = fmaf(cT, (A - d1.x) + p[4], -g); cur.t[5] = fmaf(cT, (A - d1.y) + p[5], -g);
         cur.t[6] = fmaf(cT, (A - d1.z) + p[6], -g); cur.t[7] = fmaf(cT, (A - d1.w) + p[7], -g);
-        // ---- evaluate row k-1 (its look-ahead reaches into row k, now in the ring)
+        // ---- evaluate row k-1 (its look-ahead reaches into row k, now in registers / the ring)
         const int ke = k - 1;
 #ifdef AMB_DBG_NOEVAL
-        if (ke >= ra && cur.t[0] == 12345.678f) {
+        if (ke >= ra && cur.t[0] + cur.t[3] + cur.t[7] == 12345.678f) {
 #else
         if (ke >= ra) {
 #endif
-            const float oe = a->P.one_eps;
-            uint32_t msk = 0;
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const float nxt = ahead<1>(r, prev.b, b);
-                if (prev.b[r] >= prev.t[r] && nxt <= prev.b[r] * oe) msk |= 1u << r;
-            }
-            // second pulse (:177) from registers/shuffles when its offset is the compile-time 2*SPC
+            // quick per-lane reject: a candidate needs b[i] >= t[i] and (when the second pulse sits at the
+            // compile-time offset 2*SPC) b[i+po1] >= t[i]  ->  max_r min(b, b+po1) >= min_r t
             const bool pref = (a->P.po1 == 2 * SPC);
+            float u[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) u[r] = prev.b[r];
             if (pref) {
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    const float x1 = ahead<2 * SPC>(r, prev.b, b);
-                    if (!(x1 >= prev.t[r])) msk &= ~(1u << r);
-                }
+                for (int r = 0; r < 8; r++) u[r] = fminf(u[r], ahead<2 * SPC>(r, prev.b, b));
             }
-            const int jb = ke * AMB_ROW + 8 * lane;
-            if (jb < a->j_lo || jb + 8 > a->j_hi) {           // only the first / last row of a call
-#pragma unroll
-                for (int r = 0; r < 8; r++) if (jb + r < a->j_lo || jb + r >= a->j_hi) msk &= ~(1u << r);
-            }
-            if (__any_sync(FULL, msk != 0)) {
-                const int rbase = (ke & 1) * 256 + 8 * lane;
-                const int po1 = a->P.po1, po2 = a->P.po2, po3 = a->P.po3;
-                uint32_t todo = msk;
-                while (todo) {                                 // rare: a few lanes, usually one bit each
-                    const int r = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    float th = prev.t[0];
-#pragma unroll
-                    for (int rr = 1; rr < 8; rr++) th = (r == rr) ? prev.t[rr] : th;
-                    const int q = rbase + r;
-                    const float x1 = pref ? th : bbr[swz((q + po1) & 511)];
-                    const float x2 = bbr[swz((q + po2) & 511)];
-                    const float x3 = bbr[swz((q + po3) & 511)];
-                    if (!(fminf(fminf(x1, x2), x3) >= th)) msk &= ~(1u << r);
-                }
-            }
-            if (__any_sync(FULL, msk != 0)) {
-                // natural bit order: word w covers samples 32w..32w+31 of the row = lanes 4w..4w+3
-                uint32_t e[8];
-#pragma unroll
-                for (int r = 0; r < 8; r++) e[r] = __ballot_sync(FULL, (msk >> r) & 1u);
-                if (lane < 8) {
-                    uint32_t w = 0;
+            const float umax = fmaxf(fmaxf(fmaxf(u[0], u[1]), fmaxf(u[2], u[3])), fmaxf(fmaxf(u[4], u[5]), fmaxf(u[6], u[7])));
+            const float tmin = fminf(fminf(fminf(prev.t[0], prev.t[1]), fminf(prev.t[2], prev.t[3])),
+                                     fminf(fminf(prev.t[4], prev.t[5]), fminf(prev.t[6], prev.t[7])));
+            const bool hot = umax >= tmin;
+            const float nx = ahead<1>(7, prev.b, b);           // first sample of the next lane / row
+            if (__any_sync(FULL, hot)) {
+                uint32_t msk = 0;
+                if (hot) {
+                    const float oe = a->P.one_eps;
 #pragma unroll
                     for (int r = 0; r < 8; r++) {
-                        const uint32_t x = (e[r] >> (4 * lane)) & 0xFu;
-                        w |= ((x & 1u) | ((x & 2u) << 7) | ((x & 4u) << 14) | ((x & 8u) << 21)) << r;
+                        const float nxt = (r < 7) ? prev.b[r + 1] : nx;
+                        if (u[r] >= prev.t[r] && nxt <= prev.b[r] * oe) msk |= 1u << r;
                     }
-                    a->fine[(size_t)ke * 8 + lane] = w;
-                }
+                    const int jb = ke * AMB_ROW + 8 * lane;
+                    if (jb < a->j_lo || jb + 8 > a->j_hi) {   // only the first / last row of a call
 #pragma unroll
-                for (int r = 0; r < 8; r++) cnt += __popc(e[r]);
-                cw |= 1u << (ke & 31);
+                        for (int r = 0; r < 8; r++) if (jb + r < a->j_lo || jb + r >= a->j_hi) msk &= ~(1u << r);
+                    }
+                    const int rbase = (ke & 1) * 256 + 8 * lane;
+                    const int po1 = a->P.po1, po2 = a->P.po2, po3 = a->P.po3;
+                    uint32_t todo = msk;
+                    while (todo) {                             // tests :177-179 from the shared-memory ring
+                        const int r = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        float th = prev.t[0];
+#pragma unroll
+                        for (int rr = 1; rr < 8; rr++) th = (r == rr) ? prev.t[rr] : th;
+                        const int q = rbase + r;
+                        const float x1 = pref ? th : bbr[swz((q + po1) & 511)];
+                        const float x2 = bbr[swz((q + po2) & 511)];
+                        const float x3 = bbr[swz((q + po3) & 511)];
+                        if (!(fminf(fminf(x1, x2), x3) >= th)) msk &= ~(1u << r);
+                    }
+                }
+                if (__any_sync(FULL, msk != 0)) {
+                    // natural bit order: word w covers samples 32w..32w+31 of the row = lanes 4w..4w+3
+                    uint32_t e[8];
+#pragma unroll
+                    for (int r = 0; r < 8; r++) e[r] = __ballot_sync(FULL, (msk >> r) & 1u);
+                    if (lane < 8) {
+                        uint32_t w = 0;
+#pragma unroll
+                        for (int r = 0; r < 8; r++) {
+                            const uint32_t x = (e[r] >> (4 * lane)) & 0xFu;
+                            w |= ((x & 1u) | ((x & 2u) << 7) | ((x & 4u) << 14) | ((x & 8u) << 21)) << r;
+                        }
+                        a->fine[(size_t)ke * 8 + lane] = w;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 8; r++) cnt += __popc(e[r]);
+                    cw |= 1u << (ke & 31);
+                }
             }
             if ((ke & 31) == 31 || ke == rb - 1) {
                 if (lane == 0) a->coarse[ke >> 5] = cw;
@@ -300,12 +290,6 @@ struct ScanWarp {
         for (int mm = C::RB; mm > 0; mm--) rth[mm] = rth[mm - 1];
         rth[0] = Rt;
         __syncwarp();
-        // ---- refill this slot with row k+NST
-        if (lane == 0 && k + C::NST <= rb) {
-            if (AMB_PROXY_FENCE) fence_proxy_async();
-            issue(k + C::NST, slot);
-        }
-        if (++cur_slot == C::NST) { cur_slot = 0; cur_par ^= 1u; }
     }
 };
 
@@ -339,11 +323,12 @@ __global__ void __launch_bounds__(128) amb_scan_kernel(const __grid_constant__ A
     for (int m = 0; m <= C::RB; m++) w.rth[m] = 0.f;
 #pragma unroll
     for (int r = 0; r < 8; r++) w.lastm[r] = 0.f;
-    w.cw = 0; w.cnt = 0; w.cur_slot = 0; w.cur_par = 0;
+    w.cw = 0; w.cnt = 0;
     w.ra = a.row_lo + span * a.rows_per_span;              // evaluate rows [ra, rb)
     w.rb = min(w.ra + a.rows_per_span, a.row_hi);
-    const int rs = max(w.ra - C::WARM, 0);                 // first row computed (window warm-up)
-    const int nrows = w.rb - rs + 1;                       // row rb is computed as look-ahead only
+    const int rs = max(w.ra - C::WARM, 0);                 // first row computed (even; window warm-up)
+    const int t0 = rs >> 1;
+    const int ntiles = (w.rb >> 1) - t0 + 1;               // row rb is computed as look-ahead only
 
     for (int i = lane; i < 512; i += 32) w.bbr[i] = 0.f;
     for (int i = lane; i < C::PRR * 256; i += 32) w.prr[i] = 0.f;
@@ -353,18 +338,34 @@ __global__ void __launch_bounds__(128) amb_scan_kernel(const __grid_constant__ A
     }
     __syncwarp();
     if (lane == 0) {
-        const int pre = nrows < C::NST ? nrows : C::NST;
-        for (int s = 0; s < pre; s++) w.issue(rs + s, s);
+        const int pre = ntiles < C::NST ? ntiles : C::NST;
+        for (int s = 0; s < pre; s++) w.issue(t0 + s, s);
     }
     RowRegs ra_, rb_;
 #pragma unroll
     for (int r = 0; r < 8; r++) { ra_.b[r] = ra_.t[r] = rb_.b[r] = rb_.t[r] = 0.f; }
-    int gl = 0;
-    for (; gl + 1 < nrows; gl += 2) {
-        w.step(rs + gl, gl, ra_, rb_);
-        w.step(rs + gl + 1, gl + 1, rb_, ra_);
+    int slot = 0; uint32_t par = 0;
+    for (int tl = 0; tl < ntiles; tl++) {
+        while (!mbar_try_wait(w.bar0 + 8 * slot, par)) {}
+        const unsigned char* st = w.iq + slot * 4096;
+        const int k = (t0 + tl) << 1;
+#ifdef AMB_DBG_LOADONLY
+        {
+            const float4 v0 = *reinterpret_cast<const float4*>(st + w.off[0]);
+            const float4 v1 = *reinterpret_cast<const float4*>(st + 2048 + w.off[3]);
+            if (v0.x + v1.w == 12345.678f) w.cnt++;
+        }
+#else
+        w.step(k, st, ra_, rb_);
+        if (k + 1 <= w.rb) w.step(k + 1, st + 2048, rb_, ra_);
+#endif
+        __syncwarp();
+        if (lane == 0 && tl + C::NST < ntiles) {            // refill this slot with tile tl+NST
+            if (AMB_PROXY_FENCE) fence_proxy_async();
+            w.issue(t0 + tl + C::NST, slot);
+        }
+        if (++slot == C::NST) { slot = 0; par ^= 1u; }
     }
-    if (gl < nrows) w.step(rs + gl, gl, ra_, rb_);
     if (lane == 0) {
         a.span_count[span] = w.cnt;
         if (w.cnt) atomicAdd(&a.group_count[span >> 6], w.cnt);
@@ -510,7 +511,13 @@ __global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a)
         } else {
             const int b_bb = c - L + 1;               // bbs[i] <-> bb[b_bb + i]
             const int b_m2 = b_bb - (fl - 1);
-            for (int i = lane; i < NM; i += 32) m2s[i] = canon_m2(a.S, b_m2 + i);
+            for (int i0 = 0; i0 < NM; i0 += 256) {            // 8 independent loads in flight per lane
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; v[u] = i < NM ? canon_m2(a.S, b_m2 + i) : 0.f; }
+#pragma unroll
+                for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; if (i < NM) m2s[i] = v[u]; }
+            }
             __syncwarp();
             for (int i = lane; i < NB; i += 32) {
                 if (P.use_pmf) {
@@ -672,7 +679,8 @@ struct AmbParScratch {
     AmbWalkState saved;
     unsigned long long max_pos_rel1;   // 1 + (largest consume point - org), 0 = none
     unsigned long long max_p_rel1;     // 1 + (largest exit p - org)
-    unsigned int violation, pad;
+    unsigned int violation;
+    unsigned int zone_idx1;            // 1 + index of the first candidate with start >= zone (0 = none)
 };
 
 __global__ void __launch_bounds__(256) amb_walk_par1_kernel(const AmbWalkArgs a, AmbParScratch* sc, long long* first_fin,
@@ -686,6 +694,7 @@ __global__ void __launch_bounds__(256) amb_walk_par1_kernel(const AmbWalkArgs a,
         const long long s0 = a.org + a.cand_j[c];
         if (a.cand_info[c] & (1u << 8)) nreal++;
         const bool head = (c == 0) || (a.cand_j[c] - a.cand_j[c - 1] >= gap);
+        if (s0 >= zone && (c == 0 || a.org + a.cand_j[c - 1] < zone)) sc->zone_idx1 = (unsigned)c + 1u;
         long long ff = -1;
         if (head && s0 < zone) {
             long long pos = -1, p = -1;                     // unknown / "not beyond this cluster's start"
@@ -744,7 +753,7 @@ __global__ void __launch_bounds__(256) amb_walk_par2_kernel(const AmbWalkArgs a,
     if (__any_sync(FULL, viol) && (threadIdx.x & 31) == 0) sc->violation = 1;
 }
 
-__global__ void amb_walk_finalize_kernel(const AmbWalkArgs a, AmbParScratch* sc, long long zone)
+__global__ void amb_walk_finalize_kernel(const AmbWalkArgs a, AmbParScratch* sc)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     AmbWalkState st = *a.st;
@@ -763,8 +772,7 @@ __global__ void amb_walk_finalize_kernel(const AmbWalkArgs a, AmbParScratch* sc,
     if (sc->max_p_rel1) { const long long v = (long long)sc->max_p_rel1 - 1 + a.org; if (v > st.p) st.p = v; }
     unsigned int extra = 0;
     if (a.flush) {
-        int lo = 0, hi = n;                                  // first candidate with start >= zone
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.org + a.cand_j[mid] < zone) lo = mid + 1; else hi = mid; }
+        const int lo = sc->zone_idx1 ? (int)sc->zone_idx1 - 1 : n;   // first candidate with start >= zone (from pass 1)
         extra = seq_walk(a, st, lo, n);
     } else if (st.p < a.r_safe) {
         st.p = a.r_safe;
@@ -795,7 +803,7 @@ cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, unsigned in
     amb_walk_par2_kernel<<<148, 256, 0, s>>>(a, sc, first_fin, buckets);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    amb_walk_finalize_kernel<<<1, 32, 0, s>>>(a, sc, zone);
+    amb_walk_finalize_kernel<<<1, 32, 0, s>>>(a, sc);
     return cudaGetLastError();
 }
 
@@ -906,7 +914,13 @@ __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
         } else {
             float* m2s = s_m2[STREAMS ? 0 : warp];
             const int b0 = fin - fl + 1;                       // m2s[i] <-> m2[b0 + i]; independent coalesced loads
-            for (int i = lane; i < span; i += 32) m2s[i] = canon_m2(a.S, b0 + i);
+            for (int i0 = 0; i0 < span; i0 += 256) {           // 8 independent loads in flight per lane
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; v[u] = i < span ? canon_m2(a.S, b0 + i) : 0.f; }
+#pragma unroll
+                for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; if (i < span) m2s[i] = v[u]; }
+            }
             __syncwarp();
             for (int j = lane; j < 240; j += 32) {
                 const int o = c_chip_off[j];                   // bb[fin + o] = PMF over m2[fin+o-fl+1 .. fin+o]

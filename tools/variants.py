@@ -5,7 +5,7 @@ import os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "gr_air_modes_b200", "variants")
-VARIANTS = {"nst2": ["AMB_NST=2"], "nst2_noeval": ["AMB_NST=2", "AMB_DBG_NOEVAL"], "nst2_loadonly": ["AMB_NST=2", "AMB_DBG_LOADONLY"], "nst4_loadonly": ["AMB_NST=4", "AMB_DBG_LOADONLY"]}
+VARIANTS = {"nst2": ["AMB_NST=2"], "nst3": ["AMB_NST=3"], "nst2_noeval": ["AMB_NST=2", "AMB_DBG_NOEVAL"], "nst2_loadonly": ["AMB_NST=2", "AMB_DBG_LOADONLY"]}
 if sys.argv[1] == "build":
     from gr_air_modes_b200 import build
     os.makedirs(VDIR, exist_ok=True)
