@@ -60,6 +60,7 @@ SYMBOLS = [
     ("amb_get_stats", C.c_int, [_vp, C.POINTER(Stats)]),
     ("amb_get_scan_times", C.c_int, [_vp, _f32p, C.c_int]),
     ("amb_synchronize", C.c_int, [_vp]),
+    ("amb_join", C.c_int, [_vp]),
     ("amb_debug_candidates", C.c_int, [_vp, _u64p, C.POINTER(C.c_uint32), C.c_int]),
     ("amb_set_option", C.c_int, [_vp, C.c_char_p, C.c_int]),
     ("amb_strerror", C.c_char_p, [C.c_int]),

@@ -153,6 +153,10 @@ class _Context:
         n = self.call("amb_get_scan_times", buf, max_n)
         return [buf[i] for i in range(n)]
 
+    def join(self):
+        """Make the caller-visible CUDA stream wait for everything enqueued so far (no host sync)."""
+        self.call("amb_join")
+
     def use_stream(self, cuda_stream_ptr: int):
         self.call("amb_set_stream", C.c_void_p(cuda_stream_ptr))
 

@@ -20,19 +20,24 @@ typedef CUresult (*amb_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct amb_ctx {
     int device = 0, sm_count = 0;
     amb_encode_fn encode = nullptr;
-    CUtensorMap tm_carry[2], tm_tail;
-    cudaStream_t stream = nullptr;
+    CUtensorMap tm_carry[3], tm_tail[2];
+    cudaStream_t stream = nullptr;       // stream A: prologue, scan, carry (the caller-visible stream)
+    cudaStream_t stream_b = nullptr;     // stream B: compact, exact, resolve, slice - overlaps the next call's scan
     bool own_stream = false;
+    int overlap = 1;
+    cudaEvent_t e_scan[2] = {nullptr, nullptr}, e_done[2] = {nullptr, nullptr};
+    bool done_valid[2] = {false, false};
+    unsigned long long call_idx = 0;
+    int carry_in = 2;                    // index of the carry buffer the next call reads (2 = the all-zero one)
     float rate_arg = 0.f, thr_db = 0.f;
     int use_pmf = 0;
     AmbParams P{};
     int chip_off[240];
     int kc = 0, guard = 0;
-    float2* carry[2] = {nullptr, nullptr};
-    int cur = 0;
-    float2* tail = nullptr; int tail_cap = 0;
+    float2* carry[3] = {nullptr, nullptr, nullptr};   // [2] stays all zero (sample history before the stream)
+    float2* tail[2] = {nullptr, nullptr}; int tail_cap = 0;
     float2* staging = nullptr; size_t staging_cap = 0;
-    uint32_t* coarse = nullptr; uint32_t* fine = nullptr; uint32_t* span_count = nullptr;
+    uint32_t* coarse[2] = {nullptr, nullptr}; uint32_t* fine[2] = {nullptr, nullptr}; uint32_t* span_count[2] = {nullptr, nullptr};
     size_t rows_cap = 0; int spans_cap = 0;
     int* cand_j = nullptr; uint32_t* cand_info = nullptr; float* cand_avg = nullptr; unsigned cand_cap = 0;
     void* walk_scratch = nullptr;
@@ -66,6 +71,13 @@ static int fail(amb_ctx* c, int code, const char* what, cudaError_t e = cudaSucc
 }
 #define CK(call)                                                                  \
     do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, AMB_ERR_CUDA, #call, e_); } while (0)
+
+static cudaError_t sync_all(amb_ctx* c)
+{
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return e;
+    return c->stream_b ? cudaStreamSynchronize(c->stream_b) : cudaSuccess;
+}
 
 // IQ as a 2-D tensor of 128-byte lines (16 complex samples each); tiles of 32 lines = 512 samples land in
 // shared memory with the 128B swizzle the scan kernel reads through.
@@ -140,12 +152,15 @@ static int compute_params(float channel_rate, float threshold_db, int use_pmf, A
 
 static void free_dev(amb_ctx* c)
 {
-    cudaFree(c->carry[0]); cudaFree(c->carry[1]); cudaFree(c->tail); cudaFree(c->staging);
-    cudaFree(c->coarse); cudaFree(c->fine); cudaFree(c->span_count);
+    for (int k = 0; k < 3; k++) { cudaFree(c->carry[k]); c->carry[k] = nullptr; }
+    for (int k = 0; k < 2; k++) {
+        cudaFree(c->tail[k]); cudaFree(c->coarse[k]); cudaFree(c->fine[k]); cudaFree(c->span_count[k]);
+        c->tail[k] = nullptr; c->coarse[k] = c->fine[k] = c->span_count[k] = nullptr;
+    }
+    cudaFree(c->staging);
     cudaFree(c->cand_j); cudaFree(c->cand_info); cudaFree(c->cand_avg); cudaFree(c->walk_scratch); c->walk_scratch = nullptr;
     cudaFree(c->frames); cudaFree(c->chips); cudaFree(c->ctr); cudaFree(c->st);
-    c->carry[0] = c->carry[1] = c->tail = c->staging = nullptr;
-    c->coarse = c->fine = c->span_count = nullptr;
+    c->staging = nullptr;
     c->cand_j = nullptr; c->cand_info = nullptr; c->cand_avg = nullptr;
     c->frames = nullptr; c->chips = nullptr; c->ctr = nullptr; c->st = nullptr;
     c->rows_cap = 0; c->spans_cap = 0; c->cand_cap = 0; c->frame_cap = 0; c->staging_cap = 0;
@@ -162,23 +177,28 @@ static int setup_rate(amb_ctx* ctx)
     ctx->guard = P.maxlate + (int)ceilf(P.skip_f) + 4;
     int need = ctx->guard + P.L + 2 * P.spc_i + 64;
     ctx->kc = (need + AMB_STAGE - 1) / AMB_STAGE * AMB_STAGE;
-    cudaFree(ctx->carry[0]); cudaFree(ctx->carry[1]); cudaFree(ctx->tail);
-    CK(cudaMalloc(&ctx->carry[0], (size_t)ctx->kc * sizeof(float2)));
-    CK(cudaMalloc(&ctx->carry[1], (size_t)ctx->kc * sizeof(float2)));
     ctx->tail_cap = 4 * AMB_STAGE;
-    CK(cudaMalloc(&ctx->tail, (size_t)ctx->tail_cap * sizeof(float2)));
-    for (int k = 0; k < 2; k++) { int rc2 = make_tmap(ctx, &ctx->tm_carry[k], ctx->carry[k], (size_t)ctx->kc); if (rc2) return rc2; }
-    { int rc2 = make_tmap(ctx, &ctx->tm_tail, ctx->tail, (size_t)ctx->tail_cap); if (rc2) return rc2; }
+    for (int k = 0; k < 3; k++) {
+        cudaFree(ctx->carry[k]); ctx->carry[k] = nullptr;
+        CK(cudaMalloc(&ctx->carry[k], (size_t)ctx->kc * sizeof(float2)));
+        CK(cudaMemset(ctx->carry[k], 0, (size_t)ctx->kc * sizeof(float2)));
+        int rc2 = make_tmap(ctx, &ctx->tm_carry[k], ctx->carry[k], (size_t)ctx->kc); if (rc2) return rc2;
+    }
+    for (int k = 0; k < 2; k++) {
+        cudaFree(ctx->tail[k]); ctx->tail[k] = nullptr;
+        CK(cudaMalloc(&ctx->tail[k], (size_t)ctx->tail_cap * sizeof(float2)));
+        int rc2 = make_tmap(ctx, &ctx->tm_tail[k], ctx->tail[k], (size_t)ctx->tail_cap); if (rc2) return rc2;
+    }
     return AMB_OK;
 }
 
 static int reset_stream(amb_ctx* ctx)
 {
-    CK(cudaMemsetAsync(ctx->carry[0], 0, (size_t)ctx->kc * sizeof(float2), ctx->stream));
-    CK(cudaMemsetAsync(ctx->carry[1], 0, (size_t)ctx->kc * sizeof(float2), ctx->stream));
-    CK(cudaMemsetAsync(ctx->ctr, 0, sizeof(AmbCounters), ctx->stream));
-    CK(cudaMemsetAsync(ctx->st, 0, sizeof(AmbWalkState), ctx->stream));
-    ctx->cur = 0; ctx->n_in = 0; ctx->r_done = 0; ctx->flushed = false; ctx->have_last = false;
+    // counters and resolver state belong to stream B (in order after the previous call's tail kernels);
+    // the sample history restarts from the all-zero carry buffer, so nothing has to be cleared on stream A
+    CK(cudaMemsetAsync(ctx->ctr, 0, sizeof(AmbCounters), ctx->stream_b));
+    CK(cudaMemsetAsync(ctx->st, 0, sizeof(AmbWalkState), ctx->stream_b));
+    ctx->carry_in = 2; ctx->n_in = 0; ctx->r_done = 0; ctx->flushed = false; ctx->have_last = false;
     ctx->frames_ub = 0;
     ctx->pending.clear();
     return AMB_OK;
@@ -224,6 +244,11 @@ int amb_create(int device, float rate, float threshold_db, int use_pmf, int use_
         if (cudaSetDevice(device) != cudaSuccess) { rc = AMB_ERR_NO_DEVICE; break; }
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
         ctx->own_stream = true;
+        if (cudaStreamCreateWithFlags(&ctx->stream_b, cudaStreamNonBlocking) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
+        for (int k = 0; k < 2 && rc == AMB_OK; k++)
+            if (cudaEventCreateWithFlags(&ctx->e_scan[k], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ctx->e_done[k], cudaEventDisableTiming) != cudaSuccess) rc = AMB_ERR_CUDA;
+        if (rc != AMB_OK) break;
         if (cudaMalloc(&ctx->ctr, sizeof(AmbCounters)) != cudaSuccess || cudaMalloc(&ctx->st, sizeof(AmbWalkState)) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
         for (int k = 0; k < 4; k++) if (cudaEventCreate(&ctx->ev[k]) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
         for (int k = 0; k < 128 && rc == AMB_OK; k++) if (cudaEventCreate(&ctx->ring[k]) != cudaSuccess) rc = AMB_ERR_CUDA;
@@ -246,8 +271,10 @@ void amb_destroy(amb_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) sync_all(ctx);
     free_dev(ctx);
+    for (int k = 0; k < 2; k++) { if (ctx->e_scan[k]) cudaEventDestroy(ctx->e_scan[k]); if (ctx->e_done[k]) cudaEventDestroy(ctx->e_done[k]); }
+    if (ctx->stream_b) cudaStreamDestroy(ctx->stream_b);
     for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < 128; k++) if (ctx->ring[k]) cudaEventDestroy(ctx->ring[k]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -265,7 +292,7 @@ int amb_set_rate(amb_ctx* ctx, float channel_rate)
 {
     if (!ctx) return AMB_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_all(ctx));
     const float old = ctx->rate_arg;
     ctx->rate_arg = channel_rate;
     int rc = setup_rate(ctx);
@@ -291,7 +318,7 @@ int amb_get_pmf(const amb_ctx* ctx) { return ctx ? ctx->use_pmf : 0; }
 int amb_set_stream(amb_ctx* ctx, void* cuda_stream)
 {
     if (!ctx) return AMB_ERR_INVALID;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_all(ctx));
     if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
     ctx->stream = (cudaStream_t)cuda_stream;
     return AMB_OK;
@@ -304,6 +331,7 @@ int amb_set_option(amb_ctx* ctx, const char* name, int value)
     if (!ctx || !name) return AMB_ERR_INVALID;
     if (!strcmp(name, "resolver")) { ctx->resolver = value; return AMB_OK; }
     if (!strcmp(name, "keep_chips")) { ctx->keep_chips = value != 0; return AMB_OK; }
+    if (!strcmp(name, "overlap")) { ctx->overlap = value != 0; return AMB_OK; }
     return AMB_ERR_INVALID;
 }
 
@@ -311,7 +339,7 @@ int amb_synchronize(amb_ctx* ctx)
 {
     if (!ctx) return AMB_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_all(ctx));
     return AMB_OK;
 }
 
@@ -321,24 +349,29 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
     if (ctx->flushed) return fail(ctx, AMB_ERR_STATE, "stream already flushed; amb_reset first");
     if (n_complex > 0x60000000ull) return fail(ctx, AMB_ERR_INVALID, "at most 1.5 Gi samples per call");
     CK(cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
+    cudaStream_t sa = ctx->stream, sb = ctx->stream_b;
     const AmbParams& P = ctx->P;
     const int kc = ctx->kc;
-    if (ctx->timing) CK(cudaEventRecord(ctx->ev[2], s));
+    const int set = (int)(ctx->call_idx & 1u);             // double-buffered per-call scratch
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[2], sa));
+    // this set's buffers were last used by call k-2: its tail kernels must be finished
+    if (ctx->done_valid[set]) CK(cudaStreamWaitEvent(sa, ctx->e_done[set], 0));
 
     // ---- input placement: device pointers are used in place, host data goes through a staging buffer
     const float2* src = reinterpret_cast<const float2*>(iq);
     if (mem_kind == AMB_MEM_HOST || ((uintptr_t)iq & 15u)) {
         if (ctx->staging_cap < n_complex) {
-            CK(cudaStreamSynchronize(s));
+            CK(sync_all(ctx));
             cudaFree(ctx->staging); ctx->staging = nullptr;
             size_t ncap = n_complex + 1024;
             CK(cudaMalloc(&ctx->staging, ncap * sizeof(float2)));
             ctx->staging_cap = ncap;
         }
+        // the previous call's exact/slice kernels may still read the staging buffer
+        if (ctx->done_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_done[set ^ 1], 0));
         if (n_complex)
             CK(cudaMemcpyAsync(ctx->staging, iq, n_complex * sizeof(float2),
-                               mem_kind == AMB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+                               mem_kind == AMB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, sa));
         src = ctx->staging;
     }
     const int n_new = (int)n_complex;
@@ -346,8 +379,10 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
     const int n_tv = n_new - n_main;
     const int n_tail = (n_tv + 512 + AMB_STAGE - 1) / AMB_STAGE * AMB_STAGE;   // <= 3 tiles
 
+    const int cin = ctx->carry_in;                         // carry this call reads
+    const int cout = (cin == 0) ? 1 : 0;                   // carry this call writes (never the zero buffer [2])
     AmbSegs S;
-    S.carry = ctx->carry[ctx->cur]; S.main_ = src; S.tail = ctx->tail;
+    S.carry = ctx->carry[cin]; S.main_ = src; S.tail = ctx->tail[set];
     S.n_carry = kc; S.n_main = n_main; S.n_tail = n_tail; S.n_valid = kc + n_new;
 
     const long long org = (long long)ctx->n_in - kc + P.H;        // reported index of j = 0
@@ -357,7 +392,6 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
     if (flush) { ntot = n_after + P.H; j_hi = S.n_valid; }
     else { r_safe = n_after + P.H - ctx->guard; if (r_safe < ctx->r_done) r_safe = ctx->r_done; j_hi = r_safe - org; }
     ctx->last_org = org; ctx->have_last = true;
-
 
     AmbWalkArgs wa{};
     wa.P = P; wa.org = org; wa.ntot = ntot; wa.r_safe = r_safe; wa.flush = flush ? 1 : 0;
@@ -375,25 +409,29 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         if (rps < AMB_SPAN_ROWS_ALIGN) rps = AMB_SPAN_ROWS_ALIGN;
         a.rows_per_span = rps;
         a.n_spans = (rows + rps - 1) / rps;
-        // buffers
+        // ---- buffers (growth synchronises both streams; steady state does not)
         const size_t rows_need = (size_t)a.row_hi + 64;
         if (ctx->rows_cap < rows_need) {
-            CK(cudaStreamSynchronize(s));
-            cudaFree(ctx->fine); cudaFree(ctx->coarse); ctx->fine = ctx->coarse = nullptr;
+            CK(sync_all(ctx));
             const size_t rc = rows_need + rows_need / 8;
-            CK(cudaMalloc(&ctx->fine, rc * 8 * sizeof(uint32_t)));
-            CK(cudaMalloc(&ctx->coarse, (rc / 32 + 2) * sizeof(uint32_t)));
+            for (int k = 0; k < 2; k++) {
+                cudaFree(ctx->fine[k]); cudaFree(ctx->coarse[k]); ctx->fine[k] = ctx->coarse[k] = nullptr;
+                CK(cudaMalloc(&ctx->fine[k], rc * 8 * sizeof(uint32_t)));
+                CK(cudaMalloc(&ctx->coarse[k], (rc / 32 + 2) * sizeof(uint32_t)));
+            }
             ctx->rows_cap = rc;
         }
         if (ctx->spans_cap < a.n_spans) {
-            CK(cudaStreamSynchronize(s));
-            cudaFree(ctx->span_count); ctx->span_count = nullptr;
-            CK(cudaMalloc(&ctx->span_count, (size_t)(a.n_spans + 64 + 128) * sizeof(uint32_t)));
+            CK(sync_all(ctx));
+            for (int k = 0; k < 2; k++) {
+                cudaFree(ctx->span_count[k]); ctx->span_count[k] = nullptr;
+                CK(cudaMalloc(&ctx->span_count[k], (size_t)(a.n_spans + 64 + 128) * sizeof(uint32_t)));
+            }
             ctx->spans_cap = a.n_spans + 64;
         }
         unsigned cap_need = (unsigned)std::max<long long>(1 << 16, (j_hi - j_lo) / 8 + 1024);
         if (ctx->cand_cap < cap_need) {
-            CK(cudaStreamSynchronize(s));
+            CK(sync_all(ctx));
             cudaFree(ctx->cand_j); cudaFree(ctx->cand_info); cudaFree(ctx->cand_avg); cudaFree(ctx->walk_scratch);
             ctx->cand_j = nullptr; ctx->cand_info = nullptr; ctx->cand_avg = nullptr; ctx->walk_scratch = nullptr;
             CK(cudaMalloc(&ctx->walk_scratch, amb_walk_scratch_bytes(cap_need, (long long)cap_need * 8 + 4096)));
@@ -405,7 +443,7 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         // a detection consumes >= skip0 samples (preamble_impl.cc:237): bound on frames of this call
         const unsigned fr_ub = (unsigned)((j_hi - j_lo) / std::max(P.skip0, 1) + 2);
         if (ctx->frame_cap < ctx->frames_ub + fr_ub) {
-            CK(cudaStreamSynchronize(s));
+            CK(sync_all(ctx));
             const unsigned ncap = (ctx->frames_ub + fr_ub) * 2 + 1024;
             amb_frame* nf = nullptr; float* nc = nullptr;
             CK(cudaMalloc(&nf, (size_t)ncap * sizeof(amb_frame)));
@@ -419,36 +457,45 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         }
         if (ctx->keep_chips && !ctx->chips) CK(cudaMalloc(&ctx->chips, (size_t)ctx->frame_cap * 240 * sizeof(float)));
         ctx->frames_ub += fr_ub;
-        a.coarse = ctx->coarse; a.fine = ctx->fine; a.span_count = ctx->span_count;
-        a.group_count = ctx->span_count + ctx->spans_cap;          // 128 words behind the span counts
-        CK(amb_launch_prologue(ctx->tail, ctx->tail_cap, src + n_main, n_tv, ctx->ctr, a.group_count, 128,
-                               ctx->resolver == 1 ? nullptr : ctx->walk_scratch, (long long)S.n_carry + S.n_main + S.n_tail, s));
-        a.tm_carry = ctx->tm_carry[ctx->cur]; a.tm_tail = ctx->tm_tail;
+        a.coarse = ctx->coarse[set]; a.fine = ctx->fine[set]; a.span_count = ctx->span_count[set];
+        a.group_count = ctx->span_count[set] + ctx->spans_cap;     // 128 words behind the span counts
+        a.tm_carry = ctx->tm_carry[cin]; a.tm_tail = ctx->tm_tail[set];
         if (n_main) { int rc2 = make_tmap(ctx, &a.tm_main, src, (size_t)n_main); if (rc2) return rc2; }
-        else a.tm_main = ctx->tm_tail;
+        else a.tm_main = ctx->tm_tail[set];
 
+        // ---- stream A: stage the tail, reset the group counts, stream over the IQ
+        CK(amb_launch_prologue(ctx->tail[set], ctx->tail_cap, src + n_main, n_tv, a.group_count, 128, sa));
         const unsigned slot = (ctx->ring_n & 63u) * 2;
-        if (ctx->timing) { CK(cudaEventRecord(ctx->ev[0], s)); CK(cudaEventRecord(ctx->ring[slot], s)); }
-        CK(amb_launch_scan(a, ctx->sm_count, s));
-        if (ctx->timing) { CK(cudaEventRecord(ctx->ev[1], s)); CK(cudaEventRecord(ctx->ring[slot + 1], s)); ctx->ring_n++; }
-        CK(amb_launch_compact(a, ctx->cand_j, ctx->cand_cap, ctx->ctr, s));
+        if (ctx->timing) { CK(cudaEventRecord(ctx->ev[0], sa)); CK(cudaEventRecord(ctx->ring[slot], sa)); }
+        CK(amb_launch_scan(a, ctx->sm_count, sa));
+        if (ctx->timing) { CK(cudaEventRecord(ctx->ev[1], sa)); CK(cudaEventRecord(ctx->ring[slot + 1], sa)); ctx->ring_n++; }
+        CK(cudaEventRecord(ctx->e_scan[set], sa));
+
+        // ---- stream B: everything sparse; runs under the NEXT call's scan
+        CK(cudaStreamWaitEvent(sb, ctx->e_scan[set], 0));
+        const bool par = ctx->resolver != 1;
+        CK(amb_launch_compact(a, ctx->cand_j, ctx->cand_cap, ctx->ctr, par ? ctx->walk_scratch : nullptr,
+                              (long long)S.n_carry + S.n_main + S.n_tail, sb));
         AmbExactArgs ea{};
         ea.P = P; ea.S = S; ea.cand_j = ctx->cand_j; ea.cand_info = ctx->cand_info; ea.cand_avg = ctx->cand_avg; ea.ctr = ctx->ctr;
-        CK(amb_launch_exact(ea, ctx->sm_count, s));
+        CK(amb_launch_exact(ea, ctx->sm_count, sb));
         wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info;
-        if (ctx->resolver == 1) { CK(amb_launch_walk_seq(wa, s)); ctx->stats.kernel_launches += 1; }
-        else { CK(amb_launch_walk_par(wa, ctx->walk_scratch, ctx->cand_cap, (long long)S.n_carry + S.n_main + S.n_tail, s)); ctx->stats.kernel_launches += 3; }
-        AmbSliceArgs sa{};
-        sa.P = P; sa.S = S; sa.cand_j = ctx->cand_j; sa.cand_info = ctx->cand_info; sa.cand_avg = ctx->cand_avg;
-        sa.ctr = ctx->ctr; sa.frames = ctx->frames; sa.frame_cap = ctx->frame_cap;
-        sa.chips_out = ctx->keep_chips ? ctx->chips : nullptr; sa.org = org;
-        CK(amb_launch_slice(sa, ctx->sm_count, s));
+        if (!par) { CK(amb_launch_walk_seq(wa, sb)); ctx->stats.kernel_launches += 1; }
+        else { CK(amb_launch_walk_par(wa, ctx->walk_scratch, ctx->cand_cap, (long long)S.n_carry + S.n_main + S.n_tail, sb)); ctx->stats.kernel_launches += 3; }
+        AmbSliceArgs sl{};
+        sl.P = P; sl.S = S; sl.cand_j = ctx->cand_j; sl.cand_info = ctx->cand_info; sl.cand_avg = ctx->cand_avg;
+        sl.ctr = ctx->ctr; sl.frames = ctx->frames; sl.frame_cap = ctx->frame_cap;
+        sl.chips_out = ctx->keep_chips ? ctx->chips : nullptr; sl.org = org;
+        CK(amb_launch_slice(sl, ctx->sm_count, sb));
         ctx->stats.kernel_launches += 5;
         ctx->ev_valid = ctx->timing;
     } else {
-        // nothing can be decided yet; on flush the resolver still has to close the stream
-        CK(amb_launch_prologue(ctx->tail, ctx->tail_cap, src + n_main, n_tv, ctx->ctr, nullptr, 0, nullptr, 0, s));
-        if (flush) {
+        // nothing can be decided yet (tiny call): keep it simple and serial
+        if (ctx->done_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_done[set ^ 1], 0));
+        CK(amb_launch_prologue(ctx->tail[set], ctx->tail_cap, src + n_main, n_tv, nullptr, 0, sa));
+        CK(cudaEventRecord(ctx->e_scan[set], sa));
+        CK(cudaStreamWaitEvent(sb, ctx->e_scan[set], 0));
+        if (flush) {   // the resolver still has to close the stream
             if (!ctx->cand_j) {
                 CK(cudaMalloc(&ctx->cand_j, 64 * sizeof(int)));
                 CK(cudaMalloc(&ctx->cand_info, 64 * sizeof(uint32_t)));
@@ -456,19 +503,35 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
                 ctx->cand_cap = 64;
             }
             wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info;
-            CK(amb_launch_walk_seq(wa, s));
+            CK(cudaMemsetAsync(&ctx->ctr->ncand, 0, sizeof(unsigned), sb));
+            CK(amb_launch_walk_seq(wa, sb));
             ctx->stats.kernel_launches += 1;
         }
         ctx->ev_valid = false;
     }
-    // ---- carry the tail of the stream into the next call
-    CK(amb_launch_carry(S, ctx->carry[ctx->cur ^ 1], kc, s));
-    ctx->stats.kernel_launches += 1;
-    ctx->cur ^= 1;
+    CK(cudaEventRecord(ctx->e_done[set], sb));
+    ctx->done_valid[set] = true;
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[3], sb));
+    // ---- carry the tail of the stream into the next call (stream A). The buffer written here is the one
+    // the PREVIOUS call's tail kernels read as their carry: wait for them (normally long finished).
+    if (ctx->done_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_done[set ^ 1], 0));
+    CK(amb_launch_carry(S, ctx->carry[cout], kc, sa));
+    ctx->stats.kernel_launches += 2;
+    ctx->carry_in = cout;
     ctx->n_in = (uint64_t)n_after;
     if (flush) ctx->flushed = true;
     else if (j_hi > j_lo) ctx->r_done = r_safe;
-    if (ctx->timing) CK(cudaEventRecord(ctx->ev[3], s));
+    ctx->call_idx++;
+    if (!ctx->overlap) CK(cudaStreamWaitEvent(sa, ctx->e_done[set], 0));   // strict stream-ordered behaviour on stream A
+    return AMB_OK;
+}
+
+/* Make the caller-visible stream wait for everything enqueued so far (no host synchronisation). */
+int amb_join(amb_ctx* ctx)
+{
+    if (!ctx) return AMB_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    for (int k = 0; k < 2; k++) if (ctx->done_valid[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->e_done[k], 0));
     return AMB_OK;
 }
 
@@ -484,7 +547,7 @@ static void stamp(amb_frame* f, int rate_int)
 static int collect(amb_ctx* ctx)
 {
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_all(ctx));
     AmbCounters h;
     CK(cudaMemcpy(&h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost));
     ctx->stats.candidates = h.ncand;
@@ -529,7 +592,7 @@ int amb_get_stats(amb_ctx* ctx, amb_stats* out)
 {
     if (!ctx || !out) return AMB_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_all(ctx));
     AmbCounters h; AmbWalkState st;
     CK(cudaMemcpy(&h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(&st, ctx->st, sizeof st, cudaMemcpyDeviceToHost));
@@ -552,7 +615,7 @@ int amb_get_scan_times(amb_ctx* ctx, float* ms_out, int max)
 {
     if (!ctx || (!ms_out && max > 0)) return AMB_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_all(ctx));
     const unsigned have = ctx->ring_n < 64u ? ctx->ring_n : 64u;
     const unsigned n = have < (unsigned)(max > 0 ? max : 0) ? have : (unsigned)(max > 0 ? max : 0);
     for (unsigned k = 0; k < n; k++) {
@@ -568,7 +631,7 @@ int amb_debug_candidates(amb_ctx* ctx, uint64_t* index, uint32_t* info, int max)
 {
     if (!ctx) return AMB_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_all(ctx));
     if (!ctx->have_last || !ctx->cand_j) return 0;
     AmbCounters h;
     CK(cudaMemcpy(&h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost));

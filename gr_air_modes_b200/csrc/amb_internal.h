@@ -106,7 +106,8 @@ struct AmbSliceArgs {
 
 // kernel launchers (amb_kernels.cu)
 cudaError_t amb_launch_scan(const AmbScanArgs& a, int sm_count, cudaStream_t s);
-cudaError_t amb_launch_compact(const AmbScanArgs& a, int* cand_j, unsigned int cand_cap, AmbCounters* ctr, cudaStream_t s);
+cudaError_t amb_launch_compact(const AmbScanArgs& a, int* cand_j, unsigned int cand_cap, AmbCounters* ctr,
+                               void* walk_scratch, long long n_samples, cudaStream_t s);
 cudaError_t amb_launch_exact(const AmbExactArgs& a, int sm_count, cudaStream_t s);
 cudaError_t amb_launch_walk_seq(const AmbWalkArgs& a, cudaStream_t s);
 cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, unsigned int cand_cap, long long n_samples, cudaStream_t s);
@@ -119,6 +120,6 @@ cudaError_t amb_launch_stream_candidates(const AmbParams& P, const float* in0, c
 cudaError_t amb_launch_slice_chips(const float* chips, int ndet, amb_frame* frames, cudaStream_t s);
 cudaError_t amb_launch_crc(const uint8_t* data, int n, int length, uint32_t* out, cudaStream_t s);
 cudaError_t amb_upload_tables(const int* chip_off);
-cudaError_t amb_launch_prologue(float2* tail, int tail_cap, const float2* src_rem, int n_rem, AmbCounters* ctr,
-                                uint32_t* group_count, int n_groups, void* scratch, long long n_samples, cudaStream_t s);
+cudaError_t amb_launch_prologue(float2* tail, int tail_cap, const float2* src_rem, int n_rem,
+                                uint32_t* group_count, int n_groups, cudaStream_t s);
 size_t amb_scan_smem_bytes(int spc_i);

