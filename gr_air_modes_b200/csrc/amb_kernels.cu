@@ -86,7 +86,7 @@ template <int SPC, bool PMF> struct ScanCfg {
     static constexpr int LW = L / 8;               // ... in lanes
     static constexpr int RB = L / AMB_ROW;
     static constexpr int LMOD = L % AMB_ROW;
-    static constexpr int PRR = (RB + 2 <= 2) ? 2 : 4;
+    static constexpr int PRR = RB + 2;             // prefix ring rows: k, ..., k-RB-1
     static constexpr int NST = AMB_NST;            // TMA tile ring depth per warp (tile = 2 rows = 4 KiB)
     static constexpr int WARM = (RB + 2 + 1) & ~1;
     static constexpr int IQ_BYTES = NST * 4096;                    // per warp, 1 KiB aligned
@@ -160,12 +160,27 @@ struct ScanWarp {
                 const float src = (lane > 31 - d) ? lastm[ridx] : m[ridx];
                 v[C::FL - 1 - t] = __shfl_sync(FULL, src, (lane - d) & 31);
             }
+            if (C::FL >= 4) {
+                // pair sums shared between neighbouring outputs: s2[i] = v[i] + v[i+1]; all-positive, same bound
+                float s2[C::FL - 1 + 8 - 1];
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                float s = v[C::FL - 1 + r];
+                for (int i = 0; i < C::FL - 1 + 8 - 1; i++) s2[i] = v[i] + v[i + 1];
 #pragma unroll
-                for (int t = 1; t < C::FL; t++) s += v[C::FL - 1 + r - t];
-                b[r] = s;
+                for (int r = 0; r < 8; r++) {          // window v[r .. r+FL-1]
+                    float s = s2[r];
+#pragma unroll
+                    for (int t = 2; t + 1 < C::FL; t += 2) s += s2[r + t];
+                    if (C::FL & 1) s += v[r + C::FL - 1];
+                    b[r] = s;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    float s = v[C::FL - 1 + r];
+#pragma unroll
+                    for (int t = 1; t < C::FL; t++) s += v[C::FL - 1 + r - t];
+                    b[r] = s;
+                }
             }
 #pragma unroll
             for (int r = 0; r < 8; r++) lastm[r] = m[r];
@@ -190,7 +205,7 @@ struct ScanWarp {
 #pragma unroll
         for (int r = 0; r < 8; r++) p[r] += exc;
         float* bslot = bbr + (k & 1) * 256;
-        float* pslot = prr + (k & (C::PRR - 1)) * 256;
+        float* pslot = prr + (k % C::PRR) * 256;
         *reinterpret_cast<float4*>(bslot + own) = make_float4(b[0], b[1], b[2], b[3]);
         *reinterpret_cast<float4*>(bslot + (own ^ 4)) = make_float4(b[4], b[5], b[6], b[7]);
         *reinterpret_cast<float4*>(pslot + own) = make_float4(p[0], p[1], p[2], p[3]);
@@ -201,7 +216,7 @@ struct ScanWarp {
 #pragma unroll
         for (int mm = 0; mm < C::RB; mm++) A += rth[mm];
         if (hi) A += rth[C::RB];
-        const float* dslot = prr + ((k - rows_back) & (C::PRR - 1)) * 256;
+        const float* dslot = prr + ((k + C::PRR - rows_back) % C::PRR) * 256;
         const float4 d0 = *reinterpret_cast<const float4*>(dslot + ownd);
         const float4 d1 = *reinterpret_cast<const float4*>(dslot + (ownd ^ 4));
         const float cT = a->P.cT;
