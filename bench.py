@@ -320,7 +320,7 @@ def main():
                 line["roofline"]["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch_2p%d" % args.log2n)
             except Exception:
                 pass
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_leg(args.log2n)
         print(json.dumps(line))
     if world > 1:

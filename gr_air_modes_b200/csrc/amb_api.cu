@@ -343,6 +343,56 @@ int amb_synchronize(amb_ctx* ctx)
     return AMB_OK;
 }
 
+// Grow the per-call scratch (bitmaps, span counts, candidate arrays, frame buffer). Growth synchronises both
+// streams; in steady state nothing happens here.
+static int ensure_call_buffers(amb_ctx* ctx, size_t rows_need, int n_spans, unsigned cap_need, unsigned fr_ub)
+{
+    if (ctx->rows_cap < rows_need) {
+        CK(sync_all(ctx));
+        const size_t rc = rows_need + rows_need / 8;
+        for (int k = 0; k < 2; k++) {
+            cudaFree(ctx->fine[k]); cudaFree(ctx->coarse[k]); ctx->fine[k] = ctx->coarse[k] = nullptr;
+            CK(cudaMalloc(&ctx->fine[k], rc * 8 * sizeof(uint32_t)));
+            CK(cudaMalloc(&ctx->coarse[k], (rc / 32 + 2) * sizeof(uint32_t)));
+        }
+        ctx->rows_cap = rc;
+    }
+    if (ctx->spans_cap < n_spans) {
+        CK(sync_all(ctx));
+        for (int k = 0; k < 2; k++) {
+            cudaFree(ctx->span_count[k]); ctx->span_count[k] = nullptr;
+            CK(cudaMalloc(&ctx->span_count[k], (size_t)(n_spans + 64 + 128) * sizeof(uint32_t)));
+        }
+        ctx->spans_cap = n_spans + 64;
+    }
+    if (ctx->cand_cap < cap_need) {
+        CK(sync_all(ctx));
+        cudaFree(ctx->cand_j); cudaFree(ctx->cand_info); cudaFree(ctx->cand_avg); cudaFree(ctx->walk_scratch);
+        ctx->cand_j = nullptr; ctx->cand_info = nullptr; ctx->cand_avg = nullptr; ctx->walk_scratch = nullptr;
+        CK(cudaMalloc(&ctx->walk_scratch, amb_walk_scratch_bytes(cap_need, (long long)cap_need * 8 + 4096)));
+        CK(cudaMalloc(&ctx->cand_j, (size_t)cap_need * sizeof(int)));
+        CK(cudaMalloc(&ctx->cand_info, (size_t)cap_need * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->cand_avg, (size_t)cap_need * sizeof(float)));
+        ctx->cand_cap = cap_need;
+    }
+    // a detection consumes >= skip0 samples (preamble_impl.cc:237): that bounds the frames of a call
+    if (ctx->frame_cap < ctx->frames_ub + fr_ub) {
+        CK(sync_all(ctx));
+        const unsigned ncap = (ctx->frames_ub + fr_ub) * 2 + 1024;
+        amb_frame* nf = nullptr; float* nc = nullptr;
+        CK(cudaMalloc(&nf, (size_t)ncap * sizeof(amb_frame)));
+        if (ctx->frames && ctx->frames_ub) CK(cudaMemcpy(nf, ctx->frames, (size_t)std::min(ctx->frames_ub, ctx->frame_cap) * sizeof(amb_frame), cudaMemcpyDeviceToDevice));
+        if (ctx->keep_chips) {
+            CK(cudaMalloc(&nc, (size_t)ncap * 240 * sizeof(float)));
+            if (ctx->chips && ctx->frames_ub) CK(cudaMemcpy(nc, ctx->chips, (size_t)std::min(ctx->frames_ub, ctx->frame_cap) * 240 * sizeof(float), cudaMemcpyDeviceToDevice));
+        }
+        cudaFree(ctx->frames); cudaFree(ctx->chips);
+        ctx->frames = nf; ctx->chips = nc; ctx->frame_cap = ncap;
+    }
+    if (ctx->keep_chips && !ctx->chips) CK(cudaMalloc(&ctx->chips, (size_t)ctx->frame_cap * 240 * sizeof(float)));
+    return AMB_OK;
+}
+
 int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, int flush)
 {
     if (!ctx || (!iq && n_complex)) return AMB_ERR_INVALID;
@@ -410,52 +460,9 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         a.rows_per_span = rps;
         a.n_spans = (rows + rps - 1) / rps;
         // ---- buffers (growth synchronises both streams; steady state does not)
-        const size_t rows_need = (size_t)a.row_hi + 64;
-        if (ctx->rows_cap < rows_need) {
-            CK(sync_all(ctx));
-            const size_t rc = rows_need + rows_need / 8;
-            for (int k = 0; k < 2; k++) {
-                cudaFree(ctx->fine[k]); cudaFree(ctx->coarse[k]); ctx->fine[k] = ctx->coarse[k] = nullptr;
-                CK(cudaMalloc(&ctx->fine[k], rc * 8 * sizeof(uint32_t)));
-                CK(cudaMalloc(&ctx->coarse[k], (rc / 32 + 2) * sizeof(uint32_t)));
-            }
-            ctx->rows_cap = rc;
-        }
-        if (ctx->spans_cap < a.n_spans) {
-            CK(sync_all(ctx));
-            for (int k = 0; k < 2; k++) {
-                cudaFree(ctx->span_count[k]); ctx->span_count[k] = nullptr;
-                CK(cudaMalloc(&ctx->span_count[k], (size_t)(a.n_spans + 64 + 128) * sizeof(uint32_t)));
-            }
-            ctx->spans_cap = a.n_spans + 64;
-        }
-        unsigned cap_need = (unsigned)std::max<long long>(1 << 16, (j_hi - j_lo) / 8 + 1024);
-        if (ctx->cand_cap < cap_need) {
-            CK(sync_all(ctx));
-            cudaFree(ctx->cand_j); cudaFree(ctx->cand_info); cudaFree(ctx->cand_avg); cudaFree(ctx->walk_scratch);
-            ctx->cand_j = nullptr; ctx->cand_info = nullptr; ctx->cand_avg = nullptr; ctx->walk_scratch = nullptr;
-            CK(cudaMalloc(&ctx->walk_scratch, amb_walk_scratch_bytes(cap_need, (long long)cap_need * 8 + 4096)));
-            CK(cudaMalloc(&ctx->cand_j, (size_t)cap_need * sizeof(int)));
-            CK(cudaMalloc(&ctx->cand_info, (size_t)cap_need * sizeof(uint32_t)));
-            CK(cudaMalloc(&ctx->cand_avg, (size_t)cap_need * sizeof(float)));
-            ctx->cand_cap = cap_need;
-        }
-        // a detection consumes >= skip0 samples (preamble_impl.cc:237): bound on frames of this call
         const unsigned fr_ub = (unsigned)((j_hi - j_lo) / std::max(P.skip0, 1) + 2);
-        if (ctx->frame_cap < ctx->frames_ub + fr_ub) {
-            CK(sync_all(ctx));
-            const unsigned ncap = (ctx->frames_ub + fr_ub) * 2 + 1024;
-            amb_frame* nf = nullptr; float* nc = nullptr;
-            CK(cudaMalloc(&nf, (size_t)ncap * sizeof(amb_frame)));
-            if (ctx->frames && ctx->frames_ub) CK(cudaMemcpy(nf, ctx->frames, (size_t)std::min(ctx->frames_ub, ctx->frame_cap) * sizeof(amb_frame), cudaMemcpyDeviceToDevice));
-            if (ctx->keep_chips) {
-                CK(cudaMalloc(&nc, (size_t)ncap * 240 * sizeof(float)));
-                if (ctx->chips && ctx->frames_ub) CK(cudaMemcpy(nc, ctx->chips, (size_t)std::min(ctx->frames_ub, ctx->frame_cap) * 240 * sizeof(float), cudaMemcpyDeviceToDevice));
-            }
-            cudaFree(ctx->frames); cudaFree(ctx->chips);
-            ctx->frames = nf; ctx->chips = nc; ctx->frame_cap = ncap;
-        }
-        if (ctx->keep_chips && !ctx->chips) CK(cudaMalloc(&ctx->chips, (size_t)ctx->frame_cap * 240 * sizeof(float)));
+        { int rc2 = ensure_call_buffers(ctx, (size_t)a.row_hi + 64, a.n_spans,
+                                        (unsigned)std::max<long long>(1 << 16, (j_hi - j_lo) / 8 + 1024), fr_ub); if (rc2) return rc2; }
         ctx->frames_ub += fr_ub;
         a.coarse = ctx->coarse[set]; a.fine = ctx->fine[set]; a.span_count = ctx->span_count[set];
         a.group_count = ctx->span_count[set] + ctx->spans_cap;     // 128 words behind the span counts
@@ -718,9 +725,89 @@ int amb_slicer_process(amb_ctx* ctx, const float* chips, int ndet, const uint64_
     return ndet;
 }
 
-int amb_preamble_process(amb_ctx* ctx, const float*, const float*, size_t, int, float*, uint64_t*, int)
+int amb_preamble_process(amb_ctx* ctx, const float* in0, const float* in1, size_t n, int flush,
+                         float* chips_out, uint64_t* index_out, int max_det)
 {
-    return fail(ctx, AMB_ERR_UNSUPPORTED, "split-form preamble not built yet");
+    if (!ctx || (n && (!in0 || !in1)) || max_det < 0 || (max_det && (!chips_out || !index_out))) return AMB_ERR_INVALID;
+    if (!flush) return fail(ctx, AMB_ERR_UNSUPPORTED, "split-form preamble processes whole streams (flush=1)");
+    if (n > 0x40000000ull) return fail(ctx, AMB_ERR_INVALID, "at most 2^30 items per call");
+    CK(cudaSetDevice(ctx->device));
+    CK(sync_all(ctx));
+    const AmbParams& P = ctx->P;
+    cudaStream_t s = ctx->stream;
+    const long long ntot = (long long)n + P.H;                       // items incl. history (reported coordinates)
+    float* d0 = nullptr; float* d1 = nullptr;
+    CK(cudaMalloc(&d0, (n + 1) * sizeof(float)));
+    CK(cudaMalloc(&d1, (n + 1) * sizeof(float)));
+    int rc = AMB_OK;
+    do {
+        cudaError_t e = cudaMemcpyAsync(d0, in0, n * sizeof(float), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d1, in1, n * sizeof(float), cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) { rc = fail(ctx, AMB_ERR_CUDA, "H2D", e); break; }
+        AmbScanArgs a{};
+        a.P = P; a.j_lo = 0; a.j_hi = (int)ntot; a.row_lo = 0; a.row_hi = (int)((ntot + AMB_ROW - 1) / AMB_ROW);
+        const int rows = a.row_hi;
+        const int target = ctx->sm_count * 16;
+        int rps = ((rows + target - 1) / target + AMB_SPAN_ROWS_ALIGN - 1) / AMB_SPAN_ROWS_ALIGN * AMB_SPAN_ROWS_ALIGN;
+        if (rps < AMB_SPAN_ROWS_ALIGN) rps = AMB_SPAN_ROWS_ALIGN;
+        a.rows_per_span = rps; a.n_spans = std::max(1, (rows + rps - 1) / rps);
+        ctx->frames_ub = 0;
+        const unsigned fr_ub = (unsigned)(ntot / std::max(P.skip0, 1) + 2);
+        const bool keep = ctx->keep_chips; ctx->keep_chips = true;
+        rc = ensure_call_buffers(ctx, (size_t)a.row_hi + 64, a.n_spans, (unsigned)std::max<long long>(1 << 16, ntot / 8 + 1024), fr_ub);
+        ctx->keep_chips = keep;
+        if (rc != AMB_OK) break;
+        a.coarse = ctx->coarse[0]; a.fine = ctx->fine[0]; a.span_count = ctx->span_count[0];
+        a.group_count = ctx->span_count[0] + ctx->spans_cap;
+        e = cudaMemsetAsync(ctx->coarse[0], 0, ((size_t)a.row_hi / 32 + 2) * sizeof(uint32_t), s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ctx->span_count[0], 0, (size_t)(ctx->spans_cap + 128) * sizeof(uint32_t), s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ctx->ctr, 0, sizeof(AmbCounters), s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ctx->st, 0, sizeof(AmbWalkState), s);
+        if (e == cudaSuccess) e = amb_launch_stream_candidates(a, d0, d1, (long long)n, s);
+        if (e == cudaSuccess) e = amb_launch_compact(a, ctx->cand_j, ctx->cand_cap, ctx->ctr, ctx->walk_scratch, ntot + 4096, s);
+        AmbExactArgs ea{};
+        ea.P = P; ea.cand_j = ctx->cand_j; ea.cand_info = ctx->cand_info; ea.cand_avg = ctx->cand_avg; ea.ctr = ctx->ctr;
+        ea.in0 = d0; ea.in1 = d1; ea.n_streams = (long long)n;
+        if (e == cudaSuccess) e = amb_launch_exact(ea, ctx->sm_count, s);
+        AmbWalkArgs wa{};
+        wa.P = P; wa.org = 0; wa.ntot = ntot; wa.r_safe = 0; wa.flush = 1; wa.ctr = ctx->ctr; wa.st = ctx->st;
+        wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info;
+        if (e == cudaSuccess) e = (ctx->resolver == 1) ? amb_launch_walk_seq(wa, s)
+                                                       : amb_launch_walk_par(wa, ctx->walk_scratch, ctx->cand_cap, ntot + 4096, s);
+        AmbSliceArgs sl{};
+        sl.P = P; sl.cand_j = ctx->cand_j; sl.cand_info = ctx->cand_info; sl.cand_avg = ctx->cand_avg; sl.ctr = ctx->ctr;
+        sl.frames = ctx->frames; sl.frame_cap = ctx->frame_cap; sl.chips_out = ctx->chips; sl.org = 0;
+        sl.in0 = d0; sl.in1 = d1; sl.n_streams = (long long)n;
+        if (e == cudaSuccess) e = amb_launch_slice(sl, ctx->sm_count, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        ctx->stats.kernel_launches += 8;
+        if (e != cudaSuccess) { rc = fail(ctx, AMB_ERR_CUDA, "amb_preamble_process", e); break; }
+        AmbCounters h;
+        e = cudaMemcpy(&h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { rc = fail(ctx, AMB_ERR_CUDA, "counters", e); break; }
+        if (h.overflow || h.frame_overflow) { rc = fail(ctx, AMB_ERR_OVERFLOW, "buffer overflow"); break; }
+        const unsigned nd = h.nframes;
+        std::vector<amb_frame> fr(nd);
+        std::vector<float> ch((size_t)nd * 240);
+        if (nd) {
+            e = cudaMemcpy(fr.data(), ctx->frames, (size_t)nd * sizeof(amb_frame), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(ch.data(), ctx->chips, (size_t)nd * 240 * sizeof(float), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { rc = fail(ctx, AMB_ERR_CUDA, "D2H", e); break; }
+        }
+        std::vector<unsigned> order(nd);
+        for (unsigned k = 0; k < nd; k++) order[k] = k;
+        std::sort(order.begin(), order.end(), [&](unsigned x, unsigned y) { return fr[x].sample_index < fr[y].sample_index; });
+        const int nout = (int)std::min<unsigned>(nd, (unsigned)max_det);
+        for (int k = 0; k < nout; k++) {
+            index_out[k] = fr[order[k]].sample_index;
+            memcpy(chips_out + (size_t)k * 240, ch.data() + (size_t)order[k] * 240, 240 * sizeof(float));
+        }
+        cudaMemset(&ctx->ctr->nframes, 0, sizeof(unsigned));
+        ctx->frames_ub = 0;
+        rc = nd > (unsigned)max_det ? fail(ctx, AMB_ERR_OVERFLOW, "max_det too small") : nout;
+    } while (0);
+    cudaFree(d0); cudaFree(d1);
+    return rc;
 }
 
 }  // extern "C"

@@ -1061,6 +1061,48 @@ cudaError_t amb_launch_prologue(float2* tail, int tail_cap, const float2* src_re
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// split-form preamble block: the two float streams are given; the first four tests (:173-179) are evaluated
+// exactly per item and written in the same (coarse, fine) bitmap format the scan kernel produces.
+// Indices are reported coordinates (item + history-1). coarse / span_count / group_count are pre-zeroed.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) amb_stream_cand_kernel(const __grid_constant__ AmbScanArgs a, const float* __restrict__ in0,
+                                                              const float* __restrict__ in1, long long n)
+{
+    const AmbParams& P = a.P;
+    const long long nwords = ((long long)a.row_hi * AMB_ROW) / 32;
+    const int lane = threadIdx.x & 31;
+    for (long long w = (long long)(blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwords; w += (long long)(gridDim.x * blockDim.x) >> 5) {
+        const long long r = w * 32 + lane;
+        bool c = false;
+        if (r < a.j_hi) {
+            const float x = stream_at(in0, n, P.H, r);
+            const float thr = __fmul_rn(stream_at(in1, n, P.H, r), P.thr);                 // :173
+            c = x > thr;                                                                    // :174
+            if (c && (stream_at(in0, n, P.H, r + 1) > x)) c = false;                        // :175
+            if (c && (stream_at(in0, n, P.H, r + P.po1) < thr)) c = false;                  // :177
+            if (c && (stream_at(in0, n, P.H, r + P.po2) < thr)) c = false;                  // :178
+            if (c && (stream_at(in0, n, P.H, r + P.po3) < thr)) c = false;                  // :179
+        }
+        const uint32_t word = __ballot_sync(FULL, c);
+        if (lane == 0) {
+            a.fine[w] = word;                                   // row = w / 8, word q = w % 8
+            if (word) {
+                const int row = (int)(w >> 3);
+                atomicOr(&a.coarse[row >> 5], 1u << (row & 31));
+                const int span = row / a.rows_per_span;
+                atomicAdd(&a.span_count[span], (unsigned)__popc(word));
+                atomicAdd(&a.group_count[span >> 6], (unsigned)__popc(word));
+            }
+        }
+    }
+}
+cudaError_t amb_launch_stream_candidates(const AmbScanArgs& a, const float* in0, const float* in1, long long n, cudaStream_t s)
+{
+    amb_stream_cand_kernel<<<592, 256, 0, s>>>(a, in0, in1, n);
+    return cudaGetLastError();
+}
+
 cudaError_t amb_upload_tables(const int* chip_off)
 {
     cudaError_t e = cudaMemcpyToSymbol(c_chip_off, chip_off, 240 * sizeof(int));

@@ -227,3 +227,53 @@ def test_full_size_properties():
     assert [m.split()[3:] for m in c] == [m.split()[3:] for m in a]
     for x, y in zip(a, c):
         assert abs(parse_msg(y)[2] / parse_msg(x)[2] - 16.0) < 1e-5
+
+
+def test_split_form_preamble_and_slicer_blocks(port):
+    """The two reference blocks used separately: preamble(in0, in1) -> 240-chip packets + tags -> slicer."""
+    for rate, pmf in ((4e6, True), (10e6, True), (2e6, False), (5e6, True)):
+        sc = synth.make_scene(rate, 500_000, 40, 55)
+        bb, avg = port.frontend(sc.iq, rate, pmf, co.MA_CANONICAL)
+        want = port.run_streams(bb, avg, rate, 7.0)
+        pre = am.preamble(rate, 7.0)
+        assert pre.get_rate() == float(int(rate)) and pre.get_threshold() == 7.0
+        chips, tags = pre.process(bb, avg)
+        assert [t[0] for t in tags] == [int(x) for x in want.index]
+        assert np.array_equal(chips, want.chips)                       # bit-exact soft symbols
+        assert [(t[1], t[2]) for t in tags] == list(zip([int(x) for x in want.secs], [float(x) for x in want.frac]))
+        q = am.msg_queue()
+        am.slicer(q).process(chips, [(t[1], t[2]) for t in tags])
+        assert q.strings() == want.msgs
+
+
+def test_dense_traffic_threshold_sweep_matches_reference(port):
+    """BASELINE configs[4]: ~10 k overlapping squitters/s with garbled CRCs and Mode A/C-like FRUIT; detection
+    sets and messages (hence P_d / P_fa at every threshold) must equal the reference's."""
+    rate, n = 4e6, 2_000_000
+    sc = synth.make_scene(rate, n, 5000, 99, garble_frac=0.2, fruit=2000, snr_db=(4.0, 30.0))
+    sent = {b.frame.hex() for b in sc.bursts}
+    roc = []
+    for thr in (3.0, 5.0, 7.0, 9.0, 12.0):
+        want = port.run_iq(sc.iq, rate, thr, True, co.MA_CANONICAL)
+        msgs, frames, rx = run_cuda(sc.iq, rate, thr, True)
+        assert [f.sample_index for f in frames] == [int(x) for x in want.index]
+        assert msgs == want.msgs
+        got = {m.split()[0] for m in msgs}
+        roc.append((thr, len(frames), len(got & sent), len(got - sent)))
+    assert roc[0][1] > roc[-1][1]                                       # fewer detections at higher thresholds
+    # streaming over the same dense scene
+    want = port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL)
+    msgs, _, _ = run_cuda(sc.iq, rate, 7.0, True, chunks=[123_457] * 40)
+    assert msgs == want.msgs
+
+
+def test_overlap_off_is_identical(port):
+    sc = synth.make_scene(4e6, 700_000, 50, 17)
+    want = port.run_iq(sc.iq, 4e6, 7.0, True, co.MA_CANONICAL).msgs
+    q = am.msg_queue()
+    rx = am.rx_path(4e6, 7.0, q, use_pmf=True)
+    rx._ctx.call("amb_set_option", b"overlap", 0)
+    for k in range(0, 700_000, 100_000):
+        rx.process(sc.iq[2 * k: 2 * (k + 100_000)], flush=(k + 100_000 >= 700_000), collect=False)
+    rx.drain()
+    assert q.strings() == want
