@@ -80,7 +80,7 @@ __device__ __forceinline__ const float2* seg_ptr(const AmbSegs& S, int j) {
 //   32 roundings of 2^-24 enter it, gfac = 2^-19. Tests :177-179 use the same lowered threshold; the
 //   peak test in[i+1] > in[i] (:175) is relaxed by (1+eps); eps = 2^-15 dwarfs the <= 2^-19 relative error
 //   of bbs. Result: a superset of the reference's candidates, typically < 0.01 % larger.
-template <int SPC, bool PMF> struct ScanCfg {
+template <int SPC, bool PMF, bool PREF> struct ScanCfg {
     static constexpr int FL = PMF ? SPC : 1;       // pulse-matched-filter length (rx_path.py:48-51)
     static constexpr int L = 48 * SPC;             // noise-floor window (rx_path.py:54)
     static constexpr int LW = L / 8;               // ... in lanes
@@ -90,7 +90,8 @@ template <int SPC, bool PMF> struct ScanCfg {
     static constexpr int NST = AMB_NST;            // TMA tile ring depth per warp (tile = 2 rows = 4 KiB)
     static constexpr int WARM = (RB + 2 + 1) & ~1;
     static constexpr int IQ_BYTES = NST * 4096;                    // per warp, 1 KiB aligned
-    static constexpr int WORK_BYTES = 2 * 1024 + PRR * 1024 + 64;  // bb ring, pr ring, mbarriers
+    static constexpr int BB_FLOATS = PREF ? 0 : 512;               // look-ahead ring only when pulse offsets are run-time values
+    static constexpr int WORK_BYTES = BB_FLOATS * 4 + PRR * 1024 + 64;  // [bb ring,] pr ring, mbarriers
     static constexpr int CTA_BYTES = 4 * (IQ_BYTES + WORK_BYTES);
 };
 
@@ -99,9 +100,9 @@ __device__ __forceinline__ int swz(int p) { return p ^ ((p >> 3) & 4); }
 
 struct RowRegs { float b[8]; float t[8]; };
 
-template <int SPC, bool PMF>
+template <int SPC, bool PMF, bool PREF>
 struct ScanWarp {
-    using C = ScanCfg<SPC, PMF>;
+    using C = ScanCfg<SPC, PMF, PREF>;
     int lane;
     const AmbScanArgs* a;
     unsigned char* iq;      // tile ring
@@ -206,8 +207,10 @@ struct ScanWarp {
         for (int r = 0; r < 8; r++) p[r] += exc;
         float* bslot = bbr + (k & 1) * 256;
         float* pslot = prr + (k % C::PRR) * 256;
-        *reinterpret_cast<float4*>(bslot + own) = make_float4(b[0], b[1], b[2], b[3]);
-        *reinterpret_cast<float4*>(bslot + (own ^ 4)) = make_float4(b[4], b[5], b[6], b[7]);
+        if (!PREF) {
+            *reinterpret_cast<float4*>(bslot + own) = make_float4(b[0], b[1], b[2], b[3]);
+            *reinterpret_cast<float4*>(bslot + (own ^ 4)) = make_float4(b[4], b[5], b[6], b[7]);
+        }
         *reinterpret_cast<float4*>(pslot + own) = make_float4(p[0], p[1], p[2], p[3]);
         *reinterpret_cast<float4*>(pslot + (own ^ 4)) = make_float4(p[4], p[5], p[6], p[7]);
         __syncwarp();
@@ -232,49 +235,53 @@ struct ScanWarp {
 #else
         if (ke >= ra) {
 #endif
-            // quick per-lane reject: a candidate needs b[i] >= t[i] and (when the second pulse sits at the
-            // compile-time offset 2*SPC) b[i+po1] >= t[i]  ->  max_r min(b, b+po1) >= min_r t
-            const bool pref = (a->P.po1 == 2 * SPC);
+            // A candidate needs all four preamble pulses above the (lowered) threshold of its start sample
+            // (:174, :177-179). With integer samples/chip the pulse offsets are the compile-time 2,7,9*SPC and
+            // the look-ahead comes from registers + one shuffle each; otherwise only the first pulse is
+            // tested here and the rest from the shared-memory ring below.
             float u[8];
 #pragma unroll
             for (int r = 0; r < 8; r++) u[r] = prev.b[r];
-            if (pref) {
+            if (PREF) {
 #pragma unroll
-                for (int r = 0; r < 8; r++) u[r] = fminf(u[r], ahead<2 * SPC>(r, prev.b, b));
+                for (int r = 0; r < 8; r++)
+                    u[r] = fminf(fminf(u[r], ahead<2 * SPC>(r, prev.b, b)),
+                                 fminf(ahead<7 * SPC>(r, prev.b, b), ahead<9 * SPC>(r, prev.b, b)));
             }
-            const float umax = fmaxf(fmaxf(fmaxf(u[0], u[1]), fmaxf(u[2], u[3])), fmaxf(fmaxf(u[4], u[5]), fmaxf(u[6], u[7])));
-            const float tmin = fminf(fminf(fminf(prev.t[0], prev.t[1]), fminf(prev.t[2], prev.t[3])),
-                                     fminf(fminf(prev.t[4], prev.t[5]), fminf(prev.t[6], prev.t[7])));
-            const bool hot = umax >= tmin;
-            const float nx = ahead<1>(7, prev.b, b);           // first sample of the next lane / row
+            bool hot = false;
+#pragma unroll
+            for (int r = 0; r < 8; r++) hot = hot || (u[r] >= prev.t[r]);
             if (__any_sync(FULL, hot)) {
+                const float nx = ahead<1>(7, prev.b, b);       // first sample of the next lane / row
                 uint32_t msk = 0;
                 if (hot) {
                     const float oe = a->P.one_eps;
 #pragma unroll
                     for (int r = 0; r < 8; r++) {
                         const float nxt = (r < 7) ? prev.b[r + 1] : nx;
-                        if (u[r] >= prev.t[r] && nxt <= prev.b[r] * oe) msk |= 1u << r;
+                        if (u[r] >= prev.t[r] && nxt <= prev.b[r] * oe) msk |= 1u << r;   // + peak test :175
                     }
                     const int jb = ke * AMB_ROW + 8 * lane;
                     if (jb < a->j_lo || jb + 8 > a->j_hi) {   // only the first / last row of a call
 #pragma unroll
                         for (int r = 0; r < 8; r++) if (jb + r < a->j_lo || jb + r >= a->j_hi) msk &= ~(1u << r);
                     }
-                    const int rbase = (ke & 1) * 256 + 8 * lane;
-                    const int po1 = a->P.po1, po2 = a->P.po2, po3 = a->P.po3;
-                    uint32_t todo = msk;
-                    while (todo) {                             // tests :177-179 from the shared-memory ring
-                        const int r = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        float th = prev.t[0];
+                    if (!PREF) {
+                        const int rbase = (ke & 1) * 256 + 8 * lane;
+                        const int po1 = a->P.po1, po2 = a->P.po2, po3 = a->P.po3;
+                        uint32_t todo = msk;
+                        while (todo) {                         // tests :177-179 from the shared-memory ring
+                            const int r = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            float th = prev.t[0];
 #pragma unroll
-                        for (int rr = 1; rr < 8; rr++) th = (r == rr) ? prev.t[rr] : th;
-                        const int q = rbase + r;
-                        const float x1 = pref ? th : bbr[swz((q + po1) & 511)];
-                        const float x2 = bbr[swz((q + po2) & 511)];
-                        const float x3 = bbr[swz((q + po3) & 511)];
-                        if (!(fminf(fminf(x1, x2), x3) >= th)) msk &= ~(1u << r);
+                            for (int rr = 1; rr < 8; rr++) th = (r == rr) ? prev.t[rr] : th;
+                            const int q = rbase + r;
+                            const float x1 = bbr[swz((q + po1) & 511)];
+                            const float x2 = bbr[swz((q + po2) & 511)];
+                            const float x3 = bbr[swz((q + po3) & 511)];
+                            if (!(fminf(fminf(x1, x2), x3) >= th)) msk &= ~(1u << r);
+                        }
                     }
                 }
                 if (__any_sync(FULL, msk != 0)) {
@@ -308,21 +315,21 @@ struct ScanWarp {
     }
 };
 
-template <int SPC, bool PMF>
+template <int SPC, bool PMF, bool PREF>
 __global__ void __launch_bounds__(128) amb_scan_kernel(const __grid_constant__ AmbScanArgs a)
 {
-    using C = ScanCfg<SPC, PMF>;
+    using C = ScanCfg<SPC, PMF, PREF>;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int span = blockIdx.x * 4 + warp;
     if (span >= a.n_spans) return;
 
-    ScanWarp<SPC, PMF> w;
+    ScanWarp<SPC, PMF, PREF> w;
     w.lane = lane; w.a = &a;
     w.iq = smem + warp * C::IQ_BYTES;
     unsigned char* work = smem + 4 * C::IQ_BYTES + warp * C::WORK_BYTES;
     w.bbr = reinterpret_cast<float*>(work);
-    w.prr = w.bbr + 512;
+    w.prr = w.bbr + C::BB_FLOATS;
     w.iq_s = smem_u32(w.iq);
     w.bar0 = smem_u32(w.prr + C::PRR * 256);
     {   // TMA 128B swizzle: 16 B chunk index (bits 4-6) ^= 128 B line index (bits 7-9)
@@ -345,7 +352,7 @@ __global__ void __launch_bounds__(128) amb_scan_kernel(const __grid_constant__ A
     const int t0 = rs >> 1;
     const int ntiles = (w.rb >> 1) - t0 + 1;               // row rb is computed as look-ahead only
 
-    for (int i = lane; i < 512; i += 32) w.bbr[i] = 0.f;
+    for (int i = lane; i < C::BB_FLOATS; i += 32) w.bbr[i] = 0.f;
     for (int i = lane; i < C::PRR * 256; i += 32) w.prr[i] = 0.f;
     if (lane == 0) {
         for (int s = 0; s < C::NST; s++) mbar_init(w.bar0 + 8 * s, 1);
@@ -390,28 +397,31 @@ __global__ void __launch_bounds__(128) amb_scan_kernel(const __grid_constant__ A
 size_t amb_scan_smem_bytes(int spc_i)
 {
     switch (spc_i) {
-#define CASE(n) case n: return (size_t)ScanCfg<n, true>::CTA_BYTES;
+#define CASE(n) case n: return (size_t)ScanCfg<n, true, false>::CTA_BYTES;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
 #undef CASE
     }
     return 0;
 }
 
-template <int SPC, bool PMF>
+template <int SPC, bool PMF, bool PREF>
 static cudaError_t launch_scan_t(const AmbScanArgs& a, cudaStream_t s)
 {
-    const size_t smem = (size_t)ScanCfg<SPC, PMF>::CTA_BYTES;
-    cudaError_t e = cudaFuncSetAttribute(amb_scan_kernel<SPC, PMF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)ScanCfg<SPC, PMF, PREF>::CTA_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(amb_scan_kernel<SPC, PMF, PREF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int blocks = (a.n_spans + 3) / 4;
-    amb_scan_kernel<SPC, PMF><<<blocks, 128, smem, s>>>(a);
+    amb_scan_kernel<SPC, PMF, PREF><<<blocks, 128, smem, s>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t amb_launch_scan(const AmbScanArgs& a, int, cudaStream_t s)
 {
+    // integer samples/chip: pulse offsets are the compile-time 2,7,9*SPC (register/shuffle look-ahead)
+    const bool pref = a.P.po1 == 2 * a.P.spc_i && a.P.po2 == 7 * a.P.spc_i && a.P.po3 == 9 * a.P.spc_i;
     switch (a.P.spc_i) {
-#define CASE(n) case n: return a.P.use_pmf ? launch_scan_t<n, true>(a, s) : launch_scan_t<n, false>(a, s);
+#define CASE(n) case n: return a.P.use_pmf ? (pref ? launch_scan_t<n, true, true>(a, s) : launch_scan_t<n, true, false>(a, s)) \
+                                          : (pref ? launch_scan_t<n, false, true>(a, s) : launch_scan_t<n, false, false>(a, s));
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
 #undef CASE
         default: break;
