@@ -23,6 +23,9 @@ struct amb_ctx {
     CUtensorMap tm_carry[3], tm_tail[2];
     cudaStream_t stream = nullptr;       // stream A: prologue, scan, carry (the caller-visible stream)
     cudaStream_t stream_b = nullptr;     // stream B: compact, exact, resolve, slice - overlaps the next call's scan
+    cudaStream_t stream_c = nullptr;     // stream C: prologue + carry, so that stream A is scans back to back
+    cudaEvent_t e_aux[2] = {nullptr, nullptr}, e_in = nullptr;
+    bool aux_valid[2] = {false, false};
     bool own_stream = false;
     int overlap = 1;
     cudaEvent_t e_scan[2] = {nullptr, nullptr}, e_done[2] = {nullptr, nullptr};
@@ -75,8 +78,9 @@ static int fail(amb_ctx* c, int code, const char* what, cudaError_t e = cudaSucc
 static cudaError_t sync_all(amb_ctx* c)
 {
     cudaError_t e = cudaStreamSynchronize(c->stream);
-    if (e != cudaSuccess) return e;
-    return c->stream_b ? cudaStreamSynchronize(c->stream_b) : cudaSuccess;
+    if (e == cudaSuccess && c->stream_c) e = cudaStreamSynchronize(c->stream_c);
+    if (e == cudaSuccess && c->stream_b) e = cudaStreamSynchronize(c->stream_b);
+    return e;
 }
 
 // IQ as a 2-D tensor of 128-byte lines (16 complex samples each); tiles of 32 lines = 512 samples land in
@@ -245,8 +249,11 @@ int amb_create(int device, float rate, float threshold_db, int use_pmf, int use_
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
         ctx->own_stream = true;
         if (cudaStreamCreateWithFlags(&ctx->stream_b, cudaStreamNonBlocking) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
+        if (cudaStreamCreateWithFlags(&ctx->stream_c, cudaStreamNonBlocking) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
+        if (cudaEventCreateWithFlags(&ctx->e_in, cudaEventDisableTiming) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
         for (int k = 0; k < 2 && rc == AMB_OK; k++)
             if (cudaEventCreateWithFlags(&ctx->e_scan[k], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ctx->e_aux[k], cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&ctx->e_done[k], cudaEventDisableTiming) != cudaSuccess) rc = AMB_ERR_CUDA;
         if (rc != AMB_OK) break;
         if (cudaMalloc(&ctx->ctr, sizeof(AmbCounters)) != cudaSuccess || cudaMalloc(&ctx->st, sizeof(AmbWalkState)) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
@@ -273,8 +280,14 @@ void amb_destroy(amb_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) sync_all(ctx);
     free_dev(ctx);
-    for (int k = 0; k < 2; k++) { if (ctx->e_scan[k]) cudaEventDestroy(ctx->e_scan[k]); if (ctx->e_done[k]) cudaEventDestroy(ctx->e_done[k]); }
+    for (int k = 0; k < 2; k++) {
+        if (ctx->e_scan[k]) cudaEventDestroy(ctx->e_scan[k]);
+        if (ctx->e_done[k]) cudaEventDestroy(ctx->e_done[k]);
+        if (ctx->e_aux[k]) cudaEventDestroy(ctx->e_aux[k]);
+    }
+    if (ctx->e_in) cudaEventDestroy(ctx->e_in);
     if (ctx->stream_b) cudaStreamDestroy(ctx->stream_b);
+    if (ctx->stream_c) cudaStreamDestroy(ctx->stream_c);
     for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < 128; k++) if (ctx->ring[k]) cudaEventDestroy(ctx->ring[k]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -399,13 +412,16 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
     if (ctx->flushed) return fail(ctx, AMB_ERR_STATE, "stream already flushed; amb_reset first");
     if (n_complex > 0x60000000ull) return fail(ctx, AMB_ERR_INVALID, "at most 1.5 Gi samples per call");
     CK(cudaSetDevice(ctx->device));
-    cudaStream_t sa = ctx->stream, sb = ctx->stream_b;
+    cudaStream_t sa = ctx->stream, sb = ctx->stream_b, sc = ctx->stream_c;
     const AmbParams& P = ctx->P;
     const int kc = ctx->kc;
     const int set = (int)(ctx->call_idx & 1u);             // double-buffered per-call scratch
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[2], sa));
-    // this set's buffers were last used by call k-2: its tail kernels must be finished
-    if (ctx->done_valid[set]) CK(cudaStreamWaitEvent(sa, ctx->e_done[set], 0));
+    // stream C stages the tail and the next carry. It starts where the caller's stream is now (the input is
+    // ready there) and after call k-2's sparse kernels, the last users of this set's buffers.
+    CK(cudaEventRecord(ctx->e_in, sa));
+    CK(cudaStreamWaitEvent(sc, ctx->e_in, 0));
+    if (ctx->done_valid[set]) { CK(cudaStreamWaitEvent(sc, ctx->e_done[set], 0)); CK(cudaStreamWaitEvent(sa, ctx->e_done[set], 0)); }
 
     // ---- input placement: device pointers are used in place, host data goes through a staging buffer
     const float2* src = reinterpret_cast<const float2*>(iq);
@@ -423,6 +439,8 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
             CK(cudaMemcpyAsync(ctx->staging, iq, n_complex * sizeof(float2),
                                mem_kind == AMB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, sa));
         src = ctx->staging;
+        CK(cudaEventRecord(ctx->e_in, sa));
+        CK(cudaStreamWaitEvent(sc, ctx->e_in, 0));
     }
     const int n_new = (int)n_complex;
     const int n_main = n_new & ~(AMB_STAGE - 1);
@@ -470,8 +488,11 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         if (n_main) { int rc2 = make_tmap(ctx, &a.tm_main, src, (size_t)n_main); if (rc2) return rc2; }
         else a.tm_main = ctx->tm_tail[set];
 
-        // ---- stream A: stage the tail, reset the group counts, stream over the IQ
-        CK(amb_launch_prologue(ctx->tail[set], ctx->tail_cap, src + n_main, n_tv, a.group_count, 128, sa));
+        // ---- stream C: stage the tail, reset the group counts; stream A: stream over the IQ
+        CK(amb_launch_prologue(ctx->tail[set], ctx->tail_cap, src + n_main, n_tv, a.group_count, 128, sc));
+        CK(cudaEventRecord(ctx->e_aux[set], sc));
+        CK(cudaStreamWaitEvent(sa, ctx->e_aux[set], 0));
+        if (ctx->aux_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_aux[set ^ 1], 0));   // carry written by the previous call
         const unsigned slot = (ctx->ring_n & 63u) * 2;
         if (ctx->timing) { CK(cudaEventRecord(ctx->ev[0], sa)); CK(cudaEventRecord(ctx->ring[slot], sa)); }
         CK(amb_launch_scan(a, ctx->sm_count, sa));
@@ -499,7 +520,10 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
     } else {
         // nothing can be decided yet (tiny call): keep it simple and serial
         if (ctx->done_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_done[set ^ 1], 0));
-        CK(amb_launch_prologue(ctx->tail[set], ctx->tail_cap, src + n_main, n_tv, nullptr, 0, sa));
+        CK(amb_launch_prologue(ctx->tail[set], ctx->tail_cap, src + n_main, n_tv, nullptr, 0, sc));
+        CK(cudaEventRecord(ctx->e_aux[set], sc));
+        CK(cudaStreamWaitEvent(sa, ctx->e_aux[set], 0));
+        if (ctx->aux_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_aux[set ^ 1], 0));
         CK(cudaEventRecord(ctx->e_scan[set], sa));
         CK(cudaStreamWaitEvent(sb, ctx->e_scan[set], 0));
         if (flush) {   // the resolver still has to close the stream
@@ -519,17 +543,22 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
     CK(cudaEventRecord(ctx->e_done[set], sb));
     ctx->done_valid[set] = true;
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[3], sb));
-    // ---- carry the tail of the stream into the next call (stream A). The buffer written here is the one
-    // the PREVIOUS call's tail kernels read as their carry: wait for them (normally long finished).
-    if (ctx->done_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_done[set ^ 1], 0));
-    CK(amb_launch_carry(S, ctx->carry[cout], kc, sa));
+    // ---- carry the tail of the stream into the next call (stream C, concurrently with this call's scan).
+    // The buffer written here is the one the PREVIOUS call's scan and sparse kernels read as their carry.
+    if (ctx->done_valid[set ^ 1]) CK(cudaStreamWaitEvent(sc, ctx->e_done[set ^ 1], 0));
+    CK(amb_launch_carry(S, ctx->carry[cout], kc, sc));
+    CK(cudaEventRecord(ctx->e_aux[set], sc));
+    ctx->aux_valid[set] = true;
     ctx->stats.kernel_launches += 2;
     ctx->carry_in = cout;
     ctx->n_in = (uint64_t)n_after;
     if (flush) ctx->flushed = true;
     else if (j_hi > j_lo) ctx->r_done = r_safe;
     ctx->call_idx++;
-    if (!ctx->overlap) CK(cudaStreamWaitEvent(sa, ctx->e_done[set], 0));   // strict stream-ordered behaviour on stream A
+    if (!ctx->overlap) {                                                    // strict stream-ordered behaviour on stream A
+        CK(cudaStreamWaitEvent(sa, ctx->e_done[set], 0));
+        CK(cudaStreamWaitEvent(sa, ctx->e_aux[set], 0));
+    }
     return AMB_OK;
 }
 
@@ -538,7 +567,10 @@ int amb_join(amb_ctx* ctx)
 {
     if (!ctx) return AMB_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    for (int k = 0; k < 2; k++) if (ctx->done_valid[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->e_done[k], 0));
+    for (int k = 0; k < 2; k++) {
+        if (ctx->done_valid[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->e_done[k], 0));
+        if (ctx->aux_valid[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->e_aux[k], 0));
+    }
     return AMB_OK;
 }
 

@@ -80,7 +80,10 @@ __device__ __forceinline__ const float2* seg_ptr(const AmbSegs& S, int j) {
 //   32 roundings of 2^-24 enter it, gfac = 2^-19. Tests :177-179 use the same lowered threshold; the
 //   peak test in[i+1] > in[i] (:175) is relaxed by (1+eps); eps = 2^-15 dwarfs the <= 2^-19 relative error
 //   of bbs. Result: a superset of the reference's candidates, typically < 0.01 % larger.
-template <int SPC, bool PMF, bool PREF> struct ScanCfg {
+// PREF (compile-time pulse offsets 2,7,9*SPC): 2 = all four pulses from registers + shuffles, no look-ahead ring
+// (best for short filters, where noise crosses the threshold often); 1 = second pulse from registers as a quick
+// per-lane reject, the others from the shared-memory ring (best for SPC >= 4); 0 = run-time offsets, ring only.
+template <int SPC, bool PMF, int PREF> struct ScanCfg {
     static constexpr int FL = PMF ? SPC : 1;       // pulse-matched-filter length (rx_path.py:48-51)
     static constexpr int L = 48 * SPC;             // noise-floor window (rx_path.py:54)
     static constexpr int LW = L / 8;               // ... in lanes
@@ -90,7 +93,7 @@ template <int SPC, bool PMF, bool PREF> struct ScanCfg {
     static constexpr int NST = AMB_NST;            // TMA tile ring depth per warp (tile = 2 rows = 4 KiB)
     static constexpr int WARM = (RB + 2 + 1) & ~1;
     static constexpr int IQ_BYTES = NST * 4096;                    // per warp, 1 KiB aligned
-    static constexpr int BB_FLOATS = PREF ? 0 : 512;               // look-ahead ring only when pulse offsets are run-time values
+    static constexpr int BB_FLOATS = (PREF == 2) ? 0 : 512;               // look-ahead ring only when pulse offsets are run-time values
     static constexpr int WORK_BYTES = BB_FLOATS * 4 + PRR * 1024 + 64;  // [bb ring,] pr ring, mbarriers
     static constexpr int CTA_BYTES = 4 * (IQ_BYTES + WORK_BYTES);
 };
@@ -100,7 +103,7 @@ __device__ __forceinline__ int swz(int p) { return p ^ ((p >> 3) & 4); }
 
 struct RowRegs { float b[8]; float t[8]; };
 
-template <int SPC, bool PMF, bool PREF>
+template <int SPC, bool PMF, int PREF>
 struct ScanWarp {
     using C = ScanCfg<SPC, PMF, PREF>;
     int lane;
@@ -207,7 +210,7 @@ struct ScanWarp {
         for (int r = 0; r < 8; r++) p[r] += exc;
         float* bslot = bbr + (k & 1) * 256;
         float* pslot = prr + (k % C::PRR) * 256;
-        if (!PREF) {
+        if (PREF != 2) {
             *reinterpret_cast<float4*>(bslot + own) = make_float4(b[0], b[1], b[2], b[3]);
             *reinterpret_cast<float4*>(bslot + (own ^ 4)) = make_float4(b[4], b[5], b[6], b[7]);
         }
@@ -242,11 +245,14 @@ struct ScanWarp {
             float u[8];
 #pragma unroll
             for (int r = 0; r < 8; r++) u[r] = prev.b[r];
-            if (PREF) {
+            if (PREF == 2) {
 #pragma unroll
                 for (int r = 0; r < 8; r++)
                     u[r] = fminf(fminf(u[r], ahead<2 * SPC>(r, prev.b, b)),
                                  fminf(ahead<7 * SPC>(r, prev.b, b), ahead<9 * SPC>(r, prev.b, b)));
+            } else if (PREF == 1) {
+#pragma unroll
+                for (int r = 0; r < 8; r++) u[r] = fminf(u[r], ahead<2 * SPC>(r, prev.b, b));
             }
             bool hot = false;
 #pragma unroll
@@ -266,7 +272,7 @@ struct ScanWarp {
 #pragma unroll
                         for (int r = 0; r < 8; r++) if (jb + r < a->j_lo || jb + r >= a->j_hi) msk &= ~(1u << r);
                     }
-                    if (!PREF) {
+                    if (PREF != 2) {
                         const int rbase = (ke & 1) * 256 + 8 * lane;
                         const int po1 = a->P.po1, po2 = a->P.po2, po3 = a->P.po3;
                         uint32_t todo = msk;
@@ -315,7 +321,7 @@ struct ScanWarp {
     }
 };
 
-template <int SPC, bool PMF, bool PREF>
+template <int SPC, bool PMF, int PREF>
 __global__ void __launch_bounds__(128) amb_scan_kernel(const __grid_constant__ AmbScanArgs a)
 {
     using C = ScanCfg<SPC, PMF, PREF>;
@@ -397,14 +403,14 @@ __global__ void __launch_bounds__(128) amb_scan_kernel(const __grid_constant__ A
 size_t amb_scan_smem_bytes(int spc_i)
 {
     switch (spc_i) {
-#define CASE(n) case n: return (size_t)ScanCfg<n, true, false>::CTA_BYTES;
+#define CASE(n) case n: return (size_t)ScanCfg<n, true, 0>::CTA_BYTES;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
 #undef CASE
     }
     return 0;
 }
 
-template <int SPC, bool PMF, bool PREF>
+template <int SPC, bool PMF, int PREF>
 static cudaError_t launch_scan_t(const AmbScanArgs& a, cudaStream_t s)
 {
     const size_t smem = (size_t)ScanCfg<SPC, PMF, PREF>::CTA_BYTES;
@@ -420,8 +426,8 @@ cudaError_t amb_launch_scan(const AmbScanArgs& a, int, cudaStream_t s)
     // integer samples/chip: pulse offsets are the compile-time 2,7,9*SPC (register/shuffle look-ahead)
     const bool pref = a.P.po1 == 2 * a.P.spc_i && a.P.po2 == 7 * a.P.spc_i && a.P.po3 == 9 * a.P.spc_i;
     switch (a.P.spc_i) {
-#define CASE(n) case n: return a.P.use_pmf ? (pref ? launch_scan_t<n, true, true>(a, s) : launch_scan_t<n, true, false>(a, s)) \
-                                          : (pref ? launch_scan_t<n, false, true>(a, s) : launch_scan_t<n, false, false>(a, s));
+#define CASE(n) case n: return a.P.use_pmf ? (pref ? launch_scan_t<n, true, (n <= 3 ? 2 : 1)>(a, s) : launch_scan_t<n, true, 0>(a, s)) \
+                                          : (pref ? launch_scan_t<n, false, 2>(a, s) : launch_scan_t<n, false, 0>(a, s));
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
 #undef CASE
         default: break;
