@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -269,7 +269,6 @@ def main():
     scan_ms = rx._ctx.scan_times_ms(min(args.steps, 64))
     launches = rx.stats().kernel_launches - launches0
     rx.drain(); q.flush()
-    clocks = sampler.stop() if rank == 0 else None
     ms_max = shard.max_over_ranks(ms, world, device)
     scan_avg = shard.max_over_ranks(float(np.mean(scan_ms)), world, device)
 
@@ -292,6 +291,7 @@ def main():
     e2e_ms = 1e3 * (time.perf_counter() - t0) / args.e2e_steps
     e2e_ms = shard.max_over_ranks(e2e_ms, world, device)
     q.flush()
+    clocks = sampler.stop() if rank == 0 else None     # sampled across both timed regions (device + end to end)
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
