@@ -520,22 +520,21 @@ __device__ __forceinline__ float stream_at(const float* in, long long n, int H, 
     return (k >= 0 && k < n) ? in[k] : 0.f;
 }
 
-#define EX_MAXB 704   // >= L + maxlate + fwd + spc_i for spc_i <= 10
 
 // One warp per candidate. Writes info = late | real<<8 | valid<<9 and avg at the shifted index.
 template <bool STREAMS>
 __global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a)
 {
-    __shared__ float s_m2[4][EX_MAXB];
-    __shared__ float s_bb[4][EX_MAXB];
+    extern __shared__ float ex_smem[];                 // per warp: m2s[NMp] then bbs[NMp], sized by the launcher
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* m2s = s_m2[warp];
-    float* bbs = s_bb[warp];
     const AmbParams& P = a.P;
     const int L = P.L, spc = P.spc_i, maxlate = P.maxlate;
     const int fl = P.use_pmf ? spc : 1;
     const int NB = STREAMS ? (maxlate + P.fwd + 1) : (L + maxlate + P.fwd + 1);
     const int NM = NB + fl - 1;
+    const int NMp = (NM + 31) & ~31;
+    float* m2s = ex_smem + (size_t)warp * 2 * NMp;
+    float* bbs = m2s + NMp;
     const int c0off = STREAMS ? 0 : (L - 1);       // bbs index of the candidate start
     const unsigned int ncand = a.ctr->ncand;
     const int nwarps = gridDim.x * 4;
@@ -620,9 +619,13 @@ __global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a)
 
 cudaError_t amb_launch_exact(const AmbExactArgs& a, int sm_count, cudaStream_t s)
 {
-    const int blocks = sm_count * 8;
-    if (a.in0) amb_exact_kernel<true><<<blocks, 128, 0, s>>>(a);
-    else amb_exact_kernel<false><<<blocks, 128, 0, s>>>(a);
+    const int fl = a.P.use_pmf ? a.P.spc_i : 1;
+    const int NB = a.in0 ? (a.P.maxlate + a.P.fwd + 1) : (a.P.L + a.P.maxlate + a.P.fwd + 1);
+    const int NMp = (NB + fl - 1 + 31) & ~31;
+    const size_t smem = (size_t)4 * 2 * NMp * sizeof(float);            // <= 22 KiB at 20 Msps, ~1.3 KiB at 4 Msps
+    const int blocks = sm_count * 12;
+    if (a.in0) amb_exact_kernel<true><<<blocks, 128, smem, s>>>(a);
+    else amb_exact_kernel<false><<<blocks, 128, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -867,7 +870,7 @@ __device__ __forceinline__ int llslice(float bit0, float bit1, float ref)
 
 // Packet rules of slicer_impl::work (slicer_impl.cc:117-182) on 240 chips held in shared memory.
 // Executed by a full warp; lane 0 fills *f (sample_index/secs/frac are the caller's business).
-__device__ void slice_packet_warp(const float* chips, amb_frame* f, int lane)
+__device__ bool slice_packet_warp(const float* chips, amb_frame* f, int lane)
 {
     const float ref = (float)((double)__fadd_rn(__fadd_rn(__fadd_rn(chips[0], chips[2]), chips[7]), chips[9]) / 4.0); // :128-131
     uint32_t dw[4], lw[4];
@@ -894,30 +897,33 @@ __device__ void slice_packet_warp(const float* chips, amb_frame* f, int lane)
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) crc ^= __shfl_xor_sync(FULL, crc, d);
-    if (lane == 0) {
-        unsigned char data[14];
-#pragma unroll
-        for (int m = 0; m < 14; m++) data[m] = (unsigned char)(dw[m >> 2] >> (24 - 8 * (m & 3)));
-        unsigned numlow = 0;
-#pragma unroll
-        for (int m = 0; m < 24; m++) f->lowconfbits[m] = 0;
-        for (int k = 0; k < 4 && numlow < 24; k++)                            // :152-158, ascending j, cap 24
-            for (uint32_t w = lw[k]; w && numlow < 24; w &= w - 1) f->lowconfbits[numlow++] = (uint8_t)(32 * k + __ffs(w) - 1);
-        const unsigned df = (data[0] >> 3) & 0x1F;                            // :168
-        const uint32_t ap = ((uint32_t)data[nbits / 8 - 3] << 16) | ((uint32_t)data[nbits / 8 - 2] << 8) | data[nbits / 8 - 1];
-        bool zeroes = true;                                                   // :162-166
-#pragma unroll
-        for (int m = 0; m < 14; m++) if (data[m]) zeroes = false;
-        bool passed = !zeroes;
-        if (passed && !is_long && df != 11 && numlow > 0) passed = false;     // :170
-        if (passed && df == 11 && numlow >= 10) passed = false;               // :171
-        uint32_t syn = 0;
-        if (passed) {
-            syn = crc ^ ap;                                                   // :173-177
-            if (syn && (df == 11 || df == 17)) passed = false;                // :182
+    // ---- packet rules, evaluated by every lane on warp-uniform values; the stores are spread over lanes
+    const uint32_t lowtot = __popc(lw[0]) + __popc(lw[1]) + __popc(lw[2]) + __popc(lw[3]);
+    const unsigned numlow = lowtot < 24u ? lowtot : 24u;                      // :157 saturates at 24
+    const unsigned df = dw[0] >> 27;                                          // :168 (data[0] >> 3) & 0x1F
+    // last three bytes = bits nbits-24 .. nbits-1
+    const uint32_t ap = is_long ? (((dw[2] & 0xFFu) << 16) | (dw[3] >> 16)) : (dw[1] >> 8) & 0xFFFFFFu;
+    const bool zeroes = (dw[0] | dw[1] | dw[2] | dw[3]) == 0;                 // :162-166
+    bool passed = !zeroes;
+    if (passed && !is_long && df != 11 && numlow > 0) passed = false;         // :170
+    if (passed && df == 11 && numlow >= 10) passed = false;                   // :171
+    uint32_t syn = 0;
+    if (passed) {
+        syn = crc ^ ap;                                                       // :173-177
+        if (syn && (df == 11 || df == 17)) passed = false;                    // :182
+    }
+    if (lane < 14) f->data[lane] = (uint8_t)(dw[lane >> 2] >> (24 - 8 * (lane & 3)));
+    if (lane < 24) {                                                          // :152-158: ascending j, first 24
+        uint8_t v = 0;
+        if ((unsigned)lane < numlow) {
+            unsigned need = (unsigned)lane, k = 0;
+            while (need >= (unsigned)__popc(lw[k])) { need -= __popc(lw[k]); k++; }
+            v = (uint8_t)(32 * k + __fns(lw[k], 0, (int)need + 1));
         }
-#pragma unroll
-        for (int m = 0; m < 14; m++) f->data[m] = data[m];
+        f->lowconfbits[lane] = v;
+    }
+    if (lane >= 24 && lane < 30) f->pad_[lane - 24] = 0;
+    if (lane == 31) {
         f->ref_level = ref;
         f->crc = syn;
         f->nbits = (uint8_t)nbits;
@@ -925,15 +931,14 @@ __device__ void slice_packet_warp(const float* chips, amb_frame* f, int lane)
         f->numlowconf = (uint8_t)numlow;
         f->passed = passed ? 1 : 0;
     }
+    return passed;
 }
-
-#define SL_MAXM 2416   // >= int(239*spc) + spc for spc <= 10
 
 template <bool STREAMS>
 __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
 {
     __shared__ float s_chips[4][240];
-    __shared__ float s_m2[STREAMS ? 1 : 4][STREAMS ? 1 : SL_MAXM];
+    extern __shared__ float sl_smem[];                         // per warp: m2 of the packet span (not in STREAMS mode)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* chips = s_chips[warp];
     const AmbParams& P = a.P;
@@ -941,6 +946,7 @@ __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
     const int nwarps = gridDim.x * 4;
     const int fl = P.use_pmf ? P.spc_i : 1;
     const int span = c_chip_off[239] + fl;                     // m2 samples a packet touches
+    const int spanp = (span + 31) & ~31;
     for (unsigned int ci = blockIdx.x * 4 + warp; ci < ncand; ci += nwarps) {
         const uint32_t info = a.cand_info[ci];
         if (!(info & (1u << 10))) continue;                    // warp-uniform
@@ -950,7 +956,7 @@ __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
             for (int j = lane; j < 240; j += 32)               // preamble_impl.cc:219-221
                 chips[j] = __fsub_rn(stream_at(a.in0, a.n_streams, P.H, (long long)fin + c_chip_off[j]), avg_fin);
         } else {
-            float* m2s = s_m2[STREAMS ? 0 : warp];
+            float* m2s = sl_smem + (size_t)warp * spanp;
             const int b0 = fin - fl + 1;                       // m2s[i] <-> m2[b0 + i]; independent coalesced loads
             for (int i0 = 0; i0 < span; i0 += 256) {           // 8 independent loads in flight per lane
                 float v[8];
@@ -979,12 +985,11 @@ __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
         slot = __shfl_sync(FULL, slot, 0);
         if (slot < a.frame_cap) {
             amb_frame* f = a.frames + slot;
-            slice_packet_warp(chips, f, lane);
+            const bool passed = slice_packet_warp(chips, f, lane);
             if (lane == 0) {
                 f->sample_index = (uint64_t)(a.org + fin);
                 f->secs = 0; f->frac = 0.0;
-                for (int m = 0; m < 6; m++) f->pad_[m] = 0;
-                if (f->passed) atomicAdd(&a.ctr->npassed_call, 1u);
+                if (passed) atomicAdd(&a.ctr->npassed_call, 1u);
             }
             if (a.chips_out) for (int j = lane; j < 240; j += 32) a.chips_out[(size_t)slot * 240 + j] = chips[j];
         } else if (lane == 0) {
@@ -996,9 +1001,12 @@ __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
 
 cudaError_t amb_launch_slice(const AmbSliceArgs& a, int sm_count, cudaStream_t s)
 {
-    const int blocks = sm_count * 4;
-    if (a.in0) amb_slice_kernel<true><<<blocks, 128, 0, s>>>(a);
-    else amb_slice_kernel<false><<<blocks, 128, 0, s>>>(a);
+    const int fl = a.P.use_pmf ? a.P.spc_i : 1;
+    const int spanp = ((int)(239 * a.P.spc_f) + fl + 31) & ~31;        // = c_chip_off[239] + fl, rounded
+    const size_t smem = a.in0 ? 0 : (size_t)4 * spanp * sizeof(float);  // 38 KiB at 20 Msps, 8 KiB at 4 Msps
+    const int blocks = sm_count * 8;
+    if (a.in0) amb_slice_kernel<true><<<blocks, 128, smem, s>>>(a);
+    else amb_slice_kernel<false><<<blocks, 128, smem, s>>>(a);
     return cudaGetLastError();
 }
 
