@@ -34,6 +34,13 @@ class Stats(C.Structure):
                 ("reserved_", C.c_int)]
 
 
+class Geometry(C.Structure):
+    _fields_ = [("samples_per_chip", C.c_float), ("samples_per_symbol", C.c_float), ("threshold", C.c_float),
+                ("rate_int", C.c_int), ("history", C.c_int), ("check_width", C.c_int), ("pulse_offset", C.c_int * 4),
+                ("quiet_a", C.c_int * 2), ("quiet_b", C.c_int * 2), ("max_late", C.c_int), ("packet_skip", C.c_int),
+                ("pmf_len", C.c_int), ("floor_len", C.c_int), ("chip_offset_239", C.c_int)]
+
+
 assert C.sizeof(Frame) == 80
 
 # every symbol include/airmodes_b200.h declares: (name, restype, argtypes)
@@ -47,6 +54,7 @@ SYMBOLS = [
     ("amb_get_rate", C.c_float, [_vp]),
     ("amb_get_threshold", C.c_float, [_vp]),
     ("amb_get_pmf", C.c_int, [_vp]),
+    ("amb_query_geometry", C.c_int, [C.c_float, C.c_float, C.c_int, C.POINTER(Geometry)]),
     ("amb_process", C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_int]),
     ("amb_poll_frames", C.c_int, [_vp, C.POINTER(Frame), C.c_int]),
     ("amb_pending_frames", C.c_int, [_vp]),

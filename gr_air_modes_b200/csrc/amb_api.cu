@@ -328,6 +328,22 @@ float amb_get_rate(const amb_ctx* ctx) { return ctx ? (float)ctx->P.rate_int : 0
 float amb_get_threshold(const amb_ctx* ctx) { return ctx ? ctx->thr_db : 0.f; }         // :70-72
 int amb_get_pmf(const amb_ctx* ctx) { return ctx ? ctx->use_pmf : 0; }
 
+int amb_query_geometry(float rate, float threshold_db, int use_pmf, amb_geometry* out)
+{
+    if (!out) return AMB_ERR_INVALID;
+    AmbParams P; int off[240];
+    int rc = compute_params(rate, threshold_db, use_pmf, &P, off);
+    if (rc != AMB_OK) return rc;
+    out->samples_per_chip = P.spc_f; out->samples_per_symbol = P.sps_f; out->threshold = P.thr;
+    out->rate_int = P.rate_int; out->history = P.H + 1; out->check_width = (int)(120 * P.sps_f);   // preamble_impl.cc:59
+    out->pulse_offset[0] = 0; out->pulse_offset[1] = P.po1; out->pulse_offset[2] = P.po2; out->pulse_offset[3] = P.po3;
+    out->quiet_a[0] = P.qa0; out->quiet_a[1] = P.qa1; out->quiet_b[0] = P.qb0; out->quiet_b[1] = P.qb1;
+    out->max_late = P.maxlate; out->packet_skip = P.skip0;
+    out->pmf_len = use_pmf ? P.spc_i : 1; out->floor_len = P.L;
+    out->chip_offset_239 = off[239];
+    return AMB_OK;
+}
+
 int amb_set_stream(amb_ctx* ctx, void* cuda_stream)
 {
     if (!ctx) return AMB_ERR_INVALID;

@@ -94,6 +94,20 @@ AMB_API float amb_get_rate(const amb_ctx* ctx);                 /* (float)(int)r
 AMB_API float amb_get_threshold(const amb_ctx* ctx);            /* dB, as preamble_impl.cc:70-72 */
 AMB_API int amb_get_pmf(const amb_ctx* ctx);                    /* rx_path.get_pmf (rx_path.py:83-84) */
 
+/* Host-only (no GPU needed): the geometry preamble_impl derives from (rate, threshold) - preamble_impl.cc:56-68
+ * (set_rate/set_threshold), :158-162 (pulse offsets), :205-208 (quiet-zone loop bounds), :184-192 (late-gate
+ * budget), :212/:237 (240*spc) - as the kernels will use it. Returns AMB_ERR_RATE for unsupported rates. */
+typedef struct amb_geometry {
+    float samples_per_chip, samples_per_symbol, threshold;   /* d_samples_per_chip, d_samples_per_symbol, d_threshold */
+    int rate_int, history, check_width;                      /* d_sample_rate, history(), d_check_width */
+    int pulse_offset[4];
+    int quiet_a[2], quiet_b[2];                              /* inclusive j ranges of the two space checks */
+    int max_late, packet_skip;                               /* late shifts allowed; (int)(240*spc) */
+    int pmf_len, floor_len;                                  /* rx_path.py:49,54 */
+    int chip_offset_239;                                     /* int(239*spc), last extracted chip (:220) */
+} amb_geometry;
+AMB_API int amb_query_geometry(float rate, float threshold_db, int use_pmf, amb_geometry* out);
+
 /* ---- the hot path -----------------------------------------------------------------------------
  * Feed n_complex samples (2*n_complex floats). Replaces the scheduler calling
  * complex_to_mag_squared/moving_average_ff work() (rx_path.py:38-54),

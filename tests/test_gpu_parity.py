@@ -277,3 +277,27 @@ def test_overlap_off_is_identical(port):
         rx.process(sc.iq[2 * k: 2 * (k + 100_000)], flush=(k + 100_000 >= 700_000), collect=False)
     rx.drain()
     assert q.strings() == want
+
+
+def test_config0_pr1_golden_single_df17(port, tmp_path):
+    """BASELINE configs[0]: 10 s at 2 Msps, one injected DF17 8D4840D6202CC371C32CE0576098, noise sigma 0.01.
+    (A) fed to rx_path at 2 Msps directly, (B) the same scene rendered at 4 Msps (what modes_rx runs after its
+    2->4 Msps resampler). The oracle's message list is the golden; the CLI tool must print the same lines."""
+    import subprocess, sys, os
+    frame = bytes.fromhex("8D4840D6202CC371C32CE0576098")
+    for rate, n in ((2e6, 20_000_000), (4e6, 40_000_000)):
+        rng = np.random.Generator(np.random.PCG64(1))
+        iq = (rng.standard_normal(2 * n, dtype=np.float32) * np.float32(0.01))
+        n0, w = synth.burst_waveform(synth.Burst(n / 2 + 0.37, frame, 0.5, 1.0), rate / 2e6)
+        iq[2 * n0: 2 * (n0 + w.size)] += w.view(np.float32)
+        want = port.run_iq(iq, rate, 7.0, True, co.MA_CANONICAL)
+        assert any(m.startswith(frame.hex() + " 000000") for m in want.msgs)
+        msgs, frames, _ = run_cuda(iq, rate, 7.0, True)
+        assert msgs == want.msgs and [f.sample_index for f in frames] == [int(x) for x in want.index]
+        if rate == 2e6:
+            path = tmp_path / "pr1.cfile"
+            iq.tofile(path)
+            root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+            out = subprocess.run([sys.executable, os.path.join(root, "tools", "modes_rx_b200.py"), "-s", str(path), "-r", "2e6",
+                                  "--chunk", "3000001"], capture_output=True, text=True, check=True).stdout.split("\n")
+            assert [ln for ln in out if ln] == want.msgs

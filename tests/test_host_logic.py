@@ -103,3 +103,25 @@ def test_product_does_not_touch_oracle():
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "cpu_oracle" not in txt and "liboracle" not in txt and "modes_oracle" not in txt, fn
     assert "oracle" not in open(os.path.join(ROOT, "include", "airmodes_b200.h")).read().lower()
+
+
+def test_geometry_matches_reference_blocks(lib, port, ref):
+    """Host-side parameter derivation (no GPU): same numbers as preamble_impl's set_rate/set_threshold and the
+    loop bounds its general_work evaluates, for integer and fractional samples/chip."""
+    g = _lib.Geometry()
+    for rate in (2e6, 2.4e6, 3e6, 3.2e6, 4e6, 5e6, 6e6, 8e6, 10e6, 12.5e6, 16e6, 20e6):
+        for thr in (3.0, 7.0, 11.5):
+            assert lib.amb_query_geometry(rate, thr, 1, C.byref(g)) == 0
+            p = port.params(rate, thr)
+            r_rate, r_thr, r_hist = ref.preamble_params(rate, thr)
+            assert (float(g.rate_int), g.history) == (r_rate, r_hist)
+            assert (g.samples_per_chip, g.samples_per_symbol, g.threshold, g.check_width) == (p.spc, p.sps, p.threshold, p.check_width)
+            assert list(g.pulse_offset) == list(p.po)
+            sps = np.float32(p.sps)
+            qa = [j for j in range(int(1.5 * float(sps)), 4000) if np.float32(j) <= np.float32(3) * sps]
+            qb = [j for j in range(int(np.float32(5) * sps), 4000) if float(j) <= 7.5 * float(sps)]
+            assert [g.quiet_a[0], g.quiet_a[1]] == [qa[0], qa[-1]] and [g.quiet_b[0], g.quiet_b[1]] == [qb[0], qb[-1]]
+            assert g.packet_skip == int(np.float32(240) * np.float32(p.spc)) and g.max_late == max(1, int(np.ceil(p.spc)))
+            assert g.pmf_len == int(rate / 2e6) and g.floor_len == 48 * int(rate / 2e6)
+    for bad in (1e6, 1.99e6, 21e6, 40e6):
+        assert lib.amb_query_geometry(bad, 7.0, 1, C.byref(g)) == -4          # AMB_ERR_RATE
