@@ -54,6 +54,7 @@ SYMBOLS = [
     ("amb_get_rate", C.c_float, [_vp]),
     ("amb_get_threshold", C.c_float, [_vp]),
     ("amb_get_pmf", C.c_int, [_vp]),
+    ("amb_set_start_time", C.c_int, [_vp, C.c_uint64, C.c_double]),
     ("amb_query_geometry", C.c_int, [C.c_float, C.c_float, C.c_int, C.POINTER(Geometry)]),
     ("amb_process", C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_int]),
     ("amb_poll_frames", C.c_int, [_vp, C.POINTER(Frame), C.c_int]),

@@ -264,6 +264,10 @@ class rx_path:
         self._ctx.call("amb_set_threshold", float(threshold))
         self._threshold = threshold
 
+    def set_start_time(self, secs: int, frac: float):
+        """rx_time tag of the stream's first item (what a UHD source provides; preamble_impl.cc:164-170)."""
+        self._ctx.call("amb_set_start_time", int(secs), float(frac))
+
     def set_pmf(self, pmf):
         pass                                        # rx_path.py:79-81: "must be done when top block is stopped"
 

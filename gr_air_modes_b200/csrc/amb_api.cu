@@ -49,6 +49,7 @@ struct amb_ctx {
     AmbCounters* ctr = nullptr; AmbWalkState* st = nullptr;
     // stream state
     uint64_t n_in = 0; long long r_done = 0; bool flushed = false;
+    uint64_t t0_secs = 0; double t0_frac = 0.0;          // rx_time tag at item 0 (preamble_impl.cc:104-116)
     long long last_org = 0; bool have_last = false;
     std::vector<amb_frame> pending;
     // stats / timing
@@ -328,6 +329,13 @@ float amb_get_rate(const amb_ctx* ctx) { return ctx ? (float)ctx->P.rate_int : 0
 float amb_get_threshold(const amb_ctx* ctx) { return ctx ? ctx->thr_db : 0.f; }         // :70-72
 int amb_get_pmf(const amb_ctx* ctx) { return ctx ? ctx->use_pmf : 0; }
 
+int amb_set_start_time(amb_ctx* ctx, uint64_t secs, double frac)
+{
+    if (!ctx) return AMB_ERR_INVALID;
+    ctx->t0_secs = secs; ctx->t0_frac = frac;
+    return AMB_OK;
+}
+
 int amb_query_geometry(float rate, float threshold_db, int use_pmf, amb_geometry* out)
 {
     if (!out) return AMB_ERR_INVALID;
@@ -591,12 +599,12 @@ int amb_join(amb_ctx* ctx)
 }
 
 // tag_to_timestamp with no rx_time tag (preamble_impl.cc:100-137)
-static void stamp(amb_frame* f, int rate_int)
+static void stamp(amb_frame* f, int rate_int, uint64_t t0_secs, double t0_frac)
 {
     const uint64_t cnt = f->sample_index;
-    f->secs = cnt / (uint64_t)rate_int;
-    f->frac = (double)(cnt % (uint64_t)rate_int) / (double)rate_int;
-    if (f->frac > 1.0f) { f->frac -= 1.0f; f->secs += 1; }
+    f->secs = t0_secs + cnt / (uint64_t)rate_int;                                  // :122,:125
+    f->frac = t0_frac + (double)(cnt % (uint64_t)rate_int) / (double)rate_int;     // :123,:126
+    if (f->frac > 1.0f) { f->frac -= 1.0f; f->secs += 1; }                         // :127-130
 }
 
 static int collect(amb_ctx* ctx)
@@ -617,7 +625,7 @@ static int collect(amb_ctx* ctx)
         CK(cudaMemcpy(ctx->pending.data() + base, ctx->frames, (size_t)h.nframes * sizeof(amb_frame), cudaMemcpyDeviceToHost));
         std::sort(ctx->pending.begin() + base, ctx->pending.end(),
                   [](const amb_frame& x, const amb_frame& y) { return x.sample_index < y.sample_index; });
-        for (size_t k = base; k < ctx->pending.size(); k++) stamp(&ctx->pending[k], ctx->P.rate_int);
+        for (size_t k = base; k < ctx->pending.size(); k++) stamp(&ctx->pending[k], ctx->P.rate_int, ctx->t0_secs, ctx->t0_frac);
         CK(cudaMemset(&ctx->ctr->nframes, 0, sizeof(unsigned)));
     }
     ctx->frames_ub = 0;

@@ -93,6 +93,10 @@ AMB_API int amb_set_threshold(amb_ctx* ctx, float threshold_db);/* takes effect 
 AMB_API float amb_get_rate(const amb_ctx* ctx);                 /* (float)(int)rate, as preamble_impl.cc:74-76 */
 AMB_API float amb_get_threshold(const amb_ctx* ctx);            /* dB, as preamble_impl.cc:70-72 */
 AMB_API int amb_get_pmf(const amb_ctx* ctx);                    /* rx_path.get_pmf (rx_path.py:83-84) */
+/* The rx_time stream tag a UHD source attaches to item 0 (lib/preamble_impl.cc:104-116,164-170): frames are then
+ * stamped tag + sample_index/rate with the reference's `frac > 1.0f` carry (:127-130). Default (0, 0.0) = no tag.
+ * Applies to frames collected afterwards. Later rx_time tags (overflows) are not modelled. */
+AMB_API int amb_set_start_time(amb_ctx* ctx, uint64_t secs, double frac);
 
 /* Host-only (no GPU needed): the geometry preamble_impl derives from (rate, threshold) - preamble_impl.cc:56-68
  * (set_rate/set_threshold), :158-162 (pulse offsets), :205-208 (quiet-zone loop bounds), :184-192 (late-gate

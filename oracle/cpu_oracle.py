@@ -62,6 +62,7 @@ class Port:
         L = C.CDLL(PORT_SO)
         vp, u64, f32p = C.c_void_p, C.c_uint64, C.POINTER(C.c_float)
         L.amo_make_params.argtypes = [C.c_float, C.c_float, C.POINTER(Params)]
+        L.amo_set_start_time.argtypes = [C.c_uint64, C.c_double]
         L.amo_crc24.argtypes = [C.c_char_p, C.c_int]; L.amo_crc24.restype = C.c_uint32
         L.amo_mag2.argtypes = [f32p, u64, f32p]
         L.amo_moving_average.argtypes = [f32p, u64, C.c_int, C.c_float, C.c_int, C.c_int, f32p]
@@ -84,6 +85,9 @@ class Port:
         self.L = L
 
     # -- helpers
+    def set_start_time(self, secs: int, frac: float):
+        self.L.amo_set_start_time(int(secs), float(frac))
+
     def params(self, rate, threshold_db) -> Params:
         p = Params(); self.L.amo_make_params(rate, threshold_db, C.byref(p)); return p
 
@@ -171,6 +175,8 @@ class Ref:
         L = C.CDLL(REF_SO)
         vp, u64, f32p = C.c_void_p, C.c_uint64, C.POINTER(C.c_float)
         L.aref_run.argtypes = [f32p, f32p, u64, C.c_float, C.c_float, C.c_int]; L.aref_run.restype = vp
+        L.aref_run_tagged.argtypes = [f32p, f32p, u64, C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint64, C.c_double]
+        L.aref_run_tagged.restype = vp
         L.aref_run_slicer.argtypes = [f32p, u64, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         L.aref_run_slicer.restype = vp
         L.aref_num_det.argtypes = [vp]; L.aref_num_det.restype = u64
@@ -204,8 +210,11 @@ class Ref:
         L.aref_free(h)
         return Result(index, secs, frac, chips, msgs, None, calls)
 
-    def run_streams(self, bb, avg, rate, threshold_db, slice_=True) -> Result:
+    def run_streams(self, bb, avg, rate, threshold_db, slice_=True, start_time=None) -> Result:
         bb, pb = _f32(bb); avg, pa = _f32(avg)
+        if start_time is not None:
+            return self._collect(self.L.aref_run_tagged(pb, pa, bb.size, rate, threshold_db, int(slice_), 1,
+                                                        int(start_time[0]), float(start_time[1])))
         return self._collect(self.L.aref_run(pb, pa, bb.size, rate, threshold_db, int(slice_)))
 
     def run_slicer(self, chips, secs, frac) -> Result:

@@ -257,13 +257,16 @@ static int general_work_once(const amo_params* p, int mininputs, const float* in
     return 0;
 }
 
-/* tag_to_timestamp with no rx_time tag (preamble_impl.cc:100-137): offset 0, stamps 0. */
+/* tag_to_timestamp (preamble_impl.cc:100-137) with the last rx_time tag at item 0 (or none: stamps 0). */
+static uint64_t g_tag_secs = 0;
+static double g_tag_frac = 0.0;
+void amo_set_start_time(uint64_t secs, double frac) { g_tag_secs = secs; g_tag_frac = frac; }
 static void tag_to_timestamp(uint64_t abs_sample_cnt, int rate, uint64_t* secs, double* frac)
 {
     uint64_t int_offset = abs_sample_cnt / (uint64_t)rate;                    /* :122 */
     double frac_offset = (abs_sample_cnt % (uint64_t)rate) / (double)rate;    /* :123 */
-    uint64_t abs_whole = 0 + int_offset;
-    double abs_frac = 0 + frac_offset;
+    uint64_t abs_whole = g_tag_secs + int_offset;                             /* :125 */
+    double abs_frac = g_tag_frac + frac_offset;                               /* :126 */
     if (abs_frac > 1.0f) { abs_frac -= 1.0f; abs_whole += 1; }               /* :127-130 */
     *secs = abs_whole;
     *frac = abs_frac;

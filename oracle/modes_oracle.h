@@ -53,6 +53,9 @@ void amo_moving_average(const float* u, uint64_t n, int length, float scale, int
 void amo_frontend(const float* iq, uint64_t n, float rate, int use_pmf, int ma_mode, int chunk,
                   float* bb, float* avg);
 
+/* rx_time tag at item 0 used by tag_to_timestamp (preamble_impl.cc:104-116); (0, 0.0) = no tag. Test hook, global. */
+void amo_set_start_time(uint64_t secs, double frac);
+
 /* Opaque result of a run. */
 typedef struct amo_result amo_result;
 

@@ -66,10 +66,29 @@ extern "C" {
 /* Drive the reference preamble + slicer over whole float streams `bb` (stream 0) and `avg`
  * (stream 1) of n items each. */
 __attribute__((visibility("default")))
+void* aref_run_tagged(const float* bb, const float* avg, uint64_t n, float rate, float threshold_db, int run_slice,
+                      int have_tag, uint64_t tag_secs, double tag_frac);
+
+__attribute__((visibility("default")))
 void* aref_run(const float* bb, const float* avg, uint64_t n, float rate, float threshold_db, int run_slice)
+{
+    return aref_run_tagged(bb, avg, n, rate, threshold_db, run_slice, 0, 0, 0.0);
+}
+
+/* Same with an rx_time stream tag at item 0 (what a UHD source attaches at stream start; preamble_impl.cc:164-170). */
+__attribute__((visibility("default")))
+void* aref_run_tagged(const float* bb, const float* avg, uint64_t n, float rate, float threshold_db, int run_slice,
+                      int have_tag, uint64_t tag_secs, double tag_frac)
 {
     ref_result* r = new ref_result();
     gr::air_modes::preamble_impl blk(rate, threshold_db);
+    if (have_tag) {
+        gr::tag_t t;
+        t.offset = 0;
+        t.key = pmt::string_to_symbol("rx_time");
+        t.value = pmt::make_tuple(pmt::from_uint64(tag_secs), pmt::from_double(tag_frac));
+        blk.shim_in_tags.push_back(t);
+    }
     const uint64_t H = blk.history() - 1;
     const uint64_t slack = 64 + (uint64_t)(40.0 * (rate / 2.0e6));
     /* one pad element in front: the (unused) early-gate correlation reads in[i-1] (preamble_impl.cc:187) */
@@ -105,7 +124,8 @@ void* aref_run(const float* bb, const float* avg, uint64_t n, float rate, float 
             double frac = pmt::to_double(pmt::tuple_ref(t.value, 1));
             r->det_secs.push_back(secs);
             r->det_frac.push_back(frac);
-            r->det_index.push_back(secs * (uint64_t)rate_int + (uint64_t)llround(frac * (double)rate_int));
+            r->det_index.push_back(have_tag ? (pos + (uint64_t)blk.shim_consumed - (uint64_t)(240 * (rate / 2000000)))   /* integer spc only */
+                                            : secs * (uint64_t)rate_int + (uint64_t)llround(frac * (double)rate_int));
             r->chips.insert(r->chips.end(), out, out + 240);
         }
         pos += (uint64_t)blk.shim_consumed;

@@ -301,3 +301,18 @@ def test_config0_pr1_golden_single_df17(port, tmp_path):
             out = subprocess.run([sys.executable, os.path.join(root, "tools", "modes_rx_b200.py"), "-s", str(path), "-r", "2e6",
                                   "--chunk", "3000001"], capture_output=True, text=True, check=True).stdout.split("\n")
             assert [ln for ln in out if ln] == want.msgs
+
+
+def test_rx_time_start_tag(port):
+    sc = synth.make_scene(4e6, 400_000, 30, 3)
+    for st in ((1234567, 0.25), (7, 0.9999999)):
+        port.set_start_time(*st)
+        try:
+            want = port.run_iq(sc.iq, 4e6, 7.0, True, co.MA_CANONICAL)
+        finally:
+            port.set_start_time(0, 0.0)
+        q = am.msg_queue()
+        rx = am.rx_path(4e6, 7.0, q, use_pmf=True)
+        rx.set_start_time(*st)
+        rx.process(sc.iq, flush=True)
+        assert q.strings() == want.msgs

@@ -119,3 +119,17 @@ def test_golden_fixtures_against_live_reference(port, ref):
         r = ref.run_streams(bb, avg, s["rate"], s["threshold_db"])
         assert r.msgs == s["msgs"]
         assert hashlib.sha256(np.ascontiguousarray(r.chips).tobytes()).hexdigest() == s["chips_sha256"]
+
+
+def test_rx_time_tag_at_stream_start(port, ref):
+    """tag_to_timestamp with an rx_time tag at item 0 (preamble_impl.cc:100-137), incl. the `> 1.0f` carry."""
+    sc = synth.make_scene(4e6, 400_000, 30, 3)
+    bb, avg = port.frontend(sc.iq, 4e6, True, co.MA_CANONICAL)
+    for st in ((1234567, 0.25), (7, 0.9999999), (0, 0.5)):
+        r = ref.run_streams(bb, avg, 4e6, 7.0, start_time=st)
+        port.set_start_time(*st)
+        try:
+            p = port.run_streams(bb, avg, 4e6, 7.0)
+        finally:
+            port.set_start_time(0, 0.0)
+        assert r.msgs == p.msgs and np.array_equal(r.secs, p.secs) and np.array_equal(r.frac, p.frac)
