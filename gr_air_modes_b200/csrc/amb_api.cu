@@ -40,6 +40,9 @@ struct amb_ctx {
     float2* carry[3] = {nullptr, nullptr, nullptr};   // [2] stays all zero (sample history before the stream)
     float2* tail[2] = {nullptr, nullptr}; int tail_cap = 0;
     float2* staging = nullptr; size_t staging_cap = 0;
+    // optional DC blocker (rx_path.py:39-41)
+    int use_dcblock = 0, dc_D = 0, dc_nc = 0, dc_cur = 0;
+    float2* dc_carry[2] = {nullptr, nullptr}; float2* dc_out = nullptr; float2* dc_ma0 = nullptr; size_t dc_cap = 0;
     uint32_t* coarse[2] = {nullptr, nullptr}; uint32_t* fine[2] = {nullptr, nullptr}; uint32_t* span_count[2] = {nullptr, nullptr};
     size_t rows_cap = 0; int spans_cap = 0;
     int* cand_j = nullptr; uint32_t* cand_info = nullptr; float* cand_avg = nullptr; unsigned cand_cap = 0;
@@ -163,6 +166,8 @@ static void free_dev(amb_ctx* c)
         c->tail[k] = nullptr; c->coarse[k] = c->fine[k] = c->span_count[k] = nullptr;
     }
     cudaFree(c->staging);
+    cudaFree(c->dc_carry[0]); cudaFree(c->dc_carry[1]); cudaFree(c->dc_out); cudaFree(c->dc_ma0);
+    c->dc_carry[0] = c->dc_carry[1] = c->dc_out = c->dc_ma0 = nullptr; c->dc_cap = 0;
     cudaFree(c->cand_j); cudaFree(c->cand_info); cudaFree(c->cand_avg); cudaFree(c->walk_scratch); c->walk_scratch = nullptr;
     cudaFree(c->frames); cudaFree(c->chips); cudaFree(c->ctr); cudaFree(c->st);
     c->staging = nullptr;
@@ -182,6 +187,14 @@ static int setup_rate(amb_ctx* ctx)
     ctx->guard = P.maxlate + (int)ceilf(P.skip_f) + 4;
     int need = ctx->guard + P.L + 2 * P.spc_i + 64;
     ctx->kc = (need + AMB_STAGE - 1) / AMB_STAGE * AMB_STAGE;
+    if (ctx->use_dcblock) {                              // filter.dc_blocker_cc(100*self._spc, False)  rx_path.py:40
+        ctx->dc_D = 100 * P.spc_i;
+        ctx->dc_nc = 2 * ctx->dc_D - 2;
+        for (int k = 0; k < 2; k++) {
+            cudaFree(ctx->dc_carry[k]); ctx->dc_carry[k] = nullptr;
+            CK(cudaMalloc(&ctx->dc_carry[k], (size_t)ctx->dc_nc * sizeof(float2)));
+        }
+    }
     ctx->tail_cap = 4 * AMB_STAGE;
     for (int k = 0; k < 3; k++) {
         cudaFree(ctx->carry[k]); ctx->carry[k] = nullptr;
@@ -203,6 +216,11 @@ static int reset_stream(amb_ctx* ctx)
     // the sample history restarts from the all-zero carry buffer, so nothing has to be cleared on stream A
     CK(cudaMemsetAsync(ctx->ctr, 0, sizeof(AmbCounters), ctx->stream_b));
     CK(cudaMemsetAsync(ctx->st, 0, sizeof(AmbWalkState), ctx->stream_b));
+    if (ctx->use_dcblock) {   // raw-sample history of the DC blocker restarts from zeros (only stream A touches it)
+        CK(cudaMemsetAsync(ctx->dc_carry[0], 0, (size_t)ctx->dc_nc * sizeof(float2), ctx->stream));
+        CK(cudaMemsetAsync(ctx->dc_carry[1], 0, (size_t)ctx->dc_nc * sizeof(float2), ctx->stream));
+        ctx->dc_cur = 0;
+    }
     ctx->carry_in = 2; ctx->n_in = 0; ctx->r_done = 0; ctx->flushed = false; ctx->have_last = false;
     ctx->frames_ub = 0;
     ctx->pending.clear();
@@ -235,7 +253,6 @@ int amb_create(int device, float rate, float threshold_db, int use_pmf, int use_
 {
     if (!out) return AMB_ERR_INVALID;
     *out = nullptr;
-    if (use_dcblock) return AMB_ERR_UNSUPPORTED;     // filter.dc_blocker_cc (rx_path.py:39-41): not built yet
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return AMB_ERR_NO_DEVICE;
     cudaDeviceProp prop;
@@ -244,6 +261,7 @@ int amb_create(int device, float rate, float threshold_db, int use_pmf, int use_
     amb_ctx* ctx = new amb_ctx();
     ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
     ctx->rate_arg = rate; ctx->thr_db = threshold_db; ctx->use_pmf = use_pmf ? 1 : 0;
+    ctx->use_dcblock = use_dcblock ? 1 : 0;
     int rc = AMB_OK;
     do {
         if (cudaSetDevice(device) != cudaSuccess) { rc = AMB_ERR_NO_DEVICE; break; }
@@ -463,6 +481,26 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
             CK(cudaMemcpyAsync(ctx->staging, iq, n_complex * sizeof(float2),
                                mem_kind == AMB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, sa));
         src = ctx->staging;
+        CK(cudaEventRecord(ctx->e_in, sa));
+        CK(cudaStreamWaitEvent(sc, ctx->e_in, 0));
+    }
+    if (ctx->use_dcblock) {
+        // ---- DC blocker: x -> out[n] = x[n-D+1] - MA(MA(x))[n] into a ctx-owned buffer that then plays the input
+        if (ctx->dc_cap < n_complex + (size_t)ctx->dc_D) {
+            CK(sync_all(ctx));
+            cudaFree(ctx->dc_out); cudaFree(ctx->dc_ma0); ctx->dc_out = ctx->dc_ma0 = nullptr;
+            const size_t ncap = n_complex + (size_t)ctx->dc_D + 1024;
+            CK(cudaMalloc(&ctx->dc_out, ncap * sizeof(float2)));
+            CK(cudaMalloc(&ctx->dc_ma0, ncap * sizeof(float2)));
+            ctx->dc_cap = ncap;
+        }
+        // the previous call's exact/slice kernels still read dc_out
+        if (ctx->done_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_done[set ^ 1], 0));
+        CK(amb_launch_dcblock(ctx->dc_carry[ctx->dc_cur], ctx->dc_nc, src, (long long)n_complex, ctx->dc_D,
+                              ctx->dc_ma0, ctx->dc_out, ctx->dc_carry[ctx->dc_cur ^ 1], sa));
+        ctx->dc_cur ^= 1;
+        ctx->stats.kernel_launches += n_complex ? 3 : 1;
+        src = ctx->dc_out;
         CK(cudaEventRecord(ctx->e_in, sa));
         CK(cudaStreamWaitEvent(sc, ctx->e_in, 0));
     }

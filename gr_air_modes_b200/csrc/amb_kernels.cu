@@ -1127,6 +1127,69 @@ cudaError_t amb_launch_stream_candidates(const AmbScanArgs& a, const float* in0,
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// optional DC blocker in front of the demodulator: filter.dc_blocker_cc(100*spc, False) (rx_path.py:39-41).
+// GNU Radio's short form is  out[n] = x[n-D+1] - MA_D(MA_D(x))[n]  with complex fp32 moving averages. Canonical
+// arithmetic (same as the CPU checker): every window sum in fp64, ascending, per component, rounded once to
+// fp32 and divided by (float)D. Brute force on purpose - it keeps the summation order, hence bit-exactness; this
+// stage is off by default (radio.py:118-119) and costs ~16x the scan kernel when enabled.
+// `raw` is the logical stream rawcarry(2D-2 samples) ++ new samples, addressed through two pointers.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 dc_raw(const float2* carry, int nc, const float2* fresh, long long r)
+{
+    return r < nc ? carry[r] : fresh[r - nc];
+}
+
+// pass 0: ma0[i] = MA_D(x) at raw index (D-1)+i, i in [0, n_new + D - 1);  pass 1: out[m] for the n_new new samples
+template <int PASS>
+__global__ void __launch_bounds__(256) amb_dcblock_kernel(const float2* __restrict__ carry, int nc, const float2* __restrict__ fresh,
+                                                          const float2* __restrict__ ma0, float2* __restrict__ dst,
+                                                          long long n_out, int D)
+{
+    extern __shared__ float2 dc_s[];
+    const long long base = (long long)blockIdx.x * 256;
+    const int tid = threadIdx.x;
+    // window of output base+t covers source elements base+t .. base+t+D-1
+    for (int i = tid; i < 256 + D - 1; i += 256) {
+        const long long q = base + i;
+        float2 v = make_float2(0.f, 0.f);
+        if (PASS == 0) { if (q < (long long)nc + (n_out - (D - 1))) v = dc_raw(carry, nc, fresh, q); }   // raw index
+        else { if (q < n_out + D - 1) v = ma0[q]; }                                                      // ma0 index
+        dc_s[i] = v;
+    }
+    __syncthreads();
+    const long long m = base + tid;
+    if (m >= n_out) return;
+    double ar = 0.0, ai = 0.0;
+    for (int t = 0; t < D; t++) { ar += (double)dc_s[tid + t].x; ai += (double)dc_s[tid + t].y; }
+    const float fD = (float)D;
+    const float mr = __fdiv_rn((float)ar, fD), mi = __fdiv_rn((float)ai, fD);
+    if (PASS == 0) dst[m] = make_float2(mr, mi);
+    else {
+        const float2 d = dc_raw(carry, nc, fresh, m + D - 1);        // x[n-D+1]: raw index of new sample m is nc+m
+        dst[m] = make_float2(__fsub_rn(d.x, mr), __fsub_rn(d.y, mi));
+    }
+}
+
+cudaError_t amb_launch_dcblock(const float2* rawcarry, int nc, const float2* fresh, long long n_new, int D,
+                               float2* ma0_tmp, float2* out, float2* rawcarry_next, cudaStream_t s)
+{
+    const size_t smem = (size_t)(256 + D - 1) * sizeof(float2);
+    if (n_new > 0) {
+        const long long n0 = n_new + D - 1;
+        amb_dcblock_kernel<0><<<(unsigned)((n0 + 255) / 256), 256, smem, s>>>(rawcarry, nc, fresh, nullptr, ma0_tmp, n0, D);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        amb_dcblock_kernel<1><<<(unsigned)((n_new + 255) / 256), 256, smem, s>>>(rawcarry, nc, fresh, ma0_tmp, out, n_new, D);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    // next raw carry = last nc samples of rawcarry ++ fresh
+    AmbSegs S; S.carry = rawcarry; S.main_ = fresh; S.tail = fresh; S.n_carry = nc; S.n_main = (int)n_new; S.n_tail = 0;
+    S.n_valid = nc + (int)n_new;
+    return amb_launch_carry(S, rawcarry_next, nc, s);
+}
+
 cudaError_t amb_upload_tables(const int* chip_off)
 {
     cudaError_t e = cudaMemcpyToSymbol(c_chip_off, chip_off, 240 * sizeof(int));

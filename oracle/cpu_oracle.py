@@ -67,9 +67,11 @@ class Port:
         L.amo_mag2.argtypes = [f32p, u64, f32p]
         L.amo_moving_average.argtypes = [f32p, u64, C.c_int, C.c_float, C.c_int, C.c_int, f32p]
         L.amo_frontend.argtypes = [f32p, u64, C.c_float, C.c_int, C.c_int, C.c_int, f32p, f32p]
+        L.amo_dc_blocker.argtypes = [f32p, u64, C.c_int, C.c_int, f32p]
         for name, args in (("amo_scan", [f32p, f32p, u64, C.c_float, C.c_float]),
                            ("amo_run_streams", [f32p, f32p, u64, C.c_float, C.c_float]),
                            ("amo_run_iq", [f32p, u64, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]),
+                           ("amo_run_iq_dc", [f32p, u64, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]),
                            ("amo_run_slicer", [f32p, u64, C.POINTER(C.c_uint64), C.POINTER(C.c_double)])):
             fn = getattr(L, name); fn.argtypes = args; fn.restype = vp
         L.amo_num_det.argtypes = [vp]; L.amo_num_det.restype = u64
@@ -137,9 +139,15 @@ class Port:
         bb, pb = _f32(bb); avg, pa = _f32(avg)
         return self._collect(self.L.amo_run_streams(pb, pa, bb.size, rate, threshold_db))
 
-    def run_iq(self, iq, rate, threshold_db, use_pmf=True, ma_mode=MA_CANONICAL, chunk=4096) -> Result:
+    def run_iq(self, iq, rate, threshold_db, use_pmf=True, ma_mode=MA_CANONICAL, chunk=4096, use_dcblock=False) -> Result:
         iq, p = _f32(iq)
-        return self._collect(self.L.amo_run_iq(p, iq.size // 2, rate, threshold_db, int(use_pmf), ma_mode, chunk))
+        return self._collect(self.L.amo_run_iq_dc(p, iq.size // 2, rate, threshold_db, int(use_pmf), int(use_dcblock),
+                                                  ma_mode, chunk))
+
+    def dc_blocker(self, iq, D, mode=MA_CANONICAL):
+        iq, p = _f32(iq); out = np.empty(iq.size, np.float32)
+        self.L.amo_dc_blocker(p, iq.size // 2, int(D), mode, out.ctypes.data_as(C.POINTER(C.c_float)))
+        return out
 
     def run_slicer(self, chips, secs, frac) -> Result:
         chips, pc = _f32(chips)

@@ -117,6 +117,47 @@ void amo_moving_average(const float* u, uint64_t n, int length, float scale, int
     }
 }
 
+/* filter.dc_blocker_cc(D, False) (rx_path.py:39-41, D = 100*spc). GNU Radio 3.8 gr-filter/lib/dc_blocker_cc_impl.cc,
+ * long_form == false:  y1 = ma0.filter(x); y2 = ma1.filter(y1); out = ma0.delayed_sig() - y2, where
+ * moving_averager_c(D).filter keeps a D-sample running complex sum and returns sum / (float)D, and delayed_sig()
+ * is the input D-1 samples ago. NOT in /root/reference: restated from the published algorithm; parity UNPINNED.
+ *   mode AMO_MA_CANONICAL: each window sum in fp64, ascending, per component, rounded once to fp32, then / (float)D
+ *   mode AMO_MA_GR_FLOAT : GNU Radio's recursive fp32 running sum  y = x - x[n-D] + y_prev  (never restarted) */
+void amo_dc_blocker(const float* iq, uint64_t n, int D, int mode, float* out)
+{
+    float* ma0 = (float*)calloc(2 * (n ? n : 1), sizeof(float));
+    const float fD = (float)D;
+    if (mode == AMO_MA_GR_FLOAT) {
+        float s0r = 0, s0i = 0, s1r = 0, s1i = 0;
+        for (uint64_t k = 0; k < n; k++) {
+            float xr = iq[2 * k], xi = iq[2 * k + 1];
+            float or_ = k >= (uint64_t)D ? iq[2 * (k - D)] : 0.0f, oi = k >= (uint64_t)D ? iq[2 * (k - D) + 1] : 0.0f;
+            s0r = xr - or_ + s0r; s0i = xi - oi + s0i;
+            ma0[2 * k] = s0r / fD; ma0[2 * k + 1] = s0i / fD;
+            float pr = k >= (uint64_t)D ? ma0[2 * (k - D)] : 0.0f, pi = k >= (uint64_t)D ? ma0[2 * (k - D) + 1] : 0.0f;
+            s1r = ma0[2 * k] - pr + s1r; s1i = ma0[2 * k + 1] - pi + s1i;
+            float dr = k >= (uint64_t)(D - 1) ? iq[2 * (k - D + 1)] : 0.0f, di = k >= (uint64_t)(D - 1) ? iq[2 * (k - D + 1) + 1] : 0.0f;
+            out[2 * k] = dr - s1r / fD; out[2 * k + 1] = di - s1i / fD;
+        }
+    } else {
+        for (uint64_t k = 0; k < n; k++) {
+            int64_t lo = (int64_t)k - D + 1; if (lo < 0) lo = 0;
+            double ar = 0.0, ai = 0.0;
+            for (int64_t j = lo; j <= (int64_t)k; j++) { ar += (double)iq[2 * j]; ai += (double)iq[2 * j + 1]; }
+            ma0[2 * k] = (float)ar / fD; ma0[2 * k + 1] = (float)ai / fD;
+        }
+        for (uint64_t k = 0; k < n; k++) {
+            int64_t lo = (int64_t)k - D + 1; if (lo < 0) lo = 0;
+            double ar = 0.0, ai = 0.0;
+            for (int64_t j = lo; j <= (int64_t)k; j++) { ar += (double)ma0[2 * j]; ai += (double)ma0[2 * j + 1]; }
+            float m1r = (float)ar / fD, m1i = (float)ai / fD;
+            float dr = k >= (uint64_t)(D - 1) ? iq[2 * (k - D + 1)] : 0.0f, di = k >= (uint64_t)(D - 1) ? iq[2 * (k - D + 1) + 1] : 0.0f;
+            out[2 * k] = dr - m1r; out[2 * k + 1] = di - m1i;
+        }
+    }
+    free(ma0);
+}
+
 /* rx_path.py:34-35 (_spc = int(rate/2e6)), :38 (demod), :48-51 (pmf), :54 (floor), :63-64 (wiring). */
 void amo_frontend(const float* iq, uint64_t n, float rate, int use_pmf, int ma_mode, int chunk,
                   float* bb, float* avg)
@@ -416,6 +457,19 @@ amo_result* amo_run_iq(const float* iq, uint64_t n, float rate, float threshold_
     amo_frontend(iq, n, rate, use_pmf, ma_mode, chunk, bb, avg);
     amo_result* r = amo_run_streams(bb, avg, n, rate, threshold_db);
     free(bb); free(avg);
+    return r;
+}
+
+/* the whole rx_path incl. the optional DC blocker in front of the demodulator (rx_path.py:39-41) */
+amo_result* amo_run_iq_dc(const float* iq, uint64_t n, float rate, float threshold_db, int use_pmf, int use_dcblock,
+                          int ma_mode, int chunk)
+{
+    if (!use_dcblock) return amo_run_iq(iq, n, rate, threshold_db, use_pmf, ma_mode, chunk);
+    const int spc = (int)((double)rate / 2e6);
+    float* y = (float*)malloc(2 * (n ? n : 1) * sizeof(float));
+    amo_dc_blocker(iq, n, 100 * spc, ma_mode == AMO_MA_GR_FLOAT ? AMO_MA_GR_FLOAT : AMO_MA_CANONICAL, y);
+    amo_result* r = amo_run_iq(y, n, rate, threshold_db, use_pmf, ma_mode, chunk);
+    free(y);
     return r;
 }
 

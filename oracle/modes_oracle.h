@@ -53,6 +53,9 @@ void amo_moving_average(const float* u, uint64_t n, int length, float scale, int
 void amo_frontend(const float* iq, uint64_t n, float rate, int use_pmf, int ma_mode, int chunk,
                   float* bb, float* avg);
 
+/* filter.dc_blocker_cc(D, long_form=False) (rx_path.py:39-41); GNU Radio code, parity unpinned (see .c) */
+void amo_dc_blocker(const float* iq, uint64_t n, int D, int mode, float* out);
+
 /* rx_time tag at item 0 used by tag_to_timestamp (preamble_impl.cc:104-116); (0, 0.0) = no tag. Test hook, global. */
 void amo_set_start_time(uint64_t secs, double frac);
 
@@ -66,6 +69,8 @@ amo_result* amo_run_streams(const float* bb, const float* avg, uint64_t n, float
 /* front end + scan + slice from interleaved IQ. */
 amo_result* amo_run_iq(const float* iq, uint64_t n, float rate, float threshold_db, int use_pmf,
                        int ma_mode, int chunk);
+amo_result* amo_run_iq_dc(const float* iq, uint64_t n, float rate, float threshold_db, int use_pmf, int use_dcblock,
+                          int ma_mode, int chunk);
 /* slicer only on 240-chip packets. */
 amo_result* amo_run_slicer(const float* chips, uint64_t ndet, const uint64_t* secs, const double* frac);
 

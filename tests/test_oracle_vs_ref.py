@@ -133,3 +133,23 @@ def test_rx_time_tag_at_stream_start(port, ref):
         finally:
             port.set_start_time(0, 0.0)
         assert r.msgs == p.msgs and np.array_equal(r.secs, p.secs) and np.array_equal(r.frac, p.frac)
+
+
+def test_dc_blocker_restatement_sanity(port):
+    """a2 (rx_path.py:39-41) is GNU Radio code that is not in /root/reference: parity UNPINNED. What can be
+    checked: the canonical (fp64 window) and the GNU Radio recursive-fp32 formulations agree to rounding, a
+    constant offset is removed after the 2(D-1)-sample transient, the delay is D-1, and both formulations
+    decode the same payloads."""
+    rate, D = 4e6, 200
+    sc = synth.make_scene(rate, 300_000, 30, 3)
+    iq = sc.iq.copy(); iq[0::2] += np.float32(0.05); iq[1::2] -= np.float32(0.03)
+    y0 = port.dc_blocker(iq, D, co.MA_CANONICAL)
+    y1 = port.dc_blocker(iq, D, co.MA_GR_FLOAT)
+    assert np.abs(y0 - y1).max() < 1e-5
+    assert abs(y0[2 * 5000::2].mean()) < 1e-4 and abs(y0[2 * 5000 + 1::2].mean()) < 1e-4
+    imp = np.zeros(2 * 1000, np.float32); imp[2 * 10] = 1.0
+    h = port.dc_blocker(imp, D, co.MA_CANONICAL)[0::2]
+    assert np.argmax(h) == 10 + D - 1 and abs(h.sum()) < 1e-5            # delayed impulse minus a unit-area triangle
+    a = port.run_iq(iq, rate, 7.0, True, co.MA_CANONICAL, use_dcblock=True).msgs
+    b = port.run_iq(iq, rate, 7.0, True, co.MA_GR_FLOAT, 4096, use_dcblock=True).msgs
+    assert [m.split()[:2] for m in a] == [m.split()[:2] for m in b] and len(a) > 0
