@@ -125,3 +125,25 @@ def test_geometry_matches_reference_blocks(lib, port, ref):
             assert g.pmf_len == int(rate / 2e6) and g.floor_len == 48 * int(rate / 2e6)
     for bad in (1e6, 1.99e6, 21e6, 40e6):
         assert lib.amb_query_geometry(bad, 7.0, 1, C.byref(g)) == -4          # AMB_ERR_RATE
+
+
+def test_zmq_dl_data_publisher():
+    """f3: messages leave as ZMQ multipart [b'dl_data', text], the framing radio.py/zmq_socket.py use."""
+    zmq = pytest.importorskip("zmq")
+    import time
+    from gr_air_modes_b200.zmq_pub import zmq_queue
+    ctx = zmq.Context()
+    q = zmq_queue("inproc://amb-test-pub", context=ctx)
+    sub = ctx.socket(zmq.SUB)
+    sub.connect("inproc://amb-test-pub")
+    sub.setsockopt(zmq.SUBSCRIBE, b"dl_data")
+    time.sleep(0.05)
+    texts = ["8d4840d6202cc371c32ce0576098 000000 0.2475689948 5 1.25e-06", "5d4840d6a1b2c3 000000 0.01 6 0.5"]
+    for t in texts:
+        q.handle(am.message_from_string(t))
+    got = []
+    for _ in texts:
+        assert sub.poll(1000)
+        got.append(sub.recv_multipart())
+    assert got == [[b"dl_data", t.encode()] for t in texts] and q.sent == 2
+    sub.close(linger=0); q.close(); ctx.term()
