@@ -21,12 +21,15 @@
 #define AMB_PROXY_FENCE 0
 #endif
 
-__constant__ int c_chip_off[240];        // int(j*spc) (preamble_impl.cc:220)
 __constant__ unsigned int c_crc_rem[96]; // x^(t+24) mod 0xFFF409, t = distance of a message bit from the parity field
 
 // ------------------------------------------------------------------------------------------------
 // small PTX helpers: mbarrier + TMA tensor copy (SASS: UTMALDG / SYNCS)
 // ------------------------------------------------------------------------------------------------
+// int(j * d_samples_per_chip) of preamble_impl.cc:220: int -> float, float multiply, truncation (per context, so no
+// shared table: two contexts with different rates can coexist on one device)
+__device__ __forceinline__ int chip_off(int j, float spc_f) { return __float2int_rz(__fmul_rn((float)j, spc_f)); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -958,7 +961,7 @@ __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
     const unsigned int ncand = a.ctr->ncand;
     const int nwarps = gridDim.x * 4;
     const int fl = P.use_pmf ? P.spc_i : 1;
-    const int span = c_chip_off[239] + fl;                     // m2 samples a packet touches
+    const int span = chip_off(239, P.spc_f) + fl;              // m2 samples a packet touches
     const int spanp = (span + 31) & ~31;
     for (unsigned int ci = blockIdx.x * 4 + warp; ci < ncand; ci += nwarps) {
         const uint32_t info = a.cand_info[ci];
@@ -967,7 +970,7 @@ __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
         const float avg_fin = a.cand_avg[ci];
         if (STREAMS) {
             for (int j = lane; j < 240; j += 32)               // preamble_impl.cc:219-221
-                chips[j] = __fsub_rn(stream_at(a.in0, a.n_streams, P.H, (long long)fin + c_chip_off[j]), avg_fin);
+                chips[j] = __fsub_rn(stream_at(a.in0, a.n_streams, P.H, (long long)fin + chip_off(j, P.spc_f)), avg_fin);
         } else {
             float* m2s = sl_smem + (size_t)warp * spanp;
             const int b0 = fin - fl + 1;                       // m2s[i] <-> m2[b0 + i]; independent coalesced loads
@@ -980,7 +983,7 @@ __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
             }
             __syncwarp();
             for (int j = lane; j < 240; j += 32) {
-                const int o = c_chip_off[j];                   // bb[fin + o] = PMF over m2[fin+o-fl+1 .. fin+o]
+                const int o = chip_off(j, P.spc_f);            // bb[fin + o] = PMF over m2[fin+o-fl+1 .. fin+o]
                 float bb;
                 if (P.use_pmf) {
                     double acc = 0.0;
@@ -1015,7 +1018,7 @@ __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
 cudaError_t amb_launch_slice(const AmbSliceArgs& a, int sm_count, cudaStream_t s)
 {
     const int fl = a.P.use_pmf ? a.P.spc_i : 1;
-    const int spanp = ((int)(239 * a.P.spc_f) + fl + 31) & ~31;        // = c_chip_off[239] + fl, rounded
+    const int spanp = ((int)(239 * a.P.spc_f) + fl + 31) & ~31;        // = int(239*spc) + fl, rounded
     const size_t smem = a.in0 ? 0 : (size_t)4 * spanp * sizeof(float);  // 38 KiB at 20 Msps, 8 KiB at 4 Msps
     const int blocks = sm_count * 8;
     if (a.in0) amb_slice_kernel<true><<<blocks, 128, smem, s>>>(a);
@@ -1203,11 +1206,9 @@ cudaError_t amb_launch_dcblock(const float2* rawcarry, int nc, const float2* fre
     return amb_launch_carry(S, rawcarry_next, nc, s);
 }
 
-cudaError_t amb_upload_tables(const int* chip_off)
+cudaError_t amb_upload_tables(const int*)
 {
-    cudaError_t e = cudaMemcpyToSymbol(c_chip_off, chip_off, 240 * sizeof(int));
-    if (e != cudaSuccess) return e;
-    unsigned int rem[96];
+    unsigned int rem[96];                               // rate independent: safe to share between contexts
     unsigned int r = 0xFFF409u;                         // x^24 mod G
     for (int t = 0; t < 96; t++) {
         rem[t] = r;

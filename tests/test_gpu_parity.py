@@ -342,3 +342,19 @@ def test_dc_blocker_option(port):
         without = port.run_iq(iq, rate, 7.0, True, co.MA_CANONICAL).index
         clean = port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL).index
         assert len(want.index) > 0 and len(without) <= len(clean)
+
+
+def test_two_contexts_with_different_rates_coexist(port):
+    """Contexts are independent: interleaving calls at 4 and 10 Msps on one device changes nothing."""
+    a = synth.make_scene(4e6, 400_000, 30, 71)
+    b = synth.make_scene(10e6, 600_000, 30, 72)
+    wa = port.run_iq(a.iq, 4e6, 7.0, True, co.MA_CANONICAL).msgs
+    wb = port.run_iq(b.iq, 10e6, 7.0, True, co.MA_CANONICAL).msgs
+    qa, qb = am.msg_queue(), am.msg_queue()
+    ra = am.rx_path(4e6, 7.0, qa, use_pmf=True)
+    rb = am.rx_path(10e6, 7.0, qb, use_pmf=True)
+    for k in range(4):
+        ra.process(a.iq[2 * k * 100_000: 2 * (k + 1) * 100_000], flush=(k == 3), collect=False)
+        rb.process(b.iq[2 * k * 150_000: 2 * (k + 1) * 150_000], flush=(k == 3), collect=False)
+    ra.drain(); rb.drain()
+    assert qa.strings() == wa and qb.strings() == wb
