@@ -758,28 +758,43 @@ __global__ void __launch_bounds__(256) amb_walk_par1_kernel(const AmbWalkArgs a,
             if (c == 0) { pos = a.st->pos; p = a.st->p; }   // the first cluster continues the previous call
             bool pos_known = (c == 0), any = false;
             long long last_pos = -1;
-            int k = c;
-            for (;;) {
-                const long long s = a.org + a.cand_j[k];
-                if (s >= zone) break;
-                const uint32_t info = a.cand_info[k];
-                if ((info & (1u << 8)) && s >= p) {
-                    const long long fin = s + (long long)(info & 0xffu);
-                    any = true;
-                    if (!(info & (1u << 9))) p = fin + 1;
-                    else {
-                        long long consumed;
-                        if (pos_known) consumed = (long long)(int)((float)(fin - pos) + P.skip_f) - (fin - pos);
-                        else { consumed = P.skip0; ff = fin; }
-                        a.cand_info[k] = info | (1u << 10);
-                        ndet++;
-                        pos = fin + consumed; p = pos; pos_known = true;
-                        last_pos = pos;
-                        atomicMax(&buckets[(fin - a.org) >> AMB_BUCKET_SHIFT], (unsigned long long)(pos - a.org + 1));
+            // walk the cluster; candidate records are fetched 8 at a time (independent loads) because in dense
+            // traffic one cluster can hold most of the list and this loop is then the whole resolver
+            int k = c, prevj = a.cand_j[c];
+            bool more = true;
+            while (more) {
+                int jj[8]; uint32_t ii[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int q = k + u < n ? k + u : n - 1;
+                    jj[u] = a.cand_j[q]; ii[u] = a.cand_info[q];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    if (!more) break;
+                    if (k + u >= n) { more = false; break; }
+                    if ((k + u > c) && (jj[u] - prevj >= gap)) { more = false; break; }   // next cluster's head
+                    prevj = jj[u];
+                    const long long s = a.org + jj[u];
+                    if (s >= zone) { more = false; break; }
+                    const uint32_t info = ii[u];
+                    if ((info & (1u << 8)) && s >= p) {
+                        const long long fin = s + (long long)(info & 0xffu);
+                        any = true;
+                        if (!(info & (1u << 9))) p = fin + 1;
+                        else {
+                            long long consumed;
+                            if (pos_known) consumed = (long long)(int)((float)(fin - pos) + P.skip_f) - (fin - pos);
+                            else { consumed = P.skip0; ff = fin; }
+                            a.cand_info[k + u] = info | (1u << 10);
+                            ndet++;
+                            pos = fin + consumed; p = pos; pos_known = true;
+                            last_pos = pos;
+                            atomicMax(&buckets[(fin - a.org) >> AMB_BUCKET_SHIFT], (unsigned long long)(pos - a.org + 1));
+                        }
                     }
                 }
-                k++;
-                if (k >= n || a.cand_j[k] - a.cand_j[k - 1] >= gap) break;
+                k += 8;
             }
             if (last_pos >= 0) atomicMax(&sc->max_pos_rel1, (unsigned long long)(last_pos - a.org + 1));
             if (any && p >= a.org) atomicMax(&sc->max_p_rel1, (unsigned long long)(p - a.org + 1));
