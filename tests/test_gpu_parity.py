@@ -40,7 +40,8 @@ def run_cuda(iq, rate, thr, pmf, chunks=None, resolver=0, keep=False):
     (10e6, 1_200_000, 40, True, 7.0, 4), (20e6, 2_000_000, 30, True, 7.0, 5), (4e6, 800_000, 50, True, 4.0, 6),
     (5e6, 600_000, 30, True, 7.0, 7), (3e6, 600_000, 30, True, 7.0, 8), (2.4e6, 600_000, 30, True, 6.0, 9),
     (6e6, 600_000, 30, True, 7.0, 10), (8e6, 800_000, 30, True, 7.0, 11), (16e6, 1_600_000, 20, True, 7.0, 12),
-    (4e6, 600_000, 700, True, 6.0, 13),
+    (4e6, 600_000, 700, True, 6.0, 13), (10e6, 1_000_000, 30, False, 7.0, 14), (20e6, 1_600_000, 20, False, 8.0, 15),
+    (7e6, 700_000, 30, True, 7.0, 16), (18e6, 1_500_000, 20, True, 7.0, 17),
 ])
 def test_frames_bit_exact_vs_oracle(port, rate, n, nb, pmf, thr, seed):
     """Payload, CRC, timestamp, reference level: every queue message identical to the oracle's."""

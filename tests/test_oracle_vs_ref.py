@@ -38,7 +38,7 @@ def test_params_match_reference(port, ref, rate, thr):
     (2e6, 400_000, 30, True, 7.0, 1), (4e6, 400_000, 30, True, 7.0, 2), (4e6, 400_000, 30, False, 7.0, 3),
     (10e6, 600_000, 20, True, 7.0, 4), (20e6, 1_000_000, 16, True, 7.0, 5), (4e6, 400_000, 30, True, 4.0, 6),
     (5e6, 300_000, 20, True, 7.0, 7), (3e6, 300_000, 20, True, 7.0, 8), (2.4e6, 300_000, 20, True, 6.0, 9),
-    (4e6, 300_000, 300, True, 6.0, 10),
+    (4e6, 300_000, 300, True, 6.0, 10), (10e6, 500_000, 20, False, 7.0, 11), (7e6, 400_000, 20, True, 7.0, 12),
 ])
 def test_port_matches_reference_on_scenes(port, ref, rate, n, nb, pmf, thr, seed):
     sc = synth.make_scene(rate, n, nb, seed, garble_frac=0.2 if nb > 100 else 0.0, fruit=50 if nb > 100 else 0)
