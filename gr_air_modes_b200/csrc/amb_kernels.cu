@@ -239,7 +239,7 @@ struct ScanWarp {
         // t = cT*W - G with cT*W = (cT*A - q_kd[posd]) + q_k[pos]; every term is a product of cT and a partial sum
         // <= Rt+A, so the absolute guard G = cT*gfac*(Rt+A) still covers all roundings (two more than before).
         const float cA = cT * A;
-        const float g = cT * a->P.gfac * (Rt + A);
+        const float g = fmaf(cT * a->P.gfac, Rt + A, 1e-42f);   // + absolute slack for sums of denormals
         const float cAg = cA - g;
         cur.t[0] = (cAg - d0.x) + p[0]; cur.t[1] = (cAg - d0.y) + p[1];
         cur.t[2] = (cAg - d0.z) + p[2]; cur.t[3] = (cAg - d0.w) + p[3];
@@ -279,7 +279,9 @@ struct ScanWarp {
 #pragma unroll
                     for (int r = 0; r < 8; r++) {
                         const float nxt = (r < 7) ? prev.b[r + 1] : nx;
-                        if (u[r] >= prev.t[r] && nxt <= prev.b[r] * oe) msk |= 1u << r;   // + peak test :175
+                        // :174 is strict (an all-zero stretch has b == t == 0 and must not flood the list), the pulse
+                        // tests :177-179 are not; peak test :175 with relative + absolute (denormal) slack
+                        if (prev.b[r] > prev.t[r] && u[r] >= prev.t[r] && nxt <= fmaf(prev.b[r], oe, 1e-42f)) msk |= 1u << r;
                     }
                     const int jb = ke * AMB_ROW + 8 * lane;
                     if (jb < a->j_lo || jb + 8 > a->j_hi) {   // only the first / last row of a call
