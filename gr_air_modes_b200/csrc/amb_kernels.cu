@@ -279,9 +279,10 @@ struct ScanWarp {
 #pragma unroll
                     for (int r = 0; r < 8; r++) {
                         const float nxt = (r < 7) ? prev.b[r + 1] : nx;
-                        // :174 is strict (an all-zero stretch has b == t == 0 and must not flood the list), the pulse
-                        // tests :177-179 are not; peak test :175 with relative + absolute (denormal) slack
-                        if (prev.b[r] > prev.t[r] && u[r] >= prev.t[r] && nxt <= fmaf(prev.b[r], oe, 1e-42f)) msk |= 1u << r;
+                        // an all-zero stretch has b == 0 and must not flood the list although 0 >= lowered threshold;
+                        // peak test :175 with relative + absolute (denormal) slack
+                        // (b > 0 is necessary for :174 because the threshold is never negative)
+                        if (prev.b[r] > 0.f && u[r] >= prev.t[r] && nxt <= fmaf(prev.b[r], oe, 1e-42f)) msk |= 1u << r;
                     }
                     const int jb = ke * AMB_ROW + 8 * lane;
                     if (jb < a->j_lo || jb + 8 > a->j_hi) {   // only the first / last row of a call
