@@ -270,7 +270,7 @@ struct ScanWarp {
             }
             bool hot = false;
 #pragma unroll
-            for (int r = 0; r < 8; r++) hot = hot || (u[r] >= prev.t[r]);
+            for (int r = 0; r < 8; r++) hot = hot || !(u[r] < prev.t[r]);   // negated '<': a NaN/Inf-contaminated threshold must not hide candidates
             if (__any_sync(FULL, hot)) {
                 const float nx = ahead<1>(7, prev.b, b);       // first sample of the next lane / row
                 uint32_t msk = 0;
@@ -282,7 +282,8 @@ struct ScanWarp {
                         // an all-zero stretch has b == 0 and must not flood the list although 0 >= lowered threshold;
                         // peak test :175 with relative + absolute (denormal) slack
                         // (b > 0 is necessary for :174 because the threshold is never negative)
-                        if (prev.b[r] > 0.f && u[r] >= prev.t[r] && nxt <= fmaf(prev.b[r], oe, 1e-42f)) msk |= 1u << r;
+                        // comparisons are written the way the reference's are (:175 '>' and :177-179 '<' are false on NaN)
+                        if (prev.b[r] > 0.f && !(u[r] < prev.t[r]) && !(nxt > fmaf(prev.b[r], oe, 1e-42f))) msk |= 1u << r;
                     }
                     const int jb = ke * AMB_ROW + 8 * lane;
                     if (jb < a->j_lo || jb + 8 > a->j_hi) {   // only the first / last row of a call
@@ -303,7 +304,7 @@ struct ScanWarp {
                             const float x1 = bbr[swz((q + po1) & 511)];
                             const float x2 = bbr[swz((q + po2) & 511)];
                             const float x3 = bbr[swz((q + po3) & 511)];
-                            if (!(fminf(fminf(x1, x2), x3) >= th)) msk &= ~(1u << r);
+                            if (fminf(fminf(x1, x2), x3) < th) msk &= ~(1u << r);
                         }
                     }
                 }
