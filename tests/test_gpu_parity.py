@@ -359,3 +359,13 @@ def test_two_contexts_with_different_rates_coexist(port):
         rb.process(b.iq[2 * k * 150_000: 2 * (k + 1) * 150_000], flush=(k == 3), collect=False)
     ra.drain(); rb.drain()
     assert qa.strings() == wa and qb.strings() == wb
+
+
+def test_randomised_stress_including_pathological_inputs():
+    """tools/stress_parity.py: random rates / thresholds / PMF / chunkings / resolvers plus inputs scaled to the
+    denormal range or near overflow, stretches of exact zeros, NaN / Inf samples, DC offsets, dense bursts."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_parity.py"), "3", "40"],
+                         capture_output=True, text=True, timeout=900).stdout
+    assert "40 cases, 0 mismatches" in out, out[-2000:]
