@@ -124,6 +124,19 @@ def make_device_scene(n, seed, device):
     return iq, frames
 
 
+def _tame_malloc():
+    """Keep multi-MB buffers on the heap instead of mmap/munmap per call: the per-call allocations are an artefact
+    of the oracle's whole-buffer driver (GNU Radio keeps persistent ring buffers), and first-touch page faults
+    would otherwise dominate the CPU arm."""
+    try:
+        import ctypes
+        libc = ctypes.CDLL("libc.so.6")
+        libc.mallopt(-3, 1 << 30)            # M_MMAP_THRESHOLD
+        libc.mallopt(-1, (1 << 31) - 1)      # M_TRIM_THRESHOLD
+    except Exception:
+        pass
+
+
 def reference_arm(args, rank, world):
     """The reference's own CPU implementation of the path, all host threads, bounded sample per step."""
     if rank != 0:
@@ -131,13 +144,14 @@ def reference_arm(args, rank, world):
     from concurrent.futures import ThreadPoolExecutor
     from oracle import cpu_oracle as co
     from gr_air_modes_b200 import synth
+    _tame_malloc()
     port = co.Port()
     kind = "reference" if co.ref_available() else "port"
     ref = co.Ref() if kind == "reference" else None
-    cores = max(1, min(len(os.sched_getaffinity(0)), 64))
-    n_slice = 1 << 23
+    cores = max(1, min(len(os.sched_getaffinity(0)), 256))       # every host thread we are allowed to use
+    n_slice = 1 << (23 if cores <= 64 else 22)
     sc = synth.make_scene(RATE, n_slice, max(1, int(N_BURSTS * n_slice / (1 << args.log2n))), 7, noise_sigma=NOISE_SIGMA)
-    slices = [np.roll(sc.iq, 2 * 1000 * k) for k in range(cores)]
+    slices = [sc.iq] * cores                                     # read-only input shared by the threads
 
     def work(iq):
         bb, avg = port.frontend(iq, RATE, True, co.MA_GR_FLOAT, 4096)     # GNU Radio's fp32 running-sum schedule
@@ -145,7 +159,7 @@ def reference_arm(args, rank, world):
         return len(r.msgs)
 
     with ThreadPoolExecutor(cores) as ex:
-        for _ in range(max(args.warmup, 1)):
+        for _ in range(max(args.warmup, 2)):
             list(ex.map(work, slices))
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -153,8 +167,8 @@ def reference_arm(args, rank, world):
         dt = time.perf_counter() - t0
     total = args.steps * cores * n_slice
     val = total / dt / 1e6
-    sample = "%d threads x 2^23-sample slices of the 4 Msps scene per step (GR fp32 moving averages + %s scan/slice/CRC)" % (
-        cores, "unmodified reference" if ref else "oracle port")
+    sample = "%d threads x 2^%d-sample cuts of the 4 Msps scene per step (GR fp32 moving averages + %s scan/slice/CRC)" % (
+        cores, int(np.log2(n_slice)), "unmodified reference" if ref else "oracle port")
     line = {"impl": "reference", "metric": "Msamples/s IQ demod+slice+CRC", "value": val, "unit": "Msamples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -170,13 +184,14 @@ def cpu_baseline_leg(log2n):
     from concurrent.futures import ThreadPoolExecutor
     from oracle import cpu_oracle as co
     from gr_air_modes_b200 import synth
+    _tame_malloc()
     port = co.Port()
     kind = "reference" if co.ref_available() else "port"
     ref = co.Ref() if kind == "reference" else None
-    cores = max(1, min(len(os.sched_getaffinity(0)), 64))
-    n_slice = 1 << 23
+    cores = max(1, min(len(os.sched_getaffinity(0)), 256))       # every host thread we are allowed to use
+    n_slice = 1 << (23 if cores <= 64 else 22)
     sc = synth.make_scene(RATE, n_slice, max(1, int(N_BURSTS * n_slice / (1 << log2n))), 7, noise_sigma=NOISE_SIGMA)
-    reps = max(1, int(round(64 / cores)))         # ~64 slice-passes in total: 10-30 s of CPU work
+    reps = max(1, int(round(2 * (1 << 29) / (cores * n_slice))))  # ~2^30 samples in total: 10-30 s of CPU work
 
     def work(k):
         bb, avg = port.frontend(sc.iq, RATE, True, co.MA_GR_FLOAT, 4096)
@@ -185,14 +200,15 @@ def cpu_baseline_leg(log2n):
 
     with ThreadPoolExecutor(cores) as ex:
         list(ex.map(work, range(cores)))
+        list(ex.map(work, range(cores)))
         t0 = time.perf_counter()
         for _ in range(reps):
             list(ex.map(work, range(cores)))
         dt = time.perf_counter() - t0
     val = reps * cores * n_slice / dt / 1e6
     return {"value": val, "unit": "Msamples/s", "cores": cores, "kind": kind,
-            "sample": "%d passes x %d threads over a 2^23-sample cut of the same 4 Msps scene; GR fp32 moving averages + "
-                      "%s preamble/slicer/CRC" % (reps, cores, "unmodified reference" if ref else "oracle port")}
+            "sample": "%d passes x %d threads over a 2^%d-sample cut of the same 4 Msps scene; GR fp32 moving averages + "
+                      "%s preamble/slicer/CRC" % (reps, cores, int(np.log2(n_slice)), "unmodified reference" if ref else "oracle port")}
 
 
 def main():
