@@ -58,3 +58,16 @@ def build_native(force: bool = False, verbose: bool = False, defines=(), out_pat
 
 if __name__ == "__main__":
     print(build_native(force=True, verbose=True))
+
+
+def build_c_example(force: bool = False) -> str:
+    """Compile examples/modes_rx_c.c against the C ABI with plain gcc (proves the boundary has no C++/torch types)."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "examples", "modes_rx_c.c")
+    out = os.path.join(root, "examples", "modes_rx_c")
+    if not force and os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return out
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([cc, "-std=c99", "-O2", "-Wall", "-I" + os.path.join(root, "include"), src, "-L" + HERE,
+                    "-lairmodes_b200", "-Wl,-rpath," + HERE, "-o", out], check=True)
+    return out

@@ -369,3 +369,16 @@ def test_randomised_stress_including_pathological_inputs():
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_parity.py"), "3", "40"],
                          capture_output=True, text=True, timeout=900).stdout
     assert "40 cases, 0 mismatches" in out, out[-2000:]
+
+
+def test_c_abi_example_program(port, tmp_path):
+    """examples/modes_rx_c.c (C only, no Python in the loop) prints the oracle's message list."""
+    import subprocess
+    from gr_air_modes_b200 import build
+    exe = build.build_c_example()
+    sc = synth.make_scene(4e6, 600_000, 40, 81)
+    path = tmp_path / "c.cfile"
+    sc.iq.tofile(path)
+    want = port.run_iq(sc.iq, 4e6, 7.0, True, co.MA_CANONICAL).msgs
+    out = subprocess.run([exe, str(path), "4e6", "7.0", "100003"], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert [ln for ln in out if ln] == want

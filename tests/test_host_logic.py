@@ -147,3 +147,12 @@ def test_zmq_dl_data_publisher():
         got.append(sub.recv_multipart())
     assert got == [[b"dl_data", t.encode()] for t in texts] and q.sent == 2
     sub.close(linger=0); q.close(); ctx.term()
+
+
+def test_c_example_builds_against_the_header(lib):
+    """A C99 translation unit that only includes airmodes_b200.h links against the library."""
+    exe = build.build_c_example(force=True)
+    assert os.path.exists(exe)
+    import subprocess
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 2 and "usage" in out.stderr
