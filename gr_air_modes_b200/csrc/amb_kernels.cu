@@ -586,7 +586,33 @@ __global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a)
                 }
             }
             __syncwarp();
-            if (lane <= maxlate) {                    // inavg at c+lane: window bb[c+lane-L+1 .. c+lane]
+            // inavg at c+k, k <= maxlate: fp64 ascending sum of bb[c+k-L+1 .. c+k] (canonical definition).
+            // If every non-zero addend's exponent lies within 19 of the others, every partial sum of <= 1024 such
+            // floats is exactly representable in fp64 (24 + 19 + 10 = 53 bits), so ANY summation order - incl. a
+            // lane-parallel one and the sliding update - gives the canonical bits. Otherwise (huge dynamic range,
+            // Inf/NaN) fall back to the literal ascending loop.
+            unsigned emax = 0u, emin = 255u;
+            for (int i = lane; i < L + maxlate; i += 32) {
+                const unsigned bits = __float_as_uint(bbs[i]) & 0x7fffffffu;
+                if (bits) { unsigned e = bits >> 23; e = e ? e : 1u; emax = max(emax, e); emin = min(emin, e); }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                emax = max(emax, __shfl_xor_sync(FULL, emax, d));
+                emin = min(emin, __shfl_xor_sync(FULL, emin, d));
+            }
+            if (emax < 255u && emax <= emin + 19u) {
+                double part = 0.0;
+                for (int i = lane; i < L; i += 32) part += (double)bbs[i];
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
+                double w = part;                                  // window of k = 0, identical in all lanes
+                if (lane == 0) avgk = __fmul_rn((float)w, P.scale_a);
+                for (int k = 1; k <= maxlate; k++) {
+                    w = (w - (double)bbs[k - 1]) + (double)bbs[k + L - 1];
+                    if (lane == k) avgk = __fmul_rn((float)w, P.scale_a);
+                }
+            } else if (lane <= maxlate) {
                 double acc = 0.0;
                 for (int t = 0; t < L; t++) acc += (double)bbs[lane + t];
                 avgk = __fmul_rn((float)acc, P.scale_a);
@@ -886,34 +912,35 @@ cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, unsigned in
 // ------------------------------------------------------------------------------------------------
 // slicer: one warp per accepted preamble
 // ------------------------------------------------------------------------------------------------
-// llslicer (slicer_impl.cc:67-100): bit 0 = decision, bit 1 = confidence
-__device__ __forceinline__ int llslice(float bit0, float bit1, float ref)
+// llslicer (slicer_impl.cc:67-100): bit 0 = decision, bit 1 = confidence. The three limits depend only on the
+// packet's reference level, so they are computed once per packet: highlimit = (float)(ref*1.414) (:71),
+// lowlimit = (float)(ref*0.707) (:72), and the fp64 product lowlimit*0.5 of :91/:94.
+__device__ __forceinline__ int llslice(float bit0, float bit1, float highlimit, float lowlimit, double lowhalf)
 {
-    const float highlimit = (float)((double)ref * 1.414);     // :71
-    const float lowlimit = (float)((double)ref * 0.707);      // :72
     const bool f = (bit0 > lowlimit) && (bit0 < highlimit);
     const bool s = (bit1 > lowlimit) && (bit1 < highlimit);
     if (f && !s) return 1 | 2;
     if (s && !f) return 0 | 2;
     if (f && s) return (bit0 > bit1) ? 1 : 0;
     const bool d = bit0 > bit1;
-    bool c;
-    if (d) c = (double)bit1 < (double)lowlimit * 0.5;         // :91
-    else c = (double)bit0 < (double)lowlimit * 0.5;           // :94
+    const bool c = d ? ((double)bit1 < lowhalf) : ((double)bit0 < lowhalf);   // :91 / :94
     return (d ? 1 : 0) | (c ? 2 : 0);
 }
 
 // Packet rules of slicer_impl::work (slicer_impl.cc:117-182) on 240 chips held in shared memory.
 // Executed by a full warp; lane 0 fills *f (sample_index/secs/frac are the caller's business).
-__device__ bool slice_packet_warp(const float* chips, amb_frame* f, int lane)
+__device__ bool slice_packet_warp(const float* chips, amb_frame* f, int lane, const unsigned int* crc_rem)
 {
     const float ref = (float)((double)__fadd_rn(__fadd_rn(__fadd_rn(chips[0], chips[2]), chips[7]), chips[9]) / 4.0); // :128-131
+    const float highlimit = (float)((double)ref * 1.414);                     // :71
+    const float lowlimit = (float)((double)ref * 0.707);                      // :72
+    const double lowhalf = (double)lowlimit * 0.5;
     uint32_t dw[4], lw[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {                      // bit j = 32k + lane, chips 16+2j, 17+2j (:133,:147)
         const int j = 32 * k + lane;
         int r = 2;
-        if (j < 112) r = llslice(chips[16 + 2 * j], chips[17 + 2 * j], ref);
+        if (j < 112) r = llslice(chips[16 + 2 * j], chips[17 + 2 * j], highlimit, lowlimit, lowhalf);
         dw[k] = __brev(__ballot_sync(FULL, r & 1));    // MSB-first: bit 31 <-> j = 32k
         lw[k] = __ballot_sync(FULL, !(r & 2));         // bit lane <-> low confidence at j
     }
@@ -928,7 +955,7 @@ __device__ bool slice_packet_warp(const float* chips, amb_frame* f, int lane)
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int j = 32 * k + lane;
-        if (j < nmsg && ((dw[k] >> (31 - lane)) & 1u)) crc ^= c_crc_rem[nmsg - 1 - j];
+        if (j < nmsg && ((dw[k] >> (31 - lane)) & 1u)) crc ^= crc_rem[nmsg - 1 - j];   // shared memory: per-lane index
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) crc ^= __shfl_xor_sync(FULL, crc, d);
@@ -973,7 +1000,10 @@ template <bool STREAMS>
 __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
 {
     __shared__ float s_chips[4][240];
+    __shared__ unsigned int s_crc[96];
     extern __shared__ float sl_smem[];                         // per warp: m2 of the packet span (not in STREAMS mode)
+    if (threadIdx.x < 96) s_crc[threadIdx.x] = c_crc_rem[threadIdx.x];
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* chips = s_chips[warp];
     const AmbParams& P = a.P;
@@ -1020,7 +1050,7 @@ __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
         slot = __shfl_sync(FULL, slot, 0);
         if (slot < a.frame_cap) {
             amb_frame* f = a.frames + slot;
-            const bool passed = slice_packet_warp(chips, f, lane);
+            const bool passed = slice_packet_warp(chips, f, lane, s_crc);
             if (lane == 0) {
                 f->sample_index = (uint64_t)(a.org + fin);
                 f->secs = 0; f->frac = 0.0;
@@ -1049,12 +1079,15 @@ cudaError_t amb_launch_slice(const AmbSliceArgs& a, int sm_count, cudaStream_t s
 __global__ void __launch_bounds__(128) amb_slice_chips_kernel(const float* __restrict__ chips_in, int ndet, amb_frame* frames)
 {
     __shared__ float s_chips[4][240];
+    __shared__ unsigned int s_crc[96];
+    if (threadIdx.x < 96) s_crc[threadIdx.x] = c_crc_rem[threadIdx.x];
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* chips = s_chips[warp];
     for (int d = blockIdx.x * 4 + warp; d < ndet; d += gridDim.x * 4) {
         for (int j = lane; j < 240; j += 32) chips[j] = chips_in[(size_t)d * 240 + j];
         __syncwarp();
-        slice_packet_warp(chips, frames + d, lane);
+        slice_packet_warp(chips, frames + d, lane, s_crc);
         __syncwarp();
     }
 }
