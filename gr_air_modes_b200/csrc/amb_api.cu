@@ -46,6 +46,7 @@ struct amb_ctx {
     uint32_t* coarse[2] = {nullptr, nullptr}; uint32_t* fine[2] = {nullptr, nullptr}; uint32_t* span_count[2] = {nullptr, nullptr};
     size_t rows_cap = 0; int spans_cap = 0;
     int* cand_j = nullptr; uint32_t* cand_info = nullptr; float* cand_avg = nullptr; unsigned cand_cap = 0;
+    int* det_list = nullptr;
     void* walk_scratch = nullptr;
     amb_frame* frames = nullptr; unsigned frame_cap = 0; unsigned frames_ub = 0;
     float* chips = nullptr; bool keep_chips = false;
@@ -169,6 +170,7 @@ static void free_dev(amb_ctx* c)
     cudaFree(c->dc_carry[0]); cudaFree(c->dc_carry[1]); cudaFree(c->dc_out); cudaFree(c->dc_ma0);
     c->dc_carry[0] = c->dc_carry[1] = c->dc_out = c->dc_ma0 = nullptr; c->dc_cap = 0;
     cudaFree(c->cand_j); cudaFree(c->cand_info); cudaFree(c->cand_avg); cudaFree(c->walk_scratch); c->walk_scratch = nullptr;
+    cudaFree(c->det_list); c->det_list = nullptr;
     cudaFree(c->frames); cudaFree(c->chips); cudaFree(c->ctr); cudaFree(c->st);
     c->staging = nullptr;
     c->cand_j = nullptr; c->cand_info = nullptr; c->cand_avg = nullptr;
@@ -422,8 +424,9 @@ static int ensure_call_buffers(amb_ctx* ctx, size_t rows_need, int n_spans, unsi
     }
     if (ctx->cand_cap < cap_need) {
         CK(sync_all(ctx));
-        cudaFree(ctx->cand_j); cudaFree(ctx->cand_info); cudaFree(ctx->cand_avg); cudaFree(ctx->walk_scratch);
-        ctx->cand_j = nullptr; ctx->cand_info = nullptr; ctx->cand_avg = nullptr; ctx->walk_scratch = nullptr;
+        cudaFree(ctx->cand_j); cudaFree(ctx->cand_info); cudaFree(ctx->cand_avg); cudaFree(ctx->walk_scratch); cudaFree(ctx->det_list);
+        ctx->cand_j = nullptr; ctx->cand_info = nullptr; ctx->cand_avg = nullptr; ctx->walk_scratch = nullptr; ctx->det_list = nullptr;
+        CK(cudaMalloc(&ctx->det_list, (size_t)cap_need * sizeof(int)));
         CK(cudaMalloc(&ctx->walk_scratch, amb_walk_scratch_bytes(cap_need, (long long)cap_need * 8 + 4096)));
         CK(cudaMalloc(&ctx->cand_j, (size_t)cap_need * sizeof(int)));
         CK(cudaMalloc(&ctx->cand_info, (size_t)cap_need * sizeof(uint32_t)));
@@ -569,11 +572,12 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         AmbExactArgs ea{};
         ea.P = P; ea.S = S; ea.cand_j = ctx->cand_j; ea.cand_info = ctx->cand_info; ea.cand_avg = ctx->cand_avg; ea.ctr = ctx->ctr;
         CK(amb_launch_exact(ea, ctx->sm_count, sb));
-        wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info;
+        wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info; wa.det_list = ctx->det_list;
         if (!par) { CK(amb_launch_walk_seq(wa, sb)); ctx->stats.kernel_launches += 1; }
         else { CK(amb_launch_walk_par(wa, ctx->walk_scratch, ctx->cand_cap, (long long)S.n_carry + S.n_main + S.n_tail, sb)); ctx->stats.kernel_launches += 3; }
         AmbSliceArgs sl{};
         sl.P = P; sl.S = S; sl.cand_j = ctx->cand_j; sl.cand_info = ctx->cand_info; sl.cand_avg = ctx->cand_avg;
+        sl.det_list = ctx->det_list;
         sl.ctr = ctx->ctr; sl.frames = ctx->frames; sl.frame_cap = ctx->frame_cap;
         sl.chips_out = ctx->keep_chips ? ctx->chips : nullptr; sl.org = org;
         CK(amb_launch_slice(sl, ctx->sm_count, sb));
@@ -593,9 +597,10 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
                 CK(cudaMalloc(&ctx->cand_j, 64 * sizeof(int)));
                 CK(cudaMalloc(&ctx->cand_info, 64 * sizeof(uint32_t)));
                 CK(cudaMalloc(&ctx->cand_avg, 64 * sizeof(float)));
+                CK(cudaMalloc(&ctx->det_list, 64 * sizeof(int)));
                 ctx->cand_cap = 64;
             }
-            wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info;
+            wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info; wa.det_list = ctx->det_list;
             CK(cudaMemsetAsync(&ctx->ctr->ncand, 0, sizeof(unsigned), sb));
             CK(amb_launch_walk_seq(wa, sb));
             ctx->stats.kernel_launches += 1;
@@ -865,11 +870,12 @@ int amb_preamble_process(amb_ctx* ctx, const float* in0, const float* in1, size_
         if (e == cudaSuccess) e = amb_launch_exact(ea, ctx->sm_count, s);
         AmbWalkArgs wa{};
         wa.P = P; wa.org = 0; wa.ntot = ntot; wa.r_safe = 0; wa.flush = 1; wa.ctr = ctx->ctr; wa.st = ctx->st;
-        wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info;
+        wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info; wa.det_list = ctx->det_list;
         if (e == cudaSuccess) e = (ctx->resolver == 1) ? amb_launch_walk_seq(wa, s)
                                                        : amb_launch_walk_par(wa, ctx->walk_scratch, ctx->cand_cap, ntot + 4096, s);
         AmbSliceArgs sl{};
         sl.P = P; sl.cand_j = ctx->cand_j; sl.cand_info = ctx->cand_info; sl.cand_avg = ctx->cand_avg; sl.ctr = ctx->ctr;
+        sl.det_list = ctx->det_list;
         sl.frames = ctx->frames; sl.frame_cap = ctx->frame_cap; sl.chips_out = ctx->chips; sl.org = 0;
         sl.in0 = d0; sl.in1 = d1; sl.n_streams = (long long)n;
         if (e == cudaSuccess) e = amb_launch_slice(sl, ctx->sm_count, s);

@@ -61,7 +61,7 @@ struct AmbCounters {
     unsigned int ndet_call;    // detections in this call
     unsigned int npassed_call;
     unsigned int nreal_call;
-    unsigned int pad;
+    unsigned int ndet_list;    // entries of the detection list of this call (indices into the candidate arrays)
 };
 
 struct AmbScanArgs {
@@ -87,6 +87,7 @@ struct AmbExactArgs {
 struct AmbWalkArgs {
     AmbParams P;
     const int* cand_j; uint32_t* cand_info;
+    int* det_list;        // out: candidate indices of accepted preambles, unordered (the slicer's work list)
     AmbCounters* ctr; AmbWalkState* st;
     long long org;        // absolute reported index of j = 0
     long long ntot;       // flush: total items incl. history (N + H); else unused
@@ -97,6 +98,7 @@ struct AmbWalkArgs {
 struct AmbSliceArgs {
     AmbParams P; AmbSegs S;
     const int* cand_j; const uint32_t* cand_info; const float* cand_avg;
+    const int* det_list;
     AmbCounters* ctr;
     amb_frame* frames; unsigned int frame_cap;
     float* chips_out;     // optional 240 floats per detection (same slot as the frame)

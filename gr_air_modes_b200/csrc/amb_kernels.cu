@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(128) amb_compact_kernel(const __grid_constant_
 {
     // per-call resets of what the later kernels of this call accumulate into
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_scratch64; k += gridDim.x * blockDim.x) scratch64[k] = 0ull;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->ndet_call = 0; ctr->npassed_call = 0; ctr->nreal_call = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->ndet_call = 0; ctr->npassed_call = 0; ctr->nreal_call = 0; ctr->ndet_list = 0; }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int span = blockIdx.x * 4 + warp;
     if (span >= a.n_spans) return;
@@ -533,6 +533,18 @@ __device__ __forceinline__ float canon_m2(const AmbSegs& S, int j)
     const float2 v = *seg_ptr(S, j);
     return __fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y));
 }
+// pointer to the logical samples [j, j+count) when they lie inside ONE segment (the common case), else nullptr
+__device__ __forceinline__ const float2* seg_span(const AmbSegs& S, int j, int count)
+{
+    if (j < 0) return nullptr;
+    if (j + count <= S.n_carry) return S.carry + j;
+    const int t0 = S.n_carry + S.n_main;
+    if (j >= S.n_carry && j + count <= t0) return S.main_ + (j - S.n_carry);
+    if (j >= t0 && j + count <= t0 + S.n_tail) return S.tail + (j - t0);
+    return nullptr;
+}
+__device__ __forceinline__ float canon_m2_of(float2 v) { return __fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)); }
+
 // split form: the caller supplies the two float streams; x is in reported coordinates (history-biased)
 __device__ __forceinline__ float stream_at(const float* in, long long n, int H, long long x)
 {
@@ -568,12 +580,17 @@ __global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a)
         } else {
             const int b_bb = c - L + 1;               // bbs[i] <-> bb[b_bb + i]
             const int b_m2 = b_bb - (fl - 1);
-            for (int i0 = 0; i0 < NM; i0 += 256) {            // 8 independent loads in flight per lane
-                float v[8];
+            const float2* span = seg_span(a.S, b_m2, NM);     // warp-uniform
+            if (span) {
+                for (int i0 = 0; i0 < NM; i0 += 256) {        // 8 independent loads in flight per lane
+                    float2 v[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; v[u] = i < NM ? canon_m2(a.S, b_m2 + i) : 0.f; }
+                    for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; v[u] = i < NM ? span[i] : make_float2(0.f, 0.f); }
 #pragma unroll
-                for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; if (i < NM) m2s[i] = v[u]; }
+                    for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; if (i < NM) m2s[i] = canon_m2_of(v[u]); }
+                }
+            } else {
+                for (int i = lane; i < NM; i += 32) m2s[i] = canon_m2(a.S, b_m2 + i);   // straddles a segment boundary
             }
             __syncwarp();
             for (int i = lane; i < NB; i += 32) {
@@ -720,6 +737,7 @@ __device__ unsigned int seq_walk(const AmbWalkArgs& a, AmbWalkState& st, int idx
             continue;
         }
         a.cand_info[idx] = info | (1u << 10);                              // accepted: 240-chip packet
+        a.det_list[atomicAdd(&a.ctr->ndet_list, 1u)] = idx;
         ndet++;
         const long long consumed = (long long)(int)((float)i_rel + P.skip_f);  // :237 float arithmetic
         st.pos += consumed; st.p = st.pos;
@@ -817,6 +835,7 @@ __global__ void __launch_bounds__(256) amb_walk_par1_kernel(const AmbWalkArgs a,
                             if (pos_known) consumed = (long long)(int)((float)(fin - pos) + P.skip_f) - (fin - pos);
                             else { consumed = P.skip0; ff = fin; }
                             a.cand_info[k + u] = info | (1u << 10);
+                            a.det_list[atomicAdd(&a.ctr->ndet_list, 1u)] = k + u;
                             ndet++;
                             pos = fin + consumed; p = pos; pos_known = true;
                             last_pos = pos;
@@ -862,6 +881,7 @@ __global__ void amb_walk_finalize_kernel(const AmbWalkArgs a, AmbParScratch* sc)
     const int n = (int)a.ctr->ncand;
     if (sc->violation) {                 // float rounding at :237 may matter: exact sequential walk of the whole call
         for (int k = 0; k < n; k++) a.cand_info[k] &= ~(1u << 10);
+        a.ctr->ndet_list = 0;
         st.fallback = 1;
         const unsigned int ndet = seq_walk(a, st, 0, n);
         st.ndet += ndet; st.ncand_real += a.ctr->nreal_call;
@@ -1007,14 +1027,14 @@ __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* chips = s_chips[warp];
     const AmbParams& P = a.P;
-    const unsigned int ncand = a.ctr->ncand;
+    const unsigned int ndet = a.ctr->ndet_list;                // accepted preambles of this call (any order)
     const int nwarps = gridDim.x * 4;
     const int fl = P.use_pmf ? P.spc_i : 1;
     const int span = chip_off(239, P.spc_f) + fl;              // m2 samples a packet touches
     const int spanp = (span + 31) & ~31;
-    for (unsigned int ci = blockIdx.x * 4 + warp; ci < ncand; ci += nwarps) {
+    for (unsigned int di = blockIdx.x * 4 + warp; di < ndet; di += nwarps) {
+        const int ci = a.det_list[di];
         const uint32_t info = a.cand_info[ci];
-        if (!(info & (1u << 10))) continue;                    // warp-uniform
         const int fin = a.cand_j[ci] + (int)(info & 0xffu);
         const float avg_fin = a.cand_avg[ci];
         if (STREAMS) {
@@ -1023,12 +1043,17 @@ __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
         } else {
             float* m2s = sl_smem + (size_t)warp * spanp;
             const int b0 = fin - fl + 1;                       // m2s[i] <-> m2[b0 + i]; independent coalesced loads
-            for (int i0 = 0; i0 < span; i0 += 256) {           // 8 independent loads in flight per lane
-                float v[8];
+            const float2* src = seg_span(a.S, b0, span);       // warp-uniform
+            if (src) {
+                for (int i0 = 0; i0 < span; i0 += 256) {       // 8 independent loads in flight per lane
+                    float2 v[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; v[u] = i < span ? canon_m2(a.S, b0 + i) : 0.f; }
+                    for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; v[u] = i < span ? src[i] : make_float2(0.f, 0.f); }
 #pragma unroll
-                for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; if (i < span) m2s[i] = v[u]; }
+                    for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; if (i < span) m2s[i] = canon_m2_of(v[u]); }
+                }
+            } else {
+                for (int i = lane; i < span; i += 32) m2s[i] = canon_m2(a.S, b0 + i);  // straddles a segment boundary
             }
             __syncwarp();
             for (int j = lane; j < 240; j += 32) {
