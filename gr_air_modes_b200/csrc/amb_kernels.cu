@@ -554,15 +554,20 @@ __device__ __forceinline__ float stream_at(const float* in, long long n, int H, 
 
 
 // One warp per candidate. Writes info = late | real<<8 | valid<<9 and avg at the shifted index.
-template <bool STREAMS>
+// SPC > 0: integer samples/chip geometry known at compile time (loops unroll, offsets fold); SPC == 0: run-time values.
+template <bool STREAMS, int SPC>
 __global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a)
 {
     extern __shared__ float ex_smem[];                 // per warp: m2s[NMp] then bbs[NMp], sized by the launcher
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const AmbParams& P = a.P;
-    const int L = P.L, spc = P.spc_i, maxlate = P.maxlate;
+    const int spc = SPC ? SPC : P.spc_i;
+    const int L = 48 * spc, maxlate = SPC ? SPC : P.maxlate;
+    const int po1 = SPC ? 2 * SPC : P.po1, po2 = SPC ? 7 * SPC : P.po2, po3 = SPC ? 9 * SPC : P.po3;
+    const int qa0 = SPC ? 3 * SPC : P.qa0, qa1 = SPC ? 6 * SPC : P.qa1, qb0 = SPC ? 10 * SPC : P.qb0, qb1 = SPC ? 15 * SPC : P.qb1;
+    const int fwd = SPC ? 15 * SPC + 2 : P.fwd;
     const int fl = P.use_pmf ? spc : 1;
-    const int NB = STREAMS ? (maxlate + P.fwd + 1) : (L + maxlate + P.fwd + 1);
+    const int NB = STREAMS ? (maxlate + fwd + 1) : (L + maxlate + fwd + 1);
     const int NM = NB + fl - 1;
     const int NMp = (NM + 31) & ~31;
     float* m2s = ex_smem + (size_t)warp * 2 * NMp;
@@ -649,9 +654,9 @@ __global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a)
         const float pulse_threshold = __fmul_rn(avg0, P.thr);                       // :173
         bool real = in[0] > pulse_threshold;                                        // :174
         if (real && (in[1] > in[0])) real = false;                                  // :175
-        if (real && (in[P.po1] < pulse_threshold)) real = false;                    // :177
-        if (real && (in[P.po2] < pulse_threshold)) real = false;                    // :178
-        if (real && (in[P.po3] < pulse_threshold)) real = false;                    // :179
+        if (real && (in[po1] < pulse_threshold)) real = false;                    // :177
+        if (real && (in[po2] < pulse_threshold)) real = false;                    // :178
+        if (real && (in[po3] < pulse_threshold)) real = false;                    // :179
         uint32_t info = 0;
         float avg_fin = avg0;
         if (real) {
@@ -662,16 +667,16 @@ __global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a)
                 const double late_corr = __shfl_sync(FULL, corrk, 16 + i + 1);
                 late = late_corr > now_corr;
                 if (late) { i++; how_late++; }
-            } while (late && (float)how_late < P.spc_f);
+            } while (late && (SPC ? how_late < SPC : (float)how_late < P.spc_f));
             avg_fin = __shfl_sync(FULL, avgk, i);
             const float* s = in + i;
-            const float sum4 = __fadd_rn(__fadd_rn(__fadd_rn(s[0], s[P.po1]), s[P.po2]), s[P.po3]);
+            const float sum4 = __fadd_rn(__fadd_rn(__fadd_rn(s[0], s[po1]), s[po2]), s[po3]);
             const float avgpeak = (float)((double)sum4 / 4.0);                      // :198-201
             const float space_threshold =
                 __fadd_rn(avg_fin, __fdiv_rn(__fsub_rn(avgpeak, avg_fin), P.thr));  // :203
             bool viol = false;
-            for (int j = P.qa0 + lane; j <= P.qa1; j += 32) viol |= (s[j] > space_threshold);  // :205-206
-            for (int j = P.qb0 + lane; j <= P.qb1; j += 32) viol |= (s[j] > space_threshold);  // :207-208
+            for (int j = qa0 + lane; j <= qa1; j += 32) viol |= (s[j] > space_threshold);  // :205-206
+            for (int j = qb0 + lane; j <= qb1; j += 32) viol |= (s[j] > space_threshold);  // :207-208
             const bool valid = !__any_sync(FULL, viol);
             info = (uint32_t)i | (1u << 8) | (valid ? (1u << 9) : 0u);
         }
@@ -680,16 +685,36 @@ __global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a)
     }
 }
 
+template <int SPC>
+static cudaError_t launch_exact_t(const AmbExactArgs& a, int blocks, size_t smem, cudaStream_t s)
+{
+    if (a.in0) amb_exact_kernel<true, SPC><<<blocks, 128, smem, s>>>(a);
+    else amb_exact_kernel<false, SPC><<<blocks, 128, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t amb_launch_exact(const AmbExactArgs& a, int sm_count, cudaStream_t s)
 {
-    const int fl = a.P.use_pmf ? a.P.spc_i : 1;
-    const int NB = a.in0 ? (a.P.maxlate + a.P.fwd + 1) : (a.P.L + a.P.maxlate + a.P.fwd + 1);
+    const AmbParams& P = a.P;
+    const int fl = P.use_pmf ? P.spc_i : 1;
+    // integer samples/chip: everything the kernel needs is a multiple of spc (see compute_params)
+    const int k = P.spc_i;
+    const bool integral = P.spc_f == (float)k && P.maxlate == k && P.po1 == 2 * k && P.po2 == 7 * k && P.po3 == 9 * k &&
+                          P.qa0 == 3 * k && P.qa1 == 6 * k && P.qb0 == 10 * k && P.qb1 == 15 * k && P.fwd == 15 * k + 2;
+    const int NB = a.in0 ? (P.maxlate + P.fwd + 1) : (P.L + P.maxlate + P.fwd + 1);
     const int NMp = (NB + fl - 1 + 31) & ~31;
     const size_t smem = (size_t)4 * 2 * NMp * sizeof(float);            // <= 22 KiB at 20 Msps, ~1.3 KiB at 4 Msps
     const int blocks = sm_count * 12;
-    if (a.in0) amb_exact_kernel<true><<<blocks, 128, smem, s>>>(a);
-    else amb_exact_kernel<false><<<blocks, 128, smem, s>>>(a);
-    return cudaGetLastError();
+    if (integral) {
+        switch (k) {
+            case 1: return launch_exact_t<1>(a, blocks, smem, s);
+            case 2: return launch_exact_t<2>(a, blocks, smem, s);
+            case 5: return launch_exact_t<5>(a, blocks, smem, s);
+            case 10: return launch_exact_t<10>(a, blocks, smem, s);
+            default: break;
+        }
+    }
+    return launch_exact_t<0>(a, blocks, smem, s);
 }
 
 // ------------------------------------------------------------------------------------------------
