@@ -53,7 +53,9 @@ struct amb_ctx {
     AmbCounters* ctr = nullptr; AmbWalkState* st = nullptr;
     // stream state
     uint64_t n_in = 0; long long r_done = 0; bool flushed = false;
-    uint64_t t0_secs = 0; double t0_frac = 0.0;          // rx_time tag at item 0 (preamble_impl.cc:104-116)
+    uint64_t t0_secs = 0; double t0_frac = 0.0;
+    // split-form preamble stream state: undecided tail of the two float streams + counters
+    std::vector<float> sf0, sf1; uint64_t sf_total = 0; long long sf_rdone = 0;          // rx_time tag at item 0 (preamble_impl.cc:104-116)
     long long last_org = 0; bool have_last = false;
     std::vector<amb_frame> pending;
     // stats / timing
@@ -223,6 +225,7 @@ static int reset_stream(amb_ctx* ctx)
         CK(cudaMemsetAsync(ctx->dc_carry[1], 0, (size_t)ctx->dc_nc * sizeof(float2), ctx->stream));
         ctx->dc_cur = 0;
     }
+    ctx->sf0.clear(); ctx->sf1.clear(); ctx->sf_total = 0; ctx->sf_rdone = 0;
     ctx->carry_in = 2; ctx->n_in = 0; ctx->r_done = 0; ctx->flushed = false; ctx->have_last = false;
     ctx->frames_ub = 0;
     ctx->pending.clear();
@@ -828,32 +831,45 @@ int amb_preamble_process(amb_ctx* ctx, const float* in0, const float* in1, size_
                          float* chips_out, uint64_t* index_out, int max_det)
 {
     if (!ctx || (n && (!in0 || !in1)) || max_det < 0 || (max_det && (!chips_out || !index_out))) return AMB_ERR_INVALID;
-    if (!flush) return fail(ctx, AMB_ERR_UNSUPPORTED, "split-form preamble processes whole streams (flush=1)");
     if (n > 0x40000000ull) return fail(ctx, AMB_ERR_INVALID, "at most 2^30 items per call");
     CK(cudaSetDevice(ctx->device));
     CK(sync_all(ctx));
     const AmbParams& P = ctx->P;
     cudaStream_t s = ctx->stream;
-    const long long ntot = (long long)n + P.H;                       // items incl. history (reported coordinates)
+    // combined = undecided tail of the previous calls ++ new items; item index of combined[0] is b0
+    const long long b0 = (long long)ctx->sf_total - (long long)ctx->sf0.size();
+    const size_t m = ctx->sf0.size() + n;
+    const bool first = (ctx->sf_total == 0);
+    const long long total = (long long)ctx->sf_total + (long long)n;
+    const long long ntot = total + P.H;                              // items incl. history (reported coordinates)
+    const long long r_safe = std::max<long long>(ctx->sf_rdone, total + P.H - ctx->guard);
     float* d0 = nullptr; float* d1 = nullptr;
-    CK(cudaMalloc(&d0, (n + 1) * sizeof(float)));
-    CK(cudaMalloc(&d1, (n + 1) * sizeof(float)));
+    CK(cudaMalloc(&d0, (m + 1) * sizeof(float)));
+    CK(cudaMalloc(&d1, (m + 1) * sizeof(float)));
     int rc = AMB_OK;
     do {
-        cudaError_t e = cudaMemcpyAsync(d0, in0, n * sizeof(float), cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d1, in1, n * sizeof(float), cudaMemcpyHostToDevice, s);
+        cudaError_t e = cudaSuccess;
+        const size_t nt = ctx->sf0.size();
+        if (nt) {
+            e = cudaMemcpyAsync(d0, ctx->sf0.data(), nt * sizeof(float), cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d1, ctx->sf1.data(), nt * sizeof(float), cudaMemcpyHostToDevice, s);
+        }
+        if (e == cudaSuccess && n) e = cudaMemcpyAsync(d0 + nt, in0, n * sizeof(float), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && n) e = cudaMemcpyAsync(d1 + nt, in1, n * sizeof(float), cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) { rc = fail(ctx, AMB_ERR_CUDA, "H2D", e); break; }
+        // local reported coordinate j = r - b0; evaluate starts in [r_done, flush ? ntot : r_safe)
+        const long long j_lo = ctx->sf_rdone - b0, j_hi = (flush ? ntot : r_safe) - b0;
         AmbScanArgs a{};
-        a.P = P; a.j_lo = 0; a.j_hi = (int)ntot; a.row_lo = 0; a.row_hi = (int)((ntot + AMB_ROW - 1) / AMB_ROW);
+        a.P = P; a.j_lo = (int)j_lo; a.j_hi = (int)std::max(j_hi, j_lo); a.row_lo = 0; a.row_hi = (int)((a.j_hi + AMB_ROW - 1) / AMB_ROW);
         const int rows = a.row_hi;
         const int target = ctx->sm_count * 16;
         int rps = ((rows + target - 1) / target + AMB_SPAN_ROWS_ALIGN - 1) / AMB_SPAN_ROWS_ALIGN * AMB_SPAN_ROWS_ALIGN;
         if (rps < AMB_SPAN_ROWS_ALIGN) rps = AMB_SPAN_ROWS_ALIGN;
         a.rows_per_span = rps; a.n_spans = std::max(1, (rows + rps - 1) / rps);
         ctx->frames_ub = 0;
-        const unsigned fr_ub = (unsigned)(ntot / std::max(P.skip0, 1) + 2);
+        const unsigned fr_ub = (unsigned)((long long)m / std::max(P.skip0, 1) + 2);
         const bool keep = ctx->keep_chips; ctx->keep_chips = true;
-        rc = ensure_call_buffers(ctx, (size_t)a.row_hi + 64, a.n_spans, (unsigned)std::max<long long>(1 << 16, ntot / 8 + 1024), fr_ub);
+        rc = ensure_call_buffers(ctx, (size_t)a.row_hi + 64, a.n_spans, (unsigned)std::max<long long>(1 << 16, (long long)m / 8 + 1024), fr_ub);
         ctx->keep_chips = keep;
         if (rc != AMB_OK) break;
         a.coarse = ctx->coarse[0]; a.fine = ctx->fine[0]; a.span_count = ctx->span_count[0];
@@ -861,23 +877,23 @@ int amb_preamble_process(amb_ctx* ctx, const float* in0, const float* in1, size_
         e = cudaMemsetAsync(ctx->coarse[0], 0, ((size_t)a.row_hi / 32 + 2) * sizeof(uint32_t), s);
         if (e == cudaSuccess) e = cudaMemsetAsync(ctx->span_count[0], 0, (size_t)(ctx->spans_cap + 128) * sizeof(uint32_t), s);
         if (e == cudaSuccess) e = cudaMemsetAsync(ctx->ctr, 0, sizeof(AmbCounters), s);
-        if (e == cudaSuccess) e = cudaMemsetAsync(ctx->st, 0, sizeof(AmbWalkState), s);
-        if (e == cudaSuccess) e = amb_launch_stream_candidates(a, d0, d1, (long long)n, s);
-        if (e == cudaSuccess) e = amb_launch_compact(a, ctx->cand_j, ctx->cand_cap, ctx->ctr, ctx->walk_scratch, ntot + 4096, s);
+        if (e == cudaSuccess && first) e = cudaMemsetAsync(ctx->st, 0, sizeof(AmbWalkState), s);
+        if (e == cudaSuccess) e = amb_launch_stream_candidates(a, d0, d1, (long long)m, s);
+        if (e == cudaSuccess) e = amb_launch_compact(a, ctx->cand_j, ctx->cand_cap, ctx->ctr, ctx->walk_scratch, (long long)m + P.H + 4096, s);
         AmbExactArgs ea{};
         ea.P = P; ea.cand_j = ctx->cand_j; ea.cand_info = ctx->cand_info; ea.cand_avg = ctx->cand_avg; ea.ctr = ctx->ctr;
-        ea.in0 = d0; ea.in1 = d1; ea.n_streams = (long long)n;
+        ea.in0 = d0; ea.in1 = d1; ea.n_streams = (long long)m;
         if (e == cudaSuccess) e = amb_launch_exact(ea, ctx->sm_count, s);
         AmbWalkArgs wa{};
-        wa.P = P; wa.org = 0; wa.ntot = ntot; wa.r_safe = 0; wa.flush = 1; wa.ctr = ctx->ctr; wa.st = ctx->st;
+        wa.P = P; wa.org = b0; wa.ntot = ntot; wa.r_safe = r_safe; wa.flush = flush ? 1 : 0; wa.ctr = ctx->ctr; wa.st = ctx->st;
         wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info; wa.det_list = ctx->det_list;
         if (e == cudaSuccess) e = (ctx->resolver == 1) ? amb_launch_walk_seq(wa, s)
-                                                       : amb_launch_walk_par(wa, ctx->walk_scratch, ctx->cand_cap, ntot + 4096, s);
+                                                       : amb_launch_walk_par(wa, ctx->walk_scratch, ctx->cand_cap, (long long)m + P.H + 4096, s);
         AmbSliceArgs sl{};
         sl.P = P; sl.cand_j = ctx->cand_j; sl.cand_info = ctx->cand_info; sl.cand_avg = ctx->cand_avg; sl.ctr = ctx->ctr;
         sl.det_list = ctx->det_list;
-        sl.frames = ctx->frames; sl.frame_cap = ctx->frame_cap; sl.chips_out = ctx->chips; sl.org = 0;
-        sl.in0 = d0; sl.in1 = d1; sl.n_streams = (long long)n;
+        sl.frames = ctx->frames; sl.frame_cap = ctx->frame_cap; sl.chips_out = ctx->chips; sl.org = b0;
+        sl.in0 = d0; sl.in1 = d1; sl.n_streams = (long long)m;
         if (e == cudaSuccess) e = amb_launch_slice(sl, ctx->sm_count, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         ctx->stats.kernel_launches += 8;
@@ -904,6 +920,19 @@ int amb_preamble_process(amb_ctx* ctx, const float* in0, const float* in1, size_
         }
         cudaMemset(&ctx->ctr->nframes, 0, sizeof(unsigned));
         ctx->frames_ub = 0;
+        // keep what a later call still has to look at: items from (r_safe - H) on
+        if (flush) { ctx->sf0.clear(); ctx->sf1.clear(); ctx->sf_total = 0; ctx->sf_rdone = 0; }
+        else {
+            const long long keep_from = std::max<long long>(r_safe - P.H, b0);       // item index
+            std::vector<float> t0, t1;
+            for (long long it = keep_from; it < total; it++) {
+                const long long k = it - b0;
+                t0.push_back((size_t)k < nt ? ctx->sf0[(size_t)k] : in0[(size_t)k - nt]);
+                t1.push_back((size_t)k < nt ? ctx->sf1[(size_t)k] : in1[(size_t)k - nt]);
+            }
+            ctx->sf0.swap(t0); ctx->sf1.swap(t1);
+            ctx->sf_total = (uint64_t)total; ctx->sf_rdone = r_safe;
+        }
         rc = nd > (unsigned)max_det ? fail(ctx, AMB_ERR_OVERFLOW, "max_det too small") : nout;
     } while (0);
     cudaFree(d0); cudaFree(d1);

@@ -1217,7 +1217,7 @@ __global__ void __launch_bounds__(256) amb_stream_cand_kernel(const __grid_const
     for (long long w = (long long)(blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nwords; w += (long long)(gridDim.x * blockDim.x) >> 5) {
         const long long r = w * 32 + lane;
         bool c = false;
-        if (r < a.j_hi) {
+        if (r >= a.j_lo && r < a.j_hi) {
             const float x = stream_at(in0, n, P.H, r);
             const float thr = __fmul_rn(stream_at(in1, n, P.H, r), P.thr);                 // :173
             c = x > thr;                                                                    // :174

@@ -140,9 +140,10 @@ AMB_API uint32_t amb_modes_check_crc(const uint8_t* data, int length);
 AMB_API int amb_device_crc(amb_ctx* ctx, const uint8_t* data, int n, int length, uint32_t* out);
 
 /* ---- split-form blocks (stream contract of the two reference blocks) ---------------------------
- * preamble: in0 = signal, in1 = moving-average reference (preamble_impl.cc:43), whole streams of n
- * floats in host memory; out = 240 chips per detection + reported index (tag offset). Returns the
- * number of detections (<= max_det) or <0. */
+ * preamble: in0 = signal, in1 = moving-average reference (preamble_impl.cc:43), the next n items of both streams
+ * in host memory (flush != 0 marks the end of the stream; the next call then starts a new one); out = 240 chips
+ * per detection decided in this call + reported index (tag offset). Returns the number of detections
+ * (<= max_det) or <0. */
 AMB_API int amb_preamble_process(amb_ctx* ctx, const float* in0, const float* in1, size_t n, int flush,
                          float* chips_out, uint64_t* index_out, int max_det);
 /* slicer: ndet packets of 240 chips (slicer_impl.cc:117-182) -> frames (sample_index/secs/frac are

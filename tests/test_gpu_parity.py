@@ -382,3 +382,24 @@ def test_c_abi_example_program(port, tmp_path):
     want = port.run_iq(sc.iq, 4e6, 7.0, True, co.MA_CANONICAL).msgs
     out = subprocess.run([exe, str(path), "4e6", "7.0", "100003"], capture_output=True, text=True, check=True).stdout.split("\n")
     assert [ln for ln in out if ln] == want
+
+
+def test_split_form_preamble_streaming(port):
+    """preamble.process(in0, in1, flush=False) in ragged chunks: same packets and tags as one call."""
+    rng = np.random.default_rng(3)
+    for rate in (4e6, 10e6, 2e6):
+        sc = synth.make_scene(rate, 400_000, 40, 56)
+        bb, avg = port.frontend(sc.iq, rate, True, co.MA_CANONICAL)
+        want = port.run_streams(bb, avg, rate, 7.0)
+        pre = am.preamble(rate, 7.0)
+        chips, tags, pos, n = [], [], 0, bb.size
+        for c in list(rng.integers(1, 60_000, 60)) + [n]:
+            c = int(min(c, n - pos)); last = pos + c >= n
+            ch, tg = pre.process(bb[pos:pos + c], avg[pos:pos + c], flush=last)
+            chips.append(ch); tags += tg; pos += c
+            if last: break
+        assert [t[0] for t in tags] == [int(x) for x in want.index]
+        assert np.array_equal(np.concatenate(chips), want.chips)
+        # the block starts a new stream after a flush
+        ch, tg = pre.process(bb, avg)
+        assert [t[0] for t in tg] == [int(x) for x in want.index]
