@@ -211,6 +211,97 @@ def cpu_baseline_leg(log2n):
                       "%s preamble/slicer/CRC" % (reps, cores, int(np.log2(n_slice)), "unmodified reference" if ref else "oracle port")}
 
 
+def time_shard_arm(args, rank, local_rank, world, device):
+    """Secondary multi-GPU mode: one recording, `world` time spans with halos, the scan-loop state
+    (16 bytes) handed down the ranks between the dense and the sparse stages. Strong scaling; not the headline."""
+    import torch
+    import torch.distributed as dist
+    import gr_air_modes_b200 as am
+    from gr_air_modes_b200 import shard
+    n = 1 << args.log2n
+    plan = shard.time_shard_plan(n, world, am.query_geometry(RATE, THRESHOLD_DB, True))
+    active = rank < len(plan)
+    sp = plan[rank] if active else None
+    t_f0 = time.perf_counter()
+    whole = sent = None
+    if rank == 0:
+        whole, sent = make_device_scene(n, 0, device)
+        for r in range(1, len(plan)):
+            dist.send(whole[2 * plan[r].first_sample: 2 * plan[r].end].contiguous(), dst=r)
+        iq = whole[: 2 * sp.end]
+    elif active:
+        iq = torch.empty(2 * (sp.end - sp.first_sample), dtype=torch.float32, device=device)
+        dist.recv(iq, src=0)
+    torch.cuda.synchronize()
+    fanout_s = time.perf_counter() - t_f0
+    q = am.msg_queue()
+    rx = am.rx_path(RATE, THRESHOLD_DB, q, use_pmf=True, device=local_rank)
+    rx._ctx.use_stream(torch.cuda.current_stream().cuda_stream)
+    recv, send = shard.dist_state_exchange(rank, device)
+
+    def step():
+        if not active:
+            return
+        rx.seek(sp.first_sample, sp.first_decision)
+        rx.process(iq, flush=sp.flush, collect=False)
+        entry = recv()[:2] if rank else (0, 0)
+        rx.resolve(entry)
+        if not sp.flush:
+            send(rx.walk_state() + (0,))
+
+    rx.defer_resolve(True)
+    for _ in range(args.warmup):
+        step()
+    launches0 = rx.stats().kernel_launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    rx._ctx.join()
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0)
+    if world > 1:
+        dist.barrier()
+    launches = rx.stats().kernel_launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_max = shard.max_over_ranks(ms, world, device)
+    # ---- check: the spans' messages, concatenated in rank order, are the one-shot run's
+    mine = shard.process_time_sharded(rx, iq, sp, recv, send) if active else 0
+    msgs = q.strings()
+    q.flush()
+    allm = [None] * world
+    if world > 1:
+        dist.all_gather_object(allm, msgs)
+    else:
+        allm = [msgs]
+    if rank == 0:
+        rx.defer_resolve(False)
+        rx.reset()
+        rx._slicer._first = True                  # a fresh slicer's first message has 6 digits (slicer_impl.cc:192)
+        rx.process(whole, flush=True)
+        ref_msgs = q.strings()
+        joined = [m for part in allm for m in part]
+        line = {"metric": "Msamples/s IQ demod+slice+CRC", "value": n * args.steps / (ms_max * 1e-3) / 1e6,
+                "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "mode": "time-shard",
+                "config": {"workload": "ONE synthetic 4 Msps recording of 2^%d samples cut into %d time spans with halos"
+                                       % (args.log2n, len(plan)), "parallelism": "time-shard x%d" % len(plan),
+                           "fanout_s": round(fanout_s, 3), "timing": "host clock between barrier+synchronize (the state "
+                           "hand-over is host-driven)", "spans": [repr(x) for x in plan]},
+                "identical_to_one_shot": joined == ref_msgs, "msgs": len(ref_msgs),
+                "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -220,6 +311,8 @@ def main():
     ap.add_argument("--log2n", type=int, default=28)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--time-shard", action="store_true",
+                    help="secondary mode: ONE 2^log2n-sample recording cut into --gpus spans (strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -244,6 +337,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     n = 1 << args.log2n
+    if args.time_shard:
+        time_shard_arm(args, rank, local_rank, world, device)
+        return
 
     # ---- input: rank 0 synthesises every channel and fans it out over NCCL (timed separately)
     t_f0 = time.perf_counter()

@@ -38,7 +38,13 @@ class Geometry(C.Structure):
     _fields_ = [("samples_per_chip", C.c_float), ("samples_per_symbol", C.c_float), ("threshold", C.c_float),
                 ("rate_int", C.c_int), ("history", C.c_int), ("check_width", C.c_int), ("pulse_offset", C.c_int * 4),
                 ("quiet_a", C.c_int * 2), ("quiet_b", C.c_int * 2), ("max_late", C.c_int), ("packet_skip", C.c_int),
-                ("pmf_len", C.c_int), ("floor_len", C.c_int), ("chip_offset_239", C.c_int)]
+                ("pmf_len", C.c_int), ("floor_len", C.c_int), ("chip_offset_239", C.c_int),
+                ("shard_back", C.c_int), ("shard_fwd", C.c_int)]
+
+
+class WalkState(C.Structure):
+    """struct amb_walk_state: where preamble_impl::general_work's loop stands (preamble_impl.cc:164,237)."""
+    _fields_ = [("pos", C.c_int64), ("p", C.c_int64)]
 
 
 assert C.sizeof(Frame) == 80
@@ -72,6 +78,9 @@ SYMBOLS = [
     ("amb_join", C.c_int, [_vp]),
     ("amb_debug_candidates", C.c_int, [_vp, _u64p, C.POINTER(C.c_uint32), C.c_int]),
     ("amb_set_option", C.c_int, [_vp, C.c_char_p, C.c_int]),
+    ("amb_seek", C.c_int, [_vp, C.c_uint64, C.c_uint64, C.POINTER(WalkState)]),
+    ("amb_resolve", C.c_int, [_vp, C.POINTER(WalkState)]),
+    ("amb_get_walk_state", C.c_int, [_vp, C.POINTER(WalkState)]),
     ("amb_strerror", C.c_char_p, [C.c_int]),
     ("amb_last_error", C.c_char_p, [_vp]),
     ("amb_version", C.c_char_p, []),

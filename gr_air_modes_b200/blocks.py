@@ -17,7 +17,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Frame, Stats, check
+from ._lib import Frame, Geometry, Stats, WalkState, check
 
 
 # ---------------------------------------------------------------------------------------------
@@ -86,6 +86,14 @@ def modes_check_crc(data, length: int | None = None) -> int:
 
 
 modes_crc = modes_check_crc
+
+
+def query_geometry(rate, threshold_db=7.0, use_pmf=True) -> Geometry:
+    """What preamble_impl::set_rate/set_threshold derive from the rate (preamble_impl.cc:56-68) plus the halos
+    of a time-sharded span. Host only."""
+    g = Geometry()
+    check(_lib.load().amb_query_geometry(float(rate), float(threshold_db), int(bool(use_pmf)), C.byref(g)))
+    return g
 
 
 def _as_iq(iq):
@@ -293,6 +301,25 @@ class rx_path:
 
     def reset(self):
         self._ctx.call("amb_reset")
+
+    # -- one stream time-sharded over several rx_paths / GPUs (include/airmodes_b200.h, amb_seek)
+    def seek(self, first_sample: int, first_decision: int, entry=None):
+        """Restart the stream at global sample `first_sample`; decisions start at reported index
+        `first_decision`. entry = (pos, p) handed over by the previous span, None = fresh."""
+        st = WalkState(int(entry[0]), int(entry[1])) if entry is not None else None
+        self._ctx.call("amb_seek", int(first_sample), int(first_decision), C.byref(st) if st is not None else None)
+
+    def defer_resolve(self, on: bool = True):
+        self._ctx.call("amb_set_option", b"defer_resolve", int(bool(on)))
+
+    def resolve(self, entry=None):
+        st = WalkState(int(entry[0]), int(entry[1])) if entry is not None else None
+        self._ctx.call("amb_resolve", C.byref(st) if st is not None else None)
+
+    def walk_state(self):
+        st = WalkState()
+        self._ctx.call("amb_get_walk_state", C.byref(st))
+        return int(st.pos), int(st.p)
 
     def stats(self) -> Stats:
         return self._ctx.stats()

@@ -66,6 +66,11 @@ struct amb_ctx {
     cudaEvent_t ring[128] = {};          // 64 (start, stop) pairs around the scan kernel of the last calls
     unsigned ring_n = 0;
     int resolver = 0;
+    // time-sharded operation (amb_seek / amb_resolve): a call whose walk + slice stages are still to run
+    int defer = 0;                       // option "defer_resolve"
+    int def_kind = 0;                    // 0 nothing pending, 1 full (walk + slice), 2 sequential walk only, 3 state only
+    int def_set = 0; bool def_par = false; long long def_nsamp = 0;
+    AmbWalkArgs def_wa{}; AmbSliceArgs def_sl{};
     std::string err;
 };
 
@@ -229,6 +234,7 @@ static int reset_stream(amb_ctx* ctx)
     ctx->carry_in = 2; ctx->n_in = 0; ctx->r_done = 0; ctx->flushed = false; ctx->have_last = false;
     ctx->frames_ub = 0;
     ctx->pending.clear();
+    ctx->def_kind = 0;
     return AMB_OK;
 }
 
@@ -372,6 +378,8 @@ int amb_query_geometry(float rate, float threshold_db, int use_pmf, amb_geometry
     out->max_late = P.maxlate; out->packet_skip = P.skip0;
     out->pmf_len = use_pmf ? P.spc_i : 1; out->floor_len = P.L;
     out->chip_offset_239 = off[239];
+    out->shard_back = P.H + P.L + P.spc_i;                         // block history + floor window + PMF window
+    out->shard_fwd = P.maxlate + (int)ceilf(P.skip_f) + 4 - P.H;   // = the streaming guard, in sample coordinates
     return AMB_OK;
 }
 
@@ -392,6 +400,10 @@ int amb_set_option(amb_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "resolver")) { ctx->resolver = value; return AMB_OK; }
     if (!strcmp(name, "keep_chips")) { ctx->keep_chips = value != 0; return AMB_OK; }
     if (!strcmp(name, "overlap")) { ctx->overlap = value != 0; return AMB_OK; }
+    if (!strcmp(name, "defer_resolve")) {
+        if (ctx->def_kind) return fail(ctx, AMB_ERR_STATE, "amb_resolve pending");
+        ctx->defer = value != 0; return AMB_OK;
+    }
     return AMB_ERR_INVALID;
 }
 
@@ -459,6 +471,7 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
     if (!ctx || (!iq && n_complex)) return AMB_ERR_INVALID;
     if (ctx->flushed) return fail(ctx, AMB_ERR_STATE, "stream already flushed; amb_reset first");
     if (n_complex > 0x60000000ull) return fail(ctx, AMB_ERR_INVALID, "at most 1.5 Gi samples per call");
+    if (ctx->def_kind) return fail(ctx, AMB_ERR_STATE, "amb_resolve pending (deferred mode allows one call per span)");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t sa = ctx->stream, sb = ctx->stream_b, sc = ctx->stream_c;
     const AmbParams& P = ctx->P;
@@ -576,15 +589,21 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         ea.P = P; ea.S = S; ea.cand_j = ctx->cand_j; ea.cand_info = ctx->cand_info; ea.cand_avg = ctx->cand_avg; ea.ctr = ctx->ctr;
         CK(amb_launch_exact(ea, ctx->sm_count, sb));
         wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info; wa.det_list = ctx->det_list;
-        if (!par) { CK(amb_launch_walk_seq(wa, sb)); ctx->stats.kernel_launches += 1; }
-        else { CK(amb_launch_walk_par(wa, ctx->walk_scratch, ctx->cand_cap, (long long)S.n_carry + S.n_main + S.n_tail, sb)); ctx->stats.kernel_launches += 3; }
         AmbSliceArgs sl{};
         sl.P = P; sl.S = S; sl.cand_j = ctx->cand_j; sl.cand_info = ctx->cand_info; sl.cand_avg = ctx->cand_avg;
         sl.det_list = ctx->det_list;
         sl.ctr = ctx->ctr; sl.frames = ctx->frames; sl.frame_cap = ctx->frame_cap;
         sl.chips_out = ctx->keep_chips ? ctx->chips : nullptr; sl.org = org;
-        CK(amb_launch_slice(sl, ctx->sm_count, sb));
-        ctx->stats.kernel_launches += 5;
+        if (ctx->defer) {       // time-sharded span: the loop state arrives later (amb_resolve)
+            ctx->def_kind = 1; ctx->def_set = set; ctx->def_par = par; ctx->def_wa = wa; ctx->def_sl = sl;
+            ctx->def_nsamp = (long long)S.n_carry + S.n_main + S.n_tail;
+            ctx->stats.kernel_launches += 4;
+        } else {
+            if (!par) { CK(amb_launch_walk_seq(wa, sb)); ctx->stats.kernel_launches += 1; }
+            else { CK(amb_launch_walk_par(wa, ctx->walk_scratch, ctx->cand_cap, (long long)S.n_carry + S.n_main + S.n_tail, sb)); ctx->stats.kernel_launches += 3; }
+            CK(amb_launch_slice(sl, ctx->sm_count, sb));
+            ctx->stats.kernel_launches += 5;
+        }
         ctx->ev_valid = ctx->timing;
     } else {
         // nothing can be decided yet (tiny call): keep it simple and serial
@@ -595,6 +614,7 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         if (ctx->aux_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_aux[set ^ 1], 0));
         CK(cudaEventRecord(ctx->e_scan[set], sa));
         CK(cudaStreamWaitEvent(sb, ctx->e_scan[set], 0));
+        if (ctx->defer) { ctx->def_kind = flush ? 2 : 3; ctx->def_set = set; }
         if (flush) {   // the resolver still has to close the stream
             if (!ctx->cand_j) {
                 CK(cudaMalloc(&ctx->cand_j, 64 * sizeof(int)));
@@ -605,8 +625,8 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
             }
             wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info; wa.det_list = ctx->det_list;
             CK(cudaMemsetAsync(&ctx->ctr->ncand, 0, sizeof(unsigned), sb));
-            CK(amb_launch_walk_seq(wa, sb));
-            ctx->stats.kernel_launches += 1;
+            if (ctx->defer) ctx->def_wa = wa;
+            else { CK(amb_launch_walk_seq(wa, sb)); ctx->stats.kernel_launches += 1; }
         }
         ctx->ev_valid = false;
     }
@@ -629,6 +649,63 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         CK(cudaStreamWaitEvent(sa, ctx->e_done[set], 0));
         CK(cudaStreamWaitEvent(sa, ctx->e_aux[set], 0));
     }
+    return AMB_OK;
+}
+
+/* ---- time-sharding: see the header ---------------------------------------------------------------------- */
+int amb_seek(amb_ctx* ctx, uint64_t first_sample, uint64_t first_decision, const amb_walk_state* entry)
+{
+    if (!ctx) return AMB_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const AmbParams& P = ctx->P;
+    if (first_sample) {
+        if (ctx->use_dcblock) return fail(ctx, AMB_ERR_UNSUPPORTED, "amb_seek into a stream is not available with the DC blocker");
+        if (first_decision < first_sample + (uint64_t)(P.H + P.L + P.spc_i))
+            return fail(ctx, AMB_ERR_INVALID, "first_decision must be at least first_sample + shard_back");
+    }
+    if (first_sample > (1ull << 62) || first_decision > (1ull << 62)) return fail(ctx, AMB_ERR_INVALID, "index out of range");
+    int rc = reset_stream(ctx);
+    if (rc != AMB_OK) return rc;
+    ctx->n_in = first_sample;
+    ctx->r_done = (long long)first_decision;
+    const long long pos = entry ? (long long)entry->pos : (long long)first_decision;
+    const long long p = entry ? (long long)entry->p : (long long)first_decision;
+    CK(amb_launch_set_state(ctx->st, pos, p, ctx->stream_b));          // after reset_stream's memset on stream B
+    return AMB_OK;
+}
+
+int amb_resolve(amb_ctx* ctx, const amb_walk_state* entry)
+{
+    if (!ctx) return AMB_ERR_INVALID;
+    if (!ctx->def_kind) return fail(ctx, AMB_ERR_STATE, "no deferred call to resolve");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t sb = ctx->stream_b;
+    if (entry) CK(amb_launch_set_state(ctx->st, (long long)entry->pos, (long long)entry->p, sb));
+    if (ctx->def_kind == 1) {
+        if (!ctx->def_par) { CK(amb_launch_walk_seq(ctx->def_wa, sb)); ctx->stats.kernel_launches += 1; }
+        else { CK(amb_launch_walk_par(ctx->def_wa, ctx->walk_scratch, ctx->cand_cap, ctx->def_nsamp, sb)); ctx->stats.kernel_launches += 3; }
+        CK(amb_launch_slice(ctx->def_sl, ctx->sm_count, sb));
+        ctx->stats.kernel_launches += 1;
+    } else if (ctx->def_kind == 2) {
+        CK(amb_launch_walk_seq(ctx->def_wa, sb));
+        ctx->stats.kernel_launches += 1;
+    }
+    CK(cudaEventRecord(ctx->e_done[ctx->def_set], sb));
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[3], sb));
+    if (!ctx->overlap) CK(cudaStreamWaitEvent(ctx->stream, ctx->e_done[ctx->def_set], 0));
+    ctx->def_kind = 0;
+    return AMB_OK;
+}
+
+int amb_get_walk_state(amb_ctx* ctx, amb_walk_state* out)
+{
+    if (!ctx || !out) return AMB_ERR_INVALID;
+    if (ctx->def_kind) return fail(ctx, AMB_ERR_STATE, "amb_resolve pending");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream_b));
+    AmbWalkState st;
+    CK(cudaMemcpy(&st, ctx->st, sizeof st, cudaMemcpyDeviceToHost));
+    out->pos = st.pos; out->p = st.p;
     return AMB_OK;
 }
 

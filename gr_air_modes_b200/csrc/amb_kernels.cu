@@ -792,6 +792,18 @@ cudaError_t amb_launch_walk_seq(const AmbWalkArgs& a, cudaStream_t s)
     return cudaGetLastError();
 }
 
+// Entry state of a time-sharded span (amb_seek / amb_resolve): only where the loop stands, counters stay.
+__global__ void amb_set_state_kernel(AmbWalkState* st, long long pos, long long p)
+{
+    st->pos = pos; st->p = p; st->done = 0;
+}
+
+cudaError_t amb_launch_set_state(AmbWalkState* st, long long pos, long long p, cudaStream_t s)
+{
+    amb_set_state_kernel<<<1, 1, 0, s>>>(st, pos, p);
+    return cudaGetLastError();
+}
+
 // ---- parallel resolver ----------------------------------------------------------------------------
 // Two candidates further apart than GAP = maxlate + skip0 + 4 samples cannot influence each other through the
 // scan position p: whatever happens at the earlier one, the loop index is back to plain i++ before it reaches

@@ -59,3 +59,82 @@ def gather_counts(value: int, world: int, device):
     out = [torch.zeros_like(t) for _ in range(world)]
     dist.all_gather(out, t)
     return [int(x.item()) for x in out]
+
+
+# ---- one long recording time-sharded over the ranks (secondary mode) -----------------------------
+# The dense stages of a span depend on its samples only; what the reference's scan loop carries across a cut is
+# two integers (include/airmodes_b200.h, amb_seek). So every rank runs its span's dense stages at once, and the
+# loop state then travels down the ranks: recv (16 B) -> walk + slice (sparse, tens of microseconds) -> send.
+class Span:
+    __slots__ = ("first_sample", "first_decision", "end", "flush")
+
+    def __init__(self, first_sample, first_decision, end, flush):
+        self.first_sample, self.first_decision, self.end, self.flush = first_sample, first_decision, end, flush
+
+    def __repr__(self):
+        return "Span(samples [%d, %d), decisions from %d%s)" % (self.first_sample, self.end, self.first_decision,
+                                                                ", last" if self.flush else "")
+
+
+def time_shard_plan(n_total: int, world: int, geometry, align: int = 512, boundaries=None):
+    """Cut a recording of n_total samples into at most `world` spans (fewer if it is too short to be worth it).
+
+    geometry: amb_query_geometry's struct (history, shard_back, shard_fwd). boundaries: optional explicit list of
+    the reported indices where spans 1.. start (testing); default = equal shares. first_sample is rounded down to
+    `align` samples so that device pointers into the recording stay TMA-aligned."""
+    back, fwd = int(geometry.shard_back), int(geometry.shard_fwd)
+    if boundaries is None:
+        spans = max(1, min(world, n_total // (8 * (back + fwd) + align)))
+        boundaries = [n_total * k // spans for k in range(1, spans)]
+    boundaries = [0] + sorted(int(b) for b in boundaries)
+    if len(boundaries) > world:
+        raise ValueError("more spans than ranks")
+    plan = []
+    for k, r0 in enumerate(boundaries):
+        last = k == len(boundaries) - 1
+        first = 0 if k == 0 else max(0, (r0 - back) // align * align)
+        if k and first and r0 < first + back:
+            raise ValueError("span %d starts too early for its halo" % k)
+        if k and first == 0:
+            raise ValueError("boundary %d lies inside the first span's warm-up" % r0)
+        end = n_total if last else boundaries[k + 1] + fwd
+        if end > n_total or (not last and boundaries[k + 1] <= r0):
+            raise ValueError("spans too short for the forward halo")
+        plan.append(Span(first, r0, end, last))
+    return plan
+
+
+def process_time_sharded(rx, span_iq, span, recv_entry, send_exit):
+    """Run one span on `rx` (a gr_air_modes_b200.rx_path). span_iq holds the samples [span.first_sample, span.end).
+    recv_entry() -> (pos, p, queued) from the previous span (not called for the first span); send_exit((pos, p,
+    queued)) hands this span's exit state to the next one (not called for the last). `queued` = messages queued by
+    all earlier spans: the reference's slicer prints its very first message with 6 digits (slicer_impl.cc:192),
+    and there is one slicer per stream, not per span. Returns the number of messages this span queued."""
+    rx.defer_resolve(True)
+    rx.seek(span.first_sample, span.first_decision)
+    rx.process(span_iq, flush=span.flush, collect=False)       # dense stages: concurrent on all ranks
+    pos, p, queued = (0, 0, 0) if span.first_decision == 0 else recv_entry()
+    rx.resolve((pos, p))
+    if not span.flush:
+        pos, p = rx.walk_state()
+    rx._slicer._first = queued == 0
+    mine = rx.drain()
+    if not span.flush:
+        send_exit((pos, p, queued + mine))
+    return mine
+
+
+def dist_state_exchange(rank: int, device):
+    """(recv_entry, send_exit) over torch.distributed point-to-point (nccl: device tensors; gloo: cpu)."""
+    import torch
+    import torch.distributed as dist
+
+    def recv_entry():
+        t = torch.zeros(3, dtype=torch.int64, device=device)
+        dist.recv(t, src=rank - 1)
+        return tuple(int(x) for x in t.tolist())
+
+    def send_exit(state):
+        dist.send(torch.tensor([int(x) for x in state], dtype=torch.int64, device=device), dst=rank + 1)
+
+    return recv_entry, send_exit

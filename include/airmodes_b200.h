@@ -109,6 +109,7 @@ typedef struct amb_geometry {
     int max_late, packet_skip;                               /* late shifts allowed; (int)(240*spc) */
     int pmf_len, floor_len;                                  /* rx_path.py:49,54 */
     int chip_offset_239;                                     /* int(239*spc), last extracted chip (:220) */
+    int shard_back, shard_fwd;                               /* time-sharding halos in samples, see amb_seek */
 } amb_geometry;
 AMB_API int amb_query_geometry(float rate, float threshold_db, int use_pmf, amb_geometry* out);
 
@@ -169,6 +170,28 @@ AMB_API int amb_join(amb_ctx* ctx);
  * (:205-209), bit 10 visited-and-accepted. Returns count. */
 AMB_API int amb_debug_candidates(amb_ctx* ctx, uint64_t* index, uint32_t* info, int max);
 AMB_API int amb_set_option(amb_ctx* ctx, const char* name, int value); /* "resolver": 0 auto, 1 sequential, 2 parallel */
+
+/* ---- one stream time-sharded over several contexts / GPUs (no reference equivalent) ----------
+ * The only state preamble_impl::general_work carries from one stretch of the stream to the next is where its
+ * loop stands: nitems_read at the start of the current call (`pos`, preamble_impl.cc:164) and the next index
+ * it will look at (`p`; an accepted packet jumps it 240*spc ahead, :237). Everything else is a function of
+ * the samples. So a long recording can be cut into spans, one per context:
+ *   span k is given the samples [first_sample_k, end_k) and decides the reported indices
+ *   [first_decision_k, first_decision_{k+1});  first_decision_k >= first_sample_k + shard_back (the filter
+ *   windows and the block history must be warm), end_k = first_decision_{k+1} + shard_fwd for every span but
+ *   the last (flush = 0), the last span ends with the recording (flush = 1). Reported index = sample index +
+ *   history()-1. Halos come from amb_query_geometry.
+ * amb_seek resets the stream and positions it; `entry` is the loop state at first_decision (NULL: a fresh
+ * general_work call starts there). With option "defer_resolve" = 1 amb_process stops after the dense stages
+ * (scan, candidate compaction, exact preamble tests - none of which depends on the loop state), so all spans
+ * run concurrently; amb_resolve(entry) then walks the candidates with the state handed over by the previous
+ * span and slices the accepted packets, and amb_get_walk_state returns the state to hand to the next span.
+ * In deferred mode exactly one amb_process call is allowed between amb_seek and amb_resolve, and its input
+ * buffer must stay valid until amb_resolve has completed. Frames carry stream-global sample indices. */
+typedef struct amb_walk_state { int64_t pos, p; } amb_walk_state;
+AMB_API int amb_seek(amb_ctx* ctx, uint64_t first_sample, uint64_t first_decision, const amb_walk_state* entry);
+AMB_API int amb_resolve(amb_ctx* ctx, const amb_walk_state* entry);      /* NULL: keep the context's own state */
+AMB_API int amb_get_walk_state(amb_ctx* ctx, amb_walk_state* out);       /* synchronises */
 AMB_API const char* amb_strerror(int code);
 AMB_API const char* amb_last_error(const amb_ctx* ctx);
 AMB_API const char* amb_version(void);

@@ -403,3 +403,93 @@ def test_split_form_preamble_streaming(port):
         # the block starts a new stream after a flush
         ch, tg = pre.process(bb, avg)
         assert [t[0] for t in tg] == [int(x) for x in want.index]
+
+
+# ---- one stream time-sharded over several contexts (SURVEY.md 8e secondary mode; amb_seek / amb_resolve) --------
+def run_time_sharded(iq, rate, thr, pmf, spans=None, boundaries=None, resolver=0):
+    """All spans on cuda:0, one rx_path each: dense stages of every span first, then the state chain."""
+    from gr_air_modes_b200 import shard
+    n = iq.size // 2
+    plan = shard.time_shard_plan(n, spans or (len(boundaries) + 1), am.query_geometry(rate, thr, pmf), boundaries=boundaries)
+    q = am.msg_queue()
+    rxs = [am.rx_path(rate, thr, q, use_pmf=pmf) for _ in plan]
+    for rx, sp in zip(rxs, plan):                       # what the ranks do concurrently
+        rx._ctx.call("amb_set_option", b"resolver", resolver)
+        rx.defer_resolve(True)
+        rx.seek(sp.first_sample, sp.first_decision)
+        rx.process(iq[2 * sp.first_sample: 2 * sp.end], flush=sp.flush, collect=False)
+    frames, state, queued = [], (0, 0), 0
+    for rx, sp in zip(rxs, plan):                       # the chain
+        rx.resolve(state)
+        if not sp.flush:
+            state = rx.walk_state()
+        rx._slicer._first = queued == 0
+        queued += rx.drain()
+        frames += rx.frames
+    for rx in rxs:
+        rx.close()
+    return q.strings(), frames, plan
+
+
+@pytest.mark.parametrize("rate,n,nb,pmf", [(4e6, 1_500_000, 120, True), (2e6, 900_000, 80, True),
+                                           (10e6, 2_500_000, 80, True), (20e6, 4_000_000, 60, False)])
+def test_time_sharded_equals_one_shot(port, rate, n, nb, pmf):
+    sc = synth.make_scene(rate, n, nb, int(rate / 1e6) + 70)
+    want = port.run_iq(sc.iq, rate, 7.0, pmf, co.MA_CANONICAL)
+    assert len(want.msgs) > 10
+    for spans in (2, 3, 8):
+        for resolver in (0, 1):
+            msgs, frames, plan = run_time_sharded(sc.iq, rate, 7.0, pmf, spans=spans, resolver=resolver)
+            assert len(plan) == spans
+            assert [f.sample_index for f in frames] == [int(x) for x in want.index]
+            assert msgs == want.msgs
+            for f, g in zip(frames, want.frames):
+                assert bytes(f.data) == bytes(g.data) and f.ref_level == g.ref_level and f.secs == g.secs and f.frac == g.frac
+
+
+def test_time_shard_cut_inside_packets_and_dense_traffic(port):
+    """Cuts placed on, just before and just after accepted preambles (the previous span's packet skip then
+    reaches into the next span: the handed-over `p` matters), and cuts through one long cluster of a dense scene."""
+    rate = 4e6
+    sc = synth.make_scene(rate, 1_200_000, 150, 404)
+    want = port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL)
+    idx = [int(x) for x in want.index if 300_000 < int(x) < 1_100_000]
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        picks = sorted(rng.choice(len(idx), 3, replace=False))
+        cuts = [idx[picks[0]] + int(rng.integers(-3, 4)), idx[picks[1]] + int(rng.integers(1, 480)), idx[picks[2]] + 481]
+        msgs, frames, _ = run_time_sharded(sc.iq, rate, 7.0, True, boundaries=cuts, resolver=trial & 1)
+        assert [f.sample_index for f in frames] == [int(x) for x in want.index], cuts
+        assert msgs == want.msgs
+    dense = synth.make_scene(rate, 2_000_000, 5000, 99, garble_frac=0.2, fruit=2000, snr_db=(4.0, 30.0))
+    want = port.run_iq(dense.iq, rate, 5.0, True, co.MA_CANONICAL)
+    for spans in (2, 5):
+        msgs, frames, _ = run_time_sharded(dense.iq, rate, 5.0, True, spans=spans)
+        assert [f.sample_index for f in frames] == [int(x) for x in want.index]
+        assert msgs == want.msgs
+
+
+def test_time_shard_api_errors():
+    q = am.msg_queue()
+    rx = am.rx_path(4e6, 7.0, q, use_pmf=True)
+    g = am.query_geometry(4e6, 7.0, True)
+    assert g.shard_back == g.history - 1 + g.floor_len + g.pmf_len and g.shard_fwd > g.packet_skip - g.history
+    with pytest.raises(RuntimeError):
+        rx.seek(4096, 4096 + g.shard_back - 1)            # halo too short
+    with pytest.raises(RuntimeError):
+        rx.resolve((0, 0))                                  # nothing deferred
+    rx.defer_resolve(True)
+    rx.seek(0, 0)
+    iq = synth.make_scene(4e6, 100_000, 5, 3).iq
+    rx.process(iq, flush=False, collect=False)
+    with pytest.raises(RuntimeError):
+        rx.process(iq, flush=False, collect=False)          # one call per span in deferred mode
+    with pytest.raises(RuntimeError):
+        rx.walk_state()
+    rx.resolve((0, 0))
+    pos, p = rx.walk_state()
+    assert p >= 100_000 + g.history - 1 - (g.shard_fwd + g.history - 1)
+    rx.defer_resolve(False)
+    rx.reset()
+    assert rx.process(iq, flush=True) >= 5                  # normal operation afterwards
+    rx.close()

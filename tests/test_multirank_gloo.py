@@ -53,3 +53,73 @@ def test_channel_ownership():
     assert shard.channels_of(1, 4, 8) == [1, 5]
     assert sorted(sum((shard.channels_of(r, 3, 8) for r in range(3)), [])) == list(range(8))
     assert shard.max_over_ranks(3.5, 1, None) == 3.5 and shard.gather_counts(7, 1, None) == [7]
+
+
+# ---- time-sharded single stream: plan + hand-over chain (the CUDA side is tested under -m gpu) ----------------
+class _Geom:
+    def __init__(self, history, back, fwd):
+        self.history, self.shard_back, self.shard_fwd = history, back, fwd
+
+
+class _FakeRx:
+    """Stands in for rx_path: records the protocol and turns an entry state into an exit state."""
+    class _S:
+        _first = True
+
+    def __init__(self, n_msgs):
+        self._slicer, self.log, self.n_msgs, self.entry = self._S(), [], n_msgs, None
+
+    def defer_resolve(self, on=True): self.log.append(("defer", on))
+    def seek(self, a, b): self.log.append(("seek", a, b)); self.span = (a, b)
+    def process(self, iq, flush=False, collect=True): self.log.append(("process", len(iq), flush)); self.n = len(iq)
+    def resolve(self, entry): self.log.append(("resolve", entry)); self.entry = entry
+    def walk_state(self): return self.entry[0] + 1000, self.span[0] + self.n
+    def drain(self): self.log.append(("drain", self._slicer._first)); return self.n_msgs
+
+
+def _ts_worker(rank, world, port_no, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    plan = shard.time_shard_plan(1_000_000, world, _Geom(4, 101, 483))
+    sp = plan[rank]
+    rx = _FakeRx(n_msgs=0 if rank == 0 else 3)
+    recv, send = shard.dist_state_exchange(rank, torch.device("cpu"))
+    got = shard.process_time_sharded(rx, np.zeros(sp.end - sp.first_sample, np.float32), sp, recv, send)
+    ret[rank] = (got, rx.entry, rx.log)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_time_shard_chain_world2():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ts_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    plan = shard.time_shard_plan(1_000_000, 2, _Geom(4, 101, 483))
+    assert ret[0][1] == (0, 0)
+    assert ret[1][1] == (1000, plan[0].end)                          # rank 0's exit state is rank 1's entry
+    assert ret[0][2][:3] == [("defer", True), ("seek", 0, 0), ("process", plan[0].end, False)]
+    assert ret[1][2][2] == ("process", 1_000_000 - plan[1].first_sample, True)
+    assert ret[0][2][-1] == ("drain", True) and ret[1][2][-1] == ("drain", True)   # rank 0 queued nothing
+    assert (ret[0][0], ret[1][0]) == (0, 3)
+
+
+def test_time_shard_plan_invariants():
+    g = _Geom(4, 101, 483)
+    for n in (10_000, 100_000, 1 << 20, (1 << 28) + 12345):
+        for world in (1, 2, 3, 8):
+            plan = shard.time_shard_plan(n, world, g)
+            assert 1 <= len(plan) <= world and plan[0].first_sample == 0 and plan[0].first_decision == 0
+            assert plan[-1].flush and plan[-1].end == n and not any(s.flush for s in plan[:-1])
+            for a, b in zip(plan, plan[1:]):
+                assert a.end == b.first_decision + g.shard_fwd <= n          # a decides exactly up to b's start
+                assert b.first_sample % 512 == 0 and b.first_decision >= b.first_sample + g.shard_back
+                assert b.first_decision - b.first_sample < g.shard_back + 512
+    assert len(shard.time_shard_plan(10_000, 8, g)) == 1 and len(shard.time_shard_plan(20_000, 8, g)) == 3   # too short for 8
+    import pytest
+    with pytest.raises(ValueError):
+        shard.time_shard_plan(100_000, 2, g, boundaries=[50])                # inside the first span's warm-up
+    with pytest.raises(ValueError):
+        shard.time_shard_plan(100_000, 2, g, boundaries=[99_900])            # no room for the forward halo
+    with pytest.raises(ValueError):
+        shard.time_shard_plan(100_000, 2, g, boundaries=[30_000, 60_000])    # more spans than ranks
