@@ -78,6 +78,7 @@ SYMBOLS = [
     ("amb_join", C.c_int, [_vp]),
     ("amb_debug_candidates", C.c_int, [_vp, _u64p, C.POINTER(C.c_uint32), C.c_int]),
     ("amb_set_option", C.c_int, [_vp, C.c_char_p, C.c_int]),
+    ("amb_dump_stage", C.c_int, [_vp, C.c_int, _f32p, C.c_size_t, _f32p]),
     ("amb_seek", C.c_int, [_vp, C.c_uint64, C.c_uint64, C.POINTER(WalkState)]),
     ("amb_resolve", C.c_int, [_vp, C.POINTER(WalkState)]),
     ("amb_get_walk_state", C.c_int, [_vp, C.POINTER(WalkState)]),

@@ -51,7 +51,7 @@ def build_native(force: bool = False, verbose: bool = False, defines=(), out_pat
         if verbose:
             print(out.decode())
     target = LIB if out_path is None else out_path
-    cmd = [nvcc, "-ccbin", host, "-shared", "-o", target, *objs, "-cudart", "shared"]
+    cmd = [nvcc, "-ccbin", host, "-shared", "-Wno-deprecated-gpu-targets", "-o", target, *objs, "-cudart", "shared"]
     subprocess.run(cmd, check=True, env=env)
     return target
 

@@ -880,6 +880,27 @@ int amb_device_crc(amb_ctx* ctx, const uint8_t* data, int n, int length, uint32_
     return AMB_OK;
 }
 
+int amb_dump_stage(amb_ctx* ctx, int stage, const float* iq, size_t n_complex, float* out)
+{
+    if (!ctx || stage < AMB_STAGE_M2 || stage > AMB_STAGE_AVG || (n_complex && (!iq || !out))) return AMB_ERR_INVALID;
+    if (n_complex > (1u << 26)) return fail(ctx, AMB_ERR_INVALID, "amb_dump_stage is a parity tool: at most 2^26 samples");
+    if (ctx->use_dcblock) return fail(ctx, AMB_ERR_UNSUPPORTED, "amb_dump_stage does not model the DC blocker");
+    if (n_complex == 0) return AMB_OK;
+    CK(cudaSetDevice(ctx->device));
+    float2* d = nullptr; float* t = nullptr; float* o = nullptr;
+    CK(cudaMalloc(&d, n_complex * sizeof(float2)));
+    cudaError_t e = cudaMalloc(&t, n_complex * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&o, n_complex * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d, iq, n_complex * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = amb_launch_dump(d, (long long)n_complex, ctx->P, stage, t, o, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, o, n_complex * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d); cudaFree(t); cudaFree(o);
+    ctx->stats.kernel_launches += stage == AMB_STAGE_AVG ? 2 : 1;
+    if (e != cudaSuccess) return fail(ctx, AMB_ERR_CUDA, "amb_dump_stage", e);
+    return AMB_OK;
+}
+
 int amb_slicer_process(amb_ctx* ctx, const float* chips, int ndet, const uint64_t* secs, const double* frac, amb_frame* out)
 {
     if (!ctx || ndet < 0 || (ndet && (!chips || !out))) return AMB_ERR_INVALID;

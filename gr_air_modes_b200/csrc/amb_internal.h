@@ -111,6 +111,7 @@ cudaError_t amb_launch_scan(const AmbScanArgs& a, int sm_count, cudaStream_t s);
 cudaError_t amb_launch_compact(const AmbScanArgs& a, int* cand_j, unsigned int cand_cap, AmbCounters* ctr,
                                void* walk_scratch, long long n_samples, cudaStream_t s);
 cudaError_t amb_launch_exact(const AmbExactArgs& a, int sm_count, cudaStream_t s);
+cudaError_t amb_launch_dump(const float2* iq, long long n, const AmbParams& P, int stage, float* tmp, float* out, cudaStream_t s);
 cudaError_t amb_launch_set_state(AmbWalkState* st, long long pos, long long p, cudaStream_t s);
 cudaError_t amb_launch_walk_seq(const AmbWalkArgs& a, cudaStream_t s);
 cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, unsigned int cand_cap, long long n_samples, cudaStream_t s);

@@ -792,6 +792,35 @@ cudaError_t amb_launch_walk_seq(const AmbWalkArgs& a, cudaStream_t s)
     return cudaGetLastError();
 }
 
+// ---- parity dumps of the front end (amb_dump_stage): canonical m2 / bb / avg at EVERY sample of a short buffer ---
+// Brute force on purpose: this is the definition the exact stage evaluates at candidates only, written the plain way.
+__global__ void amb_dump_bb_kernel(const float2* iq, long long n, AmbParams P, int stage, float* out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (stage == 0 || !P.use_pmf) { out[i] = canon_m2_of(iq[i]); return; }
+    double acc = 0.0;                                           // zeros before the stream start add nothing
+    for (long long k = i - P.spc_i + 1; k <= i; k++) if (k >= 0) acc += (double)canon_m2_of(iq[k]);
+    out[i] = __fmul_rn((float)acc, P.scale_p);
+}
+__global__ void amb_dump_avg_kernel(const float* bb, long long n, AmbParams P, float* out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc = 0.0;
+    for (long long k = i - P.L + 1; k <= i; k++) if (k >= 0) acc += (double)bb[k];
+    out[i] = __fmul_rn((float)acc, P.scale_a);
+}
+
+cudaError_t amb_launch_dump(const float2* iq, long long n, const AmbParams& P, int stage, float* tmp, float* out, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    amb_dump_bb_kernel<<<blocks, 256, 0, s>>>(iq, n, P, stage, stage == 2 ? tmp : out);
+    if (stage == 2) amb_dump_avg_kernel<<<blocks, 256, 0, s>>>(tmp, n, P, out);
+    return cudaGetLastError();
+}
+
 // Entry state of a time-sharded span (amb_seek / amb_resolve): only where the loop stands, counters stay.
 __global__ void amb_set_state_kernel(AmbWalkState* st, long long pos, long long p)
 {

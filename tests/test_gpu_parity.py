@@ -493,3 +493,22 @@ def test_time_shard_api_errors():
     rx.reset()
     assert rx.process(iq, flush=True) >= 5                  # normal operation afterwards
     rx.close()
+
+
+@pytest.mark.parametrize("rate,pmf", [(2e6, True), (4e6, True), (4e6, False), (10e6, True), (20e6, True), (5e6, True)])
+def test_front_end_streams_bit_exact_at_every_sample(port, rate, pmf):
+    """SURVEY 8c pin (iii): m2, the preamble block's in0 (bb) and in1 (avg) at EVERY sample, not only at candidates,
+    equal the oracle's canonical front end bit for bit - including the zero history at the stream start, strong
+    bursts inside the floor window and denormal-range noise."""
+    n = 200_000
+    sc = synth.make_scene(rate, n, 25, int(rate / 1e6) + 300)
+    iq = sc.iq.copy()
+    iq[2 * 150_000: 2 * 150_400] *= np.float32(1e-18)         # m2 in the denormal range
+    iq[2 * 160_000: 2 * 160_100] = 0.0
+    q = am.msg_queue()
+    rx = am.rx_path(rate, 7.0, q, use_pmf=pmf)
+    bb, avg = port.frontend(iq, rate, pmf, co.MA_CANONICAL)
+    assert np.array_equal(rx.dump_stage("m2", iq).view(np.uint32), port.mag2(iq).view(np.uint32))
+    assert np.array_equal(rx.dump_stage("bb", iq).view(np.uint32), bb.view(np.uint32))
+    assert np.array_equal(rx.dump_stage("avg", iq).view(np.uint32), avg.view(np.uint32))
+    rx.close()

@@ -53,4 +53,26 @@ for case in range(ncase):
         a, b = set(int(x) for x in want.index), set(f.sample_index for f in frames)
         print("   det missing", sorted(a - b)[:5], "extra", sorted(b - a)[:5])
     rx.close()
+    # the same stream time-sharded over 2..5 contexts with random cuts (amb_seek / amb_resolve)
+    if n > 60_000 and rng.random() < 0.6:
+        from gr_air_modes_b200 import shard
+        g = am.query_geometry(rate, thr, pmf)
+        k = int(rng.integers(1, 5))
+        lo, hi = g.shard_back + 600, n - g.shard_fwd - 8
+        cuts = sorted(set(int(x) for x in rng.integers(lo, hi, k)))
+        cuts = [c for i, c in enumerate(cuts) if i == 0 or c - cuts[i - 1] > 16]
+        plan = shard.time_shard_plan(n, len(cuts) + 1, g, boundaries=cuts)
+        q2 = am.msg_queue(); rxs = [am.rx_path(rate, thr, q2, use_pmf=pmf) for _ in plan]
+        for r, sp in zip(rxs, plan):
+            r.defer_resolve(True); r.seek(sp.first_sample, sp.first_decision)
+            r.process(iq[2 * sp.first_sample: 2 * sp.end], flush=sp.flush, collect=False)
+        fr2, state, queued = [], (0, 0), 0
+        for r, sp in zip(rxs, plan):
+            r.resolve(state)
+            if not sp.flush: state = r.walk_state()
+            r._slicer._first = queued == 0
+            queued += r.drain(); fr2 += r.frames; r.close()
+        if q2.strings() != want.msgs or [f.sample_index for f in fr2] != [int(x) for x in want.index]:
+            bad += 1
+            print("MISMATCH (time-shard) case", case, dict(rate=rate, pmf=pmf, thr=thr, n=n, kind=str(kind)), "cuts", cuts)
 print("stress: %d cases, %d mismatches, %.1fs" % (ncase, bad, time.time() - t0))
