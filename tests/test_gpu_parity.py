@@ -512,3 +512,67 @@ def test_front_end_streams_bit_exact_at_every_sample(port, rate, pmf):
     assert np.array_equal(rx.dump_stage("bb", iq).view(np.uint32), bb.view(np.uint32))
     assert np.array_equal(rx.dump_stage("avg", iq).view(np.uint32), avg.view(np.uint32))
     rx.close()
+
+
+def test_cli_udp_source_zmq_feed_and_dcblock(port, tmp_path):
+    """Row f1: tools/modes_rx_b200.py with the reference's other offline source (UDP datagrams of gr_complex,
+    radio.py:221-228), the -t ZMQ dl_data feed (radio.py:79-87) and -d; the lines are the oracle's."""
+    import os, socket, subprocess, sys, threading, time
+    zmq = pytest.importorskip("zmq")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "tools", "modes_rx_b200.py")
+    sc = synth.make_scene(4e6, 300_000, 25, 808)
+    want = port.run_iq(sc.iq, 4e6, 7.0, True, co.MA_CANONICAL).msgs
+    assert len(want) > 5
+
+    def free_port(kind):
+        s = socket.socket(socket.AF_INET, kind); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+    uport, zport = free_port(socket.SOCK_DGRAM), free_port(socket.SOCK_STREAM)
+    proc = subprocess.Popen([sys.executable, cli, "-s", "127.0.0.1:%d" % uport, "-r", "4e6", "-t", str(zport),
+                             "--udp-idle", "1.5", "--chunk", "70001"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    ctx = zmq.Context()
+    sub = ctx.socket(zmq.SUB); sub.connect("tcp://127.0.0.1:%d" % zport); sub.setsockopt(zmq.SUBSCRIBE, b"dl_data")
+    got = []
+
+    def listen():
+        sub.RCVTIMEO = 15000
+        try:
+            while len(got) < len(want):
+                key, val = sub.recv_multipart()
+                assert key == b"dl_data"
+                got.append(val.decode())
+        except zmq.Again:
+            pass
+
+    th = threading.Thread(target=listen); th.start()
+    # wait until the receiver has bound its sockets (it prints "Rate is" after constructing rx_path)
+    deadline = time.time() + 120
+    while time.time() < deadline:
+        line = proc.stderr.readline()
+        if line.startswith("Rate is") or not line:
+            break
+    time.sleep(0.5)
+    tx = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+    raw = sc.iq.tobytes()
+    for a in range(0, len(raw), 1472 // 8 * 8):                       # 184 complex items per datagram
+        tx.sendto(raw[a: a + 1472 // 8 * 8], ("127.0.0.1", uport))
+        if (a // 1472) % 64 == 0:
+            time.sleep(0.002)                                         # do not overrun the receive buffer
+    out, err = proc.communicate(timeout=120)
+    th.join()
+    assert proc.returncode == 0, err
+    lines = [ln for ln in out.split("\n") if ln]
+    if len(lines) != len(want):                                       # UDP may drop under load: then only consistency
+        pytest.skip("datagrams were dropped on loopback (%d of %d lines)" % (len(lines), len(want)))
+    assert lines == want
+    assert got == want
+    # -d on a cfile
+    iq = sc.iq.copy(); iq[0::2] += np.float32(0.05)
+    path = tmp_path / "dc.cfile"; iq.tofile(path)
+    wantd = port.run_iq(iq, 4e6, 7.0, True, co.MA_CANONICAL, use_dcblock=True).msgs
+    out = subprocess.run([sys.executable, cli, "-s", str(path), "-r", "4e6", "-d"], capture_output=True, text=True, check=True).stdout
+    assert [ln for ln in out.split("\n") if ln] == wantd
+    # -n prints nothing
+    out = subprocess.run([sys.executable, cli, "-s", str(path), "-n"], capture_output=True, text=True, check=True).stdout
+    assert out.strip() == ""
