@@ -239,15 +239,35 @@ def time_shard_arm(args, rank, local_rank, world, device):
     rx._ctx.use_stream(torch.cuda.current_stream().cuda_stream)
     recv, send = shard.dist_state_exchange(rank, device)
 
+    gather = shard.dist_all_gather6(world, device) if world > 1 else (lambda v: [list(v)])
+    last = len(plan) - 1
+    fallbacks = [0]
+
     def step():
-        if not active:
+        if args.chain:
+            if not active:
+                return
+            rx.seek(sp.first_sample, sp.first_decision)
+            rx.process(iq, flush=sp.flush, collect=False)
+            entry = recv()[:2] if rank else (0, 0)
+            rx.resolve(entry)
+            if not sp.flush:
+                send(rx.walk_state() + (0,))
             return
-        rx.seek(sp.first_sample, sp.first_decision)
-        rx.process(iq, flush=sp.flush, collect=False)
-        entry = recv()[:2] if rank else (0, 0)
-        rx.resolve(entry)
-        if not sp.flush:
-            send(rx.walk_state() + (0,))
+        mine = [0] * 6                                   # speculative resolution: one all-gather, no chain
+        if active:
+            rx.seek(sp.first_sample, sp.first_decision)
+            rx.process(iq, flush=sp.flush, collect=False)
+            if rank < last:
+                rx.resolve(None)
+                s = rx.walk_summary()
+                mine = [s.pos, s.p, s.first_real, s.first_packet, s.exact_span, s.frames_passed]
+        entries, _, bad = shard.compose_entries(plan, gather(mine))
+        fallbacks[0] += bad < last
+        if active and rank >= bad:
+            rx.resolve(entries[rank] if rank == bad else recv()[:2])
+            if not sp.flush:
+                send(rx.walk_state() + (0,))
 
     rx.defer_resolve(True)
     for _ in range(args.warmup):
@@ -271,7 +291,10 @@ def time_shard_arm(args, rank, local_rank, world, device):
     clocks = sampler.stop() if rank == 0 else None
     ms_max = shard.max_over_ranks(ms, world, device)
     # ---- check: the spans' messages, concatenated in rank order, are the one-shot run's
-    mine = shard.process_time_sharded(rx, iq, sp, recv, send) if active else 0
+    if args.chain:
+        mine = shard.process_time_sharded(rx, iq, sp, recv, send) if active else 0
+    else:
+        mine = shard.process_time_sharded_speculative(rx, iq if active else None, plan, rank, gather, recv, send)
     msgs = q.strings()
     q.flush()
     allm = [None] * world
@@ -289,7 +312,8 @@ def time_shard_arm(args, rank, local_rank, world, device):
         line = {"metric": "Msamples/s IQ demod+slice+CRC", "value": n * args.steps / (ms_max * 1e-3) / 1e6,
                 "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "mode": "time-shard",
+                "dtype": "f32", "data": "synthetic", "mode": "time-shard/" + ("chain" if args.chain else "speculative"),
+                "fallback_steps": fallbacks[0],
                 "config": {"workload": "ONE synthetic 4 Msps recording of 2^%d samples cut into %d time spans with halos"
                                        % (args.log2n, len(plan)), "parallelism": "time-shard x%d" % len(plan),
                            "fanout_s": round(fanout_s, 3), "timing": "host clock between barrier+synchronize (the state "
@@ -313,6 +337,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--time-shard", action="store_true",
                     help="secondary mode: ONE 2^log2n-sample recording cut into --gpus spans (strong scaling)")
+    ap.add_argument("--chain", action="store_true", help="--time-shard: plain hand-over chain instead of speculative resolution")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

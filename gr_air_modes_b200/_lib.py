@@ -47,6 +47,12 @@ class WalkState(C.Structure):
     _fields_ = [("pos", C.c_int64), ("p", C.c_int64)]
 
 
+class WalkSummary(C.Structure):
+    """struct amb_walk_summary (speculative resolution of a time-sharded span)."""
+    _fields_ = [("pos", C.c_int64), ("p", C.c_int64), ("first_real", C.c_int64), ("first_packet", C.c_int64),
+                ("exact_span", C.c_int64), ("frames_passed", C.c_int64)]
+
+
 assert C.sizeof(Frame) == 80
 
 # every symbol include/airmodes_b200.h declares: (name, restype, argtypes)
@@ -82,6 +88,7 @@ SYMBOLS = [
     ("amb_seek", C.c_int, [_vp, C.c_uint64, C.c_uint64, C.POINTER(WalkState)]),
     ("amb_resolve", C.c_int, [_vp, C.POINTER(WalkState)]),
     ("amb_get_walk_state", C.c_int, [_vp, C.POINTER(WalkState)]),
+    ("amb_get_walk_summary", C.c_int, [_vp, C.POINTER(WalkSummary)]),
     ("amb_strerror", C.c_char_p, [C.c_int]),
     ("amb_last_error", C.c_char_p, [_vp]),
     ("amb_version", C.c_char_p, []),

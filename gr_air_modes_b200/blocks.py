@@ -17,7 +17,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Frame, Geometry, Stats, WalkState, check
+from ._lib import Frame, Geometry, Stats, WalkState, WalkSummary, check
 
 
 # ---------------------------------------------------------------------------------------------
@@ -320,6 +320,11 @@ class rx_path:
         st = WalkState()
         self._ctx.call("amb_get_walk_state", C.byref(st))
         return int(st.pos), int(st.p)
+
+    def walk_summary(self) -> WalkSummary:
+        s = WalkSummary()
+        self._ctx.call("amb_get_walk_summary", C.byref(s))
+        return s
 
     def dump_stage(self, stage: str, iq) -> np.ndarray:
         """Parity dump: "m2" | "bb" | "avg" of a short host buffer taken as a whole stream (amb_dump_stage)."""

@@ -70,6 +70,7 @@ struct amb_ctx {
     int defer = 0;                       // option "defer_resolve"
     int def_kind = 0;                    // 0 nothing pending, 1 full (walk + slice), 2 sequential walk only, 3 state only
     int def_set = 0; bool def_par = false; long long def_nsamp = 0;
+    bool def_resolved = false;           // resolved once already: amb_resolve again = re-resolution with another entry
     AmbWalkArgs def_wa{}; AmbSliceArgs def_sl{};
     std::string err;
 };
@@ -234,7 +235,7 @@ static int reset_stream(amb_ctx* ctx)
     ctx->carry_in = 2; ctx->n_in = 0; ctx->r_done = 0; ctx->flushed = false; ctx->have_last = false;
     ctx->frames_ub = 0;
     ctx->pending.clear();
-    ctx->def_kind = 0;
+    ctx->def_kind = 0; ctx->def_resolved = false;
     return AMB_OK;
 }
 
@@ -401,7 +402,8 @@ int amb_set_option(amb_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "keep_chips")) { ctx->keep_chips = value != 0; return AMB_OK; }
     if (!strcmp(name, "overlap")) { ctx->overlap = value != 0; return AMB_OK; }
     if (!strcmp(name, "defer_resolve")) {
-        if (ctx->def_kind) return fail(ctx, AMB_ERR_STATE, "amb_resolve pending");
+        if (ctx->def_kind && !ctx->def_resolved) return fail(ctx, AMB_ERR_STATE, "amb_resolve pending");
+        ctx->def_kind = 0; ctx->def_resolved = false;
         ctx->defer = value != 0; return AMB_OK;
     }
     return AMB_ERR_INVALID;
@@ -471,7 +473,9 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
     if (!ctx || (!iq && n_complex)) return AMB_ERR_INVALID;
     if (ctx->flushed) return fail(ctx, AMB_ERR_STATE, "stream already flushed; amb_reset first");
     if (n_complex > 0x60000000ull) return fail(ctx, AMB_ERR_INVALID, "at most 1.5 Gi samples per call");
-    if (ctx->def_kind) return fail(ctx, AMB_ERR_STATE, "amb_resolve pending (deferred mode allows one call per span)");
+    if (ctx->def_kind && !ctx->def_resolved)
+        return fail(ctx, AMB_ERR_STATE, "amb_resolve pending (deferred mode allows one call per span)");
+    ctx->def_kind = 0; ctx->def_resolved = false;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t sa = ctx->stream, sb = ctx->stream_b, sc = ctx->stream_c;
     const AmbParams& P = ctx->P;
@@ -595,7 +599,7 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         sl.ctr = ctx->ctr; sl.frames = ctx->frames; sl.frame_cap = ctx->frame_cap;
         sl.chips_out = ctx->keep_chips ? ctx->chips : nullptr; sl.org = org;
         if (ctx->defer) {       // time-sharded span: the loop state arrives later (amb_resolve)
-            ctx->def_kind = 1; ctx->def_set = set; ctx->def_par = par; ctx->def_wa = wa; ctx->def_sl = sl;
+            ctx->def_kind = 1; ctx->def_resolved = false; ctx->def_set = set; ctx->def_par = par; ctx->def_wa = wa; ctx->def_sl = sl;
             ctx->def_nsamp = (long long)S.n_carry + S.n_main + S.n_tail;
             ctx->stats.kernel_launches += 4;
         } else {
@@ -614,7 +618,7 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         if (ctx->aux_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_aux[set ^ 1], 0));
         CK(cudaEventRecord(ctx->e_scan[set], sa));
         CK(cudaStreamWaitEvent(sb, ctx->e_scan[set], 0));
-        if (ctx->defer) { ctx->def_kind = flush ? 2 : 3; ctx->def_set = set; }
+        if (ctx->defer) { ctx->def_kind = flush ? 2 : 3; ctx->def_resolved = false; ctx->def_set = set; }
         if (flush) {   // the resolver still has to close the stream
             if (!ctx->cand_j) {
                 CK(cudaMalloc(&ctx->cand_j, 64 * sizeof(int)));
@@ -678,8 +682,13 @@ int amb_resolve(amb_ctx* ctx, const amb_walk_state* entry)
 {
     if (!ctx) return AMB_ERR_INVALID;
     if (!ctx->def_kind) return fail(ctx, AMB_ERR_STATE, "no deferred call to resolve");
+    if (ctx->def_resolved && !entry) return fail(ctx, AMB_ERR_INVALID, "re-resolution needs an entry state");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t sb = ctx->stream_b;
+    if (ctx->def_resolved && ctx->def_kind == 1) {     // forget the earlier (speculative) resolution of this span
+        CK(amb_launch_walk_reset(ctx->def_wa, ctx->def_par ? ctx->walk_scratch : nullptr, ctx->def_nsamp, sb));
+        ctx->stats.kernel_launches += 1;
+    }
     if (entry) CK(amb_launch_set_state(ctx->st, (long long)entry->pos, (long long)entry->p, sb));
     if (ctx->def_kind == 1) {
         if (!ctx->def_par) { CK(amb_launch_walk_seq(ctx->def_wa, sb)); ctx->stats.kernel_launches += 1; }
@@ -693,19 +702,38 @@ int amb_resolve(amb_ctx* ctx, const amb_walk_state* entry)
     CK(cudaEventRecord(ctx->e_done[ctx->def_set], sb));
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[3], sb));
     if (!ctx->overlap) CK(cudaStreamWaitEvent(ctx->stream, ctx->e_done[ctx->def_set], 0));
-    ctx->def_kind = 0;
+    ctx->def_resolved = true;
     return AMB_OK;
 }
 
 int amb_get_walk_state(amb_ctx* ctx, amb_walk_state* out)
 {
     if (!ctx || !out) return AMB_ERR_INVALID;
-    if (ctx->def_kind) return fail(ctx, AMB_ERR_STATE, "amb_resolve pending");
+    if (ctx->def_kind && !ctx->def_resolved) return fail(ctx, AMB_ERR_STATE, "amb_resolve pending");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream_b));
     AmbWalkState st;
     CK(cudaMemcpy(&st, ctx->st, sizeof st, cudaMemcpyDeviceToHost));
     out->pos = st.pos; out->p = st.p;
+    return AMB_OK;
+}
+
+int amb_get_walk_summary(amb_ctx* ctx, amb_walk_summary* out)
+{
+    if (!ctx || !out) return AMB_ERR_INVALID;
+    if (!ctx->def_kind || !ctx->def_resolved) return fail(ctx, AMB_ERR_STATE, "no resolved deferred span");
+    CK(cudaSetDevice(ctx->device));
+    const bool have = ctx->def_kind == 1;
+    if (have) { CK(amb_launch_walk_summary(ctx->def_wa, ctx->stream_b)); ctx->stats.kernel_launches += 1; }
+    CK(cudaStreamSynchronize(ctx->stream_b));
+    AmbWalkState st; AmbCounters h;
+    CK(cudaMemcpy(&st, ctx->st, sizeof st, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost));
+    out->pos = st.pos; out->p = st.p;
+    out->first_real = (have && st.first_real != ~0ull) ? (int64_t)st.first_real : -1;
+    out->first_packet = (have && st.first_packet != ~0ull) ? (int64_t)st.first_packet : -1;
+    out->exact_span = ctx->P.i_exact;
+    out->frames_passed = have ? (int64_t)h.npassed_call : 0;
     return AMB_OK;
 }
 
@@ -752,6 +780,7 @@ static int collect(amb_ctx* ctx)
         CK(cudaMemset(&ctx->ctr->nframes, 0, sizeof(unsigned)));
     }
     ctx->frames_ub = 0;
+    if (ctx->def_kind && ctx->def_resolved) { ctx->def_kind = 0; ctx->def_resolved = false; }   // frames read: span is final
     return AMB_OK;
 }
 

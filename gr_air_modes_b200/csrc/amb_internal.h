@@ -51,6 +51,8 @@ struct AmbWalkState {
     int done;        // stream finished (flush processed)
     int fallback;    // parallel resolver handed over to the sequential one
     unsigned long long ncand_real, ndet;
+    unsigned long long first_real, first_packet;   // amb_get_walk_summary: smallest start of a candidate passing :174-179 /
+                                                   // smallest index of an accepted preamble in the last call (~0 = none)
 };
 
 struct AmbCounters {
@@ -112,6 +114,8 @@ cudaError_t amb_launch_compact(const AmbScanArgs& a, int* cand_j, unsigned int c
                                void* walk_scratch, long long n_samples, cudaStream_t s);
 cudaError_t amb_launch_exact(const AmbExactArgs& a, int sm_count, cudaStream_t s);
 cudaError_t amb_launch_dump(const float2* iq, long long n, const AmbParams& P, int stage, float* tmp, float* out, cudaStream_t s);
+cudaError_t amb_launch_walk_reset(const AmbWalkArgs& a, void* scratch, long long n_samples, cudaStream_t s);
+cudaError_t amb_launch_walk_summary(const AmbWalkArgs& a, cudaStream_t s);
 cudaError_t amb_launch_set_state(AmbWalkState* st, long long pos, long long p, cudaStream_t s);
 cudaError_t amb_launch_walk_seq(const AmbWalkArgs& a, cudaStream_t s);
 cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, unsigned int cand_cap, long long n_samples, cudaStream_t s);

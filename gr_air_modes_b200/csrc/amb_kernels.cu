@@ -995,6 +995,48 @@ cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, unsigned in
     return cudaGetLastError();
 }
 
+// ---- time-sharded spans resolved speculatively (amb_resolve twice, amb_get_walk_summary) ------------------------
+// Forget a previous resolution of the same call: verdict bits, work list, frames, resolver scratch.
+__global__ void amb_walk_reset_kernel(const AmbWalkArgs a, unsigned long long* scratch64, int n64)
+{
+    const int n = (int)a.ctr->ncand;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) a.cand_info[c] &= ~(1u << 10);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n64; k += gridDim.x * blockDim.x) scratch64[k] = 0ull;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.ctr->ndet_call = 0; a.ctr->npassed_call = 0; a.ctr->nreal_call = 0; a.ctr->ndet_list = 0; a.ctr->nframes = 0;
+        a.st->done = 0; a.st->fallback = 0;
+    }
+}
+
+cudaError_t amb_launch_walk_reset(const AmbWalkArgs& a, void* scratch, long long n_samples, cudaStream_t s)
+{
+    const int n64 = scratch ? (int)(32 + (n_samples >> AMB_BUCKET_SHIFT) + 8) : 0;   // as the compaction kernel clears it
+    amb_walk_reset_kernel<<<148, 256, 0, s>>>(a, reinterpret_cast<unsigned long long*>(scratch), n64);
+    return cudaGetLastError();
+}
+
+// What the NEXT resolution of this call could be sensitive to: the first candidate that passes the pulse tests
+// (an entry p beyond it changes the walk) and the first accepted preamble (its skip is computed in float from pos).
+__global__ void amb_walk_summary_kernel(const AmbWalkArgs a)
+{
+    const int n = (int)a.ctr->ncand;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        const uint32_t info = a.cand_info[c];
+        if (!(info & (1u << 8))) continue;
+        const unsigned long long s0 = (unsigned long long)(a.org + a.cand_j[c]);
+        atomicMin(&a.st->first_real, s0);
+        if (info & (1u << 10)) atomicMin(&a.st->first_packet, s0 + (info & 0xffu));
+    }
+}
+
+cudaError_t amb_launch_walk_summary(const AmbWalkArgs& a, cudaStream_t s)
+{
+    cudaError_t e = cudaMemsetAsync(&a.st->first_real, 0xff, 2 * sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    amb_walk_summary_kernel<<<148, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // slicer: one warp per accepted preamble
 // ------------------------------------------------------------------------------------------------

@@ -138,3 +138,74 @@ def dist_state_exchange(rank: int, device):
         dist.send(torch.tensor([int(x) for x in state], dtype=torch.int64, device=device), dst=rank + 1)
 
     return recv_entry, send_exit
+
+
+# ---- speculative resolution: the chain leaves the critical path ---------------------------------------------------
+# Every span but the last resolves at once with the default entry; one all-gather of six integers per span then
+# tells every rank the true entry of every span, as long as each speculative result is provably what the true entry
+# would have produced (include/airmodes_b200.h, amb_get_walk_summary). The first span that fails the test, and every
+# span after it, falls back to the hand-over chain.
+def compose_entries(plan, summaries):
+    """summaries[k] = (pos, p, first_real, first_packet, exact_span, frames_passed) of span k's speculative
+    resolution (anything for the last span). Returns (entries, queued, first_bad): entries[k] = true (pos, p) entry
+    of span k and queued[k] = messages queued before it, both valid for k <= first_bad; first_bad = index of the
+    first span whose speculation does not hold (len(plan) - 1, the never-speculated last span, if all hold)."""
+    entries, queued = [(0, 0)], [0]
+    last = len(plan) - 1
+    for k in range(last):
+        pos_in, p_in = entries[k]
+        pos, p, first_real, first_packet, exact_span, passed = (int(x) for x in summaries[k])
+        ok = (first_real < 0 or p_in <= first_real) and (first_packet < 0 or first_packet - pos_in < exact_span)
+        if not ok:
+            return entries, queued, k
+        entries.append((pos if first_packet >= 0 else pos_in, max(p, p_in)))
+        queued.append(queued[k] + passed)
+    return entries, queued, last
+
+
+def process_time_sharded_speculative(rx, span_iq, plan, rank, all_gather, recv_entry, send_exit):
+    """As process_time_sharded, for every rank of the plan at once. all_gather(list of 6 ints) -> list over ranks.
+    Returns the number of messages this span queued."""
+    if rank >= len(plan):                                  # more ranks than spans: only take part in the collective
+        all_gather([0] * 6)
+        return 0
+    span = plan[rank]
+    last = len(plan) - 1
+    rx.defer_resolve(True)
+    rx.seek(span.first_sample, span.first_decision)
+    rx.process(span_iq, flush=span.flush, collect=False)
+    mine = [0] * 6
+    if rank < last:
+        rx.resolve(None)                                   # speculative: fresh entry at first_decision
+        s = rx.walk_summary()
+        mine = [s.pos, s.p, s.first_real, s.first_packet, s.exact_span, s.frames_passed]
+    entries, queued, bad = compose_entries(plan, all_gather(mine))
+    if rank < bad:                                         # speculation holds: done, nothing to wait for
+        q = queued[rank]
+    else:
+        if rank == bad:
+            pos, p = entries[rank]
+            q = queued[rank]
+        else:
+            pos, p, q = recv_entry()
+        rx.resolve((pos, p))                               # first resolution of the last span, or a re-resolution
+    rx._slicer._first = q == 0
+    if rank >= bad and not span.flush:
+        state = rx.walk_state()
+        n = rx.drain()
+        send_exit(state + (q + n,))
+        return n
+    return rx.drain()
+
+
+def dist_all_gather6(world: int, device):
+    import torch
+    import torch.distributed as dist
+
+    def all_gather(vals):
+        t = torch.tensor([int(v) for v in vals], dtype=torch.int64, device=device)
+        out = torch.empty(world * 6, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(out, t)
+        return out.view(world, 6).tolist()
+
+    return all_gather

@@ -200,6 +200,24 @@ typedef struct amb_walk_state { int64_t pos, p; } amb_walk_state;
 AMB_API int amb_seek(amb_ctx* ctx, uint64_t first_sample, uint64_t first_decision, const amb_walk_state* entry);
 AMB_API int amb_resolve(amb_ctx* ctx, const amb_walk_state* entry);      /* NULL: keep the context's own state */
 AMB_API int amb_get_walk_state(amb_ctx* ctx, amb_walk_state* out);       /* synchronises */
+/* Speculative resolution, which takes the hand-over chain off the critical path: resolve every span but the last
+ * right away with the default entry ("a fresh general_work call starts at first_decision"), exchange the summaries,
+ * and keep a span's result if the true entry (pos, p) - the previous span's exit - cannot have changed it:
+ *   p <= first_real (or there is none): the walk never looks at p again once it is behind the first candidate that
+ *       passes the pulse tests (preamble_impl.cc:174-179), and
+ *   first_packet - pos < exact_span (or there is none): the float arithmetic of :237 is then exact for the true and
+ *       for the assumed pos alike (later packets only depend on the one before them).
+ * The span's exit state is then (first_packet >= 0 ? pos : the true entry pos, p) as reported here. Otherwise call
+ * amb_resolve again with the true entry: the earlier resolution (verdicts, frames) is discarded - allowed until the
+ * span's frames have been polled. The last span (flush) is not speculated on: the end-of-stream rules (:150,
+ * :212-216) depend on pos directly. first_real / first_packet are -1 when absent. */
+typedef struct amb_walk_summary {
+    int64_t pos, p;                  /* exit state of this resolution */
+    int64_t first_real, first_packet;
+    int64_t exact_span;
+    int64_t frames_passed;           /* messages this span would queue (slicer_impl.cc:193-194) */
+} amb_walk_summary;
+AMB_API int amb_get_walk_summary(amb_ctx* ctx, amb_walk_summary* out);   /* synchronises */
 AMB_API const char* amb_strerror(int code);
 AMB_API const char* amb_last_error(const amb_ctx* ctx);
 AMB_API const char* amb_version(void);

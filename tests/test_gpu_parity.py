@@ -576,3 +576,74 @@ def test_cli_udp_source_zmq_feed_and_dcblock(port, tmp_path):
     # -n prints nothing
     out = subprocess.run([sys.executable, cli, "-s", str(path), "-n"], capture_output=True, text=True, check=True).stdout
     assert out.strip() == ""
+
+
+def run_time_sharded_speculative(iq, rate, thr, pmf, spans=None, boundaries=None):
+    """One thread per span, each with its own rx_path on cuda:0, running shard.process_time_sharded_speculative with
+    an in-process all-gather and mailboxes for the fallback chain. Returns (messages, frames, first_bad)."""
+    import queue, threading
+    from gr_air_modes_b200 import shard
+    n = iq.size // 2
+    plan = shard.time_shard_plan(n, spans or (len(boundaries) + 1), am.query_geometry(rate, thr, pmf), boundaries=boundaries)
+    world = len(plan)
+    table, bar = [None] * world, threading.Barrier(world)
+    boxes = [queue.Queue() for _ in range(world)]
+    qs = [am.msg_queue() for _ in range(world)]
+    out, errs, bad = [None] * world, [], [None]
+
+    def work(rank):
+        try:
+            rx = am.rx_path(rate, thr, qs[rank], use_pmf=pmf)
+
+            def all_gather(vals):
+                table[rank] = list(vals)
+                bar.wait(60)
+                res = [list(r) for r in table]
+                bar.wait(60)
+                if rank == 0:
+                    bad[0] = shard.compose_entries(plan, res)[2]
+                return res
+
+            sp = plan[rank]
+            shard.process_time_sharded_speculative(rx, iq[2 * sp.first_sample: 2 * sp.end], plan, rank, all_gather,
+                                                   lambda: boxes[rank].get(timeout=60), lambda st: boxes[rank + 1].put(st))
+            out[rank] = list(rx.frames)
+            rx.close()
+        except Exception as e:                       # noqa: BLE001 - reported by the caller
+            errs.append((rank, repr(e)))
+            bar.abort()
+
+    ths = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errs, errs
+    return [m for q in qs for m in q.strings()], [f for fr in out for f in fr], bad[0], world
+
+
+def test_time_sharded_speculative_resolution(port):
+    """The chain-free variant: speculative resolution + one all-gather; spans whose speculation cannot be proven fall
+    back to the chain. Both outcomes must give the one-shot result."""
+    rate = 4e6
+    sc = synth.make_scene(rate, 1_500_000, 120, 74)
+    want = port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL)
+    for spans in (2, 3, 8):
+        msgs, frames, bad, world = run_time_sharded_speculative(sc.iq, rate, 7.0, True, spans=spans)
+        assert bad == world - 1                                           # every speculation held
+        assert [f.sample_index for f in frames] == [int(x) for x in want.index] and msgs == want.msgs
+    # cuts just after accepted preambles: the previous packet's skip covers real candidates of the next span
+    idx = [int(x) for x in want.index if 300_000 < int(x) < 1_200_000]
+    rng = np.random.default_rng(11)
+    fell_back = 0
+    for trial in range(8):
+        picks = sorted(rng.choice(len(idx), 3, replace=False))
+        cuts = [idx[k] + int(rng.integers(1, 12)) for k in picks]
+        msgs, frames, bad, world = run_time_sharded_speculative(sc.iq, rate, 7.0, True, boundaries=cuts)
+        fell_back += bad < world - 1
+        assert [f.sample_index for f in frames] == [int(x) for x in want.index], cuts
+        assert msgs == want.msgs
+    assert fell_back > 0                                                  # the fallback chain was exercised
+    dense = synth.make_scene(rate, 2_000_000, 5000, 99, garble_frac=0.2, fruit=2000, snr_db=(4.0, 30.0))
+    want = port.run_iq(dense.iq, rate, 5.0, True, co.MA_CANONICAL)
+    for spans in (2, 6):
+        msgs, frames, bad, world = run_time_sharded_speculative(dense.iq, rate, 5.0, True, spans=spans)
+        assert [f.sample_index for f in frames] == [int(x) for x in want.index] and msgs == want.msgs

@@ -123,3 +123,70 @@ def test_time_shard_plan_invariants():
         shard.time_shard_plan(100_000, 2, g, boundaries=[99_900])            # no room for the forward halo
     with pytest.raises(ValueError):
         shard.time_shard_plan(100_000, 2, g, boundaries=[30_000, 60_000])    # more spans than ranks
+
+
+def test_compose_entries_logic():
+    g = _Geom(4, 101, 483)
+    plan = shard.time_shard_plan(1 << 22, 4, g)
+    X = 1 << 24
+    # (pos, p, first_real, first_packet, exact_span, passed)
+    ok = [(900_000, plan[1].first_decision, 5_000, 5_010, X, 7), (plan[1].first_decision, plan[2].first_decision, -1, -1, X, 0),
+          (3_000_000, plan[3].first_decision + 100, plan[2].first_decision + 50, plan[2].first_decision + 60, X, 2), (0,) * 6]
+    entries, queued, bad = shard.compose_entries(plan, ok)
+    assert bad == 3 and queued == [0, 7, 7, 9]
+    assert entries[1] == (900_000, plan[1].first_decision)
+    assert entries[2] == (900_000, plan[2].first_decision)          # no packet in span 1: pos passes through
+    assert entries[3] == (3_000_000, plan[3].first_decision + 100)
+    # span 1 has a real candidate before the p handed over by span 0 -> speculation fails there
+    s = list(ok); s[0] = (900_000, plan[1].first_decision + 300, 5_000, 5_010, X, 7)
+    s[1] = (plan[1].first_decision, plan[2].first_decision, plan[1].first_decision + 200, -1, X, 0)
+    assert shard.compose_entries(plan, s)[2] == 1
+    s[1] = (plan[1].first_decision, plan[2].first_decision, plan[1].first_decision + 300, -1, X, 0)   # at p: still fine
+    assert shard.compose_entries(plan, s)[2] == 3
+    assert shard.compose_entries(plan, s)[0][2][1] == plan[2].first_decision      # exit p = max(p, entry p)
+    # the first packet of span 2 lies too far from the true pos for the float skip to be exact
+    s = list(ok); s[0] = (10, plan[1].first_decision, -1, -1, X, 0)
+    s[2] = (X + 500_000, plan[3].first_decision, 2_200_000, X + 20, X, 1)
+    assert shard.compose_entries(plan, s)[2] == 2
+    assert shard.compose_entries([plan[0]], [(0,) * 6]) == ([(0, 0)], [0], 0)     # a single span is never speculated on
+
+
+class _FakeSpecRx(_FakeRx):
+    def __init__(self, n_msgs, summary):
+        super().__init__(n_msgs); self.summary = summary
+
+    def resolve(self, entry): self.log.append(("resolve", entry)); self.entry = entry if entry is not None else (-1, -1)
+
+    def walk_summary(self):
+        class S: pass
+        s = S()
+        s.pos, s.p, s.first_real, s.first_packet, s.exact_span, s.frames_passed = self.summary
+        return s
+
+
+def _spec_worker(rank, world, port_no, fail_at, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    plan = shard.time_shard_plan(1_000_000, 2, _Geom(4, 101, 483))      # world 3, two spans: rank 2 idles
+    summary = (777, plan[1].first_decision + (600 if fail_at == 1 else 0), -1, -1, 1 << 24, 4) if rank == 0 else (0,) * 6
+    rx = _FakeSpecRx(n_msgs=4 if rank == 0 else 2, summary=summary)
+    recv, send = shard.dist_state_exchange(rank, torch.device("cpu"))
+    sp = plan[rank] if rank < len(plan) else None
+    iq = np.zeros((sp.end - sp.first_sample) if sp else 0, np.float32)
+    got = shard.process_time_sharded_speculative(rx, iq, plan, rank, shard.dist_all_gather6(world, torch.device("cpu")), recv, send)
+    ret[rank] = (got, rx.entry, [e for e in rx.log if e[0] in ("resolve", "drain")])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_speculative_runner_world3_gloo():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_spec_worker, args=(3, _free_port(), 0, ret), nprocs=3, join=True)
+    plan = shard.time_shard_plan(1_000_000, 2, _Geom(4, 101, 483))
+    # rank 0 speculated (resolve(None)) and kept it; rank 1 = last span resolves once with the composed entry
+    assert ret[0][2] == [("resolve", None), ("drain", True)]
+    assert ret[1][2] == [("resolve", (0, plan[1].first_decision)), ("drain", False)]      # 4 messages queued before it
+    assert ret[2][0] == 0 and ret[2][2] == []
+    assert (ret[0][0], ret[1][0]) == (4, 2)
