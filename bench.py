@@ -124,6 +124,28 @@ def make_device_scene(n, seed, device):
     return iq, frames
 
 
+def bind_near_gpu(index):
+    """Pin this process to the CPUs next to GPU `index` (NVML's ideal affinity) so that the pinned staging buffer of
+    the end-to-end leg lands on the NUMA node the GPU's PCIe root hangs off. Returns a note for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:                                    # CUDA's device order need not be NVML's: go through the PCI address
+            import torch
+            pr = torch.cuda.get_device_properties(index)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
+        except Exception:                       # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, v in enumerate(words) for b in range(64) if (int(v) >> b) & 1} & os.sched_getaffinity(0)
+        if not cpus:
+            return "nvml gave no usable cpu set"
+        os.sched_setaffinity(0, cpus)
+        return "%d cpus near gpu %d" % (len(cpus), index)
+    except Exception as e:                      # noqa: BLE001 - optional tuning only
+        return "not bound (%s)" % type(e).__name__
+
+
 def _tame_malloc():
     """Keep multi-MB buffers on the heap instead of mmap/munmap per call: the per-call allocations are an artefact
     of the oracle's whole-buffer driver (GNU Radio keeps persistent ring buffers), and first-touch page faults
@@ -410,6 +432,8 @@ def main():
     scan_avg = shard.max_over_ranks(float(np.mean(scan_ms)), world, device)
 
     # ---- end to end through the public API: pinned host IQ -> H2D -> chain -> frames D2H
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_near_gpu(local_rank)          # the pinned buffer is first-touched on the GPU's NUMA node
     host = torch.empty(2 * n, dtype=torch.float32, pin_memory=True)
     host.copy_(iq)
     torch.cuda.synchronize()
@@ -429,6 +453,7 @@ def main():
     e2e_ms = shard.max_over_ranks(e2e_ms, world, device)
     q.flush()
     clocks = sampler.stop() if rank == 0 else None     # sampled across both timed regions (device + end to end)
+    os.sched_setaffinity(0, all_cpus)                  # the CPU baseline leg below gets every host thread back
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -448,7 +473,8 @@ def main():
                          "traffic": None, "kernel": "amb_scan_kernel<2,true>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": 8 * n, "scan_ms": scan_avg},
             "e2e": {"value": world * n / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 8 * n,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "h2d_gbps": 8 * n / (e2e_ms * 1e-3) / 1e9,
+                    "host_numa_binding": numa},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         tr = os.path.join(ROOT, "profiles", "scan_traffic.json")

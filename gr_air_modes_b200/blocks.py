@@ -327,10 +327,10 @@ class rx_path:
         return s
 
     def dump_stage(self, stage: str, iq) -> np.ndarray:
-        """Parity dump: "m2" | "bb" | "avg" of a short host buffer taken as a whole stream (amb_dump_stage)."""
+        """Parity dump: "m2" | "bb" | "avg" | "dc" of a short host buffer taken as a whole stream (amb_dump_stage)."""
         iq = np.ascontiguousarray(np.asarray(iq).view(np.float32).reshape(-1))
-        out = np.empty(iq.size // 2, np.float32)
-        self._ctx.call("amb_dump_stage", {"m2": 0, "bb": 1, "avg": 2}[stage],
+        out = np.empty(iq.size if stage == "dc" else iq.size // 2, np.float32)
+        self._ctx.call("amb_dump_stage", {"m2": 0, "bb": 1, "avg": 2, "dc": 3}[stage],
                        iq.ctypes.data_as(C.POINTER(C.c_float)), iq.size // 2, out.ctypes.data_as(C.POINTER(C.c_float)))
         return out
 

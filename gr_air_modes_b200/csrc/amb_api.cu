@@ -911,19 +911,39 @@ int amb_device_crc(amb_ctx* ctx, const uint8_t* data, int n, int length, uint32_
 
 int amb_dump_stage(amb_ctx* ctx, int stage, const float* iq, size_t n_complex, float* out)
 {
-    if (!ctx || stage < AMB_STAGE_M2 || stage > AMB_STAGE_AVG || (n_complex && (!iq || !out))) return AMB_ERR_INVALID;
+    if (!ctx || stage < AMB_STAGE_M2 || stage > AMB_STAGE_DC || (n_complex && (!iq || !out))) return AMB_ERR_INVALID;
     if (n_complex > (1u << 26)) return fail(ctx, AMB_ERR_INVALID, "amb_dump_stage is a parity tool: at most 2^26 samples");
-    if (ctx->use_dcblock) return fail(ctx, AMB_ERR_UNSUPPORTED, "amb_dump_stage does not model the DC blocker");
+    if (ctx->use_dcblock && stage != AMB_STAGE_DC)
+        return fail(ctx, AMB_ERR_UNSUPPORTED, "m2/bb/avg dumps take the demodulator's input; dump AMB_STAGE_DC and feed it to a context without the DC blocker");
     if (n_complex == 0) return AMB_OK;
     CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (stage == AMB_STAGE_DC) {     // the whole buffer as one stream: zero history (GNU Radio's delay lines start at zero)
+        const int D = 100 * ctx->P.spc_i, nc = 2 * D - 2;                       // rx_path.py:40
+        float2 *d = nullptr, *t = nullptr, *o = nullptr, *c0 = nullptr, *c1 = nullptr;
+        cudaError_t e = cudaMalloc(&d, n_complex * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMalloc(&t, (n_complex + D) * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMalloc(&o, n_complex * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMalloc(&c0, (size_t)nc * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMalloc(&c1, (size_t)nc * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMemsetAsync(c0, 0, (size_t)nc * sizeof(float2), s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d, iq, n_complex * sizeof(float2), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = amb_launch_dcblock(c0, nc, d, (long long)n_complex, D, t, o, c1, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, o, n_complex * sizeof(float2), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaFree(d); cudaFree(t); cudaFree(o); cudaFree(c0); cudaFree(c1);
+        ctx->stats.kernel_launches += 3;
+        if (e != cudaSuccess) return fail(ctx, AMB_ERR_CUDA, "amb_dump_stage", e);
+        return AMB_OK;
+    }
     float2* d = nullptr; float* t = nullptr; float* o = nullptr;
     CK(cudaMalloc(&d, n_complex * sizeof(float2)));
     cudaError_t e = cudaMalloc(&t, n_complex * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&o, n_complex * sizeof(float));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d, iq, n_complex * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = amb_launch_dump(d, (long long)n_complex, ctx->P, stage, t, o, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out, o, n_complex * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d, iq, n_complex * sizeof(float2), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = amb_launch_dump(d, (long long)n_complex, ctx->P, stage, t, o, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, o, n_complex * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     cudaFree(d); cudaFree(t); cudaFree(o);
     ctx->stats.kernel_launches += stage == AMB_STAGE_AVG ? 2 : 1;
     if (e != cudaSuccess) return fail(ctx, AMB_ERR_CUDA, "amb_dump_stage", e);

@@ -1332,57 +1332,149 @@ cudaError_t amb_launch_stream_candidates(const AmbScanArgs& a, const float* in0,
 // optional DC blocker in front of the demodulator: filter.dc_blocker_cc(100*spc, False) (rx_path.py:39-41).
 // GNU Radio's short form is  out[n] = x[n-D+1] - MA_D(MA_D(x))[n]  with complex fp32 moving averages. Canonical
 // arithmetic (same as the CPU checker): every window sum in fp64, ascending, per component, rounded once to
-// fp32 and divided by (float)D. Brute force on purpose - it keeps the summation order, hence bit-exactness; this
-// stage is off by default (radio.py:118-119) and costs ~16x the scan kernel when enabled.
+// fp32 and divided by (float)D. This stage is off by default (radio.py:118-119).
+//
+// A tile of DC_T outputs needs W = DC_T + D - 1 source elements. If, per component, the largest magnitude and the
+// smallest non-zero quantum of the tile are at most `lim` = 29 - ceil(log2 W) binades apart, every sum of up to W of
+// these fp32 values is a multiple of that quantum below 2^53 quanta, i.e. exactly representable in fp64: the
+// reference order's partial sums never round, and neither do the tile's prefix sums nor their differences. The
+// window sums are then P[t+D] - P[t] (O(1) per output, bit-identical). Tiles that fail the test (a strong burst
+// next to a near-zero sample, NaN/Inf) take the brute-force path, which keeps the summation order literally.
 // `raw` is the logical stream rawcarry(2D-2 samples) ++ new samples, addressed through two pointers.
 // ------------------------------------------------------------------------------------------------
+#define DC_T 1024
 __device__ __forceinline__ float2 dc_raw(const float2* carry, int nc, const float2* fresh, long long r)
 {
     return r < nc ? carry[r] : fresh[r - nc];
 }
+__device__ __forceinline__ double shfl_up_f64(double v, int d)
+{
+    return __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(v), d), __shfl_up_sync(0xffffffffu, __double2loint(v), d));
+}
 
-// pass 0: ma0[i] = MA_D(x) at raw index (D-1)+i, i in [0, n_new + D - 1);  pass 1: out[m] for the n_new new samples
-template <int PASS>
+// pass 0: ma0[i] = MA_D(x) at raw index (D-1)+i, i in [0, n_new + D - 1);  pass 1: out[m] for the n_new new samples.
+// CH = elements per thread in the prefix phase, ceil(W / 256) rounded up to an ODD number: a thread's chunk is
+// contiguous, so with an odd CH the 8-byte source reads and the 16-byte prefix writes of a warp are bank-conflict free.
+template <int PASS, int CH>
 __global__ void __launch_bounds__(256) amb_dcblock_kernel(const float2* __restrict__ carry, int nc, const float2* __restrict__ fresh,
                                                           const float2* __restrict__ ma0, float2* __restrict__ dst,
-                                                          long long n_out, int D)
+                                                          long long n_out, int D, int lim)
 {
-    extern __shared__ float2 dc_s[];
-    const long long base = (long long)blockIdx.x * 256;
-    const int tid = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char dc_smem[];
+    const int W = DC_T + D - 1;
+    float2* src = reinterpret_cast<float2*>(dc_smem);                                               // W source elements
+    double2* P = reinterpret_cast<double2*>(dc_smem + (size_t)((W + 1) & ~1) * sizeof(float2));     // W + 1 prefix sums (re, im)
+    __shared__ unsigned int s_rng[8][4];
+    __shared__ double2 s_tot[8];
+    const long long base = (long long)blockIdx.x * DC_T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // window of output base+t covers source elements base+t .. base+t+D-1
-    for (int i = tid; i < 256 + D - 1; i += 256) {
-        const long long q = base + i;
+    const long long src_end = PASS == 0 ? (long long)nc + (n_out - (D - 1)) : n_out + D - 1;       // raw / ma0 index space
+    unsigned int mxr = 0, mnr = ~0u, mxi = 0, mni = ~0u;         // largest |bits|, smallest non-zero |bits| - 1
+    // interior tiles read one contiguous run of one array; only the first and last tiles need the general form
+    const float2* run = nullptr;
+    if (PASS == 0) { if (base >= nc && base + W <= src_end) run = fresh + (base - nc); }
+    else if (base + W <= src_end) run = ma0 + base;
+    for (int i = tid; i < W; i += 256) {
         float2 v = make_float2(0.f, 0.f);
-        if (PASS == 0) { if (q < (long long)nc + (n_out - (D - 1))) v = dc_raw(carry, nc, fresh, q); }   // raw index
-        else { if (q < n_out + D - 1) v = ma0[q]; }                                                      // ma0 index
-        dc_s[i] = v;
+        if (run) v = run[i];
+        else {
+            const long long q = base + i;
+            if (q < src_end) v = PASS == 0 ? dc_raw(carry, nc, fresh, q) : ma0[q];
+        }
+        src[i] = v;
+        const unsigned int ux = __float_as_uint(v.x) & 0x7fffffffu, uy = __float_as_uint(v.y) & 0x7fffffffu;
+        mxr = max(mxr, ux); mnr = min(mnr, ux - 1u);             // zero wraps to 0xffffffff and drops out of the minimum
+        mxi = max(mxi, uy); mni = min(mni, uy - 1u);
     }
+    mxr = __reduce_max_sync(0xffffffffu, mxr); mnr = __reduce_min_sync(0xffffffffu, mnr);
+    mxi = __reduce_max_sync(0xffffffffu, mxi); mni = __reduce_min_sync(0xffffffffu, mni);
+    if (lane == 0) { s_rng[warp][0] = mxr; s_rng[warp][1] = mnr; s_rng[warp][2] = mxi; s_rng[warp][3] = mni; }
     __syncthreads();
-    const long long m = base + tid;
-    if (m >= n_out) return;
-    double ar = 0.0, ai = 0.0;
-    for (int t = 0; t < D; t++) { ar += (double)dc_s[tid + t].x; ai += (double)dc_s[tid + t].y; }
+#pragma unroll
+    for (int w = 0; w < 8; w++) { mxr = max(mxr, s_rng[w][0]); mnr = min(mnr, s_rng[w][1]); mxi = max(mxi, s_rng[w][2]); mni = min(mni, s_rng[w][3]); }
+    // exponent fields; denormals share the quantum of exponent field 1
+    const int er1 = (int)max(mxr >> 23, 1u), er0 = (int)max((mnr + 1u) >> 23, 1u);
+    const int ei1 = (int)max(mxi >> 23, 1u), ei0 = (int)max((mni + 1u) >> 23, 1u);
+    const bool exact = (mxr == 0 || (er1 < 255 && er1 - er0 <= lim)) && (mxi == 0 || (ei1 < 255 && ei1 - ei0 <= lim));
     const float fD = (float)D;
-    const float mr = __fdiv_rn((float)ar, fD), mi = __fdiv_rn((float)ai, fD);
-    if (PASS == 0) dst[m] = make_float2(mr, mi);
-    else {
-        const float2 d = dc_raw(carry, nc, fresh, m + D - 1);        // x[n-D+1]: raw index of new sample m is nc+m
-        dst[m] = make_float2(__fsub_rn(d.x, mr), __fsub_rn(d.y, mi));
+    if (exact) {
+        // block-wide inclusive prefix sums in fp64 (every addition exact, so the association is free)
+        const int k0 = tid * CH;
+        double xr[CH], xi[CH];
+        double sr = 0.0, si = 0.0;
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            const float2 v = (k0 + j < W) ? src[k0 + j] : make_float2(0.f, 0.f);
+            xr[j] = (double)v.x; xi[j] = (double)v.y;
+            sr += xr[j]; si += xi[j];
+        }
+        double ar = sr, ai = si;                              // inclusive scan of the per-thread totals within the warp
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double tr = shfl_up_f64(ar, d), ti = shfl_up_f64(ai, d);
+            if (lane >= d) { ar += tr; ai += ti; }
+        }
+        if (lane == 31) s_tot[warp] = make_double2(ar, ai);
+        __syncthreads();
+        double offr = ar - sr, offi = ai - si;                // exclusive offset of this thread
+#pragma unroll
+        for (int w = 0; w < 7; w++) if (w < warp) { offr += s_tot[w].x; offi += s_tot[w].y; }
+        if (tid == 0) P[0] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            offr += xr[j]; offi += xi[j];
+            if (k0 + j < W) P[k0 + j + 1] = make_double2(offr, offi);
+        }
+        __syncthreads();
     }
+#pragma unroll
+    for (int u = 0; u < DC_T / 256; u++) {
+        const int t = tid + 256 * u;
+        const long long m = base + t;
+        if (m >= n_out) break;
+        double ar = 0.0, ai = 0.0;
+        if (exact) { const double2 hi = P[t + D], lo = P[t]; ar = hi.x - lo.x; ai = hi.y - lo.y; }
+        else for (int k = 0; k < D; k++) { ar += (double)src[t + k].x; ai += (double)src[t + k].y; }
+        const float mr = __fdiv_rn((float)ar, fD), mi = __fdiv_rn((float)ai, fD);
+        if (PASS == 0) dst[m] = make_float2(mr, mi);
+        else {
+            const float2 d = dc_raw(carry, nc, fresh, m + D - 1);        // x[n-D+1]: raw index of new sample m is nc+m
+            dst[m] = make_float2(__fsub_rn(d.x, mr), __fsub_rn(d.y, mi));
+        }
+    }
+}
+
+template <int CH>
+static cudaError_t launch_dcblock_t(const float2* rawcarry, int nc, const float2* fresh, long long n_new, int D, int lim,
+                                    size_t smem, float2* ma0_tmp, float2* out, cudaStream_t s)
+{
+    // per device, like the scan kernel: set on every launch (a host-side table write)
+    cudaError_t e = cudaFuncSetAttribute(amb_dcblock_kernel<0, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(amb_dcblock_kernel<1, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long n0 = n_new + D - 1;
+    amb_dcblock_kernel<0, CH><<<(unsigned)((n0 + DC_T - 1) / DC_T), 256, smem, s>>>(rawcarry, nc, fresh, nullptr, ma0_tmp, n0, D, lim);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    amb_dcblock_kernel<1, CH><<<(unsigned)((n_new + DC_T - 1) / DC_T), 256, smem, s>>>(rawcarry, nc, fresh, ma0_tmp, out, n_new, D, lim);
+    return cudaGetLastError();
 }
 
 cudaError_t amb_launch_dcblock(const float2* rawcarry, int nc, const float2* fresh, long long n_new, int D,
                                float2* ma0_tmp, float2* out, float2* rawcarry_next, cudaStream_t s)
 {
-    const size_t smem = (size_t)(256 + D - 1) * sizeof(float2);
+    const int W = DC_T + D - 1;
+    const size_t smem = (size_t)((W + 1) & ~1) * sizeof(float2) + (size_t)(W + 1) * sizeof(double2);
+    int c = 0;
+    while ((1 << c) < W) c++;
+    const int lim = 29 - c;                              // see the exactness argument above
+    if (smem > 96 * 1024 || W > 9 * 256) return cudaErrorInvalidValue;
     if (n_new > 0) {
-        const long long n0 = n_new + D - 1;
-        amb_dcblock_kernel<0><<<(unsigned)((n0 + 255) / 256), 256, smem, s>>>(rawcarry, nc, fresh, nullptr, ma0_tmp, n0, D);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        amb_dcblock_kernel<1><<<(unsigned)((n_new + 255) / 256), 256, smem, s>>>(rawcarry, nc, fresh, ma0_tmp, out, n_new, D);
-        e = cudaGetLastError();
+        cudaError_t e;
+        if (W <= 5 * 256) e = launch_dcblock_t<5>(rawcarry, nc, fresh, n_new, D, lim, smem, ma0_tmp, out, s);
+        else if (W <= 7 * 256) e = launch_dcblock_t<7>(rawcarry, nc, fresh, n_new, D, lim, smem, ma0_tmp, out, s);
+        else e = launch_dcblock_t<9>(rawcarry, nc, fresh, n_new, D, lim, smem, ma0_tmp, out, s);
         if (e != cudaSuccess) return e;
     }
     // next raw carry = last nc samples of rawcarry ++ fresh

@@ -172,11 +172,12 @@ AMB_API int amb_debug_candidates(amb_ctx* ctx, uint64_t* index, uint32_t* info, 
 AMB_API int amb_set_option(amb_ctx* ctx, const char* name, int value); /* "resolver": 0 auto, 1 sequential, 2 parallel */
 /* Parity dump of the GNU Radio front end wired in rx_path.py:38-54, for a short HOST buffer taken as a whole stream
  * (zeros before sample 0): stage M2 = complex_to_mag_squared (:38), BB = the preamble block's in0 (PMF output, :48-51,
- * or m2 when the PMF is off), AVG = its in1 (:54). n_complex floats are written to `out`. The hot path never
+ * or m2 when the PMF is off), AVG = its in1 (:54). n_complex floats are written to `out` (2*n_complex for DC). The hot path never
  * materialises these streams; this evaluates the same canonical arithmetic at every sample. */
 #define AMB_STAGE_M2 0
 #define AMB_STAGE_BB 1
 #define AMB_STAGE_AVG 2
+#define AMB_STAGE_DC 3   /* output of filter.dc_blocker_cc(100*spc, False) (rx_path.py:39-41): 2*n_complex floats */
 AMB_API int amb_dump_stage(amb_ctx* ctx, int stage, const float* iq_interleaved, size_t n_complex, float* out);
 
 /* ---- one stream time-sharded over several contexts / GPUs (no reference equivalent) ----------

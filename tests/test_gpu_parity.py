@@ -647,3 +647,29 @@ def test_time_sharded_speculative_resolution(port):
     for spans in (2, 6):
         msgs, frames, bad, world = run_time_sharded_speculative(dense.iq, rate, 5.0, True, spans=spans)
         assert [f.sample_index for f in frames] == [int(x) for x in want.index] and msgs == want.msgs
+
+
+def test_dc_blocker_output_bit_exact_both_paths(port):
+    """The DC blocker kernel takes an O(1) prefix-sum path on tiles whose exponent spread proves every fp64 sum exact
+    and the literal ascending sum elsewhere; its complex output equals the CPU restatement bit for bit on inputs that
+    force both: plain noise, strong bursts next to near-zero samples, zeros, denormals, huge dynamic range, Inf/NaN."""
+    rng = np.random.default_rng(3)
+    for rate in (2e6, 4e6, 10e6, 20e6):
+        n = 120_000
+        sc = synth.make_scene(rate, n, 20, int(rate / 1e6) + 500, snr_db=(10.0, 45.0))
+        iq = sc.iq.copy()
+        iq[0::2] += np.float32(0.03)
+        iq[2 * 20_000: 2 * 23_000] = 0.0                                      # silence
+        iq[2 * 30_000: 2 * 33_000] *= np.float32(1e-38)                       # denormals
+        iq[2 * 40_000: 2 * 40_002] = np.float32(1e-30)                        # tiny samples inside ordinary noise
+        iq[2 * 50_000: 2 * 53_000: 7] *= np.float32(1e12)                     # 40 binades of spread
+        iq[2 * 60_000] = np.inf; iq[2 * 61_000 + 1] = np.nan; iq[2 * 62_000] = -np.inf
+        iq[2 * 70_000: 2 * 74_000] = rng.integers(-3, 4, 8000).astype(np.float32)   # small integers: exact with cancellation
+        q = am.msg_queue()
+        rx = am.rx_path(rate, 7.0, q, use_pmf=True, use_dcblock=True)
+        got = rx.dump_stage("dc", iq)
+        want = port.dc_blocker(iq, 100 * int(rate / 2e6), co.MA_CANONICAL)
+        nan = np.isnan(want)                                                  # NaN payloads differ between x86 and the GPU
+        assert nan.any() and np.array_equal(np.isnan(got), nan)
+        assert np.array_equal(got.view(np.uint32)[~nan], want.view(np.uint32)[~nan]), rate
+        rx.close()
