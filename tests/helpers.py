@@ -38,3 +38,74 @@ def first_four(bb, avg, rate, threshold_db, port):
     for k in (1, 2, 3):
         ok &= ~(a[p.po[k]:m + p.po[k]] < thr)
     return np.nonzero(ok)[0]
+
+
+# ---- field-decode parity -----------------------------------------------------
+def load_decode_golden():
+    import gzip
+    with gzip.open(os.path.join(HERE, "golden", "decode_golden.json.gz"), "rt") as f:
+        return json.load(f)["cases"]
+
+
+def compare_decode(rec, ref, tol=0.0, where=""):
+    """rec: one decoded record (dict with the members of struct amb_fields); ref: what the unmodified reference
+    computed for the same message (tests/golden/make_decode_golden.py). Integers and strings must be equal; floats
+    are compared with relative/absolute tolerance `tol` (0 = bit-exact)."""
+    import math
+    NO_HANDLER, METRIC, NOPOS, STRADDLE, HASPOS, HASRNG = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
+
+    def close(a, b):
+        if b is None:
+            return a is None or math.isnan(a)
+        if tol == 0.0:
+            return a == b
+        return abs(a - b) <= tol * max(1.0, abs(b))
+
+    st = rec["status"]
+    if "dropped" in ref:
+        assert st & NO_HANDLER, (where, rec, ref)
+        return
+    assert not (st & NO_HANDLER), (where, rec, ref)
+    assert rec["df"] == ref["df"], (where, rec, ref)
+    for k in ("vs", "ri", "sl", "fs", "ca", "icao", "squawk", "ftc", "cat", "eps", "tti", "ast", "subtype"):
+        if k in ref:
+            assert rec[k] == ref[k], (where, k, rec, ref)
+    if "bds" in ref:
+        assert rec["bds"] == ref["bds"], (where, rec, ref)
+    if "metric_alt" in ref:
+        assert st & METRIC, (where, rec, ref)
+    elif "altitude" in ref:
+        assert not (st & METRIC) and rec["altitude"] == ref["altitude"], (where, rec, ref)
+    if "ident" in ref:
+        assert rec["ident"] == ref["ident"], (where, rec, ref)
+    if "aux" in ref:
+        assert list(rec["aux"]) == ref["aux"], (where, rec, ref)
+    if "ara" in ref:
+        assert rec["aux"][0] == ref["ara"] and rec["aux"][1] == ref["rac"], (where, rec, ref)
+        assert rec["aux"][2] == (ref["rat"] | (ref["mte"] << 1)), (where, rec, ref)
+    if "tid" in ref:
+        assert rec["aux"][3] == ref["tid"], (where, rec, ref)
+    if "tidr" in ref:
+        assert rec["aux"][3] == (ref["tidr"] | (ref["tidb"] << 8)) and rec["threat_alt"] == ref["threat_alt"], (where, rec, ref)
+    if "threat_metric_alt" in ref:
+        assert st & METRIC, (where, rec, ref)
+    if "cpr" in ref:
+        assert [rec["cpr_format"], rec["cpr_lat"], rec["cpr_lon"]] == ref["cpr"], (where, rec, ref)
+    if "ground_track" in ref:
+        assert close(rec["val"][0], ref["ground_track"]), (where, rec, ref)
+    if "val" in ref:
+        for a, b in zip(rec["val"], ref["val"]):
+            assert close(a, b), (where, rec, ref)
+    if ref.get("cpr_error") == "straddle":
+        assert (st & STRADDLE) and (st & NOPOS) and not (st & HASPOS), (where, rec, ref)
+    elif ref.get("cpr_error") == "nopos":
+        assert (st & NOPOS) and not (st & (STRADDLE | HASPOS)), (where, rec, ref)
+    elif "pos" in ref:
+        lat, lon, rng, brg = ref["pos"]
+        assert (st & HASPOS) and not (st & NOPOS), (where, rec, ref)
+        assert close(rec["lat"], lat) and close(rec["lon"], lon), (where, rec, ref)
+        if rng is None:
+            assert not (st & HASRNG), (where, rec, ref)
+        else:
+            assert st & HASRNG, (where, rec, ref)
+            assert close(rec["range"], rng) and close(rec["bearing"], brg), (where, rec, ref)
