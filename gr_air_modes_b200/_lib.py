@@ -53,7 +53,20 @@ class WalkSummary(C.Structure):
                 ("exact_span", C.c_int64), ("frames_passed", C.c_int64)]
 
 
+class Fields(C.Structure):
+    """struct amb_fields (144 bytes): one decoded message (parse.py / altitude.py / cpr.py results)."""
+    _fields_ = [("icao", C.c_uint32), ("ecc", C.c_uint32), ("df", C.c_uint8), ("status", C.c_uint8), ("bds", C.c_uint8),
+                ("subtype", C.c_uint8), ("ca", C.c_uint8), ("fs", C.c_uint8), ("vs", C.c_uint8), ("ri", C.c_uint8),
+                ("sl", C.c_uint8), ("cc", C.c_uint8), ("dr", C.c_uint8), ("um", C.c_uint8), ("ftc", C.c_uint8),
+                ("cat", C.c_uint8), ("cpr_format", C.c_uint8), ("surface", C.c_uint8), ("eps", C.c_uint8),
+                ("ast", C.c_uint8), ("bds2", C.c_uint8), ("tti", C.c_uint8), ("altitude", C.c_int32),
+                ("squawk", C.c_int32), ("threat_alt", C.c_int32), ("cpr_lat", C.c_uint32), ("cpr_lon", C.c_uint32),
+                ("aux", C.c_uint32 * 4), ("ident", C.c_char * 8), ("lat", C.c_double), ("lon", C.c_double),
+                ("range", C.c_double), ("bearing", C.c_double), ("val", C.c_double * 4), ("pad_", C.c_uint64)]
+
+
 assert C.sizeof(Frame) == 80
+assert C.sizeof(Fields) == 144
 
 # every symbol include/airmodes_b200.h declares: (name, restype, argtypes)
 _vp, _f32p, _u64p = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64)
@@ -89,6 +102,14 @@ SYMBOLS = [
     ("amb_resolve", C.c_int, [_vp, C.POINTER(WalkState)]),
     ("amb_get_walk_state", C.c_int, [_vp, C.POINTER(WalkState)]),
     ("amb_get_walk_summary", C.c_int, [_vp, C.POINTER(WalkSummary)]),
+    ("amb_decoder_create", C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(_vp)]),
+    ("amb_decoder_destroy", None, [_vp]),
+    ("amb_decoder_set_location", C.c_int, [_vp, C.c_int, C.c_double, C.c_double]),
+    ("amb_decoder_reset", C.c_int, [_vp]),
+    ("amb_decode_frames", C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
+    ("amb_decoder_stats", C.c_int, [_vp, _u64p, _f32p]),
+    ("amb_decoder_last_error", C.c_char_p, [_vp]),
+    ("amb_frame_bits", C.c_uint64, [C.POINTER(Frame), C.c_int, C.c_int]),
     ("amb_strerror", C.c_char_p, [C.c_int]),
     ("amb_last_error", C.c_char_p, [_vp]),
     ("amb_version", C.c_char_p, []),

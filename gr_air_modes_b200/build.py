@@ -8,8 +8,10 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libairmodes_b200.so")
-SOURCES = ["amb_kernels.cu", "amb_api.cu"]
-HEADERS = ["amb_internal.h", os.path.join("..", "..", "include", "airmodes_b200.h")]
+SOURCES = ["amb_kernels.cu", "amb_api.cu", "amb_decode.cu"]
+HEADERS = ["amb_internal.h", "amb_decode_core.h", os.path.join("..", "..", "include", "airmodes_b200.h")]
+# amb_decode.cu follows cpr.py operation by operation in IEEE double: no fused multiply-add contraction there
+EXTRA_FLAGS = {"amb_decode.cu": ["-fmad=false"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--compiler-options", "-fPIC,-fvisibility=hidden", "-Xcompiler", "-Wall"]
 
@@ -39,7 +41,7 @@ def build_native(force: bool = False, verbose: bool = False, defines=(), out_pat
     procs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o" if out_path is None else "." + os.path.basename(out_path) + ".o"))
-        cmd = [nvcc, "-ccbin", host, *NVCC_FLAGS, *["-D" + d for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, "-ccbin", host, *NVCC_FLAGS, *EXTRA_FLAGS.get(src, []), *["-D" + d for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

@@ -1,0 +1,276 @@
+// Batch field decode: kernels + C ABI of amb_decoder (include/airmodes_b200.h).
+// The per-message arithmetic is in amb_decode_core.h; this file holds the three kernels, the per-aircraft report
+// table and the host orchestration. Compiled with -fmad=false: latitude/longitude follow cpr.py operation by
+// operation in IEEE double, nothing may be contracted. Citations are file:line under gr-air-modes/python.
+//
+//   amb_fields_kernel   one thread per frame: bit fields, altitude, squawk, ident, velocity; emits the CPR report
+//   amb_pair_kernel     cpr_decoder's bookkeeping (cpr.py:206-229): for every position message, the latest even and
+//                       odd report of its aircraft as of that message. The reference does this one message at a time
+//                       against four dicts; here aircraft are dealt out to warps by a hash of their key, every warp
+//                       walks the batch in stream order 32 frames per step, resolves same-aircraft reports inside a
+//                       step with match/ballot and everything older through a direct-mapped table in HBM
+//                       (2^26 x 16 B: one slot per (ICAO, surface, even/odd), so no probing, no collisions, no locks -
+//                       a slot has exactly one owner warp).
+//   amb_resolve_kernel  one thread per frame: global CPR decode, range/bearing.
+#include "amb_decode_core.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#define AMB_TABLE_SLOTS (1ull << 26)     // (24-bit ICAO, surface, even/odd)
+#define AMB_PAIR_WARPS_PER_CTA 4
+
+struct AmbCprSlot { uint32_t lat, lon; double t; };   // lat == 0xFFFFFFFF: empty
+
+struct amb_decoder {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int have_loc = 0; double lat = 0.0, lon = 0.0;
+    AmbCprSlot* table = nullptr;
+    double* nl_T = nullptr;              // device copy of the NL transition table
+    amb_frame* d_frames = nullptr; amb_fields* d_fields = nullptr; AmbPosRec* d_pos = nullptr; AmbPair* d_pair = nullptr;
+    int cap = 0;
+    uint64_t launches = 0; float ms_last = 0.f;
+    std::string err;
+};
+
+static int dfail(amb_decoder* d, int code, const char* what, cudaError_t e = cudaSuccess)
+{
+    if (d) {
+        char buf[256];
+        if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+        else snprintf(buf, sizeof buf, "%s", what);
+        d->err = buf;
+    }
+    return code;
+}
+#define DCK(call)                                                                  \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return dfail(d, AMB_ERR_CUDA, #call, e_); } while (0)
+
+// ---- kernels ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) amb_fields_kernel(const amb_frame* __restrict__ frames, int n,
+                                                         amb_fields* __restrict__ fields, AmbPosRec* __restrict__ pos,
+                                                         AmbPair* __restrict__ pair)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    amb_fields r; AmbPosRec p;
+    amb_decode_fields(frames[k], &r, &p);
+    fields[k] = r;
+    pos[k] = p;
+    AmbPair z; z.elat = z.elon = z.olat = z.olon = 0; z.have = 0; z.mostrecent = 0;
+    pair[k] = z;
+}
+
+__device__ __forceinline__ unsigned amb_key_owner(uint32_t key, unsigned n_warps)
+{
+    return (unsigned)(((uint64_t)(key * 2654435761u) * n_warps) >> 32);     // multiplicative hash -> [0, n_warps)
+}
+
+__global__ void __launch_bounds__(32 * AMB_PAIR_WARPS_PER_CTA)
+amb_pair_kernel(const AmbPosRec* __restrict__ pos, int n, AmbCprSlot* table, AmbPair* __restrict__ pair)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned warp = blockIdx.x * AMB_PAIR_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const unsigned n_warps = gridDim.x * AMB_PAIR_WARPS_PER_CTA;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < n; base += 32) {
+        const int k = base + (int)lane;
+        AmbPosRec me; me.key = AMB_NO_KEY; me.lat = me.lon = 0; me.fmt = 0; me.t = 0.0;
+        if (k < n) me = pos[k];
+        const bool mine = me.key != AMB_NO_KEY && amb_key_owner(me.key, n_warps) == warp;
+        if (!__any_sync(0xffffffffu, mine)) continue;                      // uniform: all lanes take the same branch
+        // same aircraft (same list pair) inside this step; lanes that are not ours get a private value
+        const unsigned peers = __match_any_sync(0xffffffffu, mine ? me.key : (0x80000000u | lane));
+        const unsigned evens = __ballot_sync(0xffffffffu, mine && me.fmt == 0);
+        const unsigned odds = __ballot_sync(0xffffffffu, mine && me.fmt != 0);
+        // the latest report of the OTHER format at or before this message: an earlier lane of this step, else the table
+        const unsigned other_here = peers & (me.fmt ? evens : odds) & lt;
+        const int src = other_here ? (31 - __clz(other_here)) : (int)lane;
+        uint32_t o_lat = __shfl_sync(0xffffffffu, me.lat, src);
+        uint32_t o_lon = __shfl_sync(0xffffffffu, me.lon, src);
+        double o_t = __shfl_sync(0xffffffffu, me.t, src);
+        bool o_have = other_here != 0;
+        const size_t slot_other = ((size_t)me.key << 1) | (me.fmt ? 0u : 1u);
+        const size_t slot_mine = ((size_t)me.key << 1) | (me.fmt ? 1u : 0u);
+        if (mine && !o_have) {
+            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(&table[slot_other]));     // L2, never a stale L1 line
+            if (v.x != 0xFFFFFFFFu) { o_lat = v.x; o_lon = v.y; o_t = __hiloint2double((int)v.w, (int)v.z); o_have = true; }
+        }
+        if (mine) pair[k] = amb_make_pair(me, o_have ? 1 : 0, o_lat, o_lon, o_t);
+        __syncwarp();                                                       // every table read of this step is done
+        // cpr.py:214-221: the message's own report replaces the stored one; the last lane per (aircraft, format) wins
+        const unsigned same = peers & (me.fmt ? odds : evens);
+        if (mine && (int)lane == 31 - __clz(same)) {
+            const uint4 v = make_uint4(me.lat, me.lon, (unsigned)__double2loint(me.t), (unsigned)__double2hiint(me.t));
+            __stcg(reinterpret_cast<uint4*>(&table[slot_mine]), v);
+        }
+        __syncwarp();                                                       // ... and visible to the next step's reads
+    }
+}
+
+__global__ void __launch_bounds__(128) amb_resolve_kernel(amb_fields* __restrict__ fields, const AmbPosRec* __restrict__ pos,
+                                                          const AmbPair* __restrict__ pair, int n, int have_loc,
+                                                          double mylat, double mylon, const double* __restrict__ nl_T)
+{
+    __shared__ double T[AMB_NL_MAX];
+    for (int i = threadIdx.x; i < AMB_NL_MAX; i += blockDim.x) T[i] = nl_T[i];
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (pos[k].key == AMB_NO_KEY) return;
+    amb_fields r = fields[k];
+    amb_resolve_position(&r, pair[k], have_loc, mylat, mylon, T);
+    fields[k] = r;
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------
+static void free_bufs(amb_decoder* d)
+{
+    if (d->d_frames) cudaFree(d->d_frames);
+    if (d->d_fields) cudaFree(d->d_fields);
+    if (d->d_pos) cudaFree(d->d_pos);
+    if (d->d_pair) cudaFree(d->d_pair);
+    d->d_frames = nullptr; d->d_fields = nullptr; d->d_pos = nullptr; d->d_pair = nullptr; d->cap = 0;
+}
+
+static int ensure_cap(amb_decoder* d, int n)
+{
+    if (n <= d->cap) return AMB_OK;
+    int cap = d->cap ? d->cap : 4096;
+    while (cap < n) cap *= 2;
+    free_bufs(d);
+    DCK(cudaMalloc(&d->d_frames, (size_t)cap * sizeof(amb_frame)));
+    DCK(cudaMalloc(&d->d_fields, (size_t)cap * sizeof(amb_fields)));
+    DCK(cudaMalloc(&d->d_pos, (size_t)cap * sizeof(AmbPosRec)));
+    DCK(cudaMalloc(&d->d_pair, (size_t)cap * sizeof(AmbPair)));
+    d->cap = cap;
+    return AMB_OK;
+}
+
+extern "C" {
+
+int amb_decoder_create(int device, int have_location, double lat, double lon, amb_decoder** out)
+{
+    static_assert(sizeof(amb_fields) == 144, "amb_fields layout");
+    static_assert(sizeof(AmbCprSlot) == 16, "table slot layout");
+    if (!out) return AMB_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return AMB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return AMB_ERR_NO_DEVICE;
+    if (prop.major != 10) return AMB_ERR_NO_DEVICE;      // sm_100a cubin only; there is no CPU path
+    amb_decoder* d = new (std::nothrow) amb_decoder();
+    if (!d) return AMB_ERR_INVALID;
+    d->device = device; d->sm_count = prop.multiProcessorCount;
+    d->have_loc = have_location ? 1 : 0; d->lat = lat; d->lon = lon;
+    int rc = AMB_OK;
+    do {
+        if (cudaSetDevice(device) != cudaSuccess) { rc = AMB_ERR_NO_DEVICE; break; }
+        if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreate(&d->e0) != cudaSuccess || cudaEventCreate(&d->e1) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
+        cudaError_t e = cudaMalloc(&d->table, AMB_TABLE_SLOTS * sizeof(AmbCprSlot));
+        if (e != cudaSuccess) { rc = dfail(d, AMB_ERR_CUDA, "report table (1 GiB)", e); break; }
+        if (cudaMalloc(&d->nl_T, AMB_NL_MAX * sizeof(double)) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
+        double T[AMB_NL_MAX];
+        amb_build_nl_table(T);                          // cpr.py:46-51 through the host libm, once
+        if (cudaMemcpyAsync(d->nl_T, T, sizeof T, cudaMemcpyHostToDevice, d->stream) != cudaSuccess ||
+            cudaMemsetAsync(d->table, 0xFF, AMB_TABLE_SLOTS * sizeof(AmbCprSlot), d->stream) != cudaSuccess ||
+            cudaStreamSynchronize(d->stream) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
+    } while (0);
+    if (rc != AMB_OK) { amb_decoder_destroy(d); return rc; }
+    *out = d;
+    return AMB_OK;
+}
+
+void amb_decoder_destroy(amb_decoder* d)
+{
+    if (!d) return;
+    cudaSetDevice(d->device);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    free_bufs(d);
+    if (d->table) cudaFree(d->table);
+    if (d->nl_T) cudaFree(d->nl_T);
+    if (d->e0) cudaEventDestroy(d->e0);
+    if (d->e1) cudaEventDestroy(d->e1);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+int amb_decoder_set_location(amb_decoder* d, int have_location, double lat, double lon)
+{
+    if (!d) return AMB_ERR_INVALID;
+    d->have_loc = have_location ? 1 : 0; d->lat = lat; d->lon = lon;
+    return AMB_OK;
+}
+
+int amb_decoder_reset(amb_decoder* d)
+{
+    if (!d) return AMB_ERR_INVALID;
+    DCK(cudaSetDevice(d->device));
+    DCK(cudaMemsetAsync(d->table, 0xFF, AMB_TABLE_SLOTS * sizeof(AmbCprSlot), d->stream));
+    DCK(cudaStreamSynchronize(d->stream));
+    return AMB_OK;
+}
+
+int amb_decode_frames(amb_decoder* d, const amb_frame* frames, int n, int mem_kind, amb_fields* out)
+{
+    if (!d || n < 0 || (n > 0 && (!frames || !out)) || (mem_kind != AMB_MEM_HOST && mem_kind != AMB_MEM_DEVICE))
+        return dfail(d, AMB_ERR_INVALID, "amb_decode_frames: bad argument");
+    if (n == 0) return AMB_OK;
+    DCK(cudaSetDevice(d->device));
+    int rc = ensure_cap(d, n);
+    if (rc != AMB_OK) return rc;
+    cudaStream_t s = d->stream;
+    DCK(cudaEventRecord(d->e0, s));
+    const amb_frame* src = frames;
+    if (mem_kind == AMB_MEM_HOST) {
+        DCK(cudaMemcpyAsync(d->d_frames, frames, (size_t)n * sizeof(amb_frame), cudaMemcpyHostToDevice, s));
+        src = d->d_frames;
+    }
+    const int nb = (n + 127) / 128;
+    amb_fields_kernel<<<nb, 128, 0, s>>>(src, n, d->d_fields, d->d_pos, d->d_pair);
+    DCK(cudaGetLastError());
+    // one warp per ~256 frames, at most 8 CTAs per SM: every warp reads the whole key list (L2-resident) but only
+    // touches the table for its own aircraft
+    int warps = n / 256;
+    const int max_warps = d->sm_count * 8 * AMB_PAIR_WARPS_PER_CTA;
+    if (warps > max_warps) warps = max_warps;
+    if (warps < AMB_PAIR_WARPS_PER_CTA) warps = AMB_PAIR_WARPS_PER_CTA;
+    const int pair_ctas = (warps + AMB_PAIR_WARPS_PER_CTA - 1) / AMB_PAIR_WARPS_PER_CTA;
+    amb_pair_kernel<<<pair_ctas, 32 * AMB_PAIR_WARPS_PER_CTA, 0, s>>>(d->d_pos, n, d->table, d->d_pair);
+    DCK(cudaGetLastError());
+    amb_resolve_kernel<<<nb, 128, 0, s>>>(d->d_fields, d->d_pos, d->d_pair, n, d->have_loc, d->lat, d->lon, d->nl_T);
+    DCK(cudaGetLastError());
+    d->launches += 3;
+    DCK(cudaMemcpyAsync(out, d->d_fields, (size_t)n * sizeof(amb_fields), cudaMemcpyDeviceToHost, s));
+    DCK(cudaEventRecord(d->e1, s));
+    DCK(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, d->e0, d->e1) == cudaSuccess) d->ms_last = ms;
+    return AMB_OK;
+}
+
+int amb_decoder_stats(amb_decoder* d, uint64_t* kernel_launches, float* ms_last)
+{
+    if (!d) return AMB_ERR_INVALID;
+    if (kernel_launches) *kernel_launches = d->launches;
+    if (ms_last) *ms_last = d->ms_last;
+    return AMB_OK;
+}
+
+const char* amb_decoder_last_error(const amb_decoder* d) { return d ? d->err.c_str() : ""; }
+
+uint64_t amb_frame_bits(const amb_frame* f, int start, int num)
+{
+    if (!f || start < 1 || num < 1 || num > 64) return 0;
+    return amb_bits(amb_msg_from_frame(*f), start, num);
+}
+
+}  // extern "C"

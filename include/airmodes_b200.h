@@ -219,6 +219,69 @@ typedef struct amb_walk_summary {
     int64_t frames_passed;           /* messages this span would queue (slicer_impl.cc:193-194) */
 } amb_walk_summary;
 AMB_API int amb_get_walk_summary(amb_ctx* ctx, amb_walk_summary* out);   /* synchronises */
+/* ---- batch field decode of queued frames ---------------------------------------
+ * What the reference does per message in Python after the slicer: modes_reply field extraction
+ * (python/parse.py:27-231), decode_alt (python/altitude.py:28-108), decode_id (parse.py:233-254), the BDS0,5 / 0,6 /
+ * 0,8 / 0,9 / 6,1 and MB/TCAS sub-decodes (parse.py:256-420) and the stateful CPR position decoder
+ * (python/cpr.py:183-240: latest even/odd report per aircraft, 10 s / 25 s expiry, global decode, range/bearing) -
+ * here as one GPU pass over a batch of frames in stream order. A decoder owns the per-aircraft report table in device
+ * memory (direct-mapped by (ICAO, surface, even/odd): 2^26 entries, 1 GiB) and carries it from batch to batch, like
+ * one cpr_decoder instance. One difference, by necessity: cpr.py stamps reports with time.time() when the message
+ * is parsed (cpr.py:219-221); a batch has no wall clock, so "now" is the frame's own timestamp secs + frac. Frames
+ * must come in non-decreasing time order. No CPU path: without a device amb_decoder_create fails. */
+#define AMB_FS_NO_HANDLER 0x01   /* the parser raised NoHandlerError (unknown DF / FTC / BDS0,9 subtype / MB register,
+                                    parse.py:52-68): the reference drops the message; only df, ecc (and icao) are set */
+#define AMB_FS_METRIC_ALT 0x02   /* decode_alt raised MetricAltError (altitude.py:32-43): altitude/threat_alt not set */
+#define AMB_FS_CPR_NO_POS 0x04   /* CPRNoPositionError: no live even/odd pair (cpr.py:231), or a surface report
+                                    without a receiver location (cpr.py:97-99) */
+#define AMB_FS_CPR_STRADDLE 0x08 /* CPRBoundaryStraddleError (cpr.py:120-121); AMB_FS_CPR_NO_POS is set as well */
+#define AMB_FS_HAS_POS 0x10      /* lat / lon valid */
+#define AMB_FS_HAS_RANGE 0x20    /* range / bearing valid (receiver location known, cpr.py:233-237) */
+#define AMB_FS_NOT_QUEUED 0x80   /* frame.passed == 0: the slicer never queued it, nothing was decoded */
+#define AMB_NO_ALTITUDE INT32_MIN
+
+typedef struct amb_fields {
+    uint32_t icao;        /* "aa" where the DF carries one (11, 17), else ecc = AP ^ parity, what msprint.py prints */
+    uint32_t ecc;         /* the frame's crc field = message token 2 (parse.py:425) */
+    uint8_t df;           /* modes_reply.get_type() (parse.py:228-229) */
+    uint8_t status;       /* AMB_FS_* */
+    uint8_t bds;          /* DF17: me_reply.get_type() 0x05 / 0x06 / 0x08 / 0x09 / 0x61 (parse.py:140-152); DF20/21: bds1 */
+    uint8_t subtype;      /* DF17 BDS0,9: bds09_reply.get_type() 0 / 1 / 3 (parse.py:110-117); 0xff otherwise */
+    uint8_t ca, fs, vs, ri;               /* whichever the DF has (parse.py:210-219), else 0 */
+    uint8_t sl, cc, dr, um;
+    uint8_t ftc, cat, cpr_format, surface;/* DF17 "ftc", BDS0,8 "cat", BDS0,5/0,6 "cpr"; surface = 1 for BDS0,6 */
+    uint8_t eps, ast, bds2, tti;          /* BDS6,1 "eps"; BDS0,9-3 "ast" (1 = TAS); MB "bds2"; TCAS "tti" */
+    int32_t altitude;     /* decode_alt(ac, True) for DF0/4/16/20, decode_alt(alt, False) for BDS0,5; AMB_NO_ALTITUDE if absent */
+    int32_t squawk;       /* decode_id(id) for DF5/21, else -1 */
+    int32_t threat_alt;   /* TCAS threat altitude decode_alt(tida, True) (parse.py:407) */
+    uint32_t cpr_lat, cpr_lon;            /* encoded 17-bit position */
+    uint32_t aux[4];      /* MB bds1 = 1: acs, bcs, ecs, cfs; bds1 = 3: ara, rac, rat | mte << 1, tid (tti 1) or tidr | tidb << 8 (tti 2) */
+    char ident[8];        /* BDS0,8 / MB bds1 = 2 callsign (parse.py:257-279, 374-378), no terminator */
+    double lat, lon;      /* global CPR decode (cpr.py:89-153), degrees; NaN unless AMB_FS_HAS_POS */
+    double range, bearing;/* range_bearing(my_location, position) (cpr.py:158-181): statute miles, degrees */
+    double val[4];        /* BDS0,9-0: velocity, heading, vert_spd, turn_rate (parse.py:288-313)
+                             BDS0,9-1: velocity, heading, vert_spd, alt_geo_diff (parse.py:315-348)
+                             BDS0,9-3: mag_hdg, vel, vert_spd, geo_diff (parse.py:350-364)
+                             BDS0,6  : ground_track (parse.py:283) */
+    uint64_t pad_;
+} amb_fields;             /* 144 bytes */
+
+typedef struct amb_decoder amb_decoder;
+/* cpr_decoder(my_location) (cpr.py:184-190) + the parser; have_location = 0 is my_location = None. */
+AMB_API int amb_decoder_create(int device, int have_location, double lat, double lon, amb_decoder** out);
+AMB_API void amb_decoder_destroy(amb_decoder* d);
+AMB_API int amb_decoder_set_location(amb_decoder* d, int have_location, double lat, double lon);   /* cpr.py:192-193 */
+AMB_API int amb_decoder_reset(amb_decoder* d);                      /* forget every stored report */
+/* Decode n frames (host or device array, stream order = non-decreasing time). out: n records in host memory.
+ * Frames with passed == 0 get AMB_FS_NOT_QUEUED and do not touch the CPR state. */
+AMB_API int amb_decode_frames(amb_decoder* d, const amb_frame* frames, int n, int mem_kind, amb_fields* out);
+/* Kernels launched so far / device time in ms of the last amb_decode_frames call (H2D, kernels, D2H). */
+AMB_API int amb_decoder_stats(amb_decoder* d, uint64_t* kernel_launches, float* ms_last);
+AMB_API const char* amb_decoder_last_error(const amb_decoder* d);
+/* data_field.get_bits(start, num) on a frame's payload (parse.py:71-87): host helper for the raw sub-fields that
+ * amb_fields does not carry. */
+AMB_API uint64_t amb_frame_bits(const amb_frame* f, int start, int num);
+
 AMB_API const char* amb_strerror(int code);
 AMB_API const char* amb_last_error(const amb_ctx* ctx);
 AMB_API const char* amb_version(void);

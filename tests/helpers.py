@@ -47,19 +47,25 @@ def load_decode_golden():
         return json.load(f)["cases"]
 
 
-def compare_decode(rec, ref, tol=0.0, where=""):
+def compare_decode(rec, ref, tol=0.0, where="", tol_libm=None):
     """rec: one decoded record (dict with the members of struct amb_fields); ref: what the unmodified reference
-    computed for the same message (tests/golden/make_decode_golden.py). Integers and strings must be equal; floats
-    are compared with relative/absolute tolerance `tol` (0 = bit-exact)."""
+    computed for the same message (tests/golden/make_decode_golden.py). Integers and strings must be equal.
+    Latitude/longitude/ground track (+, -, *, /, floor, fmod only) are compared with relative tolerance `tol`
+    (0 = bit-exact); velocity, heading, range and bearing go through hypot/atan2/sin/cos/pow, where CPython's own
+    hypot and each libm differ in the last place: `tol_libm` (default = tol)."""
     import math
     NO_HANDLER, METRIC, NOPOS, STRADDLE, HASPOS, HASRNG = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
 
-    def close(a, b):
+    if tol_libm is None:
+        tol_libm = tol
+
+    def close(a, b, t=None):
+        t = tol if t is None else t
         if b is None:
             return a is None or math.isnan(a)
-        if tol == 0.0:
+        if t == 0.0:
             return a == b
-        return abs(a - b) <= tol * max(1.0, abs(b))
+        return abs(a - b) <= t * max(1.0, abs(b))
 
     st = rec["status"]
     if "dropped" in ref:
@@ -95,7 +101,7 @@ def compare_decode(rec, ref, tol=0.0, where=""):
         assert close(rec["val"][0], ref["ground_track"]), (where, rec, ref)
     if "val" in ref:
         for a, b in zip(rec["val"], ref["val"]):
-            assert close(a, b), (where, rec, ref)
+            assert close(a, b, tol_libm), (where, rec, ref)
     if ref.get("cpr_error") == "straddle":
         assert (st & STRADDLE) and (st & NOPOS) and not (st & HASPOS), (where, rec, ref)
     elif ref.get("cpr_error") == "nopos":
@@ -108,4 +114,4 @@ def compare_decode(rec, ref, tol=0.0, where=""):
             assert not (st & HASRNG), (where, rec, ref)
         else:
             assert st & HASRNG, (where, rec, ref)
-            assert close(rec["range"], rng) and close(rec["bearing"], brg), (where, rec, ref)
+            assert close(rec["range"], rng, tol_libm) and close(rec["bearing"], brg, tol_libm), (where, rec, ref)

@@ -46,3 +46,89 @@ def test_decode_oracle_matches_live_reference_on_fresh_seeds():
                 compare_decode(rec, r, 0.0, "seed %d msg %d" % (seed, k))
     finally:
         mg.unload_reference()
+
+
+# ---- the product's decode arithmetic, compiled for the host by a test-only shim -------------------------------------
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    import ctypes as C
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path_factory.mktemp("shim") / "libdecode_shim.so")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", out,
+                    os.path.join(root, "tests", "decode_host_shim.cc")], check=True)
+    lib = C.CDLL(out)
+    lib.shim_decode.restype = C.c_int
+    lib.shim_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
+    lib.shim_nl.restype = C.c_int
+    lib.shim_nl.argtypes = [C.c_double]
+    return lib
+
+
+def _shim_decode(lib, msgs, location):
+    import ctypes as C
+    import numpy as np
+    from gr_air_modes_b200 import decode
+    arr, n = decode.frames_from_messages(msgs)
+    out = np.zeros(n, dtype=decode.FIELDS_DTYPE)
+    have, lat, lon = (0, 0.0, 0.0) if location is None else (1, location[0], location[1])
+    assert lib.shim_decode(C.cast(arr, C.c_void_p), n, have, lat, lon, C.c_void_p(out.ctypes.data)) == 0
+    return [decode.record_to_dict(r) for r in out]
+
+
+def test_product_decode_core_on_host_matches_reference_golden(shim):
+    assert shim.shim_sizeof_fields() == 144
+    n = 0
+    for ci, case in enumerate(load_decode_golden()):
+        recs = _shim_decode(shim, [tuple(m) for m in case["msgs"]], case["location"])
+        for k, (rec, ref) in enumerate(zip(recs, case["ref"])):
+            # lat/lon bit-exact; hypot-based values to 1e-14 (CPython's math.hypot is its own routine, not libm's)
+            compare_decode(rec, ref, 0.0, "case %d msg %d" % (ci, k), tol_libm=1e-14)
+            n += 1
+    assert n > 5000
+
+
+def test_product_decode_core_equals_oracle_record_for_record(shim):
+    """Every member of struct amb_fields, not only what the reference's consumers read."""
+    import math
+    import decode_cases
+    from oracle import decode_oracle as do
+    for seed in (201, 202):
+        loc, msgs = decode_cases.make_case(seed, location=(None if seed == 202 else (-12.0, 130.9)), seconds=25.0,
+                                           surface_share=0.5, n_random=500)
+        want = do.decode_batch(msgs, loc)
+        got = _shim_decode(shim, msgs, loc)
+        for k, (g, w) in enumerate(zip(got, want)):
+            for key, wv in w.items():
+                gv = g[key]
+                near = key in ("val", "range", "bearing")          # hypot & co: last-place differences allowed
+                for a, b in (zip(gv, wv) if isinstance(wv, list) else [(gv, wv)]):
+                    if isinstance(b, float) and math.isnan(b):
+                        assert math.isnan(a), (seed, k, key, g, w)
+                    elif near:
+                        assert abs(a - b) <= 1e-14 * max(1.0, abs(b)), (seed, k, key, g, w)
+                    else:
+                        assert a == b, (seed, k, key, g, w)
+
+
+def test_nl_table_equals_formula(shim):
+    """amb_nl() (transition table built from the host libm) against cpr.py:46-51 evaluated directly."""
+    import numpy as np
+    from oracle import decode_oracle as do
+    rng = np.random.default_rng(5)
+    lats = np.concatenate([rng.uniform(-90, 90, 20000), [0.0, 86.999, 87.0, -87.0, 89.9, 10.4704713, -10.4704713]])
+    # and a fine sweep across every transition
+    for k in range(2, 60):
+        lo, hi = 0.0, 87.0
+        for _ in range(60):
+            mid = (lo + hi) / 2
+            if do.nl(mid) >= k:
+                lo = mid
+            else:
+                hi = mid
+        lats = np.concatenate([lats, lo + np.arange(-50, 51) * 1e-13, -(lo + np.arange(-50, 51) * 1e-13)])
+    bad = [x for x in lats if shim.shim_nl(float(x)) != int(do.nl(float(x)))]
+    # only latitudes within a few ulp of a transition may differ (libm is not monotone to the last bit there)
+    assert len(bad) <= 20, bad[:10]
+    for x in bad:
+        assert any(abs(do.nl(x + d) - do.nl(x - d)) == 1 for d in (1e-12,)), x

@@ -156,3 +156,39 @@ def test_c_example_builds_against_the_header(lib):
     import subprocess
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 2 and "usage" in out.stderr
+
+
+def test_fields_layout_matches_header():
+    assert C.sizeof(_lib.Fields) == 144
+    assert _lib.Fields.altitude.offset == 28 and _lib.Fields.ident.offset == 64 and _lib.Fields.lat.offset == 72
+    assert _lib.Fields.val.offset == 104
+
+
+def test_decoder_has_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gr_air_modes_b200 import decode
+    h = C.c_void_p()
+    assert lib.amb_decoder_create(0, 0, 0.0, 0.0, C.byref(h)) == -2      # AMB_ERR_NO_DEVICE
+    with pytest.raises(RuntimeError):
+        decode.batch_decoder([37.0, -122.0])
+
+
+def test_frame_bits_host_helper_follows_get_bits(lib):
+    """amb_frame_bits = data_field.get_bits (parse.py:71-87) incl. the 'negative shift reads 0' rule."""
+    from gr_air_modes_b200 import decode
+    from oracle import decode_oracle as do
+    rng = np.random.default_rng(8)
+    for k in range(300):
+        nbytes = 14 if k % 2 else 7
+        raw = bytearray(rng.integers(0, 256, nbytes, dtype=np.uint8).tobytes())
+        if nbytes == 14:
+            raw[0] |= 0x80                      # long replies have the top DF bit set (slicer_impl.cc:140)
+        else:
+            raw[0] &= 0x7F
+        arr, _ = decode.frames_from_messages([(bytes(raw).hex(), 0, 0, 0.0)])
+        v = int.from_bytes(raw, "big")
+        for _ in range(20):
+            s, n = int(rng.integers(1, 113)), int(rng.integers(1, 57))
+            assert decode.frame_bits(arr[0], s, n) == do.bits(v, 8 * nbytes, s, n), (raw.hex(), s, n)
