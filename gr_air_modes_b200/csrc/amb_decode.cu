@@ -109,6 +109,7 @@ amb_pair_kernel(const AmbPosRec* __restrict__ pos, int n, AmbCprSlot* table, Amb
         if (mine && (int)lane == 31 - __clz(same)) {
             const uint4 v = make_uint4(me.lat, me.lon, (unsigned)__double2loint(me.t), (unsigned)__double2hiint(me.t));
             __stcg(reinterpret_cast<uint4*>(&table[slot_mine]), v);
+            __threadfence_block();
         }
         __syncwarp();                                                       // ... and visible to the next step's reads
     }
