@@ -184,6 +184,11 @@ def make_case(seed, n_aircraft=6, seconds=40.0, location=(37.4, -122.1), surface
     return (list(location) if location is not None else None), msgs
 
 
+def message_strings(msgs):
+    """(hex, ecc, secs, frac) -> the slicer's message text (slicer_impl.cc:186-192) with a made-up reference level."""
+    return ["%s %06x %r %d %r" % (h, e, 10.0 ** (-((7 * k) % 61) / 10.0), s, f) for k, (h, e, s, f) in enumerate(msgs)]
+
+
 CASES = [
     dict(seed=11, location=(37.4, -122.1)),
     dict(seed=12, location=None),

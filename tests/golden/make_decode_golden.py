@@ -148,6 +148,52 @@ def run_reference(location, msgs, mods=None):
     return out
 
 
+class PubSub(dict):
+    """Stand-in for gnuradio.gr.pubsub (a dict whose assignments call the subscribers), all msprint.py needs."""
+
+    def __init__(self):
+        dict.__init__(self)
+        self._subs = {}
+
+    def subscribe(self, key, fn):
+        self._subs.setdefault(key, []).append(fn)
+
+    def __setitem__(self, key, val):
+        dict.__setitem__(self, key, val)
+        for fn in self._subs.get(key, []):
+            fn(val)
+
+
+def run_reference_printer(location, msgs, mods=None):
+    """The reference's own consumer chain: make_parser (parse.py:422-436) -> pubsub -> output_print (msprint.py),
+    one fresh cpr_decoder. -> per message the printed line or None."""
+    exc, alt, parse, cpr = mods or load_reference()
+    pkg = sys.modules["air_modes"]
+    for name in dir(parse):
+        if not name.startswith("_"):
+            setattr(pkg, name, getattr(parse, name))
+    msprint = _load("air_modes.msprint", os.path.join(REF, "msprint.py"))
+    clock = Clock()
+    cpr.time = types.SimpleNamespace(time=clock.time)
+    dec = cpr.cpr_decoder(list(location) if location is not None else None)
+    pub = PubSub()
+    got = []
+    msprint.output_print(dec, pub, callback=got.append)
+    publish = parse.make_parser(pub)
+    lines = []
+    import decode_cases
+    for text, (hexs, ecc, secs, frac) in zip(decode_cases.message_strings(msgs), msgs):
+        clock.now = float(secs) + float(frac)
+        del got[:]
+        try:
+            publish(text)
+        except IndexError:              # parseBDS08's category table has a short row (parse.py:264,268)
+            pass
+        assert len(got) <= 1
+        lines.append(got[0] if got else None)
+    return lines
+
+
 def main():
     import decode_cases
     mods = load_reference()
@@ -162,8 +208,10 @@ def main():
         npos = sum(1 for r in ref if "pos" in r)
         nstr = sum(1 for r in ref if r.get("cpr_error") == "straddle")
         print("seed", kw["seed"], len(msgs), "msgs;", npos, "positions,", nstr, "straddles;", stat)
+        lines = run_reference_printer(loc, msgs, mods)
+        print("   printed lines:", sum(1 for x in lines if x is not None))
         cases.append({"args": {k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()},
-                      "location": loc, "msgs": [list(m) for m in msgs], "ref": ref})
+                      "location": loc, "msgs": [list(m) for m in msgs], "ref": ref, "lines": lines})
     unload_reference()
 
     def clean(o):

@@ -132,3 +132,21 @@ def test_nl_table_equals_formula(shim):
     assert len(bad) <= 20, bad[:10]
     for x in bad:
         assert any(abs(do.nl(x + d) - do.nl(x - d)) == 1 for d in (1e-12,)), x
+
+
+def test_report_lines_match_reference_printer(shim):
+    """gr_air_modes_b200.report (the text apps/modes_rx prints by default) against the lines the UNMODIFIED
+    python/msprint.py printed for the same messages (golden 'lines'); records from the host build of the product's
+    decode arithmetic."""
+    import decode_cases
+    from gr_air_modes_b200 import report
+    n = printed = 0
+    for ci, case in enumerate(load_decode_golden()):
+        msgs = [tuple(m) for m in case["msgs"]]
+        recs = _shim_decode(shim, msgs, case["location"])
+        for k, (text, rec, want) in enumerate(zip(decode_cases.message_strings(msgs), recs, case["lines"])):
+            got = report.format_report(text, rec)
+            assert got == want, (ci, k, text, got, want)
+            n += 1
+            printed += want is not None
+    assert n > 5000 and printed > 4000

@@ -227,3 +227,56 @@ def test_receive_chain_to_positions(port):
             assert abs(g["lat"] - w["lat"]) <= TOL * 90 and abs(g["lon"] - w["lon"]) <= TOL * 180
             assert abs(g["range"] - w["range"]) <= 1e-9 and abs(g["bearing"] - w["bearing"]) <= 1e-9
     assert npos >= sent - 6
+
+
+def _position_scene(rate, n, seed):
+    import decode_cases as dc
+    from gr_air_modes_b200 import synth
+    rng = np.random.default_rng(seed)
+    iq = (rng.standard_normal((n, 2)) * 0.005).astype(np.float32)
+    c = iq.view(np.complex64).reshape(n)
+    start, odd, sent = 3000.0, 0, 0
+    while start < n - 2000:
+        aa = (0x3C6444, 0xA1B2C3)[sent % 2]
+        lat, lon = (50.03 + 1e-4 * sent, 8.57) if sent % 2 == 0 else (49.9, 8.2 + 1e-4 * sent)
+        la, lo = dc.cpr_encode(lat, lon, odd, False)
+        if sent % 7 == 3:
+            me = dc.me_ident(4, 3, "DLH%03d" % sent)
+        elif sent % 7 == 5:
+            me = dc.Bits(56).put(1, 5, 19).put(6, 3, 1).put(15, 10, 200 + sent).put(26, 10, 300).put(38, 9, 17).v
+        else:
+            me = dc.me_airborne(11, dc.enc_alt12(10000 + 25 * sent), odd, la, lo)
+        frame, _ = dc.df17(aa, me)
+        n0, w = synth.burst_waveform(synth.Burst(start, frame, 0.3, float(rng.uniform(0, 6.28))), rate / 2e6)
+        c[n0:n0 + w.size] += w
+        start += 20000 + float(rng.uniform(0, 3000))
+        sent += 1
+        if sent % 2 == 0:
+            odd ^= 1
+    return iq.reshape(-1), sent
+
+
+def test_cli_prints_the_reference_printers_reports(port, tmp_path):
+    """Row f1 + f4: `modes_rx_b200.py -l LAT,LON` prints what apps/modes_rx prints by default - the text reports of
+    python/msprint.py. Expected lines: the oracle's messages, decoded by the decode oracle, formatted by report.py
+    (which tests/test_decode_cpu.py pins line for line against the unmodified msprint.py)."""
+    import os
+    import subprocess
+    import sys
+    from gr_air_modes_b200 import report
+    from oracle import cpu_oracle as co
+    from oracle import decode_oracle as do
+    rate, n = 4e6, 1 << 20
+    iq, sent = _position_scene(rate, n, 33)
+    msgs = port.run_iq(iq, rate, 7.0, True, co.MA_CANONICAL).msgs
+    recs = do.decode_batch([(m.split()[0], int(m.split()[1], 16), int(m.split()[3]), float(m.split()[4])) for m in msgs], [50.0, 8.5])
+    want = report.report_lines(msgs, recs)
+    assert sum("position report" in ln for ln in want) >= sent // 2 and any("ident DLH" in ln for ln in want)
+    assert any("track report" in ln for ln in want)
+    path = tmp_path / "pos.cfile"
+    iq.tofile(path)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for chunk in ("300001", str(1 << 24)):
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "modes_rx_b200.py"), "-s", str(path), "-r", "4e6",
+                              "-l", "50.0,8.5", "--chunk", chunk], capture_output=True, text=True, check=True).stdout.split("\n")
+        assert [ln for ln in out if ln] == want

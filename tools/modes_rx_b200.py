@@ -5,10 +5,12 @@ The receiver half of apps/modes_rx + python/radio.py: the same "Receiver setup o
 without a radio (radio.py:89-121), the same two offline sources (radio.py:221-232: a cfile or a UDP stream of
 gr_complex), and the same two outlets for the slicer's messages: printed to stdout one per line
 ("<hex> <crc> <ref> <secs> <frac>", what lands on the gr.msg_queue) and published as ZMQ "dl_data"
-(radio.py:79-87) on tcp://*:PORT with -t. Decoding to text reports (parse.py/msprint.py), KML, SBS-1 and
-FlightGear outputs are the reference's own pure-Python consumers of that feed and are not re-implemented.
+(radio.py:79-87) on tcp://*:PORT with -t. With --reports / -l LAT,LON stdout carries what apps/modes_rx prints by
+default instead: the text reports of python/msprint.py, decoded on the GPU (gr_air_modes_b200.decode: parse.py,
+altitude.py, cpr.py for whole batches). KML, SBS-1 and FlightGear outputs are the reference's own pure-Python consumers
+of the dl_data feed and are not re-implemented.
 
-    python tools/modes_rx_b200.py -s capture.cfile -r 4e6 [-T 7.0] [-d] [-t 5556] [-n]
+    python tools/modes_rx_b200.py -s capture.cfile -r 4e6 [-T 7.0] [-d] [-t 5556] [-n] [--reports | -l 37.4,-122.1]
     python tools/modes_rx_b200.py -s 127.0.0.1:12345 -r 4e6 --udp-idle 2.0
 
 Differences, all on the far side of rx_path:
@@ -101,6 +103,36 @@ class print_queue:
         self.count += 1
 
 
+class report_queue:
+    """What apps/modes_rx prints by default: air_modes.output_print(cpr_dec, publisher) (apps/modes_rx:77-78,
+    python/msprint.py) - one text report per parsed message. The numbers come from the GPU batch decoder
+    (gr_air_modes_b200.decode), the line format from gr_air_modes_b200.report."""
+
+    def __init__(self, location, device, out=sys.stdout):
+        from gr_air_modes_b200 import decode
+        self._dec = decode.batch_decoder(location, device)      # = cpr_decoder(my_position), apps/modes_rx:68
+        self._out, self._texts, self.count = out, [], 0
+
+    def handle(self, msg):
+        text = msg.to_string()
+        self._texts.append(text.decode("ascii") if isinstance(text, bytes) else text)
+
+    insert_tail = handle
+
+    def flush(self):
+        """Decode and print everything queued since the last call (one GPU batch)."""
+        from gr_air_modes_b200 import report
+        if self._texts:
+            for line in report.report_lines(self._texts, self._dec.decode_messages(self._texts)):
+                self._out.write(line + "\n")
+                self.count += 1
+            self._texts = []
+        self._out.flush()
+
+    def close(self):
+        self._dec.close()
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
     ap.add_argument("-s", "--source", required=True, help="<filename> (cfile) or <ip:port> (UDP of gr_complex)")   # radio.py:94-95
@@ -112,6 +144,10 @@ def main(argv=None):
     ap.add_argument("--no-pmf", dest="pmf", action="store_false")
     ap.add_argument("-d", "--dcblock", action="store_true", default=False)                                         # radio.py:118
     ap.add_argument("-n", "--no-print", action="store_true", default=False)                                        # apps/modes_rx:42
+    ap.add_argument("--reports", action="store_true", default=False,
+                    help="print decoded text reports (what apps/modes_rx prints by default) instead of the raw message lines")
+    ap.add_argument("-l", "--location", type=str, default=None,
+                    help="GPS coordinates of receiving station in format xx.xxxxx,xx.xxxxx (implies --reports)")   # apps/modes_rx:36-37
     ap.add_argument("--chunk", type=int, default=1 << 24, help="complex samples per amb_process call")
     ap.add_argument("--udp-idle", type=float, default=2.0, help="end a UDP stream after this many idle seconds")
     ap.add_argument("--device", type=int, default=0)
@@ -125,9 +161,15 @@ def main(argv=None):
               "reproduced); running the chain at the native rate" % rate, file=sys.stderr)
     sinks = []
     printer = None
+    reporter = None
     if not args.no_print:
-        printer = print_queue()
-        sinks.append(printer)
+        if args.reports or args.location is not None:
+            my_position = [float(x) for x in args.location.split(",")] if args.location is not None else None   # apps/modes_rx:64-65
+            reporter = report_queue(my_position, args.device)
+            sinks.append(reporter)
+        else:
+            printer = print_queue()
+            sinks.append(printer)
     pub = None
     if args.tcp is not None:
         from gr_air_modes_b200.zmq_pub import zmq_queue
@@ -151,12 +193,16 @@ def main(argv=None):
         total += rx.process(block, flush=last)
         if printer:
             sys.stdout.flush()
+        if reporter:
+            reporter.flush()
     st = rx.stats()
     print("# %d samples in, %d messages" % (st.samples_in, total), file=sys.stderr)
     if pub:
         import time
         time.sleep(0.2)                                                                                           # apps/modes_rx:88-91
         pub.close()
+    if reporter:
+        reporter.close()
     rx.close()
     return 0
 
