@@ -35,6 +35,9 @@ struct amb_decoder {
     double* nl_T = nullptr;              // device copy of the NL transition table
     amb_frame* d_frames = nullptr; amb_fields* d_fields = nullptr; AmbPosRec* d_pos = nullptr; AmbPair* d_pair = nullptr;
     int cap = 0;
+#ifdef AMB_PAIR_V2
+    uint32_t* d_keys = nullptr;
+#endif
     uint64_t launches = 0; float ms_last = 0.f;
     std::string err;
 };
@@ -115,6 +118,79 @@ amb_pair_kernel(const AmbPosRec* __restrict__ pos, int n, AmbCprSlot* table, Amb
     }
 }
 
+#ifdef AMB_PAIR_V2
+// EXPERIMENT (tools/variants.py "pair_v2"; NOT in the product build, not yet run on a GPU). The first pairing kernel is
+// L2-bandwidth-bound: each of its warps reads the whole 24-byte report list (profiles/r1_decode_summary.txt). Here
+// the ownership test reads a 4-byte key array, eight independent steps' keys are in flight per iteration, and only
+// the lanes that own a report load the rest of it. The per-step logic is the first kernel's, unchanged.
+#define AMB_PAIR_V2_U 8
+__global__ void amb_keys_kernel(const AmbPosRec* __restrict__ pos, int n, uint32_t* __restrict__ keys)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) keys[k] = pos[k].key;
+}
+
+__device__ __forceinline__ void amb_pair_step_v2(int k, bool mine, unsigned lane, unsigned lt, const AmbPosRec* __restrict__ pos,
+                                                 AmbCprSlot* table, AmbPair* __restrict__ pair)
+{
+    AmbPosRec me; me.key = AMB_NO_KEY; me.lat = me.lon = 0; me.fmt = 0; me.t = 0.0;
+    if (mine) me = pos[k];
+    const unsigned peers = __match_any_sync(0xffffffffu, mine ? me.key : (0x80000000u | lane));
+    const unsigned evens = __ballot_sync(0xffffffffu, mine && me.fmt == 0);
+    const unsigned odds = __ballot_sync(0xffffffffu, mine && me.fmt != 0);
+    const unsigned other_here = peers & (me.fmt ? evens : odds) & lt;
+    const int src = other_here ? (31 - __clz(other_here)) : (int)lane;
+    uint32_t o_lat = __shfl_sync(0xffffffffu, me.lat, src);
+    uint32_t o_lon = __shfl_sync(0xffffffffu, me.lon, src);
+    double o_t = __shfl_sync(0xffffffffu, me.t, src);
+    bool o_have = other_here != 0;
+    const size_t slot_other = ((size_t)me.key << 1) | (me.fmt ? 0u : 1u);
+    const size_t slot_mine = ((size_t)me.key << 1) | (me.fmt ? 1u : 0u);
+    if (mine && !o_have) {
+        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(&table[slot_other]));
+        if (v.x != 0xFFFFFFFFu) { o_lat = v.x; o_lon = v.y; o_t = __hiloint2double((int)v.w, (int)v.z); o_have = true; }
+    }
+    if (mine) pair[k] = amb_make_pair(me, o_have ? 1 : 0, o_lat, o_lon, o_t);
+    __syncwarp();
+    const unsigned same = peers & (me.fmt ? odds : evens);
+    if (mine && (int)lane == 31 - __clz(same)) {
+        const uint4 v = make_uint4(me.lat, me.lon, (unsigned)__double2loint(me.t), (unsigned)__double2hiint(me.t));
+        __stcg(reinterpret_cast<uint4*>(&table[slot_mine]), v);
+        __threadfence_block();
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32 * AMB_PAIR_WARPS_PER_CTA)
+amb_pair_kernel_v2(const uint32_t* __restrict__ keys, const AmbPosRec* __restrict__ pos, int n, AmbCprSlot* table,
+                   AmbPair* __restrict__ pair)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned warp = blockIdx.x * AMB_PAIR_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const unsigned n_warps = gridDim.x * AMB_PAIR_WARPS_PER_CTA;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < n; base += 32 * AMB_PAIR_V2_U) {
+        uint32_t key[AMB_PAIR_V2_U];
+#pragma unroll
+        for (int u = 0; u < AMB_PAIR_V2_U; u++) {
+            const int k = base + 32 * u + (int)lane;
+            key[u] = k < n ? __ldg(keys + k) : AMB_NO_KEY;
+        }
+        bool mine[AMB_PAIR_V2_U], any = false;
+#pragma unroll
+        for (int u = 0; u < AMB_PAIR_V2_U; u++) {
+            mine[u] = key[u] != AMB_NO_KEY && amb_key_owner(key[u], n_warps) == warp;
+            any = any || mine[u];
+        }
+        if (!__any_sync(0xffffffffu, any)) continue;
+#pragma unroll
+        for (int u = 0; u < AMB_PAIR_V2_U; u++)                     // stream order: step u before step u + 1
+            if (__any_sync(0xffffffffu, mine[u]))
+                amb_pair_step_v2(base + 32 * u + (int)lane, mine[u], lane, lt, pos, table, pair);
+    }
+}
+#endif
+
 __global__ void __launch_bounds__(128) amb_resolve_kernel(amb_fields* __restrict__ fields, const AmbPosRec* __restrict__ pos,
                                                           const AmbPair* __restrict__ pair, int n, int have_loc,
                                                           double mylat, double mylon, const double* __restrict__ nl_T)
@@ -137,6 +213,10 @@ static void free_bufs(amb_decoder* d)
     if (d->d_fields) cudaFree(d->d_fields);
     if (d->d_pos) cudaFree(d->d_pos);
     if (d->d_pair) cudaFree(d->d_pair);
+#ifdef AMB_PAIR_V2
+    if (d->d_keys) cudaFree(d->d_keys);
+    d->d_keys = nullptr;
+#endif
     d->d_frames = nullptr; d->d_fields = nullptr; d->d_pos = nullptr; d->d_pair = nullptr; d->cap = 0;
 }
 
@@ -150,6 +230,9 @@ static int ensure_cap(amb_decoder* d, int n)
     DCK(cudaMalloc(&d->d_fields, (size_t)cap * sizeof(amb_fields)));
     DCK(cudaMalloc(&d->d_pos, (size_t)cap * sizeof(AmbPosRec)));
     DCK(cudaMalloc(&d->d_pair, (size_t)cap * sizeof(AmbPair)));
+#ifdef AMB_PAIR_V2
+    DCK(cudaMalloc(&d->d_keys, (size_t)cap * sizeof(uint32_t)));
+#endif
     d->cap = cap;
     return AMB_OK;
 }
@@ -245,7 +328,21 @@ int amb_decode_frames(amb_decoder* d, const amb_frame* frames, int n, int mem_ki
     if (warps > max_warps) warps = max_warps;
     if (warps < AMB_PAIR_WARPS_PER_CTA) warps = AMB_PAIR_WARPS_PER_CTA;
     const int pair_ctas = (warps + AMB_PAIR_WARPS_PER_CTA - 1) / AMB_PAIR_WARPS_PER_CTA;
+#ifdef AMB_PAIR_V2
+    {
+        int w2 = n / 1024;
+        if (w2 > max_warps) w2 = max_warps;
+        if (w2 < AMB_PAIR_WARPS_PER_CTA) w2 = AMB_PAIR_WARPS_PER_CTA;
+        amb_keys_kernel<<<nb, 128, 0, s>>>(d->d_pos, n, d->d_keys);
+        DCK(cudaGetLastError());
+        amb_pair_kernel_v2<<<(w2 + AMB_PAIR_WARPS_PER_CTA - 1) / AMB_PAIR_WARPS_PER_CTA, 32 * AMB_PAIR_WARPS_PER_CTA, 0, s>>>(
+            d->d_keys, d->d_pos, n, d->table, d->d_pair);
+        (void)pair_ctas;
+        d->launches += 1;
+    }
+#else
     amb_pair_kernel<<<pair_ctas, 32 * AMB_PAIR_WARPS_PER_CTA, 0, s>>>(d->d_pos, n, d->table, d->d_pair);
+#endif
     DCK(cudaGetLastError());
     amb_resolve_kernel<<<nb, 128, 0, s>>>(d->d_fields, d->d_pos, d->d_pair, n, d->have_loc, d->lat, d->lon, d->nl_T);
     DCK(cudaGetLastError());

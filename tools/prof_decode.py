@@ -2,7 +2,7 @@
 """Timing / profiling driver for the batch field decoder: synthetic DF17 position traffic,
 vectorised frame construction (no torch import), decode at a few batch sizes.
 
-    python tools/prof_decode.py [log2n ...]          # prints device ms per batch (H2D + 3 kernels + D2H)
+    python tools/prof_decode.py [--check] [log2n ...]   # device ms per batch (H2D + 3 kernels + D2H); --check: parity first
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
         --log-file gpurun_out/decode_launches.csv python tools/prof_decode.py 16 20
 """
@@ -32,8 +32,32 @@ def make_frames(n, n_aircraft, seed):
     return f
 
 
+def check():
+    """Parity of whatever libairmodes_b200.so is in place against the CPU oracle on a seeded case (tests/decode_cases)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    import decode_cases
+    from oracle import decode_oracle as do
+    bad = 0
+    for seed, loc in ((501, (35.7, 139.7)), (502, None)):
+        loc_, msgs = decode_cases.make_case(seed, location=loc, seconds=30.0, surface_share=0.4, n_random=600, n_aircraft=12)
+        want = do.decode_batch(msgs, loc_)
+        d = decode.batch_decoder(loc_)
+        got = d.decode_messages(msgs)
+        d.close()
+        for g, w in zip(got, want):
+            same = g["status"] == w["status"] and g["altitude"] == w["altitude"]
+            if w["status"] & do.FS_HAS_POS:
+                same = same and abs(g["lat"] - w["lat"]) < 1e-10 and abs(g["lon"] - w["lon"]) < 1e-10
+            bad += not same
+    print("parity vs oracle: %s" % ("ok" if bad == 0 else "%d MISMATCHES" % bad))
+    return bad == 0
+
+
 def main():
-    sizes = [int(a) for a in sys.argv[1:]] or [16, 20]
+    args = [a for a in sys.argv[1:] if a != "--check"]
+    if "--check" in sys.argv[1:] and not check():
+        sys.exit(1)
+    sizes = [int(a) for a in args] or [16, 20]
     d = decode.batch_decoder([40.0, -3.0])
     for lg in sizes:
         n = 1 << lg
