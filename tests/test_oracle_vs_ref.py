@@ -153,3 +153,30 @@ def test_dc_blocker_restatement_sanity(port):
     a = port.run_iq(iq, rate, 7.0, True, co.MA_CANONICAL, use_dcblock=True).msgs
     b = port.run_iq(iq, rate, 7.0, True, co.MA_GR_FLOAT, 4096, use_dcblock=True).msgs
     assert [m.split()[:2] for m in a] == [m.split()[:2] for m in b] and len(a) > 0
+
+
+def test_port_matches_reference_random_sweep(port, ref):
+    """Seeded sweep over rates (integer and fractional samples/chip), thresholds, PMF on/off, burst density, garble and
+    FRUIT: detection indices, 240-chip packets, timestamps, message text and the number of general_work calls of the
+    port equal the unmodified reference's."""
+    rng = np.random.default_rng(2024)
+    rates = [2e6, 2.4e6, 2.5e6, 3e6, 3.2e6, 4e6, 5e6, 6e6, 8e6, 10e6, 12e6, 12.5e6, 16e6, 20e6]
+    total = 0
+    for k in range(28):
+        rate = rates[k % len(rates)]
+        thr = float(rng.choice([3.0, 4.5, 6.0, 7.0, 8.5, 10.0]))
+        pmf = bool(rng.integers(0, 2))
+        n = int(60_000 * rate / 2e6 / 2) + int(rng.integers(0, 999))
+        nb = int(rng.choice([3, 12, 60]))
+        sc = synth.make_scene(rate, n, nb, 7000 + k, garble_frac=0.3 if nb > 20 else 0.0, fruit=20 if nb > 20 else 0,
+                              snr_db=(4.0, 28.0), df_choices=(0, 4, 5, 11, 16, 17, 20, 21, 24))
+        bb, avg = port.frontend(sc.iq, rate, pmf, co.MA_CANONICAL)
+        r = ref.run_streams(bb, avg, rate, thr)
+        p = port.run_streams(bb, avg, rate, thr)
+        where = (k, rate, thr, pmf, n, nb)
+        assert np.array_equal(r.index, p.index), where
+        assert np.array_equal(r.secs, p.secs) and np.array_equal(r.frac, p.frac), where
+        assert np.array_equal(r.chips, p.chips), where
+        assert r.msgs == p.msgs and r.calls == p.calls, where
+        total += len(r.index)
+    assert total > 300
