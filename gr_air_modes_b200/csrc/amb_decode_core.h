@@ -128,10 +128,10 @@ AMB_HD void amb_fields_blank(amb_fields* r, int df, uint32_t ecc)
     r->pad_ = 0;
 }
 
-AMB_HD void amb_alt_into(amb_fields* r, int code, int bit13, int32_t* dst)
+AMB_HD void amb_alt_into(amb_fields* r, int code, int bit13, int32_t* dst, int flag = AMB_FS_METRIC_ALT)
 {
     int32_t feet;
-    if (amb_decode_alt(code, bit13, &feet)) r->status |= AMB_FS_METRIC_ALT;
+    if (amb_decode_alt(code, bit13, &feet)) r->status |= (uint8_t)flag;
     else *dst = feet;
 }
 
@@ -166,26 +166,31 @@ AMB_HD void amb_decode_fields(const amb_frame& f, amb_fields* r, AmbPosRec* pos)
     } else if (df == 4 || df == 5 || df == 20 || df == 21) {
         r->fs = (uint8_t)amb_bits(g, 6, 3); r->dr = (uint8_t)amb_bits(g, 9, 5); r->um = (uint8_t)amb_bits(g, 14, 6);
         if (df >= 20) {
-            const int bds1 = (int)amb_bits(g, 33, 4), bds2 = (int)amb_bits(g, 37, 4);
+            // "mb": (33,56, mb_reply) (parse.py:218-219): the sub-fields are read from that 56-bit word, which is 0 when
+            // the reply is short (negative shift, parse.py:83-86). b(s, n) = mb_reply/tcas_reply field at message bit s.
+            AmbMsg mb; mb.w0 = amb_bits(g, 33, 56) << 8; mb.w1 = 0; mb.numbits = 56;
+#define AMB_MB(s, n) amb_bits(mb, (s) - 32, (n))
+            const int bds1 = (int)AMB_MB(33, 4), bds2 = (int)AMB_MB(37, 4);
             r->bds = (uint8_t)bds1; r->bds2 = (uint8_t)bds2;
             if (bds1 > 3 || bds2 != 0) { amb_no_handler(r, 0); return; }     // parse.py:185-190
             if (bds1 == 1) {
-                r->aux[0] = (uint32_t)amb_bits(g, 45, 20); r->aux[1] = (uint32_t)amb_bits(g, 65, 16);
-                r->aux[2] = (uint32_t)amb_bits(g, 81, 8);  r->aux[3] = (uint32_t)amb_bits(g, 41, 4);   // acs, bcs, ecs, cfs
+                r->aux[0] = (uint32_t)AMB_MB(45, 20); r->aux[1] = (uint32_t)AMB_MB(65, 16);
+                r->aux[2] = (uint32_t)AMB_MB(81, 8);  r->aux[3] = (uint32_t)AMB_MB(41, 4);   // acs, bcs, ecs, cfs
             } else if (bds1 == 2) {
-                amb_ident48(amb_bits(g, 41, 48), r->ident);                  // parse.py:374-378
+                amb_ident48(AMB_MB(41, 48), r->ident);                      // parse.py:374-378
             } else if (bds1 == 3) {
-                const int tti = (int)amb_bits(g, 61, 2);
+                const int tti = (int)AMB_MB(61, 2);
                 r->tti = (uint8_t)tti;
                 if (tti == 3) { amb_no_handler(r, 0); return; }              // tcas_reply has types 0-2 (parse.py:157-165)
-                r->aux[0] = (uint32_t)amb_bits(g, 41, 14); r->aux[1] = (uint32_t)amb_bits(g, 55, 4);
-                r->aux[2] = (uint32_t)(amb_bits(g, 59, 1) | (amb_bits(g, 60, 1) << 1));   // rat | mte << 1
-                if (tti == 1) r->aux[3] = (uint32_t)amb_bits(g, 63, 26);     // tid
+                r->aux[0] = (uint32_t)AMB_MB(41, 14); r->aux[1] = (uint32_t)AMB_MB(55, 4);
+                r->aux[2] = (uint32_t)(AMB_MB(59, 1) | (AMB_MB(60, 1) << 1));   // rat | mte << 1
+                if (tti == 1) r->aux[3] = (uint32_t)AMB_MB(63, 26);          // tid
                 else if (tti == 2) {
-                    r->aux[3] = (uint32_t)(amb_bits(g, 76, 7) | (amb_bits(g, 83, 6) << 8));   // tidr | tidb << 8
-                    amb_alt_into(r, (int)amb_bits(g, 63, 13), 1, &r->threat_alt);             // parse.py:407
+                    r->aux[3] = (uint32_t)(AMB_MB(76, 7) | (AMB_MB(83, 6) << 8));   // tidr | tidb << 8
+                    amb_alt_into(r, (int)AMB_MB(63, 13), 1, &r->threat_alt, AMB_FS_METRIC_THREAT);   // parse.py:407
                 }
             }
+#undef AMB_MB
         }
         if (df == 4 || df == 20) amb_alt_into(r, (int)amb_bits(g, 20, 13), 1, &r->altitude);
         else r->squawk = amb_decode_id((int)amb_bits(g, 20, 13));

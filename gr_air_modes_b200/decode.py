@@ -20,7 +20,7 @@ from . import _lib
 from ._lib import Fields, Frame, check
 
 FS_NO_HANDLER, FS_METRIC_ALT, FS_CPR_NO_POS, FS_CPR_STRADDLE = 0x01, 0x02, 0x04, 0x08
-FS_HAS_POS, FS_HAS_RANGE, FS_NOT_QUEUED = 0x10, 0x20, 0x80
+FS_HAS_POS, FS_HAS_RANGE, FS_METRIC_THREAT, FS_NOT_QUEUED = 0x10, 0x20, 0x40, 0x80
 NO_ALTITUDE = -(1 << 31)
 
 FIELDS_DTYPE = np.dtype(Fields)

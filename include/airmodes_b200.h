@@ -231,12 +231,13 @@ AMB_API int amb_get_walk_summary(amb_ctx* ctx, amb_walk_summary* out);   /* sync
  * must come in non-decreasing time order. No CPU path: without a device amb_decoder_create fails. */
 #define AMB_FS_NO_HANDLER 0x01   /* the parser raised NoHandlerError (unknown DF / FTC / BDS0,9 subtype / MB register,
                                     parse.py:52-68): the reference drops the message; only df, ecc (and icao) are set */
-#define AMB_FS_METRIC_ALT 0x02   /* decode_alt raised MetricAltError (altitude.py:32-43): altitude/threat_alt not set */
+#define AMB_FS_METRIC_ALT 0x02   /* decode_alt(ac) raised MetricAltError (altitude.py:32-43): altitude not set */
 #define AMB_FS_CPR_NO_POS 0x04   /* CPRNoPositionError: no live even/odd pair (cpr.py:231), or a surface report
                                     without a receiver location (cpr.py:97-99) */
 #define AMB_FS_CPR_STRADDLE 0x08 /* CPRBoundaryStraddleError (cpr.py:120-121); AMB_FS_CPR_NO_POS is set as well */
 #define AMB_FS_HAS_POS 0x10      /* lat / lon valid */
 #define AMB_FS_HAS_RANGE 0x20    /* range / bearing valid (receiver location known, cpr.py:233-237) */
+#define AMB_FS_METRIC_THREAT 0x40 /* decode_alt(tida) raised MetricAltError in the TCAS threat sub-decode (parse.py:407): threat_alt not set */
 #define AMB_FS_NOT_QUEUED 0x80   /* frame.passed == 0: the slicer never queued it, nothing was decoded */
 #define AMB_NO_ALTITUDE INT32_MIN
 

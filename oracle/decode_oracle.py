@@ -29,7 +29,7 @@ from __future__ import annotations
 import math
 
 FS_NO_HANDLER, FS_METRIC_ALT, FS_CPR_NO_POS, FS_CPR_STRADDLE = 0x01, 0x02, 0x04, 0x08
-FS_HAS_POS, FS_HAS_RANGE, FS_NOT_QUEUED = 0x10, 0x20, 0x80
+FS_HAS_POS, FS_HAS_RANGE, FS_METRIC_THREAT, FS_NOT_QUEUED = 0x10, 0x20, 0x40, 0x80
 NO_ALT = -(1 << 31)
 
 
@@ -181,7 +181,7 @@ def _blank(df, ecc):
 def _alt(r, code, bit13, key="altitude"):
     a = decode_alt(code, bit13)
     if a is None:
-        r["status"] |= FS_METRIC_ALT
+        r["status"] |= FS_METRIC_ALT if key == "altitude" else FS_METRIC_THREAT
     else:
         r[key] = a
 
@@ -204,27 +204,29 @@ def decode_one(payload_hex: str, ecc: int, now: float, cpr: CprState) -> dict:
     elif df in (4, 5, 20, 21):
         r["fs"], r["dr"], r["um"] = g(6, 3), g(9, 5), g(14, 6)
         if df in (20, 21):
-            bds1, bds2 = g(33, 4), g(37, 4)
+            mb = g(33, 56)                                  # "mb": (33,56, mb_reply); 0 for a short reply (parse.py:83-86)
+            b = lambda s, n: bits(mb, 56, s - 32, n)        # noqa: E731  mb_reply/tcas_reply fields, message coordinates
+            bds1, bds2 = b(33, 4), b(37, 4)
             r["bds"], r["bds2"] = bds1, bds2
             if bds1 > 3 or bds2 != 0:                      # parse.py:185-190
                 r["status"] |= FS_NO_HANDLER
                 return _only_header(r)
             if bds1 == 1:
-                r["aux"] = [g(45, 20), g(65, 16), g(81, 8), g(41, 4)]          # acs, bcs, ecs, cfs
+                r["aux"] = [b(45, 20), b(65, 16), b(81, 8), b(41, 4)]          # acs, bcs, ecs, cfs
             elif bds1 == 2:
-                r["ident"] = ident48(g(41, 48))
+                r["ident"] = ident48(b(41, 48))
             elif bds1 == 3:
-                tti = g(61, 2)
+                tti = b(61, 2)
                 r["tti"] = tti
                 if tti == 3:                               # tcas_reply has no type 3 (parse.py:157-165)
                     r["status"] |= FS_NO_HANDLER
                     return _only_header(r)
-                r["aux"][0], r["aux"][1], r["aux"][2] = g(41, 14), g(55, 4), g(59, 1) | (g(60, 1) << 1)
+                r["aux"][0], r["aux"][1], r["aux"][2] = b(41, 14), b(55, 4), b(59, 1) | (b(60, 1) << 1)
                 if tti == 1:
-                    r["aux"][3] = g(63, 26)
+                    r["aux"][3] = b(63, 26)
                 elif tti == 2:
-                    r["aux"][3] = g(76, 7) | (g(83, 6) << 8)
-                    _alt(r, g(63, 13), True, "threat_alt")                   # parse.py:407
+                    r["aux"][3] = b(76, 7) | (b(83, 6) << 8)
+                    _alt(r, b(63, 13), True, "threat_alt")                   # parse.py:407
         if df in (4, 20):
             _alt(r, g(20, 13), True)
         else:

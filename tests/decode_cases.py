@@ -98,6 +98,27 @@ def long_frame(df, rng, address, mb=None):
     return finish(b.bytes(), address)
 
 
+def raw_message(rng):
+    """(frame bytes, ecc) with unconstrained contents; the DF and a few sub-type fields are steered so that every
+    branch of the parser is reached often."""
+    nb = 14 if rng.random() < 0.6 else 7
+    raw = bytearray(rng.integers(0, 256, nb, dtype=np.uint8).tobytes())
+    r = rng.random()
+    if r < 0.45:
+        raw[0] = (17 << 3) | (raw[0] & 7)
+        raw[1], raw[2], raw[3] = 0, 0, int(rng.integers(0, 40))
+        if nb == 14 and rng.random() < 0.7:
+            ftc = int(rng.choice([1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 16, 17, 18, 19, 28]))
+            raw[4] = (ftc << 3) | (raw[4] & 7)
+    elif r < 0.5:
+        raw[0], raw[1] = 0, 0                           # small value: modes_reply.is_long (parse.py:222-223)
+    elif r < 0.75:
+        raw[0] = (int(rng.choice([0, 4, 5, 11, 16, 20, 21, 24])) << 3) | (raw[0] & 7)
+        if nb == 14 and rng.random() < 0.8:
+            raw[4] = int(rng.integers(0, 4)) << 4       # MB register 0..3 / 0
+    return bytes(raw), int(rng.integers(0, 1 << 24))
+
+
 def make_case(seed, n_aircraft=6, seconds=40.0, location=(37.4, -122.1), surface_share=0.2, n_random=150):
     """Returns (location or None, [(hex, ecc, secs, frac), ...]) in time order."""
     rng = np.random.Generator(np.random.PCG64(seed))
@@ -175,6 +196,9 @@ def make_case(seed, n_aircraft=6, seconds=40.0, location=(37.4, -122.1), surface
             me = me_surface(int(rng.integers(5, 9)), int(rng.integers(0, 128)), 1, int(rng.integers(0, 128)),
                             int(rng.integers(0, 2)), int(rng.integers(0, 1 << 17)), int(rng.integers(0, 1 << 17)))
             ev.append((t, *df17(addr & 0xFF, me)))
+    for _ in range(n_random // 3):                      # what no slicer emits but a message string can carry: free bytes,
+        t = rng.uniform(0, seconds)                     # long DFs in 56 bits (sub-fields read 0), short DFs in 112 bits
+        ev.append((t, *raw_message(rng)))
     ev.sort(key=lambda e: e[0])
     base = 1_700_000_000 if seed % 2 else 0             # UTC-sized seconds lose no precision in secs + frac? (they do: tested)
     msgs = []

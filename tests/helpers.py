@@ -93,8 +93,9 @@ def compare_decode(rec, ref, tol=0.0, where="", tol_libm=None):
         assert rec["aux"][3] == ref["tid"], (where, rec, ref)
     if "tidr" in ref:
         assert rec["aux"][3] == (ref["tidr"] | (ref["tidb"] << 8)) and rec["threat_alt"] == ref["threat_alt"], (where, rec, ref)
+        assert not (st & 0x40), (where, rec, ref)
     if "threat_metric_alt" in ref:
-        assert st & METRIC, (where, rec, ref)
+        assert st & 0x40, (where, rec, ref)          # AMB_FS_METRIC_THREAT
     if "cpr" in ref:
         assert [rec["cpr_format"], rec["cpr_lat"], rec["cpr_lon"]] == ref["cpr"], (where, rec, ref)
     if "ground_track" in ref:
