@@ -180,3 +180,45 @@ def test_port_matches_reference_random_sweep(port, ref):
         assert r.msgs == p.msgs and r.calls == p.calls, where
         total += len(r.index)
     assert total > 300
+
+
+def test_port_matches_reference_on_pathological_inputs(port, ref):
+    """Same inputs tools/stress_parity.py throws at the GPU: 1e-17 / 1e-21 / 3e14 amplitude scales (denormals, near
+    overflow), NaN/Inf samples, silence, a DC offset, dense garbled traffic. (1500 such cases were run offline while
+    building this; 80 here.)"""
+    rng = np.random.default_rng(31337)
+    tot = 0
+    for case in range(80):
+        rate = float(rng.choice([2e6, 2.4e6, 3e6, 4e6, 5e6, 8e6, 10e6, 16e6, 20e6, 4e6, 7e6]))
+        pmf = bool(rng.random() < 0.8)
+        thr = float(rng.choice([0.5, 3.0, 7.0, 7.0, 12.0, 20.0]))
+        n, nb = int(rng.integers(12_000, 120_000)), int(rng.integers(0, 40))
+        sigma = float(rng.choice([0.0, 1e-3, 0.01, 0.05]))
+        kind = ["plain", "scale_small", "scale_big", "silence", "naninf", "dc", "dense", "denorm"][case % 8]
+        sc = synth.make_scene(rate, n, nb * (10 if kind == "dense" else 1), int(rng.integers(1 << 30)), noise_sigma=sigma,
+                              snr_db=(3.0, 40.0), garble_frac=0.2, fruit=int(rng.integers(0, 40)),
+                              amplitude=None if sigma > 0 else 0.3, df_choices=(0, 4, 5, 11, 16, 17, 18, 20, 21, 24))
+        iq = sc.iq.copy()
+        if kind == "scale_small":
+            iq *= np.float32(1e-17)
+        elif kind == "denorm":
+            iq *= np.float32(1e-21)
+        elif kind == "scale_big":
+            iq *= np.float32(3e14)
+        elif kind == "silence":
+            a = int(rng.integers(0, n))
+            iq[2 * a: 2 * min(n, a + int(rng.integers(1, n)))] = 0
+        elif kind == "naninf":
+            for _ in range(3):
+                iq[int(rng.integers(0, 2 * n))] = rng.choice([np.nan, np.inf, -np.inf, 3e38])
+        elif kind == "dc":
+            iq[0::2] += np.float32(0.02)
+        with np.errstate(all="ignore"):
+            bb, avg = port.frontend(iq, rate, pmf, co.MA_CANONICAL)
+        r = ref.run_streams(bb, avg, rate, thr)
+        p = port.run_streams(bb, avg, rate, thr)
+        where = (case, kind, rate, pmf, thr, n)
+        assert np.array_equal(r.index, p.index) and r.msgs == p.msgs and r.calls == p.calls, where
+        assert np.array_equal(r.chips, p.chips, equal_nan=True), where
+        tot += len(r.index)
+    assert tot > 500
