@@ -85,6 +85,7 @@ SYMBOLS = [
     ("amb_poll_frames", C.c_int, [_vp, C.POINTER(Frame), C.c_int]),
     ("amb_pending_frames", C.c_int, [_vp]),
     ("amb_format_message", C.c_int, [C.POINTER(Frame), C.c_int, C.c_char_p, C.c_size_t]),
+    ("amb_format_messages", C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
     ("amb_modes_check_crc", C.c_uint32, [C.c_char_p, C.c_int]),
     ("amb_device_crc", C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint32)]),
     ("amb_preamble_process", C.c_int, [_vp, _f32p, _f32p, C.c_size_t, C.c_int, _f32p, _u64p, C.c_int]),

@@ -143,12 +143,15 @@ class _Context:
     def call(self, name, *args):
         return check(getattr(self._lib, name)(self._h, *args), self._h)
 
-    def poll(self):
+    def poll_array(self):
+        """(ctypes Frame array, count) of everything pending, in stream order."""
         n = self.call("amb_pending_frames")
-        if n == 0:
-            return []
-        buf = (Frame * n)()
-        got = self.call("amb_poll_frames", buf, n)
+        buf = (Frame * max(n, 1))()
+        got = self.call("amb_poll_frames", buf, n) if n else 0
+        return buf, got
+
+    def poll(self):
+        buf, got = self.poll_array()
         return list(buf)[:got]
 
     def stats(self) -> Stats:
@@ -183,14 +186,25 @@ class slicer:
         self._ctx = _ctx or _Context(4e6, 7.0, False, False, device)
         self._first = True          # d_payload precision: 6 until the first message (slicer_impl.cc:192)
 
-    def emit(self, frames) -> int:
-        """Queue one message per frame that passed the slicer rules. Returns how many."""
-        k = 0
-        for f in frames:
-            if f.passed:
-                self._queue.handle(_make_gr_message(self._queue, format_message(f, self._first)))
-                self._first = False
-                k += 1
+    def emit(self, frames, n: int | None = None) -> int:
+        """Queue one message per frame that passed the slicer rules (slicer_impl.cc:186-194). Returns how many.
+        `frames`: a ctypes Frame array (first n entries) or any sequence of Frame. The text of the whole batch is
+        formatted by one library call."""
+        if isinstance(frames, (list, tuple)):
+            n = len(frames) if n is None else n
+            frames = (Frame * max(n, 1))(*frames[:n])
+        elif n is None:
+            n = len(frames)
+        if n == 0:
+            return 0
+        cap = 128 * n + 16
+        buf = C.create_string_buffer(cap)
+        k = check(_lib.load().amb_format_messages(C.cast(frames, C.c_void_p), int(n), int(self._first), buf, cap))
+        if k:
+            handle, q = self._queue.handle, self._queue
+            for text in buf.value.decode("ascii").split("\n"):
+                handle(_make_gr_message(q, text))
+            self._first = False
         return k
 
     def process(self, chips, tags) -> list:
@@ -203,9 +217,8 @@ class slicer:
         out = (Frame * max(ndet, 1))()
         self._ctx.call("amb_slicer_process", chips.ctypes.data_as(C.POINTER(C.c_float)), ndet,
                        secs.ctypes.data_as(C.POINTER(C.c_uint64)), frac.ctypes.data_as(C.POINTER(C.c_double)), out)
-        frames = list(out)[:ndet]
-        self.emit(frames)
-        return frames
+        self.emit(out, ndet)
+        return list(out)[:ndet]
 
 
 class preamble:
@@ -295,9 +308,10 @@ class rx_path:
         return self.drain() if collect else 0
 
     def drain(self) -> int:
-        self.frames = self._ctx.poll()
+        buf, got = self._ctx.poll_array()
+        self.frames = list(buf)[:got]
         self._keep = None
-        return self._slicer.emit(self.frames)
+        return self._slicer.emit(buf, got)
 
     def reset(self):
         self._ctx.call("amb_reset")

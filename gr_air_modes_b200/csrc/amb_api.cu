@@ -865,12 +865,35 @@ int amb_format_message(const amb_frame* f, int first, char* buf, size_t buflen)
     if (!f || !buf) return AMB_ERR_INVALID;
     char tmp[192];
     int o = 0;
-    for (int m = 0; m < f->nbits / 8 && m < 14; m++) o += snprintf(tmp + o, sizeof tmp - o, "%02x", (unsigned)f->data[m]);
+    static const char hexd[] = "0123456789abcdef";
+    for (int m = 0; m < f->nbits / 8 && m < 14; m++) { tmp[o++] = hexd[f->data[m] >> 4]; tmp[o++] = hexd[f->data[m] & 15]; }
     o += snprintf(tmp + o, sizeof tmp - o, " %06lx %.*g %llu %.10g", (unsigned long)f->crc, first ? 6 : 10,
                   (double)f->ref_level, (unsigned long long)f->secs, f->frac);
     if ((size_t)o + 1 > buflen) return AMB_ERR_INVALID;
     memcpy(buf, tmp, (size_t)o + 1);
     return o;
+}
+
+// The same for a whole batch: one line per frame with passed != 0, in order, separated by '\n'. The stream's first
+// message has precision 6, every later one 10 (the sticky setprecision of slicer_impl.cc:192).
+int amb_format_messages(const amb_frame* frames, int n, int first, char* buf, size_t buflen)
+{
+    if (n < 0 || (n > 0 && !frames) || !buf || buflen == 0) return AMB_ERR_INVALID;
+    size_t o = 0;
+    int count = 0;
+    buf[0] = 0;
+    for (int k = 0; k < n; k++) {
+        if (!frames[k].passed) continue;
+        char tmp[192];
+        const int len = amb_format_message(&frames[k], first && count == 0, tmp, sizeof tmp);
+        if (len < 0) return len;
+        if (o + (size_t)len + 2 > buflen) return AMB_ERR_INVALID;
+        if (count) buf[o++] = '\n';
+        memcpy(buf + o, tmp, (size_t)len + 1);
+        o += (size_t)len;
+        count++;
+    }
+    return count;
 }
 
 // modes_crc.cc:33-63

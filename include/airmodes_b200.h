@@ -132,6 +132,11 @@ AMB_API int amb_pending_frames(amb_ctx* ctx);
  * `first` != 0 formats ref with the stream's default precision 6 (the first message a slicer instance
  * emits; setprecision(10) at :192 is sticky afterwards). Returns strlen, <0 if buflen too small. */
 AMB_API int amb_format_message(const amb_frame* f, int first, char* buf, size_t buflen);
+/* The same for n frames at once: the messages of the frames with passed != 0, in order, joined by '\n' (what
+ * slicer_impl::work queues for them, slicer_impl.cc:186-194). `first` != 0: the first message written is the stream's
+ * first (precision 6), all later ones use precision 10. Returns the number of messages, <0 if buflen is too small
+ * (128 bytes per frame always suffice). */
+AMB_API int amb_format_messages(const amb_frame* frames, int n, int first, char* buf, size_t buflen);
 
 /* unsigned int modes_check_crc(unsigned char data[], int length) (include/gr_air_modes/modes_crc.h:26,
  * lib/modes_crc.cc:55-63). Host helper with the same table; the device CRC is a separate kernel path. */

@@ -192,3 +192,47 @@ def test_frame_bits_host_helper_follows_get_bits(lib):
         for _ in range(20):
             s, n = int(rng.integers(1, 113)), int(rng.integers(1, 57))
             assert decode.frame_bits(arr[0], s, n) == do.bits(v, 8 * nbytes, s, n), (raw.hex(), s, n)
+
+
+def test_batch_message_formatting_equals_per_frame(lib, port):
+    """amb_format_messages + slicer.emit (one library call per batch) give exactly the per-frame amb_format_message
+    strings, incl. the stream's first message having precision 6 only once (slicer_impl.cc:192), frames with
+    passed == 0 skipped, and the oracle's text."""
+    from oracle import cpu_oracle as co
+    from gr_air_modes_b200 import blocks
+    rng = np.random.default_rng(12)
+    for n, p_pass in ((0, 1.0), (1, 1.0), (5, 0.0), (700, 0.8), (3, 0.5)):
+        frames = (_lib.Frame * max(n, 1))()
+        oracle_frames = []
+        for k in range(n):
+            f = frames[k]
+            g = co.Frame()
+            f.nbits = g.nbits = 112 if rng.random() < 0.5 else 56
+            data = rng.integers(0, 256, 14, dtype=np.uint8)
+            for m in range(14):
+                f.data[m] = g.data[m] = int(data[m])
+            f.crc = g.crc = int(rng.integers(0, 1 << 24))
+            f.ref_level = g.ref_level = float(np.float32(10.0 ** rng.uniform(-30, 8)))
+            f.secs = g.secs = int(rng.integers(0, 1 << 40))
+            f.frac = g.frac = float(rng.random())
+            f.passed = int(rng.random() < p_pass)
+            oracle_frames.append(g)
+        for first in (True, False):
+            want, fst = [], first
+            for k in range(n):
+                if frames[k].passed:
+                    want.append(blocks.format_message(frames[k], fst))
+                    assert want[-1] == port.format_message(oracle_frames[k], fst)
+                    fst = False
+            for as_list in (False, True):
+                q = am.msg_queue()
+                sl = blocks.slicer.__new__(blocks.slicer)
+                sl._queue, sl._first = q, first
+                k = sl.emit(list(frames)[:n] if as_list else frames, n)
+                assert k == len(want) and q.strings() == want
+                assert sl._first == (first and not want)
+    # buffer too small -> error, not truncation
+    one = (_lib.Frame * 1)()
+    one[0].nbits, one[0].passed = 112, 1
+    buf = C.create_string_buffer(8)
+    assert lib.amb_format_messages(C.cast(one, C.c_void_p), 1, 1, buf, 8) < 0
