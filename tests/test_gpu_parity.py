@@ -362,11 +362,11 @@ def test_two_contexts_with_different_rates_coexist(port):
 
 
 def test_randomised_stress_including_pathological_inputs():
-    """tools/stress_parity.py: random rates / thresholds / PMF / chunkings / resolvers plus inputs scaled to the
+    """tests/tools/stress_parity.py: random rates / thresholds / PMF / chunkings / resolvers plus inputs scaled to the
     denormal range or near overflow, stretches of exact zeros, NaN / Inf samples, DC offsets, dense bursts."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_parity.py"), "3", "40"],
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "stress_parity.py"), "3", "40"],
                          capture_output=True, text=True, timeout=900).stdout
     assert "40 cases, 0 mismatches" in out, out[-2000:]
 

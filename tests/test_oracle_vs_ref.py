@@ -183,7 +183,7 @@ def test_port_matches_reference_random_sweep(port, ref):
 
 
 def test_port_matches_reference_on_pathological_inputs(port, ref):
-    """Same inputs tools/stress_parity.py throws at the GPU: 1e-17 / 1e-21 / 3e14 amplitude scales (denormals, near
+    """Same inputs tests/tools/stress_parity.py throws at the GPU: 1e-17 / 1e-21 / 3e14 amplitude scales (denormals, near
     overflow), NaN/Inf samples, silence, a DC offset, dense garbled traffic. (1500 such cases were run offline while
     building this; 80 here.)"""
     rng = np.random.default_rng(31337)

@@ -1,6 +1,6 @@
 """Dense-traffic probe (BASELINE configs[4]): ~10 k overlapping squitters/s at 4 Msps. Parity vs the oracle and timing."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import gr_air_modes_b200 as am
 from gr_air_modes_b200 import synth

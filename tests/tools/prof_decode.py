@@ -2,9 +2,9 @@
 """Timing / profiling driver for the batch field decoder: synthetic DF17 position traffic,
 vectorised frame construction (no torch import), decode at a few batch sizes.
 
-    python tools/prof_decode.py [--check] [log2n ...]   # device ms per batch (H2D + 3 kernels + D2H); --check: parity first
+    python tests/tools/prof_decode.py [--check] [log2n ...]   # device ms per batch (H2D + 3 kernels + D2H); --check: parity first
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
-        --log-file gpurun_out/decode_launches.csv python tools/prof_decode.py 16 20
+        --log-file gpurun_out/decode_launches.csv python tests/tools/prof_decode.py 16 20
 """
 import os
 import sys
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from gr_air_modes_b200 import decode  # noqa: E402
 
 
@@ -34,7 +34,7 @@ def make_frames(n, n_aircraft, seed):
 
 def check():
     """Parity of whatever libairmodes_b200.so is in place against the CPU oracle on a seeded case (tests/decode_cases)."""
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import decode_cases
     from oracle import decode_oracle as do
     bad = 0

@@ -1,6 +1,6 @@
 """Timing probe (device-resident): scan-kernel and whole-call time, plus a parity check vs the oracle."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import gr_air_modes_b200 as am
 from gr_air_modes_b200 import synth

@@ -1,6 +1,6 @@
 """Small workload for compute-sanitizer (memcheck / racecheck / initcheck)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import gr_air_modes_b200 as am
 from gr_air_modes_b200 import synth

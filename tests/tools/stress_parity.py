@@ -1,6 +1,6 @@
 """Randomised parity stress on the GPU: rates, thresholds, PMF, chunkings, amplitude scales, silence, NaN/Inf."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import gr_air_modes_b200 as am
 from gr_air_modes_b200 import synth

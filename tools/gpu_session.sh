@@ -27,13 +27,13 @@ if has scan; then       # one full capture of the dominant kernel at 4 Msps and 
       python tools/prof_run.py 28 4e6 2 > gpurun_out/scan_4msps.log 2>&1
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:amb_scan -s 1 -c 1 -f -o gpurun_out/scan_20msps \
       python tools/prof_run.py 28 20e6 2 > gpurun_out/scan_20msps.log 2>&1
-  for r in 2e6 4e6 10e6 20e6; do timeout 120 python tools/prof_time.py 28 $r 2>&1 | tail -1; done > gpurun_out/scan_times.log
+  for r in 2e6 4e6 10e6 20e6; do timeout 120 python tests/tools/prof_time.py 28 $r 2>&1 | tail -1; done > gpurun_out/scan_times.log
   cat gpurun_out/scan_times.log
 fi
 if has decode; then     # row f4: parity + timings of the batch decoder, then its launch list
-  timeout 120 python tools/prof_decode.py --check 16 20 > gpurun_out/decode_time.log 2>&1; cat gpurun_out/decode_time.log
+  timeout 120 python tests/tools/prof_decode.py --check 16 20 > gpurun_out/decode_time.log 2>&1; cat gpurun_out/decode_time.log
   timeout 120 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
-      --log-file gpurun_out/decode_launches.csv python tools/prof_decode.py 16 20 > /dev/null 2>&1
+      --log-file gpurun_out/decode_launches.csv python tests/tools/prof_decode.py 16 20 > /dev/null 2>&1
 fi
 if has variants; then   # experiment builds (python tools/variants.py build on the CPU box first)
   timeout 300 python tools/variants.py run-decode 16 20 > gpurun_out/variants_decode.log 2>&1; cat gpurun_out/variants_decode.log

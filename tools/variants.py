@@ -1,13 +1,13 @@
 """Experiment helper: build scan-kernel variants here (CPU box), time them on the GPU box.
    python tools/variants.py build   -> gr_air_modes_b200/variants/<name>.so
-   python tools/variants.py run     -> (on the GPU) swaps each variant in and runs tools/prof_time.py
-   python tools/variants.py run-decode [log2n ...] -> same with tools/prof_decode.py --check (decoder experiments)"""
+   python tools/variants.py run     -> (on the GPU) swaps each variant in and runs tests/tools/prof_time.py
+   python tools/variants.py run-decode [log2n ...] -> same with tests/tools/prof_decode.py --check (decoder experiments)"""
 import os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "gr_air_modes_b200", "variants")
 VARIANTS = {"nst2": ["AMB_NST=2"], "nst3": ["AMB_NST=3"], "nst2_noeval": ["AMB_NST=2", "AMB_DBG_NOEVAL"], "nst2_loadonly": ["AMB_NST=2", "AMB_DBG_LOADONLY"],
-            # decoder experiment (row f4): pairing kernel with a key array + 8 steps in flight; time with tools/prof_decode.py --check
+            # decoder experiment (row f4): pairing kernel with a key array + 8 steps in flight; time with tests/tools/prof_decode.py --check
             "pair_v2": ["AMB_PAIR_V2"]}
 if sys.argv[1] == "build":
     from gr_air_modes_b200 import build
@@ -24,10 +24,10 @@ else:
             shutil.copy(os.path.join(VDIR, name), lib)
             if sys.argv[1] == "run-decode":
                 if not name.startswith("pair"): continue
-                out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "prof_decode.py"), "--check"] + sys.argv[2:], capture_output=True, text=True)
+                out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "prof_decode.py"), "--check"] + sys.argv[2:], capture_output=True, text=True)
                 print(name, out.stdout.strip() if out.stdout.strip() else out.stderr[-300:])
                 continue
-            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "prof_time.py")] + sys.argv[2:], capture_output=True, text=True)
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "prof_time.py")] + sys.argv[2:], capture_output=True, text=True)
             print(name, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:])
     finally:
         shutil.copy(keep, lib); os.remove(keep)
