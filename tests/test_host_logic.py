@@ -103,6 +103,12 @@ def test_product_does_not_touch_oracle():
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert all(w not in txt for w in ("cpu_oracle", "liboracle", "modes_oracle", "decode_oracle")), fn
     assert "oracle" not in open(os.path.join(ROOT, "include", "airmodes_b200.h")).read().lower()
+    # the user-facing tools and the C example are product too; diagnostics that use the checker live in tests/tools
+    for d in ("tools", "examples"):
+        for fn in os.listdir(os.path.join(ROOT, d)):
+            if fn.endswith((".py", ".sh", ".c")):
+                txt = open(os.path.join(ROOT, d, fn)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, fn
 
 
 def test_geometry_matches_reference_blocks(lib, port, ref):
