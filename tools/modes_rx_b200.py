@@ -16,8 +16,10 @@ of the dl_data feed and are not re-implemented.
 Differences, all on the far side of rx_path:
 * live radios (-s uhd / osmocom) need GNU Radio: use gr_air_modes_b200.gr_adapter.rx_path inside modes_radio.
 * radio.py:49-53 resamples rates below 4 Msps to 4 Msps with GNU Radio's pfb.arb_resampler_ccf. That filter
-  bank is GNU Radio code and is not reproduced; the chain is run at the native rate instead (it supports every
-  rate from 2 Msps, preamble_impl.cc:56-63) and a note is printed.
+  bank is GNU Radio code and cannot be reproduced sample for sample; by default the chain is run at the native rate (it
+  supports every rate from 2 Msps, preamble_impl.cc:56-63) and a note is printed; --resample puts a documented
+  stand-in (tools/resample_standin.py: rational polyphase resampler on the host, where the reference runs its own)
+  in front and runs the chain at 4 Msps like modes_rx does.
 """
 import argparse
 import os
@@ -148,6 +150,9 @@ def main(argv=None):
                     help="print decoded text reports (what apps/modes_rx prints by default) instead of the raw message lines")
     ap.add_argument("-l", "--location", type=str, default=None,
                     help="GPS coordinates of receiving station in format xx.xxxxx,xx.xxxxx (implies --reports)")   # apps/modes_rx:36-37
+    ap.add_argument("--resample", action="store_true", default=False,
+                    help="rates below 4 Msps: resample to 4 Msps in front of the chain like radio.py:49-53 "
+                         "(stand-in for GNU Radio's pfb.arb_resampler_ccf, tools/resample_standin.py)")
     ap.add_argument("--chunk", type=int, default=1 << 24, help="complex samples per amb_process call")
     ap.add_argument("--udp-idle", type=float, default=2.0, help="end a UDP stream after this many idle seconds")
     ap.add_argument("--device", type=int, default=0)
@@ -156,9 +161,18 @@ def main(argv=None):
     if args.source in ("uhd", "osmocom"):
         raise SystemExit("live radios need GNU Radio: use gr_air_modes_b200.gr_adapter.rx_path in modes_radio (INTEGRATION.md)")
     rate = int(args.rate)                                                                                          # radio.py:44
-    if rate < 4e6:
+    resampler = None
+    rx_rate = rate
+    if rate < 4e6 and args.resample:                                                                               # radio.py:49-51
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from resample_standin import StreamResampler
+        resampler = StreamResampler(rate, 4e6)
+        rx_rate = 4000000
+        print("# rate %d < 4 Msps: resampling %d/%d to 4 Msps in front of the chain (stand-in for GNU Radio's "
+              "pfb.arb_resampler_ccf, radio.py:49-53)" % (rate, resampler.up, resampler.down), file=sys.stderr)
+    elif rate < 4e6:
         print("# rate %d < 4 Msps: the reference would resample to 4 Msps (radio.py:49-53, GNU Radio PFB, not "
-              "reproduced); running the chain at the native rate" % rate, file=sys.stderr)
+              "reproduced; --resample runs a stand-in); running the chain at the native rate" % rate, file=sys.stderr)
     sinks = []
     printer = None
     reporter = None
@@ -175,7 +189,7 @@ def main(argv=None):
         from gr_air_modes_b200.zmq_pub import zmq_queue
         pub = zmq_queue(["tcp://*:%i" % args.tcp])
         sinks.append(pub)
-    rx = air_modes.rx_path(rate, args.threshold, tee_queue(sinks), args.pmf, args.dcblock, device=args.device)
+    rx = air_modes.rx_path(rx_rate, args.threshold, tee_queue(sinks), args.pmf, args.dcblock, device=args.device)   # radio.py:55-56
 
     if ":" in args.source and not os.path.exists(args.source):
         m = re.search(r"(.*)\:(\d{1,5})$", args.source)                                                           # radio.py:223-226
@@ -190,6 +204,8 @@ def main(argv=None):
 
     total = 0
     for block, last in src:
+        if resampler is not None:
+            block = resampler.push(block, last)
         total += rx.process(block, flush=last)
         if printer:
             sys.stdout.flush()
