@@ -26,6 +26,10 @@
 
 struct AmbCprSlot { uint32_t lat, lon; double t; };   // lat == 0xFFFFFFFF: empty
 
+#ifdef AMB_PAIR_V3
+#include "amb_decode_v3.cuh"
+#endif
+
 struct amb_decoder {
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
@@ -37,6 +41,9 @@ struct amb_decoder {
     int cap = 0;
 #ifdef AMB_PAIR_V2
     uint32_t* d_keys = nullptr;
+#endif
+#ifdef AMB_PAIR_V3
+    AmbV3Bufs v3;
 #endif
     uint64_t launches = 0; float ms_last = 0.f;
     std::string err;
@@ -279,6 +286,9 @@ void amb_decoder_destroy(amb_decoder* d)
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
     free_bufs(d);
+#ifdef AMB_PAIR_V3
+    amb_v3_free(&d->v3);
+#endif
     if (d->table) cudaFree(d->table);
     if (d->nl_T) cudaFree(d->nl_T);
     if (d->e0) cudaEventDestroy(d->e0);
@@ -328,7 +338,15 @@ int amb_decode_frames(amb_decoder* d, const amb_frame* frames, int n, int mem_ki
     if (warps > max_warps) warps = max_warps;
     if (warps < AMB_PAIR_WARPS_PER_CTA) warps = AMB_PAIR_WARPS_PER_CTA;
     const int pair_ctas = (warps + AMB_PAIR_WARPS_PER_CTA - 1) / AMB_PAIR_WARPS_PER_CTA;
-#ifdef AMB_PAIR_V2
+#if defined(AMB_PAIR_V3)
+    {
+        cudaError_t e3 = cudaSuccess;
+        const int k3 = amb_v3_launch(&d->v3, d->d_pos, n, d->table, d->d_pair, s, &e3);
+        if (k3 < 0) return dfail(d, AMB_ERR_CUDA, "pairing v3", e3);
+        (void)pair_ctas;
+        d->launches += (uint64_t)(k3 - 1);
+    }
+#elif defined(AMB_PAIR_V2)
     {
         int w2 = n / 1024;
         if (w2 > max_warps) w2 = max_warps;
