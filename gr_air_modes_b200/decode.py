@@ -120,6 +120,52 @@ class batch_decoder:
             pass
 
 
+class cpr_decoder:
+    """Drop-in for the reference's `air_modes.cpr_decoder(my_location)` (python/cpr.py:183-240; constructed at
+    apps/modes_rx:69, used by parseBDS05/06, parse.py:285,291): the same two methods, the same return list
+    `[lat, lon, range, bearing]` and the same exceptions, one message per call - so the reference's unmodified
+    output plugins can run on top of the GPU decoder. Reports are aged with `clock()` (default time.time, exactly
+    as cpr.py:219-221 does). For throughput use batch_decoder; this class is the compatibility surface."""
+
+    def __init__(self, my_location, device: int = 0, clock=None, _backend=None):
+        import time
+        self.my_location = my_location
+        self._clock = clock or time.time
+        self._dec = _backend if _backend is not None else batch_decoder(my_location, device)
+        self._arr = (Frame * 1)()
+
+    def set_location(self, new_location):                       # cpr.py:192-193
+        self.my_location = new_location
+        self._dec.set_location(new_location)
+
+    def decode(self, icao24, encoded_lat, encoded_lon, cpr_format, surface):
+        from .errors import CPRBoundaryStraddleError, CPRNoPositionError
+        now = float(self._clock())
+        f = self._arr[0]
+        # a DF17 extended squitter carrying exactly this report: ME type 11 (airborne) / 6 (surface), parse.py:124-127
+        me = ((6 if surface else 11) << 51) | ((1 if cpr_format else 0) << 34) | ((int(encoded_lat) & 0x1FFFF) << 17) \
+            | (int(encoded_lon) & 0x1FFFF)
+        raw = bytes([17 << 3]) + (int(icao24) & 0xFFFFFF).to_bytes(3, "big") + me.to_bytes(7, "big") + b"\0\0\0"
+        for i, b in enumerate(raw):
+            f.data[i] = b
+        f.nbits, f.df, f.passed, f.crc = 112, 17, 1, 0
+        f.secs = int(now)
+        f.frac = now - int(now)
+        r = self._dec.decode(self._arr, 1)[0]
+        st = int(r["status"])
+        if st & FS_CPR_STRADDLE:
+            raise CPRBoundaryStraddleError
+        if not (st & FS_HAS_POS):
+            raise CPRNoPositionError
+        if st & FS_HAS_RANGE:
+            return [float(r["lat"]), float(r["lon"]), float(r["range"]), float(r["bearing"])]
+        return [float(r["lat"]), float(r["lon"]), None, None]
+
+    def close(self):
+        if hasattr(self._dec, "close"):
+            self._dec.close()
+
+
 def record_to_dict(rec) -> dict:
     """One FIELDS_DTYPE record -> plain dict (ident as str, arrays as lists)."""
     d = {}

@@ -39,3 +39,24 @@ extern "C" int shim_nl(double lat)
 }
 
 extern "C" int shim_sizeof_fields(void) { return (int)sizeof(amb_fields); }
+
+// Stateful variant (one decoder instance whose report table lives across calls), for the cpr_decoder drop-in test.
+struct ShimState { std::unordered_map<uint64_t, Slot> table; double T[AMB_NL_MAX]; };
+extern "C" void* shim_new(void) { ShimState* s = new ShimState(); amb_build_nl_table(s->T); return s; }
+extern "C" int shim_step(void* p, const amb_frame* frames, int n, int have_loc, double lat, double lon, amb_fields* out)
+{
+    ShimState* s = static_cast<ShimState*>(p);
+    for (int k = 0; k < n; k++) {
+        AmbPosRec me;
+        amb_decode_fields(frames[k], &out[k], &me);
+        if (me.key == AMB_NO_KEY) continue;
+        const uint64_t slot_other = ((uint64_t)me.key << 1) | (me.fmt ? 0u : 1u);
+        const uint64_t slot_mine = ((uint64_t)me.key << 1) | (me.fmt ? 1u : 0u);
+        auto it = s->table.find(slot_other);
+        const bool have = it != s->table.end();
+        const AmbPair pr = amb_make_pair(me, have, have ? it->second.lat : 0, have ? it->second.lon : 0, have ? it->second.t : 0.0);
+        s->table[slot_mine] = Slot{me.lat, me.lon, me.t};
+        amb_resolve_position(&out[k], pr, have_loc, lat, lon, s->T);
+    }
+    return 0;
+}

@@ -184,3 +184,84 @@ def test_fuzz_oracle_core_and_reports_against_live_reference(shim):
             assert sum("pos" in r for r in ref) > 300
     finally:
         mg.unload_reference()
+
+
+class _ShimBackend:
+    """Stands in for decode.batch_decoder in CPU tests: same decode()/set_location() surface, arithmetic from the host
+    build of the product's decode core (tests/decode_host_shim.cc), state kept across calls like the device table."""
+
+    def __init__(self, lib, location):
+        import ctypes as C
+        lib.shim_new.restype = C.c_void_p
+        lib.shim_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
+        self._lib, self._h, self._loc = lib, lib.shim_new(), location
+
+    def set_location(self, loc):
+        self._loc = loc
+
+    def decode(self, frames, n):
+        import ctypes as C
+        import numpy as np
+        from gr_air_modes_b200 import decode
+        out = np.zeros(n, dtype=decode.FIELDS_DTYPE)
+        have, lat, lon = (0, 0.0, 0.0) if self._loc is None else (1, self._loc[0], self._loc[1])
+        self._lib.shim_step(self._h, C.cast(frames, C.c_void_p), n, have, lat, lon, C.c_void_p(out.ctypes.data))
+        return out
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/python"), reason="reference tree not present")
+def test_cpr_decoder_dropin_class_against_the_reference_class(shim):
+    """decode.cpr_decoder (same methods, return list and exceptions as python/cpr.py:183-240) side by side with the
+    UNMODIFIED reference class on the reference's own self-test procedure (cpr.py:264-331: sweep of positions, even
+    then odd report) plus surface reports, expiry and a moving receiver location; both run on one injected clock."""
+    import decode_cases as dc
+    from gr_air_modes_b200 import decode
+    from gr_air_modes_b200.errors import CPRBoundaryStraddleError, CPRNoPositionError
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_decode_golden as mg
+    exc, alt, parse, cpr = mg.load_reference()
+    try:
+        clock = mg.Clock()
+        cpr.time = type("T", (), {"time": staticmethod(clock.time)})
+        rounds, ok, straddle, nopos = 1500, 0, 0, 0
+        for surface in (0, 1):
+            loc = [35.0, -100.0]
+            ref = cpr.cpr_decoder(list(loc))
+            ours = decode.cpr_decoder(list(loc), clock=clock.time, _backend=_ShimBackend(shim, list(loc)))
+            for i in range(rounds):
+                lat = i / (rounds / 170.) - 85 if not surface else 35.0 + (i % 50) * 1e-3
+                if not surface and 100 <= i < 160:
+                    lat = 10.4704713 - 7e-4 + (i - 100) * 2.5e-5          # across an NL transition: boundary straddles
+                lon = i / (rounds / 360.) - 180 if not surface else -100.0 + (i % 70) * 1e-3
+                icao = (i * 7919) & 0xFFFFFF
+                clock.now = 1000.0 + i * 0.37 + (30.0 if i == 700 else 0.0)
+                if i == 900:
+                    loc = [34.5, -99.5]
+                    ref.set_location(list(loc)); ours.set_location(list(loc))
+                for odd, dl in ((0, 0.0), (1, 1e-3)):
+                    la, lo = dc.cpr_encode(lat + dl, min(lon + dl, 180), odd, bool(surface))
+                    clock.now += 0.01
+                    want = got = None
+                    try:
+                        want = ref.decode(icao, la, lo, odd, surface)
+                    except exc.CPRBoundaryStraddleError:
+                        want = "straddle"
+                    except exc.CPRNoPositionError:
+                        want = "nopos"
+                    try:
+                        got = ours.decode(icao, la, lo, odd, surface)
+                    except CPRBoundaryStraddleError:
+                        got = "straddle"
+                    except CPRNoPositionError:
+                        got = "nopos"
+                    if isinstance(want, str):
+                        assert got == want, (surface, i, odd, got, want)
+                        straddle += want == "straddle"
+                        nopos += want == "nopos"
+                    else:
+                        assert got[0] == want[0] and got[1] == want[1], (surface, i, odd, got, want)     # lat/lon bit-exact
+                        assert abs(got[2] - want[2]) <= 1e-12 * max(1, want[2]) and abs(got[3] - want[3]) <= 1e-10
+                        ok += 1
+        assert ok > 2500 and nopos >= 2 * rounds and straddle > 0
+    finally:
+        mg.unload_reference()

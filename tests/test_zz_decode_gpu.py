@@ -280,3 +280,43 @@ def test_cli_prints_the_reference_printers_reports(port, tmp_path):
         out = subprocess.run([sys.executable, os.path.join(root, "tools", "modes_rx_b200.py"), "-s", str(path), "-r", "4e6",
                               "-l", "50.0,8.5", "--chunk", chunk], capture_output=True, text=True, check=True).stdout.split("\n")
         assert [ln for ln in out if ln] == want
+
+
+def test_cpr_decoder_dropin_class(dec_mod):
+    """decode.cpr_decoder = the reference's cpr_decoder API (cpr.py:183-240) one message per call on the GPU decoder;
+    against the decode oracle's CprState on one injected clock (the class itself is pinned against the unmodified
+    reference class in tests/test_decode_cpu.py with the host build of the same arithmetic)."""
+    import decode_cases as dc
+    from gr_air_modes_b200.errors import CPRBoundaryStraddleError, CPRNoPositionError
+    from oracle import decode_oracle as do
+    now = [1000.0]
+    loc = [35.0, -100.0]
+    ours = dec_mod.cpr_decoder(list(loc), clock=lambda: now[0])
+    ref = do.CprState(list(loc))
+    ok = 0
+    for i in range(300):
+        lat, lon = i / (300 / 170.) - 85, i / (300 / 360.) - 180
+        surface = int(i % 5 == 0)
+        if surface:
+            lat, lon = 35.0 + i * 1e-3, -100.0 + i * 1e-3
+        icao = (i * 7919) & 0xFFFFFF
+        now[0] += 0.3 + (30.0 if i == 150 else 0.0)
+        for odd, dl in ((0, 0.0), (1, 1e-3)):
+            la, lo = dc.cpr_encode(lat + dl, min(lon + dl, 180), odd, bool(surface))
+            now[0] += 0.01
+            want = ref.decode(icao, la, lo, odd, surface, now[0])
+            try:
+                got = ours.decode(icao, la, lo, odd, surface)
+            except CPRBoundaryStraddleError:
+                got = "straddle"
+            except CPRNoPositionError:
+                got = "nopos"
+            if want[0] != "ok":
+                assert got == want[0], (i, odd, got, want)
+            else:
+                assert abs(got[0] - want[1]) <= TOL * 90 and abs(got[1] - want[2]) <= TOL * 180, (i, odd, got, want)
+                rng, brg = do.range_bearing(loc, [want[1], want[2]])
+                assert abs(got[2] - rng) <= 1e-9 * max(1.0, rng) and abs(got[3] - brg) <= 1e-9 * 360
+                ok += 1
+    ours.close()
+    assert ok >= 290
