@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(128) amb_v3_pair(const AmbPosRec* __restrict__
     }
 }
 
+#ifdef __CUDACC__
 static cudaError_t amb_v3_ensure(AmbV3Bufs* v, int n)
 {
     const int n_tiles = (n + AMB_V3_TILE - 1) / AMB_V3_TILE;
@@ -207,3 +208,4 @@ static int amb_v3_launch(AmbV3Bufs* v, const AmbPosRec* pos, int n, AmbCprSlot* 
     *err = cudaGetLastError();
     return *err == cudaSuccess ? 5 : -1;
 }
+#endif  // __CUDACC__

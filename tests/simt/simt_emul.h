@@ -1,0 +1,155 @@
+// TEST INFRASTRUCTURE: a small SIMT emulator, enough to run launch-free CUDA kernel headers of this repo on the host.
+//
+// One kernel launch = blocks run one after the other; the threads of a block are cooperative fibers (ucontext) on one
+// OS thread. A fiber runs until it reaches a warp- or block-level collective (__syncthreads, __syncwarp, shuffles,
+// votes, match), parks there until every participant has arrived, then continues - i.e. the barrier semantics CUDA
+// guarantees, none of its accidental lockstep. `__shared__` becomes a function-local static (one block at a time).
+// Supported: full-mask warp collectives with all 32 lanes alive, 1-D grids/blocks (blockDim.x a multiple of 32),
+// atomicAdd on unsigned, __ldg/__ldcg/__stcg, bit intrinsics. A launch whose fibers all wait without progress is
+// reported as a deadlock (that is how a divergent collective would show up).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <functional>
+#include <vector>
+
+struct simt_dim3 { unsigned x = 1, y = 1, z = 1; };
+struct uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v = {x, y, z, w}; return v; }
+
+struct SimtWarp { unsigned arrived = 0, gen = 0; uint64_t slot[32]; unsigned pred[32]; };
+struct SimtFiber { ucontext_t ctx; char* stack = nullptr; bool done = false; simt_dim3 tid; SimtWarp* warp = nullptr; };
+struct SimtBlockBar { unsigned arrived = 0, gen = 0, n = 0; };
+
+static ucontext_t simt_sched_ctx;
+static SimtFiber* simt_cur = nullptr;
+static SimtBlockBar simt_block_bar;
+static simt_dim3 simt_block_idx, simt_block_dim, simt_grid_dim;
+static unsigned long simt_progress = 0;
+static std::function<void()> simt_body;
+
+#define threadIdx (simt_cur->tid)
+#define blockIdx simt_block_idx
+#define blockDim simt_block_dim
+#define gridDim simt_grid_dim
+#define __global__ static
+#define __device__ static
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define AMB_SIMT_EMUL 1
+
+static inline void simt_yield() { swapcontext(&simt_cur->ctx, &simt_sched_ctx); }
+
+// every lane of the warp deposits (value, pred), waits for the other 31, then reads; a second rendezvous frees the slots
+static inline void simt_warp_exchange(uint64_t value, unsigned pred, uint64_t* vals, unsigned* preds)
+{
+    SimtWarp* w = simt_cur->warp;
+    const unsigned lane = simt_cur->tid.x & 31;
+    w->slot[lane] = value; w->pred[lane] = pred;
+    unsigned g = w->gen;
+    simt_progress++;                                        // an arrival is progress; a parked fiber that stays parked is not
+    if (++w->arrived == 32) { w->arrived = 0; w->gen++; } else while (w->gen == g) simt_yield();
+    for (int i = 0; i < 32; i++) { vals[i] = w->slot[i]; preds[i] = w->pred[i]; }
+    g = w->gen;
+    simt_progress++;
+    if (++w->arrived == 32) { w->arrived = 0; w->gen++; } else while (w->gen == g) simt_yield();
+}
+
+static inline void __syncwarp(unsigned = 0xffffffffu) { uint64_t v[32]; unsigned p[32]; simt_warp_exchange(0, 0, v, p); }
+static inline void __syncthreads()
+{
+    SimtBlockBar* b = &simt_block_bar;
+    const unsigned g = b->gen;
+    simt_progress++;
+    if (++b->arrived == b->n) { b->arrived = 0; b->gen++; } else while (b->gen == g) simt_yield();
+}
+static inline void __threadfence_block() {}
+static inline unsigned __ballot_sync(unsigned, int pred)
+{
+    uint64_t v[32]; unsigned p[32]; simt_warp_exchange(0, pred ? 1u : 0u, v, p);
+    unsigned m = 0; for (int i = 0; i < 32; i++) m |= (p[i] ? 1u : 0u) << i; return m;
+}
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline unsigned __match_any_sync(unsigned, unsigned value)
+{
+    uint64_t v[32]; unsigned p[32]; simt_warp_exchange(value, 0, v, p);
+    unsigned m = 0; for (int i = 0; i < 32; i++) m |= (v[i] == (uint64_t)value ? 1u : 0u) << i; return m;
+}
+template <typename T> static inline T __shfl_sync(unsigned, T var, int src)
+{
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    uint64_t bits = 0; memcpy(&bits, &var, sizeof(T));
+    uint64_t v[32]; unsigned p[32]; simt_warp_exchange(bits, 0, v, p);
+    T out; memcpy(&out, &v[src & 31], sizeof(T)); return out;
+}
+template <typename T> static inline T __shfl_up_sync(unsigned, T var, unsigned delta)
+{
+    uint64_t bits = 0; memcpy(&bits, &var, sizeof(T));
+    uint64_t v[32]; unsigned p[32]; simt_warp_exchange(bits, 0, v, p);
+    const unsigned lane = simt_cur->tid.x & 31;
+    T out; memcpy(&out, &v[lane >= delta ? lane - delta : lane], sizeof(T)); return out;
+}
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }   // fibers never preempt
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+template <typename T> static inline T __ldcg(const T* p) { return *p; }
+template <typename T> static inline void __stcg(T* p, T v) { *p = v; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
+static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+static inline double __hiloint2double(int hi, int lo)
+{
+    const uint64_t b = ((uint64_t)(unsigned)hi << 32) | (unsigned)lo; double d; memcpy(&d, &b, 8); return d;
+}
+static inline int __double2loint(double d) { uint64_t b; memcpy(&b, &d, 8); return (int)(unsigned)(b & 0xffffffffu); }
+static inline int __double2hiint(double d) { uint64_t b; memcpy(&b, &d, 8); return (int)(unsigned)(b >> 32); }
+
+static void simt_trampoline() { simt_body(); simt_cur->done = true; simt_progress++; swapcontext(&simt_cur->ctx, &simt_sched_ctx); }
+
+// simt_launch(grid, block, [&]{ kernel(args...); })
+static inline void simt_launch(unsigned grid, unsigned block, const std::function<void()>& body)
+{
+    if (block % 32 != 0) { fprintf(stderr, "simt: block size must be a multiple of 32\n"); abort(); }
+    simt_body = body;
+    simt_grid_dim.x = grid; simt_block_dim.x = block;
+    const size_t stack_bytes = 256 * 1024;
+    std::vector<SimtFiber> fibers(block);
+    std::vector<SimtWarp> warps(block / 32);
+    for (unsigned t = 0; t < block; t++) fibers[t].stack = (char*)malloc(stack_bytes);
+    for (unsigned b = 0; b < grid; b++) {
+        simt_block_idx.x = b;
+        simt_block_bar = SimtBlockBar(); simt_block_bar.n = block;
+        for (auto& w : warps) w = SimtWarp();
+        for (unsigned t = 0; t < block; t++) {
+            SimtFiber& f = fibers[t];
+            f.done = false; f.tid.x = t; f.warp = &warps[t / 32];
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = stack_bytes; f.ctx.uc_link = &simt_sched_ctx;
+            makecontext(&f.ctx, simt_trampoline, 0);
+        }
+        unsigned alive = block;
+        while (alive) {
+            const unsigned long before = simt_progress;
+            alive = 0;
+            for (unsigned t = 0; t < block; t++) {
+                if (fibers[t].done) continue;
+                simt_cur = &fibers[t];
+                swapcontext(&simt_sched_ctx, &fibers[t].ctx);
+                if (!fibers[t].done) alive++;
+            }
+            if (alive && simt_progress == before) {
+                fprintf(stderr, "simt: deadlock in block %u (%u threads wait at a collective that not all reach)\n", b, alive);
+                abort();
+            }
+        }
+    }
+    for (unsigned t = 0; t < block; t++) free(fibers[t].stack);
+    simt_cur = nullptr;
+}
