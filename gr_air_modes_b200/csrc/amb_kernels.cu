@@ -30,6 +30,7 @@ __constant__ unsigned int c_crc_rem[96]; // x^(t+24) mod 0xFFF409, t = distance 
 // shared table: two contexts with different rates can coexist on one device)
 __device__ __forceinline__ int chip_off(int j, float spc_f) { return __float2int_rz(__fmul_rn((float)j, spc_f)); }
 
+#ifndef AMB_SIMT_EMUL   // PTX (mbarrier / TMA) and the scan kernel exist only for the device; tests/simt emulates the rest
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -58,6 +59,8 @@ __device__ __forceinline__ bool elect_one() {   // one lane of the (converged) w
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+#endif
+
 __device__ __forceinline__ const float2* seg_ptr(const AmbSegs& S, int j) {
     if (j < S.n_carry) return S.carry + j;
     j -= S.n_carry;
@@ -65,6 +68,7 @@ __device__ __forceinline__ const float2* seg_ptr(const AmbSegs& S, int j) {
     return S.tail + (j - S.n_main);
 }
 
+#ifndef AMB_SIMT_EMUL
 // ------------------------------------------------------------------------------------------------
 // scan kernel
 // ------------------------------------------------------------------------------------------------
@@ -455,6 +459,8 @@ cudaError_t amb_launch_scan(const AmbScanArgs& a, int, cudaStream_t s)
     return cudaErrorInvalidValue;
 }
 
+#endif  // AMB_SIMT_EMUL
+
 // ------------------------------------------------------------------------------------------------
 // compaction: (coarse, fine) bitmap -> ordered candidate list. One warp per scan span, so the order is
 // span order x row order x bit order = ascending sample index. Offsets come from the per-span counts.
@@ -516,7 +522,7 @@ cudaError_t amb_launch_compact(const AmbScanArgs& a, int* cand_j, unsigned int c
                                void* walk_scratch, long long n_samples, cudaStream_t s)
 {
     const int n64 = walk_scratch ? (int)(32 + (n_samples >> 20) + 8) : 0;   // AmbParScratch header + time buckets
-    amb_compact_kernel<<<(a.n_spans + 3) / 4, 128, 0, s>>>(a, cand_j, cand_cap, ctr,
+    AMB_LAUNCH((amb_compact_kernel), (a.n_spans + 3) / 4, 128, 0, s, a, cand_j, cand_cap, ctr,
                                                            reinterpret_cast<unsigned long long*>(walk_scratch), n64);
     return cudaGetLastError();
 }
@@ -558,7 +564,7 @@ __device__ __forceinline__ float stream_at(const float* in, long long n, int H, 
 template <bool STREAMS, int SPC>
 __global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a)
 {
-    extern __shared__ float ex_smem[];                 // per warp: m2s[NMp] then bbs[NMp], sized by the launcher
+    AMB_DYN_SMEM(float, ex_smem, 4);                 // per warp: m2s[NMp] then bbs[NMp], sized by the launcher
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const AmbParams& P = a.P;
     const int spc = SPC ? SPC : P.spc_i;
@@ -688,8 +694,8 @@ __global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a)
 template <int SPC>
 static cudaError_t launch_exact_t(const AmbExactArgs& a, int blocks, size_t smem, cudaStream_t s)
 {
-    if (a.in0) amb_exact_kernel<true, SPC><<<blocks, 128, smem, s>>>(a);
-    else amb_exact_kernel<false, SPC><<<blocks, 128, smem, s>>>(a);
+    if (a.in0) AMB_LAUNCH((amb_exact_kernel<true, SPC>), blocks, 128, smem, s, a);
+    else AMB_LAUNCH((amb_exact_kernel<false, SPC>), blocks, 128, smem, s, a);
     return cudaGetLastError();
 }
 
@@ -788,7 +794,7 @@ __global__ void amb_walk_seq_kernel(const AmbWalkArgs a)
 
 cudaError_t amb_launch_walk_seq(const AmbWalkArgs& a, cudaStream_t s)
 {
-    amb_walk_seq_kernel<<<1, 32, 0, s>>>(a);
+    AMB_LAUNCH((amb_walk_seq_kernel), 1, 32, 0, s, a);
     return cudaGetLastError();
 }
 
@@ -816,8 +822,8 @@ cudaError_t amb_launch_dump(const float2* iq, long long n, const AmbParams& P, i
 {
     if (n <= 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    amb_dump_bb_kernel<<<blocks, 256, 0, s>>>(iq, n, P, stage, stage == 2 ? tmp : out);
-    if (stage == 2) amb_dump_avg_kernel<<<blocks, 256, 0, s>>>(tmp, n, P, out);
+    AMB_LAUNCH((amb_dump_bb_kernel), blocks, 256, 0, s, iq, n, P, stage, stage == 2 ? tmp : out);
+    if (stage == 2) AMB_LAUNCH((amb_dump_avg_kernel), blocks, 256, 0, s, tmp, n, P, out);
     return cudaGetLastError();
 }
 
@@ -829,7 +835,7 @@ __global__ void amb_set_state_kernel(AmbWalkState* st, long long pos, long long 
 
 cudaError_t amb_launch_set_state(AmbWalkState* st, long long pos, long long p, cudaStream_t s)
 {
-    amb_set_state_kernel<<<1, 1, 0, s>>>(st, pos, p);
+    AMB_LAUNCH((amb_set_state_kernel), 1, 1, 0, s, st, pos, p);
     return cudaGetLastError();
 }
 
@@ -985,13 +991,13 @@ cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, unsigned in
     cudaError_t e;                                          // scratch header + buckets were zeroed by the prologue kernel
     const long long guard = (long long)a.P.maxlate + a.P.skip0 + 2 * a.P.spc_i + 8;
     const long long zone = a.flush ? (a.ntot - guard) : a.r_safe;
-    amb_walk_par1_kernel<<<296, 256, 0, s>>>(a, sc, first_fin, buckets, zone);
+    AMB_LAUNCH((amb_walk_par1_kernel), 296, 256, 0, s, a, sc, first_fin, buckets, zone);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    amb_walk_par2_kernel<<<148, 256, 0, s>>>(a, sc, first_fin, buckets);
+    AMB_LAUNCH((amb_walk_par2_kernel), 148, 256, 0, s, a, sc, first_fin, buckets);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    amb_walk_finalize_kernel<<<1, 32, 0, s>>>(a, sc);
+    AMB_LAUNCH((amb_walk_finalize_kernel), 1, 32, 0, s, a, sc);
     return cudaGetLastError();
 }
 
@@ -1011,7 +1017,7 @@ __global__ void amb_walk_reset_kernel(const AmbWalkArgs a, unsigned long long* s
 cudaError_t amb_launch_walk_reset(const AmbWalkArgs& a, void* scratch, long long n_samples, cudaStream_t s)
 {
     const int n64 = scratch ? (int)(32 + (n_samples >> AMB_BUCKET_SHIFT) + 8) : 0;   // as the compaction kernel clears it
-    amb_walk_reset_kernel<<<148, 256, 0, s>>>(a, reinterpret_cast<unsigned long long*>(scratch), n64);
+    AMB_LAUNCH((amb_walk_reset_kernel), 148, 256, 0, s, a, reinterpret_cast<unsigned long long*>(scratch), n64);
     return cudaGetLastError();
 }
 
@@ -1033,7 +1039,7 @@ cudaError_t amb_launch_walk_summary(const AmbWalkArgs& a, cudaStream_t s)
 {
     cudaError_t e = cudaMemsetAsync(&a.st->first_real, 0xff, 2 * sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
-    amb_walk_summary_kernel<<<148, 256, 0, s>>>(a);
+    AMB_LAUNCH((amb_walk_summary_kernel), 148, 256, 0, s, a);
     return cudaGetLastError();
 }
 
@@ -1129,7 +1135,7 @@ __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
 {
     __shared__ float s_chips[4][240];
     __shared__ unsigned int s_crc[96];
-    extern __shared__ float sl_smem[];                         // per warp: m2 of the packet span (not in STREAMS mode)
+    AMB_DYN_SMEM(float, sl_smem, 4);                         // per warp: m2 of the packet span (not in STREAMS mode)
     if (threadIdx.x < 96) s_crc[threadIdx.x] = c_crc_rem[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1203,8 +1209,8 @@ cudaError_t amb_launch_slice(const AmbSliceArgs& a, int sm_count, cudaStream_t s
     const int spanp = ((int)(239 * a.P.spc_f) + fl + 31) & ~31;        // = int(239*spc) + fl, rounded
     const size_t smem = a.in0 ? 0 : (size_t)4 * spanp * sizeof(float);  // 38 KiB at 20 Msps, 8 KiB at 4 Msps
     const int blocks = sm_count * 8;
-    if (a.in0) amb_slice_kernel<true><<<blocks, 128, smem, s>>>(a);
-    else amb_slice_kernel<false><<<blocks, 128, smem, s>>>(a);
+    if (a.in0) AMB_LAUNCH((amb_slice_kernel<true>), blocks, 128, smem, s, a);
+    else AMB_LAUNCH((amb_slice_kernel<false>), blocks, 128, smem, s, a);
     return cudaGetLastError();
 }
 
@@ -1228,7 +1234,7 @@ cudaError_t amb_launch_slice_chips(const float* chips, int ndet, amb_frame* fram
 {
     if (ndet <= 0) return cudaSuccess;
     int blocks = (ndet + 3) / 4; if (blocks > 2048) blocks = 2048;
-    amb_slice_chips_kernel<<<blocks, 128, 0, s>>>(chips, ndet, frames);
+    AMB_LAUNCH((amb_slice_chips_kernel), blocks, 128, 0, s, chips, ndet, frames);
     return cudaGetLastError();
 }
 
@@ -1249,7 +1255,7 @@ __global__ void amb_crc_kernel(const uint8_t* __restrict__ data, int n, int leng
 cudaError_t amb_launch_crc(const uint8_t* data, int n, int length, uint32_t* out, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    amb_crc_kernel<<<(n + 3) / 4, 128, 0, s>>>(data, n, length, out);
+    AMB_LAUNCH((amb_crc_kernel), (n + 3) / 4, 128, 0, s, data, n, length, out);
     return cudaGetLastError();
 }
 
@@ -1264,7 +1270,7 @@ __global__ void amb_carry_kernel(const AmbSegs S, float2* __restrict__ dst, int 
 }
 cudaError_t amb_launch_carry(const AmbSegs& S, float2* dst, int kc, cudaStream_t s)
 {
-    amb_carry_kernel<<<(kc + 255) / 256, 256, 0, s>>>(S, dst, kc);
+    AMB_LAUNCH((amb_carry_kernel), (kc + 255) / 256, 256, 0, s, S, dst, kc);
     return cudaGetLastError();
 }
 
@@ -1282,7 +1288,7 @@ __global__ void amb_prologue_kernel(float2* __restrict__ tail, int tail_cap, con
 cudaError_t amb_launch_prologue(float2* tail, int tail_cap, const float2* src_rem, int n_rem,
                                 uint32_t* group_count, int n_groups, cudaStream_t s)
 {
-    amb_prologue_kernel<<<8, 256, 0, s>>>(tail, tail_cap, src_rem, n_rem, group_count, n_groups);
+    AMB_LAUNCH((amb_prologue_kernel), 8, 256, 0, s, tail, tail_cap, src_rem, n_rem, group_count, n_groups);
     return cudaGetLastError();
 }
 
@@ -1324,7 +1330,7 @@ __global__ void __launch_bounds__(256) amb_stream_cand_kernel(const __grid_const
 }
 cudaError_t amb_launch_stream_candidates(const AmbScanArgs& a, const float* in0, const float* in1, long long n, cudaStream_t s)
 {
-    amb_stream_cand_kernel<<<592, 256, 0, s>>>(a, in0, in1, n);
+    AMB_LAUNCH((amb_stream_cand_kernel), 592, 256, 0, s, a, in0, in1, n);
     return cudaGetLastError();
 }
 
@@ -1360,7 +1366,7 @@ __global__ void __launch_bounds__(256) amb_dcblock_kernel(const float2* __restri
                                                           const float2* __restrict__ ma0, float2* __restrict__ dst,
                                                           long long n_out, int D, int lim)
 {
-    extern __shared__ __align__(16) unsigned char dc_smem[];
+    AMB_DYN_SMEM(unsigned char, dc_smem, 16);
     const int W = DC_T + D - 1;
     float2* src = reinterpret_cast<float2*>(dc_smem);                                               // W source elements
     double2* P = reinterpret_cast<double2*>(dc_smem + (size_t)((W + 1) & ~1) * sizeof(float2));     // W + 1 prefix sums (re, im)
@@ -1454,10 +1460,10 @@ static cudaError_t launch_dcblock_t(const float2* rawcarry, int nc, const float2
     if (e == cudaSuccess) e = cudaFuncSetAttribute(amb_dcblock_kernel<1, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long n0 = n_new + D - 1;
-    amb_dcblock_kernel<0, CH><<<(unsigned)((n0 + DC_T - 1) / DC_T), 256, smem, s>>>(rawcarry, nc, fresh, nullptr, ma0_tmp, n0, D, lim);
+    AMB_LAUNCH((amb_dcblock_kernel<0, CH>), (unsigned)((n0 + DC_T - 1) / DC_T), 256, smem, s, rawcarry, nc, fresh, nullptr, ma0_tmp, n0, D, lim);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    amb_dcblock_kernel<1, CH><<<(unsigned)((n_new + DC_T - 1) / DC_T), 256, smem, s>>>(rawcarry, nc, fresh, ma0_tmp, out, n_new, D, lim);
+    AMB_LAUNCH((amb_dcblock_kernel<1, CH>), (unsigned)((n_new + DC_T - 1) / DC_T), 256, smem, s, rawcarry, nc, fresh, ma0_tmp, out, n_new, D, lim);
     return cudaGetLastError();
 }
 
