@@ -22,7 +22,7 @@ struct simt_dim3 { unsigned x = 1, y = 1, z = 1; };
 struct uint4 { unsigned x, y, z, w; };
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v = {x, y, z, w}; return v; }
 
-struct SimtWarp { unsigned arrived = 0, gen = 0; uint64_t slot[32]; unsigned pred[32]; };
+struct SimtWarp { unsigned arrived = 0, gen = 0, alive = 32; uint64_t slot[32]; unsigned pred[32]; };
 struct SimtFiber { ucontext_t ctx; char* stack = nullptr; bool done = false; simt_dim3 tid; SimtWarp* warp = nullptr; };
 struct SimtBlockBar { unsigned arrived = 0, gen = 0, n = 0; };
 
@@ -56,11 +56,11 @@ static inline void simt_warp_exchange(uint64_t value, unsigned pred, uint64_t* v
     w->slot[lane] = value; w->pred[lane] = pred;
     unsigned g = w->gen;
     simt_progress++;                                        // an arrival is progress; a parked fiber that stays parked is not
-    if (++w->arrived == 32) { w->arrived = 0; w->gen++; } else while (w->gen == g) simt_yield();
+    if (++w->arrived == w->alive) { w->arrived = 0; w->gen++; } else while (w->gen == g) simt_yield();
     for (int i = 0; i < 32; i++) { vals[i] = w->slot[i]; preds[i] = w->pred[i]; }
     g = w->gen;
     simt_progress++;
-    if (++w->arrived == 32) { w->arrived = 0; w->gen++; } else while (w->gen == g) simt_yield();
+    if (++w->arrived == w->alive) { w->arrived = 0; w->gen++; } else while (w->gen == g) simt_yield();
 }
 
 static inline void __syncwarp(unsigned = 0xffffffffu) { uint64_t v[32]; unsigned p[32]; simt_warp_exchange(0, 0, v, p); }
@@ -111,7 +111,81 @@ static inline double __hiloint2double(int hi, int lo)
 static inline int __double2loint(double d) { uint64_t b; memcpy(&b, &d, 8); return (int)(unsigned)(b & 0xffffffffu); }
 static inline int __double2hiint(double d) { uint64_t b; memcpy(&b, &d, 8); return (int)(unsigned)(b >> 32); }
 
-static void simt_trampoline() { simt_body(); simt_cur->done = true; simt_progress++; swapcontext(&simt_cur->ctx, &simt_sched_ctx); }
+
+// ---- vector types, runtime stand-ins, launch macros (amb_internal.h skips the CUDA headers under AMB_SIMT_EMUL) ----
+struct float2 { float x, y; };
+struct double2 { double x, y; };
+static inline float2 make_float2(float x, float y) { float2 v = {x, y}; return v; }
+static inline double2 make_double2(double x, double y) { double2 v = {x, y}; return v; }
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+struct CUtensorMap { alignas(64) unsigned long long opaque[16]; };
+#define __constant__ static
+#define __grid_constant__
+#define __align__(n) __attribute__((aligned(n)))
+#define cudaGetLastError() (cudaSuccess)
+#define cudaFuncSetAttribute(...) (cudaSuccess)
+#define cudaMemcpyToSymbol(sym, src, n) (memcpy((void*)&(sym), (src), (n)), cudaSuccess)
+#define cudaMemsetAsync(p, v, n, s) (memset((p), (v), (n)), cudaSuccess)
+
+static unsigned char* simt_dyn_smem = nullptr;       // dynamic shared memory of the running block
+#define AMB_ID(...) __VA_ARGS__
+#define AMB_DYN_SMEM(type, name, align) type* name = reinterpret_cast<type*>(simt_dyn_smem)
+#define AMB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    simt_launch_dyn((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&] { AMB_ID kernel(__VA_ARGS__); })
+
+template <typename T> static inline T min(T a, T b) { return b < a ? b : a; }
+template <typename T> static inline T max(T a, T b) { return a < b ? b : a; }
+template <typename T> static inline T __shfl_xor_sync(unsigned, T var, int lanemask)
+{
+    uint64_t bits = 0; memcpy(&bits, &var, sizeof(T));
+    uint64_t v[32]; unsigned p[32]; simt_warp_exchange(bits, 0, v, p);
+    T out; memcpy(&out, &v[((simt_cur->tid.x & 31) ^ lanemask) & 31], sizeof(T)); return out;
+}
+static inline unsigned __reduce_max_sync(unsigned, unsigned x)
+{
+    uint64_t v[32]; unsigned p[32]; simt_warp_exchange(x, 0, v, p);
+    unsigned m = 0; for (int i = 0; i < 32; i++) m = (unsigned)v[i] > m ? (unsigned)v[i] : m; return m;
+}
+static inline unsigned __reduce_min_sync(unsigned, unsigned x)
+{
+    uint64_t v[32]; unsigned p[32]; simt_warp_exchange(x, 0, v, p);
+    unsigned m = 0xffffffffu; for (int i = 0; i < 32; i++) m = (unsigned)v[i] < m ? (unsigned)v[i] : m; return m;
+}
+static inline unsigned __brev(unsigned x) { unsigned r = 0; for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i); return r; }
+// n-th set bit of mask counting upward from `base` (fns.b32 with a positive offset; the bit at base counts)
+static inline unsigned __fns(unsigned mask, unsigned base, int offset)
+{
+    if (offset == 0) return ((mask >> base) & 1u) ? base : 0xffffffffu;
+    if (offset > 0) { for (unsigned i = base; i < 32; i++) if ((mask >> i) & 1u) { if (--offset == 0) return i; } }
+    else { for (int i = (int)base; i >= 0; i--) if ((mask >> i) & 1u) { if (++offset == 0) return (unsigned)i; } }
+    return 0xffffffffu;
+}
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline int __float2int_rz(float a) { return (int)a; }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { const unsigned o = *p; *p = o | v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; if (v > o) *p = v; return o; }
+static inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; if (v < o) *p = v; return o; }
+static inline unsigned atomicMax(unsigned* p, unsigned v) { const unsigned o = *p; if (v > o) *p = v; return o; }
+static inline unsigned atomicMin(unsigned* p, unsigned v) { const unsigned o = *p; if (v < o) *p = v; return o; }
+
+// A thread that has exited no longer takes part in barriers (CUDA semantics for __syncthreads and *_sync with exited lanes)
+static void simt_trampoline()
+{
+    simt_body();
+    simt_cur->done = true; simt_progress++;
+    SimtWarp* w = simt_cur->warp;
+    if (--w->alive && w->arrived == w->alive) { w->arrived = 0; w->gen++; }
+    SimtBlockBar* b = &simt_block_bar;
+    if (--b->n && b->arrived == b->n) { b->arrived = 0; b->gen++; }
+    swapcontext(&simt_cur->ctx, &simt_sched_ctx);
+}
 
 // simt_launch(grid, block, [&]{ kernel(args...); })
 static inline void simt_launch(unsigned grid, unsigned block, const std::function<void()>& body)
@@ -152,4 +226,20 @@ static inline void simt_launch(unsigned grid, unsigned block, const std::functio
     }
     for (unsigned t = 0; t < block; t++) free(fibers[t].stack);
     simt_cur = nullptr;
+}
+
+// launch with `smem` bytes of dynamic shared memory (AMB_LAUNCH)
+static inline void simt_launch_dyn(unsigned grid, unsigned block, size_t smem, const std::function<void()>& body)
+{
+    if (block % 32 != 0) {                              // e.g. <<<1, 1>>>: pad the block with lanes that exit at once
+        const unsigned padded = (block + 31) / 32 * 32;
+        simt_launch_dyn(grid, padded, smem, [&] { if (threadIdx.x < block) body(); });
+        return;
+    }
+    unsigned char* buf = nullptr;
+    if (posix_memalign((void**)&buf, 1024, smem ? smem : 1024) != 0) abort();
+    simt_dyn_smem = buf;
+    simt_launch(grid, block, body);
+    simt_dyn_smem = nullptr;
+    free(buf);
 }

@@ -1,0 +1,98 @@
+"""The hot path's sparse kernels WITH their launchers (gr_air_modes_b200/csrc/amb_kernels.cu minus the TMA scan kernel:
+candidate bitmap from float streams, compaction, exact preamble tests, sequential and parallel resolver, slicer, CRC)
+executed on the host by the SIMT emulator of tests/simt and compared with the oracle - the same comparison the GPU
+tests make through amb_preamble_process / amb_slicer_process / amb_device_crc, here without a GPU. Catches
+hardware-independent bugs in the warp-level logic and in the launch configuration; the GPU tests remain the gate."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from gr_air_modes_b200 import synth
+from oracle import cpu_oracle as co
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("ksimt") / "libkernels_emul.so")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-psabi", "-shared", "-fPIC",
+                    "-o", out, os.path.join(ROOT, "tests", "simt", "kernels_emul.cc")], check=True)
+    lib = C.CDLL(out)
+    lib.emul_preamble.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_int, C.c_void_p]
+    lib.emul_slicer.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.emul_crc.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+    return lib
+
+
+def _preamble(lib, bb, avg, rate, thr, resolver):
+    n = bb.size
+    max_det = n // 200 + 16
+    chips = np.zeros((max_det, 240), np.float32)
+    idx = np.zeros(max_det, np.uint64)
+    stats = np.zeros(3, np.uint32)
+    nd = lib.emul_preamble(bb.ctypes.data, avg.ctypes.data, n, rate, thr, resolver, 2, chips.ctypes.data, idx.ctypes.data,
+                           max_det, stats.ctypes.data)
+    assert nd >= 0, nd
+    return idx[:nd], chips[:nd], stats
+
+
+@pytest.mark.parametrize("rate,n,nb,pmf,thr,seed", [
+    (4e6, 60_000, 12, True, 7.0, 1), (2e6, 40_000, 10, True, 7.0, 2), (10e6, 120_000, 8, True, 7.0, 3),
+    (20e6, 200_000, 6, True, 7.0, 4), (5e6, 60_000, 8, True, 6.0, 5), (4e6, 60_000, 120, False, 5.0, 6),
+])
+def test_split_form_chain_under_the_emulator_matches_the_oracle(emul, port, rate, n, nb, pmf, thr, seed):
+    dense = nb > 50
+    sc = synth.make_scene(rate, n, nb, 900 + seed, garble_frac=0.3 if dense else 0.0, fruit=30 if dense else 0,
+                          df_choices=(0, 4, 5, 11, 16, 17, 20, 21))
+    bb, avg = port.frontend(sc.iq, rate, pmf, co.MA_CANONICAL)
+    want = port.run_streams(bb, avg, rate, thr)
+    assert len(want.index) >= (20 if dense else 5)
+    for resolver in (1, 2):                                  # sequential walk, parallel walk (cluster walk + buckets)
+        idx, chips, stats = _preamble(emul, bb, avg, rate, thr, resolver)
+        assert [int(x) for x in idx] == [int(x) for x in want.index], (resolver, stats)
+        assert np.array_equal(chips, np.asarray(want.chips, np.float32).reshape(-1, 240)), resolver
+        assert stats[1] <= stats[0] and stats[1] >= len(want.index)
+
+
+def test_end_of_stream_and_empty_streams_under_the_emulator(emul, port):
+    rate = 4e6
+    for cut in (0, 111, 333, 640):
+        sc = synth.make_scene(rate, 30_000, 0, 11, starts=[9_000.3, 29_200.0 - cut], amplitude=0.3)
+        bb, avg = port.frontend(sc.iq, rate, True, co.MA_CANONICAL)
+        want = port.run_streams(bb, avg, rate, 7.0)
+        idx, chips, _ = _preamble(emul, bb, avg, rate, 7.0, 2)
+        assert [int(x) for x in idx] == [int(x) for x in want.index], cut
+    z = np.zeros(3000, np.float32)
+    idx, _, _ = _preamble(emul, z, z, rate, 7.0, 2)
+    assert idx.size == 0
+
+
+def test_slicer_and_crc_kernels_under_the_emulator(emul, port):
+    from gr_air_modes_b200 import _lib, blocks
+    rng = np.random.default_rng(5)
+    n = 200
+    chips = rng.normal(0.0, 0.3, (n, 240)).astype(np.float32)
+    chips[:, [0, 2, 7, 9]] += 1.0
+    chips[::3, 16:240:2] += 1.0
+    secs = np.arange(n, dtype=np.uint64)
+    frac = rng.random(n)
+    want = port.run_slicer(chips, secs, frac).msgs
+    frames = (_lib.Frame * n)()
+    assert emul.emul_slicer(chips.ctypes.data, n, C.cast(frames, C.c_void_p)) == 0
+    got, first = [], True
+    for k in range(n):
+        frames[k].secs, frames[k].frac = int(secs[k]), float(frac[k])
+        if frames[k].passed:
+            got.append(blocks.format_message(frames[k], first))
+            first = False
+    assert got == want and len(want) > 0
+    for length in (4, 11):
+        data = rng.integers(0, 256, (64, length), dtype=np.uint8)
+        out = np.zeros(64, np.uint32)
+        assert emul.emul_crc(data.tobytes(), 64, length, out.ctypes.data) == 0
+        assert [int(x) for x in out] == [port.crc24(bytes(r)) for r in data]
