@@ -80,6 +80,95 @@ extern "C" int emul_preamble(const float* in0, const float* in1, int n, float ra
     return (int)nd;
 }
 
+// The fused path on IQ (amb_process, one call over a whole stream, flush): the exact and slice kernels in their IQ form
+// recompute |x|^2, the pulse matched filter and the noise-floor window from the samples (canonical arithmetic) through
+// the carry ++ main ++ tail segment view, the prologue kernel stages the tail. The TMA scan kernel cannot run here; its
+// output - the candidate bitmap in segment coordinates - is produced by the stream-candidate kernel from the (bb, avg)
+// streams the caller computed with the canonical front end, shifted into the same coordinates.
+// Returns detections in stream order: index_out, chips_out (240 each), frames_out (unstamped).
+extern "C" int emul_process_iq(const float* iq, int n, const float* bb, const float* avg, float rate, float threshold_db,
+                               int use_pmf, int resolver, int sm_count, float* chips_out, unsigned long long* index_out,
+                               amb_frame* frames_out, int max_det)
+{
+    AmbParams P; int off[240];
+    if (compute_params(rate, threshold_db, use_pmf, &P, off) != AMB_OK) return -100;
+    if (amb_upload_tables(off) != cudaSuccess) return -101;
+    const int guard = P.maxlate + (int)ceilf(P.skip_f) + 4;                       // setup_rate (amb_api.cu)
+    const int kc = (guard + P.L + 2 * P.spc_i + 64 + AMB_STAGE - 1) / AMB_STAGE * AMB_STAGE;
+    const int tail_cap = 4 * AMB_STAGE;
+    const int n_main = n & ~(AMB_STAGE - 1), n_tv = n - n_main;
+    const int n_tail = (n_tv + 512 + AMB_STAGE - 1) / AMB_STAGE * AMB_STAGE;
+    std::vector<float2> carry(kc, make_float2(0.f, 0.f)), tail(tail_cap), src(n > 0 ? n : 1);
+    memcpy(src.data(), iq, (size_t)n * sizeof(float2));
+    AmbSegs S;
+    S.carry = carry.data(); S.main_ = src.data(); S.tail = tail.data();
+    S.n_carry = kc; S.n_main = n_main; S.n_tail = n_tail; S.n_valid = kc + n;
+    const long long org = -(long long)kc + P.H;
+    const long long ntot = (long long)n + P.H;
+    const long long j_lo = 0 - org, j_hi = S.n_valid;
+    AmbScanArgs a{};
+    a.P = P; a.S = S; a.j_lo = (int)j_lo; a.j_hi = (int)j_hi;
+    a.row_lo = (int)(j_lo / AMB_ROW) & ~(AMB_SPAN_ROWS_ALIGN - 1);
+    a.row_hi = (int)((j_hi + AMB_ROW - 1) / AMB_ROW);
+    if (a.row_lo != 0) return -102;
+    const int rows = a.row_hi - a.row_lo;
+    const int target = sm_count * 16;
+    int rps = (rows + target - 1) / target;
+    rps = (rps + AMB_SPAN_ROWS_ALIGN - 1) / AMB_SPAN_ROWS_ALIGN * AMB_SPAN_ROWS_ALIGN;
+    if (rps < AMB_SPAN_ROWS_ALIGN) rps = AMB_SPAN_ROWS_ALIGN;
+    a.rows_per_span = rps; a.n_spans = (rows + rps - 1) / rps;
+    const size_t rows_cap = (size_t)a.row_hi + 64 + ((size_t)a.row_hi + 64) / 8;
+    const int spans_cap = a.n_spans + 64;
+    const unsigned cand_cap = (unsigned)std::max<long long>(1 << 16, (j_hi - j_lo) / 8 + 1024);
+    const unsigned frame_cap = (unsigned)((j_hi - j_lo) / std::max(P.skip0, 1) + 2) * 2 + 1024;
+    std::vector<uint32_t> coarse(rows_cap / 32 + 2, 0), fine(rows_cap * 8, 0), span_count((size_t)spans_cap + 128, 0);
+    std::vector<int> cand_j(cand_cap), det_list(cand_cap);
+    std::vector<uint32_t> cand_info(cand_cap);
+    std::vector<float> cand_avg(cand_cap);
+    const long long n_samples = (long long)S.n_carry + S.n_main + S.n_tail;
+    std::vector<unsigned char> walk_scratch(amb_walk_scratch_bytes(cand_cap, (long long)cand_cap * 8 + 4096), 0);
+    std::vector<amb_frame> frames(frame_cap);
+    std::vector<float> chips((size_t)frame_cap * 240);
+    AmbCounters ctr{}; AmbWalkState st{};
+    a.coarse = coarse.data(); a.fine = fine.data(); a.span_count = span_count.data();
+    a.group_count = span_count.data() + spans_cap;
+    cudaStream_t s = nullptr;
+    if (amb_launch_prologue(tail.data(), tail_cap, src.data() + n_main, n_tv, a.group_count, 128, s) != cudaSuccess) return -1;
+    {   // stand-in for the scan kernel: item i of the streams sits at segment coordinate i + kc, i.e. reported r' = i + kc
+        const int shift = kc - P.H;
+        std::vector<float> s0((size_t)n + shift + 1, 0.f), s1((size_t)n + shift + 1, 0.f);
+        std::copy(bb, bb + n, s0.begin() + shift);
+        std::copy(avg, avg + n, s1.begin() + shift);
+        if (amb_launch_stream_candidates(a, s0.data(), s1.data(), (long long)n + shift, s) != cudaSuccess) return -2;
+    }
+    const bool par = resolver != 1;
+    if (amb_launch_compact(a, cand_j.data(), cand_cap, &ctr, par ? walk_scratch.data() : nullptr, n_samples, s) != cudaSuccess) return -3;
+    AmbExactArgs ea{};
+    ea.P = P; ea.S = S; ea.cand_j = cand_j.data(); ea.cand_info = cand_info.data(); ea.cand_avg = cand_avg.data(); ea.ctr = &ctr;
+    if (amb_launch_exact(ea, sm_count, s) != cudaSuccess) return -4;
+    AmbWalkArgs wa{};
+    wa.P = P; wa.org = org; wa.ntot = ntot; wa.r_safe = 0; wa.flush = 1; wa.ctr = &ctr; wa.st = &st;
+    wa.cand_j = cand_j.data(); wa.cand_info = cand_info.data(); wa.det_list = det_list.data();
+    if ((par ? amb_launch_walk_par(wa, walk_scratch.data(), cand_cap, n_samples, s) : amb_launch_walk_seq(wa, s)) != cudaSuccess) return -5;
+    AmbSliceArgs sl{};
+    sl.P = P; sl.S = S; sl.cand_j = cand_j.data(); sl.cand_info = cand_info.data(); sl.cand_avg = cand_avg.data();
+    sl.det_list = det_list.data(); sl.ctr = &ctr; sl.frames = frames.data(); sl.frame_cap = frame_cap;
+    sl.chips_out = chips.data(); sl.org = org;
+    if (amb_launch_slice(sl, sm_count, s) != cudaSuccess) return -6;
+    if (ctr.overflow || ctr.frame_overflow) return -7;
+    const unsigned nd = ctr.nframes;
+    if (nd > (unsigned)max_det) return -8;
+    std::vector<unsigned> order(nd);
+    for (unsigned k = 0; k < nd; k++) order[k] = k;
+    std::sort(order.begin(), order.end(), [&](unsigned x, unsigned y) { return frames[x].sample_index < frames[y].sample_index; });
+    for (unsigned k = 0; k < nd; k++) {
+        index_out[k] = frames[order[k]].sample_index;
+        frames_out[k] = frames[order[k]];
+        memcpy(chips_out + (size_t)k * 240, chips.data() + (size_t)order[k] * 240, 240 * sizeof(float));
+    }
+    return (int)nd;
+}
+
 // amb_slicer_process: ndet packets of 240 chips -> frames (slicer_impl.cc:117-182)
 extern "C" int emul_slicer(const float* chips, int ndet, amb_frame* out)
 {

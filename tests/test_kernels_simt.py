@@ -24,6 +24,8 @@ def emul(tmp_path_factory):
     lib = C.CDLL(out)
     lib.emul_preamble.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_int, C.c_void_p]
+    lib.emul_process_iq.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.emul_slicer.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.emul_crc.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
     return lib
@@ -57,6 +59,41 @@ def test_split_form_chain_under_the_emulator_matches_the_oracle(emul, port, rate
         assert [int(x) for x in idx] == [int(x) for x in want.index], (resolver, stats)
         assert np.array_equal(chips, np.asarray(want.chips, np.float32).reshape(-1, 240)), resolver
         assert stats[1] <= stats[0] and stats[1] >= len(want.index)
+
+
+@pytest.mark.parametrize("rate,n,nb,pmf,thr,seed", [
+    (4e6, 60_001, 12, True, 7.0, 1), (2e6, 30_000, 10, False, 6.0, 2), (10e6, 120_777, 8, True, 7.0, 3),
+    (20e6, 200_300, 6, True, 7.0, 4), (5e6, 70_000, 8, True, 7.0, 5), (2.4e6, 40_000, 8, True, 6.0, 6),
+    (4e6, 50_000, 100, True, 5.0, 7),
+])
+def test_fused_iq_chain_under_the_emulator_matches_the_oracle(emul, port, rate, n, nb, pmf, thr, seed):
+    """amb_process's kernels on IQ - prologue (tail staging), compaction, the exact and slice kernels in their IQ form
+    (canonical |x|^2 / PMF / noise-floor arithmetic from the carry ++ main ++ tail segments), both resolvers. Only the
+    TMA scan kernel is replaced (by the stream-candidate kernel fed with the canonical front end's streams). Detection
+    indices, 240-chip packets and the message text equal the oracle's run over the same IQ."""
+    from gr_air_modes_b200 import _lib, blocks
+    dense = nb > 50
+    sc = synth.make_scene(rate, n, nb, 700 + seed, garble_frac=0.3 if dense else 0.0, fruit=30 if dense else 0)
+    bb, avg = port.frontend(sc.iq, rate, pmf, co.MA_CANONICAL)
+    want = port.run_iq(sc.iq, rate, thr, pmf, co.MA_CANONICAL)
+    assert len(want.index) >= (2 if rate == 2.4e6 else 5)
+    md = n // 200 + 16
+    for resolver in (1, 2):
+        chips = np.zeros((md, 240), np.float32)
+        idx = np.zeros(md, np.uint64)
+        frames = (_lib.Frame * md)()
+        nd = emul.emul_process_iq(sc.iq.ctypes.data, n, bb.ctypes.data, avg.ctypes.data, rate, thr, int(pmf), resolver, 2,
+                                  chips.ctypes.data, idx.ctypes.data, C.cast(frames, C.c_void_p), md)
+        assert nd >= 0, nd
+        assert [int(x) for x in idx[:nd]] == [int(x) for x in want.index], resolver
+        assert np.array_equal(chips[:nd], want.chips), resolver
+        ri, msgs, first = int(rate), [], True
+        for k in range(nd):                                  # stamp as amb_poll_frames does (tag_to_timestamp, no rx_time tag)
+            frames[k].secs, frames[k].frac = int(idx[k]) // ri, (int(idx[k]) % ri) / float(ri)
+            if frames[k].passed:
+                msgs.append(blocks.format_message(frames[k], first))
+                first = False
+        assert msgs == want.msgs, resolver
 
 
 def test_end_of_stream_and_empty_streams_under_the_emulator(emul, port):
