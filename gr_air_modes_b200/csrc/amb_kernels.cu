@@ -30,7 +30,7 @@ __constant__ unsigned int c_crc_rem[96]; // x^(t+24) mod 0xFFF409, t = distance 
 // shared table: two contexts with different rates can coexist on one device)
 __device__ __forceinline__ int chip_off(int j, float spc_f) { return __float2int_rz(__fmul_rn((float)j, spc_f)); }
 
-#ifndef AMB_SIMT_EMUL   // PTX (mbarrier / TMA) and the scan kernel exist only for the device; tests/simt emulates the rest
+#ifndef AMB_SIMT_EMUL   // PTX (mbarrier / TMA): tests/simt supplies host stand-ins for these seven helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -68,7 +68,6 @@ __device__ __forceinline__ const float2* seg_ptr(const AmbSegs& S, int j) {
     return S.tail + (j - S.n_main);
 }
 
-#ifndef AMB_SIMT_EMUL
 // ------------------------------------------------------------------------------------------------
 // scan kernel
 // ------------------------------------------------------------------------------------------------
@@ -347,7 +346,7 @@ template <int SPC, bool PMF, int PREF>
 __global__ void __launch_bounds__(128) amb_scan_kernel(const __grid_constant__ AmbScanArgs a)
 {
     using C = ScanCfg<SPC, PMF, PREF>;
-    extern __shared__ __align__(1024) unsigned char smem[];
+    AMB_DYN_SMEM(unsigned char, smem, 1024);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int span = blockIdx.x * 4 + warp;
     if (span >= a.n_spans) return;
@@ -441,7 +440,7 @@ static cudaError_t launch_scan_t(const AmbScanArgs& a, cudaStream_t s)
     cudaError_t e = cudaFuncSetAttribute(amb_scan_kernel<SPC, PMF, PREF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int blocks = (a.n_spans + 3) / 4;
-    amb_scan_kernel<SPC, PMF, PREF><<<blocks, 128, smem, s>>>(a);
+    AMB_LAUNCH((amb_scan_kernel<SPC, PMF, PREF>), blocks, 128, smem, s, a);
     return cudaGetLastError();
 }
 
@@ -458,8 +457,6 @@ cudaError_t amb_launch_scan(const AmbScanArgs& a, int, cudaStream_t s)
     }
     return cudaErrorInvalidValue;
 }
-
-#endif  // AMB_SIMT_EMUL
 
 // ------------------------------------------------------------------------------------------------
 // compaction: (coarse, fine) bitmap -> ordered candidate list. One warp per scan span, so the order is

@@ -80,11 +80,15 @@ extern "C" int emul_preamble(const float* in0, const float* in1, int n, float ra
     return (int)nd;
 }
 
+static unsigned emul_last_counts[3];
+extern "C" void emul_counts(unsigned* out) { memcpy(out, emul_last_counts, sizeof emul_last_counts); }
+
 // The fused path on IQ (amb_process, one call over a whole stream, flush): the exact and slice kernels in their IQ form
 // recompute |x|^2, the pulse matched filter and the noise-floor window from the samples (canonical arithmetic) through
 // the carry ++ main ++ tail segment view, the prologue kernel stages the tail. The TMA scan kernel cannot run here; its
 // output - the candidate bitmap in segment coordinates - is produced by the stream-candidate kernel from the (bb, avg)
-// streams the caller computed with the canonical front end, shifted into the same coordinates.
+// streams the caller computed with the canonical front end, shifted into the same coordinates. With bb == NULL the
+// scan kernel itself runs: its PTX helpers (mbarrier, 2-D TMA tile copy with the 128-byte swizzle) are emulated.
 // Returns detections in stream order: index_out, chips_out (240 each), frames_out (unstamped).
 extern "C" int emul_process_iq(const float* iq, int n, const float* bb, const float* avg, float rate, float threshold_db,
                                int use_pmf, int resolver, int sm_count, float* chips_out, unsigned long long* index_out,
@@ -134,6 +138,12 @@ extern "C" int emul_process_iq(const float* iq, int n, const float* bb, const fl
     a.group_count = span_count.data() + spans_cap;
     cudaStream_t s = nullptr;
     if (amb_launch_prologue(tail.data(), tail_cap, src.data() + n_main, n_tv, a.group_count, 128, s) != cudaSuccess) return -1;
+    if (!bb) {      // the real scan kernel: TMA tiles and mbarriers are emulated (simt_emul.h), the kernel source is the product's
+        simt_make_tmap(&a.tm_carry, carry.data(), (size_t)kc);
+        simt_make_tmap(&a.tm_tail, tail.data(), (size_t)tail_cap);
+        if (n_main) simt_make_tmap(&a.tm_main, src.data(), (size_t)n_main); else a.tm_main = a.tm_tail;
+        if (amb_launch_scan(a, sm_count, s) != cudaSuccess) return -2;
+    } else
     {   // stand-in for the scan kernel: item i of the streams sits at segment coordinate i + kc, i.e. reported r' = i + kc
         const int shift = kc - P.H;
         std::vector<float> s0((size_t)n + shift + 1, 0.f), s1((size_t)n + shift + 1, 0.f);
@@ -156,6 +166,7 @@ extern "C" int emul_process_iq(const float* iq, int n, const float* bb, const fl
     sl.chips_out = chips.data(); sl.org = org;
     if (amb_launch_slice(sl, sm_count, s) != cudaSuccess) return -6;
     if (ctr.overflow || ctr.frame_overflow) return -7;
+    emul_last_counts[0] = ctr.ncand; emul_last_counts[1] = ctr.nreal_call; emul_last_counts[2] = (unsigned)st.fallback;
     const unsigned nd = ctr.nframes;
     if (nd > (unsigned)max_det) return -8;
     std::vector<unsigned> order(nd);

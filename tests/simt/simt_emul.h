@@ -10,6 +10,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -38,7 +39,7 @@ static std::function<void()> simt_body;
 #define blockDim simt_block_dim
 #define gridDim simt_grid_dim
 #define __global__ static
-#define __device__ static
+#define __device__
 #define __host__
 #define __forceinline__ inline
 #define __restrict__
@@ -174,6 +175,47 @@ static inline unsigned long long atomicMax(unsigned long long* p, unsigned long 
 static inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; if (v < o) *p = v; return o; }
 static inline unsigned atomicMax(unsigned* p, unsigned v) { const unsigned o = *p; if (v > o) *p = v; return o; }
 static inline unsigned atomicMin(unsigned* p, unsigned v) { const unsigned o = *p; if (v < o) *p = v; return o; }
+
+// ---- stand-ins for the seven PTX helpers of amb_kernels.cu (mbarrier + TMA tile copy) -----------------------------
+// Shared-memory "addresses" are byte offsets into the block's dynamic shared memory. An mbarrier is a counter of
+// completed phases; the tile copy happens at issue time and completes the phase (complete_tx), a waiter that finds
+// the phase incomplete yields. The copy lands with the 128-byte swizzle of CU_TENSOR_MAP_SWIZZLE_128B (16-byte chunk
+// index ^= line index mod 8) and zero-fills lines beyond the tensor, like the hardware. The emulated CUtensorMap
+// holds {base pointer, number of 128-byte lines} in opaque[0..1] (see simt_make_tmap).
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 v = {x, y, z, w}; return v; }
+static inline void simt_make_tmap(CUtensorMap* m, const void* base, size_t n_samples)
+{
+    memset(m, 0, sizeof *m);
+    m->opaque[0] = (unsigned long long)(uintptr_t)base; m->opaque[1] = (unsigned long long)(n_samples / 16);
+}
+static inline uint32_t smem_u32(const void* p) { return (uint32_t)((const unsigned char*)p - simt_dyn_smem); }
+static inline void mbar_init(uint32_t bar, uint32_t) { *reinterpret_cast<uint64_t*>(simt_dyn_smem + bar) = 0; }
+static inline void mbar_expect_tx(uint32_t, uint32_t) {}
+static inline bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    if (((*reinterpret_cast<uint64_t*>(simt_dyn_smem + bar)) & 1u) != parity) return true;
+    simt_yield();
+    return false;
+}
+static inline void tma_tile_g2s(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar)
+{
+    const CUtensorMap* m = static_cast<const CUtensorMap*>(tmap);
+    const unsigned char* base = reinterpret_cast<const unsigned char*>((uintptr_t)m->opaque[0]);
+    const long long n_lines = (long long)m->opaque[1];
+    if (c0 != 0 || (dst & 1023u)) { fprintf(stderr, "simt: unsupported TMA box\n"); abort(); }
+    for (int l = 0; l < 32; l++)
+        for (int c = 0; c < 8; c++) {
+            unsigned char* d = simt_dyn_smem + dst + l * 128 + ((c ^ (l & 7)) << 4);
+            const long long line = (long long)c1 + l;
+            if (line >= 0 && line < n_lines) memcpy(d, base + line * 128 + c * 16, 16); else memset(d, 0, 16);
+        }
+    (*reinterpret_cast<uint64_t*>(simt_dyn_smem + bar))++;
+    simt_progress++;
+}
+static inline bool elect_one() { return (simt_cur->tid.x & 31) == 0; }
+static inline void fence_proxy_async() {}
+static inline void fence_mbar_init() {}
 
 // A thread that has exited no longer takes part in barriers (CUDA semantics for __syncthreads and *_sync with exited lanes)
 static void simt_trampoline()

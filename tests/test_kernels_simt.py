@@ -26,6 +26,7 @@ def emul(tmp_path_factory):
                                   C.c_void_p, C.c_int, C.c_void_p]
     lib.emul_process_iq.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.emul_counts.argtypes = [C.c_void_p]
     lib.emul_slicer.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.emul_crc.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
     return lib
@@ -67,10 +68,11 @@ def test_split_form_chain_under_the_emulator_matches_the_oracle(emul, port, rate
     (4e6, 50_000, 100, True, 5.0, 7),
 ])
 def test_fused_iq_chain_under_the_emulator_matches_the_oracle(emul, port, rate, n, nb, pmf, thr, seed):
-    """amb_process's kernels on IQ - prologue (tail staging), compaction, the exact and slice kernels in their IQ form
-    (canonical |x|^2 / PMF / noise-floor arithmetic from the carry ++ main ++ tail segments), both resolvers. Only the
-    TMA scan kernel is replaced (by the stream-candidate kernel fed with the canonical front end's streams). Detection
-    indices, 240-chip packets and the message text equal the oracle's run over the same IQ."""
+    """amb_process's kernels on IQ, all of them: the streaming scan kernel (its seven PTX helpers - mbarrier, 2-D TMA tile
+    copy - are emulated, the kernel source is the product's), prologue (tail staging), compaction, the exact and slice
+    kernels in their IQ form (canonical |x|^2 / PMF / noise-floor arithmetic from the carry ++ main ++ tail segments),
+    both resolvers. Detection indices, 240-chip packets and the message text equal the oracle's run over the same IQ;
+    the scan kernel's candidates are a superset of the exact ones."""
     from gr_air_modes_b200 import _lib, blocks
     dense = nb > 50
     sc = synth.make_scene(rate, n, nb, 700 + seed, garble_frac=0.3 if dense else 0.0, fruit=30 if dense else 0)
@@ -78,13 +80,21 @@ def test_fused_iq_chain_under_the_emulator_matches_the_oracle(emul, port, rate, 
     want = port.run_iq(sc.iq, rate, thr, pmf, co.MA_CANONICAL)
     assert len(want.index) >= (2 if rate == 2.4e6 else 5)
     md = n // 200 + 16
-    for resolver in (1, 2):
+    # (resolver, bitmap source): the REAL scan kernel (TMA tile copies with the 128-byte swizzle and mbarriers emulated,
+    # kernel source unchanged) with the parallel resolver, and the stream-candidate stand-in with both resolvers
+    for resolver, use_scan in ((2, True), (1, False), (2, False)):
         chips = np.zeros((md, 240), np.float32)
         idx = np.zeros(md, np.uint64)
         frames = (_lib.Frame * md)()
-        nd = emul.emul_process_iq(sc.iq.ctypes.data, n, bb.ctypes.data, avg.ctypes.data, rate, thr, int(pmf), resolver, 2,
-                                  chips.ctypes.data, idx.ctypes.data, C.cast(frames, C.c_void_p), md)
+        nd = emul.emul_process_iq(sc.iq.ctypes.data, n, None if use_scan else bb.ctypes.data, None if use_scan else avg.ctypes.data,
+                                  rate, thr, int(pmf), resolver, 2, chips.ctypes.data, idx.ctypes.data, C.cast(frames, C.c_void_p), md)
         assert nd >= 0, nd
+        cnt = np.zeros(3, np.uint32)
+        emul.emul_counts(cnt.ctypes.data)
+        if use_scan:
+            scan_cand, scan_real = int(cnt[0]), int(cnt[1])
+        else:                                                # the scan kernel's conservative filter: a superset, nothing real lost
+            assert scan_real == int(cnt[1]) and scan_cand >= int(cnt[0]) == int(cnt[1])
         assert [int(x) for x in idx[:nd]] == [int(x) for x in want.index], resolver
         assert np.array_equal(chips[:nd], want.chips), resolver
         ri, msgs, first = int(rate), [], True
@@ -133,3 +143,46 @@ def test_slicer_and_crc_kernels_under_the_emulator(emul, port):
         out = np.zeros(64, np.uint32)
         assert emul.emul_crc(data.tobytes(), 64, length, out.ctypes.data) == 0
         assert [int(x) for x in out] == [port.crc24(bytes(r)) for r in data]
+
+
+def test_scan_kernel_under_the_emulator_on_pathological_inputs(emul, port):
+    """The scan kernel is a conservative fp32 FILTER (FMA |x|^2, prefix-sum windows, lowered thresholds); whatever it
+    is fed - 1e-17 / 1e-21 / 3e14 amplitude scales, NaN/Inf samples, silence, a DC offset, dense garble - the chain's
+    result must still be the oracle's."""
+    from gr_air_modes_b200 import _lib
+    rng = np.random.default_rng(4242)
+    kinds = ["scale_small", "denorm", "scale_big", "silence", "naninf", "dc", "dense", "zeros"]
+    for case, kind in enumerate(kinds):
+        rate = [4e6, 2e6, 10e6, 4e6, 5e6, 20e6, 4e6, 4e6][case]
+        pmf = case % 3 != 1
+        n = int(rng.integers(20_000, 50_000)) * (2 if rate >= 10e6 else 1)
+        sc = synth.make_scene(rate, n, 150 if kind == "dense" else 10, 5000 + case, garble_frac=0.3 if kind == "dense" else 0.0,
+                              snr_db=(6.0, 35.0), fruit=20 if kind == "dense" else 0)
+        iq = sc.iq.copy()
+        if kind == "scale_small":
+            iq *= np.float32(1e-17)
+        elif kind == "denorm":
+            iq *= np.float32(1e-21)
+        elif kind == "scale_big":
+            iq *= np.float32(3e14)
+        elif kind == "silence":
+            a = int(rng.integers(0, n))
+            iq[2 * a: 2 * min(n, a + n // 3)] = 0
+        elif kind == "naninf":
+            for v in (np.nan, np.inf, -np.inf, 3e38):
+                iq[int(rng.integers(0, 2 * n))] = v
+        elif kind == "dc":
+            iq[0::2] += np.float32(0.02)
+        elif kind == "zeros":
+            iq[:] = 0
+        with np.errstate(all="ignore"):
+            want = port.run_iq(iq, rate, 7.0, pmf, co.MA_CANONICAL)
+        md = n // 200 + 16
+        chips = np.zeros((md, 240), np.float32)
+        idx = np.zeros(md, np.uint64)
+        frames = (_lib.Frame * md)()
+        nd = emul.emul_process_iq(iq.ctypes.data, n, None, None, rate, 7.0, int(pmf), 2, 2, chips.ctypes.data, idx.ctypes.data,
+                                  C.cast(frames, C.c_void_p), md)
+        assert nd >= 0, (kind, nd)
+        assert [int(x) for x in idx[:nd]] == [int(x) for x in want.index], kind
+        assert np.array_equal(chips[:nd], want.chips, equal_nan=True), kind
