@@ -196,3 +196,14 @@ extern "C" int emul_crc(const uint8_t* data, int n, int length, uint32_t* out)
     if (amb_upload_tables(off) != cudaSuccess) return -1;
     return amb_launch_crc(data, n, length, out, nullptr) == cudaSuccess ? 0 : -2;
 }
+
+// amb_launch_dcblock on a whole stream (raw-sample history = zeros): out[2n] = x[n-D+1] - MA_D(MA_D(x))[n]
+extern "C" int emul_dcblock(const float* iq, int n, int D, float* out)
+{
+    const int nc = 2 * D - 2;
+    std::vector<float2> carry(nc, make_float2(0.f, 0.f)), next(nc), fresh(n > 0 ? n : 1), ma0((size_t)n + D + 1024), o((size_t)n + D + 1024);
+    memcpy(fresh.data(), iq, (size_t)n * sizeof(float2));
+    if (amb_launch_dcblock(carry.data(), nc, fresh.data(), (long long)n, D, ma0.data(), o.data(), next.data(), nullptr) != cudaSuccess) return -1;
+    memcpy(out, o.data(), (size_t)n * sizeof(float2));
+    return 0;
+}

@@ -27,6 +27,7 @@ def emul(tmp_path_factory):
     lib.emul_process_iq.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.emul_counts.argtypes = [C.c_void_p]
+    lib.emul_dcblock.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.emul_slicer.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.emul_crc.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
     return lib
@@ -186,3 +187,21 @@ def test_scan_kernel_under_the_emulator_on_pathological_inputs(emul, port):
         assert nd >= 0, (kind, nd)
         assert [int(x) for x in idx[:nd]] == [int(x) for x in want.index], kind
         assert np.array_equal(chips[:nd], want.chips, equal_nan=True), kind
+
+
+def test_dc_blocker_kernels_under_the_emulator(emul, port):
+    """amb_dcblock_kernel<0/1> (exact fp64 prefix sums per tile, literal sums where the exponent spread forbids them):
+    output bit-identical to the CPU restatement, on ordinary samples and on tiles that force the literal path."""
+    rng = np.random.default_rng(9)
+    for D, n, kind in ((200, 5000, "plain"), (500, 6000, "plain"), (200, 4000, "spread"), (200, 3000, "naninf")):
+        iq = (rng.standard_normal(2 * n) * 0.01).astype(np.float32)
+        iq[0::2] += np.float32(0.05)
+        if kind == "spread":
+            iq[2 * 1500: 2 * 1600] *= np.float32(1e12)          # > 18 binades inside one tile: literal sums
+        if kind == "naninf":
+            iq[777], iq[2222] = np.nan, np.inf
+        with np.errstate(all="ignore"):
+            want = port.dc_blocker(iq, D, co.MA_CANONICAL)
+        got = np.zeros(2 * n, np.float32)
+        assert emul.emul_dcblock(iq.ctypes.data, n, D, got.ctypes.data) == 0
+        assert np.array_equal(got, want, equal_nan=True), (D, n, kind)
