@@ -13,10 +13,10 @@
 //                       (2^26 x 16 B: one slot per (ICAO, surface, even/odd), so no probing, no collisions, no locks -
 //                       a slot has exactly one owner warp).
 //   amb_resolve_kernel  one thread per frame: global CPR decode, range/bearing.
+#include "amb_launch.h"
 #include "amb_decode_core.h"
 #include "amb_decode_kernels.cuh"
 
-#include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -171,7 +171,7 @@ int amb_decode_frames(amb_decoder* d, const amb_frame* frames, int n, int mem_ki
         src = d->d_frames;
     }
     const int nb = (n + 127) / 128;
-    amb_fields_kernel<<<nb, 128, 0, s>>>(src, n, d->d_fields, d->d_pos, d->d_pair);
+    AMB_LAUNCH((amb_fields_kernel), nb, 128, 0, s, src, n, d->d_fields, d->d_pos, d->d_pair);
     DCK(cudaGetLastError());
     // one warp per ~256 frames, at most 8 CTAs per SM: every warp reads the whole key list (L2-resident) but only
     // touches the table for its own aircraft
@@ -193,18 +193,18 @@ int amb_decode_frames(amb_decoder* d, const amb_frame* frames, int n, int mem_ki
         int w2 = n / 1024;
         if (w2 > max_warps) w2 = max_warps;
         if (w2 < AMB_PAIR_WARPS_PER_CTA) w2 = AMB_PAIR_WARPS_PER_CTA;
-        amb_keys_kernel<<<nb, 128, 0, s>>>(d->d_pos, n, d->d_keys);
+        AMB_LAUNCH((amb_keys_kernel), nb, 128, 0, s, d->d_pos, n, d->d_keys);
         DCK(cudaGetLastError());
-        amb_pair_kernel_v2<<<(w2 + AMB_PAIR_WARPS_PER_CTA - 1) / AMB_PAIR_WARPS_PER_CTA, 32 * AMB_PAIR_WARPS_PER_CTA, 0, s>>>(
-            d->d_keys, d->d_pos, n, d->table, d->d_pair);
+        AMB_LAUNCH((amb_pair_kernel_v2), (w2 + AMB_PAIR_WARPS_PER_CTA - 1) / AMB_PAIR_WARPS_PER_CTA, 32 * AMB_PAIR_WARPS_PER_CTA, 0, s,
+                   d->d_keys, d->d_pos, n, d->table, d->d_pair);
         (void)pair_ctas;
         d->launches += 1;
     }
 #else
-    amb_pair_kernel<<<pair_ctas, 32 * AMB_PAIR_WARPS_PER_CTA, 0, s>>>(d->d_pos, n, d->table, d->d_pair);
+    AMB_LAUNCH((amb_pair_kernel), pair_ctas, 32 * AMB_PAIR_WARPS_PER_CTA, 0, s, d->d_pos, n, d->table, d->d_pair);
 #endif
     DCK(cudaGetLastError());
-    amb_resolve_kernel<<<nb, 128, 0, s>>>(d->d_fields, d->d_pos, d->d_pair, n, d->have_loc, d->lat, d->lon, d->nl_T);
+    AMB_LAUNCH((amb_resolve_kernel), nb, 128, 0, s, d->d_fields, d->d_pos, d->d_pair, n, d->have_loc, d->lat, d->lon, d->nl_T);
     DCK(cudaGetLastError());
     d->launches += 3;
     DCK(cudaMemcpyAsync(out, d->d_fields, (size_t)n * sizeof(amb_fields), cudaMemcpyDeviceToHost, s));

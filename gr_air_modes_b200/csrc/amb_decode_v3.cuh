@@ -165,7 +165,6 @@ __global__ void __launch_bounds__(128) amb_v3_pair(const AmbPosRec* __restrict__
     }
 }
 
-#ifdef __CUDACC__
 static cudaError_t amb_v3_ensure(AmbV3Bufs* v, int n)
 {
     const int n_tiles = (n + AMB_V3_TILE - 1) / AMB_V3_TILE;
@@ -200,12 +199,11 @@ static int amb_v3_launch(AmbV3Bufs* v, const AmbPosRec* pos, int n, AmbCprSlot* 
 {
     if ((*err = amb_v3_ensure(v, n)) != cudaSuccess) return -1;
     const int n_tiles = (n + AMB_V3_TILE - 1) / AMB_V3_TILE;
-    amb_v3_count<<<n_tiles, 256, 0, s>>>(pos, n, n_tiles, v->cnt);
-    amb_v3_rowscan<<<AMB_V3_B / 8, 256, 0, s>>>(v->cnt, n_tiles, v->off, v->tot);
-    amb_v3_basescan<<<1, AMB_V3_B, 0, s>>>(v->tot, v->base);
-    amb_v3_scatter<<<n_tiles, 256, 0, s>>>(pos, n, n_tiles, v->off, v->base, v->order);
-    amb_v3_pair<<<AMB_V3_B / 4, 128, 0, s>>>(pos, v->order, v->base, table, pair);
+    AMB_LAUNCH((amb_v3_count), n_tiles, 256, 0, s, pos, n, n_tiles, v->cnt);
+    AMB_LAUNCH((amb_v3_rowscan), AMB_V3_B / 8, 256, 0, s, v->cnt, n_tiles, v->off, v->tot);
+    AMB_LAUNCH((amb_v3_basescan), 1, AMB_V3_B, 0, s, v->tot, v->base);
+    AMB_LAUNCH((amb_v3_scatter), n_tiles, 256, 0, s, pos, n, n_tiles, v->off, v->base, v->order);
+    AMB_LAUNCH((amb_v3_pair), AMB_V3_B / 4, 128, 0, s, pos, v->order, v->base, table, pair);
     *err = cudaGetLastError();
     return *err == cudaSuccess ? 5 : -1;
 }
-#endif  // __CUDACC__

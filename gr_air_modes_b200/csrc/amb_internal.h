@@ -1,15 +1,7 @@
 // Internal definitions shared by the kernels (amb_kernels.cu) and the host API (amb_api.cu).
 // Reference citations are file:line under the gr-air-modes tree.
 #pragma once
-#ifndef AMB_SIMT_EMUL
-#include <cuda.h>
-#include <cuda_runtime.h>
-// Kernel launch and dynamic shared memory go through two macros so that tests/simt (a host SIMT emulator used by
-// the CPU test suite) can run the kernels and their launchers unchanged; for nvcc they expand to the usual syntax.
-#define AMB_ID(...) __VA_ARGS__
-#define AMB_LAUNCH(kernel, grid, block, smem, stream, ...) AMB_ID kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
-#define AMB_DYN_SMEM(type, name, align) extern __shared__ __align__(align) type name[]
-#endif
+#include "amb_launch.h"
 #include <stdint.h>
 #include "../../include/airmodes_b200.h"
 
