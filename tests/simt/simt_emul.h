@@ -128,7 +128,6 @@ struct CUtensorMap { alignas(64) unsigned long long opaque[16]; };
 #define cudaGetLastError() (cudaSuccess)
 #define cudaFuncSetAttribute(...) (cudaSuccess)
 #define cudaMemcpyToSymbol(sym, src, n) (memcpy((void*)&(sym), (src), (n)), cudaSuccess)
-#define cudaMemsetAsync(p, v, n, s) (memset((p), (v), (n)), cudaSuccess)
 
 static unsigned char* simt_dyn_smem = nullptr;       // dynamic shared memory of the running block
 #define AMB_ID(...) __VA_ARGS__
@@ -285,3 +284,6 @@ static inline void simt_launch_dyn(unsigned grid, unsigned block, size_t smem, c
     simt_dyn_smem = nullptr;
     free(buf);
 }
+
+static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+#include "simt_cudart.h"
