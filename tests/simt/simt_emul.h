@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <setjmp.h>
 #include <ucontext.h>
 
 #include <functional>
@@ -24,10 +25,11 @@ struct uint4 { unsigned x, y, z, w; };
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v = {x, y, z, w}; return v; }
 
 struct SimtWarp { unsigned arrived = 0, gen = 0, alive = 32; uint64_t slot[32]; unsigned pred[32]; };
-struct SimtFiber { ucontext_t ctx; char* stack = nullptr; bool done = false; simt_dim3 tid; SimtWarp* warp = nullptr; };
+struct SimtFiber { ucontext_t ctx; jmp_buf jb; char* stack = nullptr; bool done = false, started = false; simt_dim3 tid; SimtWarp* warp = nullptr; };
 struct SimtBlockBar { unsigned arrived = 0, gen = 0, n = 0; };
 
 static ucontext_t simt_sched_ctx;
+static jmp_buf simt_sched_jb;
 static SimtFiber* simt_cur = nullptr;
 static SimtBlockBar simt_block_bar;
 static simt_dim3 simt_block_idx, simt_block_dim, simt_grid_dim;
@@ -47,7 +49,8 @@ static std::function<void()> simt_body;
 #define __shared__ static
 #define AMB_SIMT_EMUL 1
 
-static inline void simt_yield() { swapcontext(&simt_cur->ctx, &simt_sched_ctx); }
+// switching is _setjmp/_longjmp once a fiber runs (swapcontext costs two sigprocmask system calls per switch)
+static inline void simt_yield() { if (!_setjmp(simt_cur->jb)) _longjmp(simt_sched_jb, 1); }
 
 // every lane of the warp deposits (value, pred), waits for the other 31, then reads; a second rendezvous frees the slots
 static inline void simt_warp_exchange(uint64_t value, unsigned pred, uint64_t* vals, unsigned* preds)
@@ -225,7 +228,7 @@ static void simt_trampoline()
     if (--w->alive && w->arrived == w->alive) { w->arrived = 0; w->gen++; }
     SimtBlockBar* b = &simt_block_bar;
     if (--b->n && b->arrived == b->n) { b->arrived = 0; b->gen++; }
-    swapcontext(&simt_cur->ctx, &simt_sched_ctx);
+    _longjmp(simt_sched_jb, 1);
 }
 
 // simt_launch(grid, block, [&]{ kernel(args...); })
@@ -237,14 +240,16 @@ static inline void simt_launch(unsigned grid, unsigned block, const std::functio
     const size_t stack_bytes = 256 * 1024;
     std::vector<SimtFiber> fibers(block);
     std::vector<SimtWarp> warps(block / 32);
-    for (unsigned t = 0; t < block; t++) fibers[t].stack = (char*)malloc(stack_bytes);
+    static std::vector<char*> stack_pool;                  // fiber stacks are reused by every later launch
+    while (stack_pool.size() < block) stack_pool.push_back((char*)malloc(stack_bytes));
+    for (unsigned t = 0; t < block; t++) fibers[t].stack = stack_pool[t];
     for (unsigned b = 0; b < grid; b++) {
         simt_block_idx.x = b;
         simt_block_bar = SimtBlockBar(); simt_block_bar.n = block;
         for (auto& w : warps) w = SimtWarp();
         for (unsigned t = 0; t < block; t++) {
             SimtFiber& f = fibers[t];
-            f.done = false; f.tid.x = t; f.warp = &warps[t / 32];
+            f.done = false; f.started = false; f.tid.x = t; f.warp = &warps[t / 32];
             getcontext(&f.ctx);
             f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = stack_bytes; f.ctx.uc_link = &simt_sched_ctx;
             makecontext(&f.ctx, simt_trampoline, 0);
@@ -256,7 +261,11 @@ static inline void simt_launch(unsigned grid, unsigned block, const std::functio
             for (unsigned t = 0; t < block; t++) {
                 if (fibers[t].done) continue;
                 simt_cur = &fibers[t];
-                swapcontext(&simt_sched_ctx, &fibers[t].ctx);
+                if (!_setjmp(simt_sched_jb)) {
+                    if (fibers[t].started) _longjmp(fibers[t].jb, 1);
+                    fibers[t].started = true;
+                    setcontext(&fibers[t].ctx);             // first entry: onto the fiber's own stack
+                }
                 if (!fibers[t].done) alive++;
             }
             if (alive && simt_progress == before) {
@@ -265,7 +274,6 @@ static inline void simt_launch(unsigned grid, unsigned block, const std::functio
             }
         }
     }
-    for (unsigned t = 0; t < block; t++) free(fibers[t].stack);
     simt_cur = nullptr;
 }
 

@@ -1,0 +1,327 @@
+"""The WHOLE library on the CPU box: tests/simt/library_emul.cc compiles the library's own three translation units
+(kernels, host orchestration + C ABI, decoder) against the SIMT emulator and CUDA-runtime stand-ins of tests/simt, and
+this module drives that build through the ordinary Python package - the same scenarios the GPU parity tests run,
+scaled down: streaming vs one-shot, end-of-stream rules, setters and the state machine, a recording time-sharded over
+several contexts (hand-over chain and speculative resolution), the split-form blocks, the DC blocker option, the
+front-end dumps, two contexts side by side, and the batch decoder through its C ABI.
+
+TEST INFRASTRUCTURE ONLY: the emulated build exists in a pytest temp directory for the duration of this module; the
+package itself only ever binds gr_air_modes_b200/libairmodes_b200.so and has no CPU path (tests/test_host_logic.py).
+It is not thread-safe (one emulated device, global fiber state): everything here is sequential.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import gr_air_modes_b200 as am
+from gr_air_modes_b200 import _lib, synth
+from oracle import cpu_oracle as co
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emulated_library(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("libsimt") / "libairmodes_b200_emulated.so")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-U_FORTIFY_SOURCE", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-psabi", "-shared", "-fPIC",
+                    "-o", out, os.path.join(ROOT, "tests", "simt", "library_emul.cc")], check=True)
+    saved = (_lib.LIB_PATH, _lib._lib)
+    _lib.LIB_PATH, _lib._lib = out, None
+    try:
+        yield out
+    finally:
+        _lib.LIB_PATH, _lib._lib = saved
+
+
+def run(iq, rate, thr, pmf, chunks=None, resolver=0, dcblock=False):
+    q = am.msg_queue()
+    rx = am.rx_path(rate, thr, q, use_pmf=pmf, use_dcblock=dcblock)
+    rx._ctx.call("amb_set_option", b"resolver", resolver)
+    frames, pos, n = [], 0, iq.size // 2
+    for c in (chunks or []) + [n]:
+        c = int(min(c, n - pos))
+        last = pos + c >= n
+        rx.process(iq[2 * pos: 2 * (pos + c)], flush=last)
+        frames += rx.frames
+        pos += c
+        if last:
+            break
+    st = rx.stats()
+    rx.close()
+    return q.strings(), frames, st
+
+
+@pytest.mark.parametrize("rate,n,nb,pmf,thr", [(4e6, 50_000, 12, True, 7.0), (2e6, 30_000, 10, False, 6.0), (10e6, 90_000, 8, True, 7.0),
+                                               (20e6, 150_000, 6, True, 7.0), (5e6, 50_000, 8, True, 7.0)])
+def test_streaming_equals_one_shot_equals_oracle(port, rate, n, nb, pmf, thr):
+    sc = synth.make_scene(rate, n, nb, int(rate / 1e6) + 300)
+    want = port.run_iq(sc.iq, rate, thr, pmf, co.MA_CANONICAL)
+    assert len(want.msgs) >= 2
+    msgs, frames, st = run(sc.iq, rate, thr, pmf)
+    assert msgs == want.msgs and [f.sample_index for f in frames] == [int(x) for x in want.index]
+    assert st.kernel_launches >= 6 and st.samples_in == n
+    rng = np.random.default_rng(1)
+    for resolver in (0, 1):
+        chunks = [int(x) for x in rng.integers(1, n // 3, 3)] + [1, 511, 513]
+        msgs2, frames2, _ = run(sc.iq, rate, thr, pmf, chunks=chunks, resolver=resolver)
+        assert msgs2 == want.msgs and [f.sample_index for f in frames2] == [int(x) for x in want.index], resolver
+    for f, g in zip(frames, want.frames):
+        assert bytes(f.data) == bytes(g.data) and f.ref_level == g.ref_level and f.crc == g.crc and f.numlowconf == g.numlowconf
+
+
+def test_end_of_stream_rules_and_tiny_inputs(port):
+    rate = 4e6
+    for cut in (0, 150, 333, 480, 640):
+        sc = synth.make_scene(rate, 30_000, 0, 11, starts=[9_000.3, 29_200.0 - cut], amplitude=0.3)
+        want = port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL)
+        msgs, frames, _ = run(sc.iq, rate, 7.0, True)
+        assert msgs == want.msgs and [f.sample_index for f in frames] == [int(x) for x in want.index], cut
+    for n in (0, 1, 3, 17, 239, 481, 2000):
+        msgs, frames, _ = run(np.zeros(2 * n, np.float32), rate, 7.0, True)
+        assert msgs == [] and frames == []
+
+
+def test_setters_errors_and_state_machine(port):
+    q = am.msg_queue()
+    rx = am.rx_path(4e6, 7.0, q, use_pmf=True)
+    assert rx.get_threshold() == 7.0 and rx.get_pmf() is True
+    with pytest.raises(RuntimeError):
+        rx.set_rate(1e6)                                    # below 2 Msps: preamble_impl would divide by zero (:150)
+    with pytest.raises(RuntimeError):
+        am.rx_path(30e6, 7.0, q)
+    rx.process(np.zeros(2000, np.float32), flush=True)
+    with pytest.raises(RuntimeError):
+        rx.process(np.zeros(2000, np.float32))              # flushed stream needs reset()
+    rx.reset()
+    sc = synth.make_scene(4e6, 40_000, 10, 77)
+    lo = port.run_iq(sc.iq, 4e6, 4.0, True, co.MA_CANONICAL).msgs
+    hi = port.run_iq(sc.iq, 4e6, 12.0, True, co.MA_CANONICAL).msgs
+    rx.set_threshold(4.0)
+    rx.process(sc.iq, flush=True)
+    assert q.strings() == lo
+    q.flush(); rx.reset(); rx._slicer._first = True
+    rx.set_threshold(12.0)
+    rx.process(sc.iq, flush=True)
+    assert q.strings() == hi and hi != lo
+    rx.set_rate(10e6)                                       # re-tune (rx_path.py:67-72): a new stream at the new rate
+    sc10 = synth.make_scene(10e6, 80_000, 8, 78)
+    q.flush(); rx._slicer._first = True
+    rx.set_threshold(7.0)
+    rx.process(sc10.iq, flush=True)
+    assert q.strings() == port.run_iq(sc10.iq, 10e6, 7.0, True, co.MA_CANONICAL).msgs
+    rx.close()
+
+
+def test_rx_time_start_tag(port):
+    sc = synth.make_scene(4e6, 40_000, 10, 3)
+    q = am.msg_queue()
+    rx = am.rx_path(4e6, 7.0, q, use_pmf=True)
+    rx.set_start_time(1234567, 0.9999999)
+    rx.process(sc.iq, flush=True)
+    port.set_start_time(1234567, 0.9999999)
+    try:
+        want = port.run_iq(sc.iq, 4e6, 7.0, True, co.MA_CANONICAL).msgs
+    finally:
+        port.set_start_time(0, 0.0)
+    assert q.strings() == want
+    rx.close()
+
+
+def _time_sharded_chain(iq, rate, thr, pmf, plan, resolver=0):
+    q = am.msg_queue()
+    rxs = [am.rx_path(rate, thr, q, use_pmf=pmf) for _ in plan]
+    for rx, sp in zip(rxs, plan):
+        rx._ctx.call("amb_set_option", b"resolver", resolver)
+        rx.defer_resolve(True)
+        rx.seek(sp.first_sample, sp.first_decision)
+        rx.process(iq[2 * sp.first_sample: 2 * sp.end], flush=sp.flush, collect=False)
+    frames, state, queued = [], (0, 0), 0
+    for rx, sp in zip(rxs, plan):
+        rx.resolve(state)
+        if not sp.flush:
+            state = rx.walk_state()
+        rx._slicer._first = queued == 0
+        queued += rx.drain()
+        frames += rx.frames
+    for rx in rxs:
+        rx.close()
+    return q.strings(), frames
+
+
+def _time_sharded_speculative(iq, rate, thr, pmf, plan):
+    """shard.process_time_sharded_speculative for every rank, sequentially (the emulated device is not thread-safe)."""
+    from gr_air_modes_b200 import shard
+    qs = [am.msg_queue() for _ in plan]
+    rxs = [am.rx_path(rate, thr, q, use_pmf=pmf) for q in qs]
+    last = len(plan) - 1
+    mines = []
+    for rank, (rx, sp) in enumerate(zip(rxs, plan)):
+        rx.defer_resolve(True)
+        rx.seek(sp.first_sample, sp.first_decision)
+        rx.process(iq[2 * sp.first_sample: 2 * sp.end], flush=sp.flush, collect=False)
+        mine = [0] * 6
+        if rank < last:
+            rx.resolve(None)
+            s = rx.walk_summary()
+            mine = [s.pos, s.p, s.first_real, s.first_packet, s.exact_span, s.frames_passed]
+        mines.append(mine)
+    entries, queued, bad = shard.compose_entries(plan, mines)
+    frames, handed = [], None
+    for rank, (rx, sp) in enumerate(zip(rxs, plan)):
+        if rank < bad:
+            qd = queued[rank]
+        else:
+            if rank == bad:
+                (pos, p), qd = entries[rank], queued[rank]
+            else:
+                pos, p, qd = handed
+            rx.resolve((pos, p))
+        rx._slicer._first = qd == 0
+        if rank >= bad and not sp.flush:
+            state = rx.walk_state()
+            n = rx.drain()
+            handed = state + (qd + n,)
+        else:
+            rx.drain()
+        frames += rx.frames
+        rx.close()
+    return [m for q in qs for m in q.strings()], frames, bad
+
+
+def test_one_recording_time_sharded_over_several_contexts(port):
+    from gr_air_modes_b200 import shard
+    rate, n = 4e6, 120_000
+    sc = synth.make_scene(rate, n, 45, 74)
+    want = port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL)
+    idx = [int(x) for x in want.index]
+    geo = am.query_geometry(rate, 7.0, True)
+    for spans in (2, 3):
+        plan = shard.time_shard_plan(n, spans, geo)
+        for resolver in ((0, 1) if spans == 2 else (0,)):
+            msgs, frames = _time_sharded_chain(sc.iq, rate, 7.0, True, plan, resolver)
+            assert [f.sample_index for f in frames] == idx and msgs == want.msgs, (spans, resolver)
+        msgs, frames, bad = _time_sharded_speculative(sc.iq, rate, 7.0, True, plan)
+        assert bad == spans - 1 and [f.sample_index for f in frames] == idx and msgs == want.msgs
+    # cuts right behind accepted preambles: the hand-over matters, speculation must fall back to the chain
+    mid = [x for x in idx if 30_000 < x < 105_000]
+    fell_back = 0
+    for a, b, d in ((2, 9, 3), (1, 11, 1)):
+        cuts = [mid[a] + d, mid[b] + d + 1]
+        plan = shard.time_shard_plan(n, 3, geo, boundaries=cuts)
+        msgs, frames = _time_sharded_chain(sc.iq, rate, 7.0, True, plan)
+        assert [f.sample_index for f in frames] == idx and msgs == want.msgs, cuts
+        msgs, frames, bad = _time_sharded_speculative(sc.iq, rate, 7.0, True, plan)
+        fell_back += bad < 2
+        assert [f.sample_index for f in frames] == idx and msgs == want.msgs, cuts
+    assert fell_back > 0
+
+
+def test_time_shard_api_errors():
+    q = am.msg_queue()
+    rx = am.rx_path(4e6, 7.0, q, use_pmf=True)
+    g = am.query_geometry(4e6, 7.0, True)
+    with pytest.raises(RuntimeError):
+        rx.seek(4096, 4096 + g.shard_back - 1)
+    with pytest.raises(RuntimeError):
+        rx.resolve((0, 0))
+    rx.defer_resolve(True)
+    rx.seek(0, 0)
+    iq = synth.make_scene(4e6, 30_000, 5, 3).iq
+    rx.process(iq, flush=False, collect=False)
+    with pytest.raises(RuntimeError):
+        rx.process(iq, flush=False, collect=False)
+    with pytest.raises(RuntimeError):
+        rx.walk_state()
+    rx.resolve((0, 0))
+    rx.walk_state()
+    rx.defer_resolve(False)
+    rx.reset()
+    assert rx.process(iq, flush=True) >= 4
+    rx.close()
+
+
+def test_split_form_blocks(port):
+    rng = np.random.default_rng(3)
+    for rate in (4e6, 10e6):
+        sc = synth.make_scene(rate, 60_000, 12, 56)
+        bb, avg = port.frontend(sc.iq, rate, True, co.MA_CANONICAL)
+        want = port.run_streams(bb, avg, rate, 7.0)
+        pre = am.preamble(rate, 7.0)
+        assert pre.get_rate() == rate and pre.get_threshold() == 7.0
+        chips, tags, pos, n = [], [], 0, bb.size
+        for c in list(rng.integers(1, 25_000, 5)) + [n]:
+            c = int(min(c, n - pos))
+            last = pos + c >= n
+            ch, tg = pre.process(bb[pos:pos + c], avg[pos:pos + c], flush=last)
+            chips.append(ch)
+            tags += tg
+            pos += c
+            if last:
+                break
+        assert [t[0] for t in tags] == [int(x) for x in want.index]
+        assert np.array_equal(np.concatenate(chips), want.chips)
+        q = am.msg_queue()
+        am.slicer(q).process(np.concatenate(chips), [(t[1], t[2]) for t in tags])
+        assert q.strings() == want.msgs
+
+
+def test_dc_blocker_option_and_front_end_dumps(port):
+    rate = 4e6
+    sc = synth.make_scene(rate, 40_000, 12, 5)
+    iq = sc.iq.copy()
+    iq[0::2] += np.float32(0.05)
+    want = port.run_iq(iq, rate, 7.0, True, co.MA_CANONICAL, use_dcblock=True)
+    msgs, frames, _ = run(iq, rate, 7.0, True, chunks=[9_000, 7, 12_000], dcblock=True)
+    assert msgs == want.msgs and len(msgs) >= 1            # the 50 us blocker distorts 120 us bursts, as in the reference
+    q = am.msg_queue()
+    rx = am.rx_path(rate, 7.0, q, use_pmf=True, use_dcblock=True)
+    small = iq[: 2 * 6000]
+    assert np.array_equal(rx.dump_stage("dc", small), port.dc_blocker(small, 200, co.MA_CANONICAL))
+    rx.close()
+    for r, pmf in ((4e6, True), (10e6, True), (2e6, False)):
+        rx = am.rx_path(r, 7.0, q, use_pmf=pmf)
+        x = synth.make_scene(r, 5000, 2, 9).iq
+        bb, avg = port.frontend(x, r, pmf, co.MA_CANONICAL)
+        assert np.array_equal(rx.dump_stage("bb", x), bb) and np.array_equal(rx.dump_stage("avg", x), avg)
+        rx.close()
+
+
+def test_two_contexts_and_device_crc(port):
+    import ctypes as C
+    a, b = synth.make_scene(4e6, 40_000, 10, 1), synth.make_scene(10e6, 80_000, 8, 2)
+    qa, qb = am.msg_queue(), am.msg_queue()
+    ra, rb = am.rx_path(4e6, 7.0, qa, use_pmf=True), am.rx_path(10e6, 7.0, qb, use_pmf=True)
+    ra.process(a.iq[: 2 * 20_000]); rb.process(b.iq[: 2 * 30_000])
+    ra.process(a.iq[2 * 20_000:], flush=True); rb.process(b.iq[2 * 30_000:], flush=True)
+    assert qa.strings() == port.run_iq(a.iq, 4e6, 7.0, True, co.MA_CANONICAL).msgs
+    assert qb.strings() == port.run_iq(b.iq, 10e6, 7.0, True, co.MA_CANONICAL).msgs
+    out = (C.c_uint32 * 1)()
+    ra._ctx.call("amb_device_crc", bytes.fromhex("8D4840D6202CC371C32CE0"), 1, 11, out)
+    assert out[0] == 0x576098
+    ra.close(); rb.close()
+
+
+def test_decoder_through_its_c_abi():
+    from gr_air_modes_b200 import decode, report
+    from helpers import compare_decode, load_decode_golden
+    import decode_cases
+    case = load_decode_golden()[0]
+    msgs = [tuple(m) for m in case["msgs"]][:600]
+    d = decode.batch_decoder(case["location"])
+    one = [decode.record_to_dict(r) for r in d.decode_messages(msgs)]
+    assert d.stats()[0] == 3
+    texts = decode_cases.message_strings([tuple(m) for m in case["msgs"]])[:600]
+    for k, (rec, ref) in enumerate(zip(one, case["ref"])):
+        compare_decode(rec, ref, 0.0, "msg %d" % k, tol_libm=1e-13)
+        assert report.format_report(texts[k], rec) == case["lines"][k]
+    d.reset()
+    got = []
+    for a, b in ((0, 1), (1, 33), (33, 400), (400, 600)):          # the report table carries over from batch to batch
+        got += [decode.record_to_dict(r) for r in d.decode_messages(msgs[a:b])]
+    assert [g["status"] for g in got] == [o["status"] for o in one]
+    assert all(g["lat"] == o["lat"] or (g["lat"] != g["lat"] and o["lat"] != o["lat"]) for g, o in zip(got, one))
+    d.close()
