@@ -10,6 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run by the driver with -m gpu)")
+    # tests/test_emulated_gpu_suite.py re-runs the gpu-marked parity tests on the CPU box in a child pytest whose
+    # package is pointed at the emulated build of the library (tests/simt/library_emul.cc). Test infrastructure only:
+    # the variable is read here, never by the package.
+    emulated = os.environ.get("AMB_TEST_EMULATED_LIB")
+    if emulated:
+        from gr_air_modes_b200 import _lib
+        _lib.LIB_PATH, _lib._lib = emulated, None
 
 
 @pytest.fixture(scope="session")
