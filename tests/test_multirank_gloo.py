@@ -190,3 +190,71 @@ def test_speculative_runner_world3_gloo():
     assert ret[1][2] == [("resolve", (0, plan[1].first_decision)), ("drain", False)]      # 4 messages queued before it
     assert ret[2][0] == 0 and ret[2][2] == []
     assert (ret[0][0], ret[1][0]) == (4, 2)
+
+
+# ---- both multi-GPU modes end to end at world size 2: gloo for the plumbing, the EMULATED build of the library (tests/
+# simt/library_emul.cc: the library's own sources on a host SIMT emulator, see tests/test_library_simt.py) as each rank's
+# "GPU". Every rank is its own process, so one emulated device per rank.
+def _emul_worker(rank, world, port_no, lib_path, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gr_air_modes_b200 import _lib
+    _lib.LIB_PATH, _lib._lib = lib_path, None
+    import gr_air_modes_b200 as am
+    from oracle import cpu_oracle as co
+    dev = torch.device("cpu")
+    port = co.Port()
+    rate, n = 4e6, 90_000
+
+    # (1) headline mode: one independent channel per rank, inputs fanned out from rank 0, no data-path collective
+    def make(ch):
+        sc = synth.make_scene(rate, n, 14, seed=300 + ch)
+        return torch.from_numpy(sc.iq.copy()), [b.frame.hex() for b in sc.bursts]
+
+    iq, _ = shard.fan_out(make, rank, world, dev, 2 * n)
+    q = am.msg_queue()
+    rx = am.rx_path(rate, 7.0, q, use_pmf=True)
+    rx.process(iq.numpy(), flush=True)
+    mine = port.run_iq(synth.make_scene(rate, n, 14, seed=300 + rank).iq, rate, 7.0, True, co.MA_CANONICAL).msgs
+    assert q.strings() == mine and len(mine) >= 5
+    counts = shard.gather_counts(len(mine), world, dev)
+    rx.close()
+
+    # (2) secondary mode: ONE recording cut into `world` time spans; hand-over chain, then speculative resolution
+    rec = synth.make_scene(rate, 2 * n, 40, seed=555)
+    want = port.run_iq(rec.iq, rate, 7.0, True, co.MA_CANONICAL).msgs
+    plan = shard.time_shard_plan(2 * n, world, am.query_geometry(rate, 7.0, True))
+    sp = plan[rank]
+    span_iq = rec.iq[2 * sp.first_sample: 2 * sp.end]
+    recv, send = shard.dist_state_exchange(rank, dev)
+    out = {}
+    for mode in ("chain", "speculative"):
+        q = am.msg_queue()
+        rx = am.rx_path(rate, 7.0, q, use_pmf=True)
+        if mode == "chain":
+            shard.process_time_sharded(rx, span_iq, sp, recv, send)
+        else:
+            shard.process_time_sharded_speculative(rx, span_iq, plan, rank, shard.dist_all_gather6(world, dev), recv, send)
+        out[mode] = q.strings()
+        rx.close()
+        dist.barrier()
+    ret[rank] = (counts, out["chain"], out["speculative"], want)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_both_multi_gpu_modes_world2_with_the_emulated_library(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = str(tmp_path / "libairmodes_b200_emulated.so")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-U_FORTIFY_SOURCE", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-psabi",
+                    "-shared", "-fPIC", "-o", lib, os.path.join(root, "tests", "simt", "library_emul.cc")], check=True)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_emul_worker, args=(2, _free_port(), lib, ret), nprocs=2, join=True)
+    assert ret[0][0] == ret[1][0] and all(c >= 5 for c in ret[0][0])
+    want = ret[0][3]
+    assert len(want) >= 15
+    assert ret[0][1] + ret[1][1] == want                 # the spans' messages, in rank order, are the one-shot run's
+    assert ret[0][2] + ret[1][2] == want
