@@ -325,3 +325,11 @@ def test_decoder_through_its_c_abi():
     assert [g["status"] for g in got] == [o["status"] for o in one]
     assert all(g["lat"] == o["lat"] or (g["lat"] != g["lat"] and o["lat"] != o["lat"]) for g, o in zip(got, one))
     d.close()
+
+
+def test_graft_entry_smoke_rehearsal(capsys):
+    """__graft_entry__.smoke() - what the driver runs on the B200 before the bench - against the emulated build."""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as entry
+    entry.smoke()
+    assert "smoke ok" in capsys.readouterr().out
