@@ -365,6 +365,16 @@ int amb_synchronize(amb_ctx* ctx)
     return AMB_OK;
 }
 
+// Candidate capacity for a call that evaluates `len` start positions. Up to 2^25 positions (24 bytes per candidate
+// over the five arrays = 800 MB) the list can hold every position, so not even a flood of candidates (all-pass
+// filter on denormal-power input) can overflow it; longer calls get len / 8, at least 2^25.
+static unsigned cand_capacity(long long len)
+{
+    const long long big = 1ll << 25;
+    const long long cap = len <= big ? len : std::max<long long>(len / 8, big);
+    return (unsigned)std::max<long long>(1 << 16, cap + 1024);
+}
+
 // Grow the per-call scratch (bitmaps, span counts, candidate arrays, frame buffer). Growth synchronises both
 // streams; in steady state nothing happens here.
 static int ensure_call_buffers(amb_ctx* ctx, size_t rows_need, int n_spans, unsigned cap_need, unsigned fr_ub)
@@ -513,7 +523,7 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         // ---- buffers (growth synchronises both streams; steady state does not)
         const unsigned fr_ub = (unsigned)((j_hi - j_lo) / std::max(P.skip0, 1) + 2);
         { int rc2 = ensure_call_buffers(ctx, (size_t)a.row_hi + 64, a.n_spans,
-                                        (unsigned)std::max<long long>(1 << 16, (j_hi - j_lo) / 8 + 1024), fr_ub); if (rc2) return rc2; }
+                                        cand_capacity(j_hi - j_lo), fr_ub); if (rc2) return rc2; }
         ctx->frames_ub += fr_ub;
         a.coarse = ctx->coarse[set]; a.fine = ctx->fine[set]; a.span_count = ctx->span_count[set];
         a.group_count = ctx->span_count[set] + ctx->spans_cap;     // 128 words behind the span counts
@@ -987,7 +997,7 @@ int amb_preamble_process(amb_ctx* ctx, const float* in0, const float* in1, size_
         ctx->frames_ub = 0;
         const unsigned fr_ub = (unsigned)((long long)m / std::max(P.skip0, 1) + 2);
         const bool keep = ctx->keep_chips; ctx->keep_chips = true;
-        rc = ensure_call_buffers(ctx, (size_t)a.row_hi + 64, a.n_spans, (unsigned)std::max<long long>(1 << 16, (long long)m / 8 + 1024), fr_ub);
+        rc = ensure_call_buffers(ctx, (size_t)a.row_hi + 64, a.n_spans, cand_capacity((long long)m + P.H), fr_ub);
         ctx->keep_chips = keep;
         if (rc != AMB_OK) break;
         a.coarse = ctx->coarse[0]; a.fine = ctx->fine[0]; a.span_count = ctx->span_count[0];

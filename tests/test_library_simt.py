@@ -333,3 +333,20 @@ def test_graft_entry_smoke_rehearsal(capsys):
     import __graft_entry__ as entry
     entry.smoke()
     assert "smoke ok" in capsys.readouterr().out
+
+
+def test_candidate_flood_does_not_overflow(port):
+    """Input whose |x|^2 is denormal: the scan kernel's filter (absolute 1e-42 slack) passes every non-zero sample,
+    more than n / 8 candidates. Calls of up to 2^25 samples size the candidate list for every position, so the exact
+    stage simply weeds them out and the result is still the oracle's (found by fuzzing the emulated chain)."""
+    rate, n = 2.5e6, 60_000
+    sc = synth.make_scene(rate, n, 30, 1234, noise_sigma=0.05, snr_db=(3.0, 40.0))
+    iq = sc.iq * np.float32(1e-21)
+    want = port.run_iq(iq, rate, 0.5, True, co.MA_CANONICAL)
+    q = am.msg_queue()
+    rx = am.rx_path(rate, 0.5, q, use_pmf=True)
+    rx.process(iq, flush=True)
+    st = rx.stats()
+    assert st.candidates > n // 8                         # the flood is real ...
+    assert q.strings() == want.msgs and len(want.msgs) > 20   # ... and harmless
+    rx.close()
