@@ -18,6 +18,7 @@
 #include <ucontext.h>
 
 #include <functional>
+#include <utility>
 #include <vector>
 
 struct simt_dim3 { unsigned x = 1, y = 1, z = 1; };
@@ -35,6 +36,7 @@ static SimtBlockBar simt_block_bar;
 static simt_dim3 simt_block_idx, simt_block_dim, simt_grid_dim;
 static unsigned long simt_progress = 0;
 static std::function<void()> simt_body;
+static unsigned long long simt_shuffle_state = [] { const char* e = getenv("SIMT_SHUFFLE"); return e ? strtoull(e, nullptr, 10) * 2 + 1 : 0ull; }();
 
 #define threadIdx (simt_cur->tid)
 #define blockIdx simt_block_idx
@@ -50,6 +52,9 @@ static std::function<void()> simt_body;
 #define AMB_SIMT_EMUL 1
 
 // switching is _setjmp/_longjmp once a fiber runs (swapcontext costs two sigprocmask system calls per switch)
+// every harness is one translation unit, so this is exported once per test library
+extern "C" void simt_set_shuffle(unsigned long long seed) { simt_shuffle_state = seed ? seed * 2 + 1 : 0; }
+
 static inline void simt_yield() { if (!_setjmp(simt_cur->jb)) _longjmp(simt_sched_jb, 1); }
 
 // every lane of the warp deposits (value, pred), waits for the other 31, then reads; a second rendezvous frees the slots
@@ -255,10 +260,19 @@ static inline void simt_launch(unsigned grid, unsigned block, const std::functio
             makecontext(&f.ctx, simt_trampoline, 0);
         }
         unsigned alive = block;
+        std::vector<unsigned> order(block);
+        for (unsigned t = 0; t < block; t++) order[t] = t;
         while (alive) {
             const unsigned long before = simt_progress;
             alive = 0;
-            for (unsigned t = 0; t < block; t++) {
+            if (simt_shuffle_state) {                       // SIMT_SHUFFLE=<seed>: a different thread interleaving every round
+                for (unsigned i = block - 1; i > 0; i--) {  // (a kernel that is missing a barrier stops getting away with it)
+                    simt_shuffle_state = simt_shuffle_state * 6364136223846793005ull + 1442695040888963407ull;
+                    std::swap(order[i], order[(unsigned)((simt_shuffle_state >> 33) % (i + 1))]);
+                }
+            }
+            for (unsigned oi = 0; oi < block; oi++) {
+                const unsigned t = order[oi];
                 if (fibers[t].done) continue;
                 simt_cur = &fibers[t];
                 if (!_setjmp(simt_sched_jb)) {

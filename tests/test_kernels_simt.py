@@ -205,3 +205,27 @@ def test_dc_blocker_kernels_under_the_emulator(emul, port):
         got = np.zeros(2 * n, np.float32)
         assert emul.emul_dcblock(iq.ctypes.data, n, D, got.ctypes.data) == 0
         assert np.array_equal(got, want, equal_nan=True), (D, n, kind)
+
+
+def test_random_thread_interleavings(emul, port):
+    """The emulator normally resumes the threads of a block in index order; with a shuffle seed every scheduling round
+    uses another order. A kernel that only works because of an accidental execution order (a missing barrier) stops
+    getting away with it. Whole IQ chain incl. the scan kernel, three seeds."""
+    from gr_air_modes_b200 import _lib
+    emul.simt_set_shuffle.argtypes = [C.c_ulonglong]
+    rate, n = 4e6, 50_000
+    sc = synth.make_scene(rate, n, 100, 31, garble_frac=0.3, fruit=30)
+    want = port.run_iq(sc.iq, rate, 6.0, True, co.MA_CANONICAL)
+    md = n // 200 + 16
+    try:
+        for seed in (1, 2, 3):
+            emul.simt_set_shuffle(seed)
+            chips = np.zeros((md, 240), np.float32)
+            idx = np.zeros(md, np.uint64)
+            frames = (_lib.Frame * md)()
+            nd = emul.emul_process_iq(sc.iq.ctypes.data, n, None, None, rate, 6.0, 1, 2, 2, chips.ctypes.data, idx.ctypes.data,
+                                      C.cast(frames, C.c_void_p), md)
+            assert nd == len(want.index) and [int(x) for x in idx[:nd]] == [int(x) for x in want.index], seed
+            assert np.array_equal(chips[:nd], want.chips), seed
+    finally:
+        emul.simt_set_shuffle(0)
