@@ -8,6 +8,7 @@
 // atomicAdd on unsigned, __ldg/__ldcg/__stcg, bit intrinsics. A launch whose fibers all wait without progress is
 // reported as a deadlock (that is how a divergent collective would show up).
 #pragma once
+#undef _FORTIFY_SOURCE       // fibers switch stacks with _longjmp; the fortified longjmp refuses that (include this header first)
 #include <math.h>
 #include <stdint.h>
 #include <stddef.h>
@@ -55,7 +56,12 @@ static unsigned long long simt_shuffle_state = [] { const char* e = getenv("SIMT
 // every harness is one translation unit, so this is exported once per test library
 extern "C" void simt_set_shuffle(unsigned long long seed) { simt_shuffle_state = seed ? seed * 2 + 1 : 0; }
 
+// (-DSIMT_SWAPCONTEXT: plain swapcontext everywhere, for builds with -fsanitize=address, which tracks swapcontext)
+#ifdef SIMT_SWAPCONTEXT
+static inline void simt_yield() { swapcontext(&simt_cur->ctx, &simt_sched_ctx); }
+#else
 static inline void simt_yield() { if (!_setjmp(simt_cur->jb)) _longjmp(simt_sched_jb, 1); }
+#endif
 
 // every lane of the warp deposits (value, pred), waits for the other 31, then reads; a second rendezvous frees the slots
 static inline void simt_warp_exchange(uint64_t value, unsigned pred, uint64_t* vals, unsigned* preds)
@@ -233,7 +239,11 @@ static void simt_trampoline()
     if (--w->alive && w->arrived == w->alive) { w->arrived = 0; w->gen++; }
     SimtBlockBar* b = &simt_block_bar;
     if (--b->n && b->arrived == b->n) { b->arrived = 0; b->gen++; }
+#ifdef SIMT_SWAPCONTEXT
+    swapcontext(&simt_cur->ctx, &simt_sched_ctx);
+#else
     _longjmp(simt_sched_jb, 1);
+#endif
 }
 
 // simt_launch(grid, block, [&]{ kernel(args...); })
@@ -275,11 +285,15 @@ static inline void simt_launch(unsigned grid, unsigned block, const std::functio
                 const unsigned t = order[oi];
                 if (fibers[t].done) continue;
                 simt_cur = &fibers[t];
+#ifdef SIMT_SWAPCONTEXT
+                swapcontext(&simt_sched_ctx, &fibers[t].ctx);
+#else
                 if (!_setjmp(simt_sched_jb)) {
                     if (fibers[t].started) _longjmp(fibers[t].jb, 1);
                     fibers[t].started = true;
                     setcontext(&fibers[t].ctx);             // first entry: onto the fiber's own stack
                 }
+#endif
                 if (!fibers[t].done) alive++;
             }
             if (alive && simt_progress == before) {
