@@ -42,6 +42,8 @@ struct amb_decoder {
     std::string err;
 };
 
+static thread_local std::string g_create_err;          // why the last amb_decoder_create on this thread failed
+
 static int dfail(amb_decoder* d, int code, const char* what, cudaError_t e = cudaSuccess)
 {
     if (d) {
@@ -117,7 +119,8 @@ int amb_decoder_create(int device, int have_location, double lat, double lon, am
             cudaMemsetAsync(d->table, 0xFF, AMB_TABLE_SLOTS * sizeof(AmbCprSlot), d->stream) != cudaSuccess ||
             cudaStreamSynchronize(d->stream) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
     } while (0);
-    if (rc != AMB_OK) { amb_decoder_destroy(d); return rc; }
+    if (rc != AMB_OK) { g_create_err = d->err.empty() ? "CUDA resource creation failed" : d->err; amb_decoder_destroy(d); return rc; }
+    g_create_err.clear();
     *out = d;
     return AMB_OK;
 }
@@ -223,7 +226,7 @@ int amb_decoder_stats(amb_decoder* d, uint64_t* kernel_launches, float* ms_last)
     return AMB_OK;
 }
 
-const char* amb_decoder_last_error(const amb_decoder* d) { return d ? d->err.c_str() : ""; }
+const char* amb_decoder_last_error(const amb_decoder* d) { return d ? d->err.c_str() : g_create_err.c_str(); }
 
 uint64_t amb_frame_bits(const amb_frame* f, int start, int num)
 {

@@ -56,7 +56,10 @@ class batch_decoder:
         self._lib = _lib.load()
         h = C.c_void_p()
         have, lat, lon = self._loc(my_location)
-        check(self._lib.amb_decoder_create(int(device), have, lat, lon, C.byref(h)))
+        rc = self._lib.amb_decoder_create(int(device), have, lat, lon, C.byref(h))
+        if rc < 0:
+            detail = self._lib.amb_decoder_last_error(None).decode()
+            raise RuntimeError("libairmodes_b200: %s%s" % (self._lib.amb_strerror(rc).decode(), (" (%s)" % detail) if detail else ""))
         self._h = h
         self.my_location = my_location
 

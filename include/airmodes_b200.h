@@ -283,7 +283,7 @@ AMB_API int amb_decoder_reset(amb_decoder* d);                      /* forget ev
 AMB_API int amb_decode_frames(amb_decoder* d, const amb_frame* frames, int n, int mem_kind, amb_fields* out);
 /* Kernels launched so far / device time in ms of the last amb_decode_frames call (H2D, kernels, D2H). */
 AMB_API int amb_decoder_stats(amb_decoder* d, uint64_t* kernel_launches, float* ms_last);
-AMB_API const char* amb_decoder_last_error(const amb_decoder* d);
+AMB_API const char* amb_decoder_last_error(const amb_decoder* d);   /* d == NULL: why the last amb_decoder_create of this thread failed */
 /* data_field.get_bits(start, num) on a frame's payload (parse.py:71-87): host helper for the raw sub-fields that
  * amb_fields does not carry. */
 AMB_API uint64_t amb_frame_bits(const amb_frame* f, int start, int num);
