@@ -35,7 +35,7 @@ extern "C" int emul_preamble(const float* in0, const float* in1, int n, float ra
     // buffers as ensure_call_buffers sizes them
     const size_t rows_cap = (size_t)a.row_hi + 64 + ((size_t)a.row_hi + 64) / 8;
     const int spans_cap = a.n_spans + 64;
-    const unsigned cand_cap = (unsigned)std::max<long long>(1 << 16, (long long)m / 8 + 1024);
+    const unsigned cand_cap = (unsigned)std::max<long long>(1 << 16, (long long)m + P.H + 1024);   // cand_capacity() of amb_api.cu
     const unsigned frame_cap = (unsigned)((long long)m / std::max(P.skip0, 1) + 2) * 2 + 1024;
     std::vector<uint32_t> coarse(rows_cap / 32 + 2, 0), fine(rows_cap * 8, 0), span_count((size_t)spans_cap + 128, 0);
     std::vector<int> cand_j(cand_cap), det_list(cand_cap);
@@ -123,7 +123,7 @@ extern "C" int emul_process_iq(const float* iq, int n, const float* bb, const fl
     a.rows_per_span = rps; a.n_spans = (rows + rps - 1) / rps;
     const size_t rows_cap = (size_t)a.row_hi + 64 + ((size_t)a.row_hi + 64) / 8;
     const int spans_cap = a.n_spans + 64;
-    const unsigned cand_cap = (unsigned)std::max<long long>(1 << 16, (j_hi - j_lo) / 8 + 1024);
+    const unsigned cand_cap = (unsigned)std::max<long long>(1 << 16, (j_hi - j_lo) + 1024);      // cand_capacity() of amb_api.cu
     const unsigned frame_cap = (unsigned)((j_hi - j_lo) / std::max(P.skip0, 1) + 2) * 2 + 1024;
     std::vector<uint32_t> coarse(rows_cap / 32 + 2, 0), fine(rows_cap * 8, 0), span_count((size_t)spans_cap + 128, 0);
     std::vector<int> cand_j(cand_cap), det_list(cand_cap);
