@@ -90,38 +90,166 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_bursts(n, seed):
-    """Host-side burst overlays of the scene (sparse): list of (first_sample, complex64 array)."""
+# ---- BASELINE.json configs. "c1" is the N = 1 headline, "c2" the N > 1 headline -----------------------
+CONFIGS = {
+    "c1": dict(rate=4e6, seed=0, dense=False,
+               what="synthetic 1090 MHz IQ @ 4 Msps, 1000 DF11/DF17 bursts at mixed SNR (BASELINE configs[1])"),
+    "c2": dict(rate=10e6, seed=30, dense=False,
+               what="one synthetic 10 Msps channel per GPU, seeds 30+rank, 1000 DF11/DF17 bursts each (BASELINE configs[2])"),
+    "c3": dict(rate=20e6, seed=4, dense=False,
+               what="20 Msps oversampled input, 10 samples/chip, 1000 DF11/DF17 bursts (BASELINE configs[3])"),
+    "c4": dict(rate=4e6, seed=5, dense=True,
+               what="dense-traffic stress @ 4 Msps: 10 000 overlapping squitters/s, 20 % with 1-5 flipped bits, plus "
+                    "Mode A/C-like FRUIT pulse pairs (BASELINE configs[4])"),
+}
+
+
+def scene_args(cfg, n):
+    if cfg["dense"]:
+        nb = int(10_000 * n / cfg["rate"])
+        return dict(n_bursts=nb, garble_frac=0.2, fruit=nb // 4, snr_db=(4.0, 30.0))
+    return dict(n_bursts=N_BURSTS)
+
+
+def make_device_scene(cfg, n, channel, device, out=None):
+    """(iq float32[2n] on `device`, hex payloads sent or None). Seeded; noise from torch's device generator."""
     from gr_air_modes_b200 import synth
-    rng = np.random.Generator(np.random.PCG64(seed))
-    spc = RATE / 2e6
-    span = 240 * spc + 8
-    starts = np.sort(rng.uniform(span, n - 2 * span, N_BURSTS))
-    out = []
-    for s in starts:
-        df = (11, 17)[int(rng.integers(0, 2))]
-        frame = synth.make_frame(df, rng)
-        snr = rng.uniform(6.0, 30.0)
-        amp = float(np.sqrt(2.0 * NOISE_SIGMA ** 2 * 10 ** (snr / 10)))
-        b = synth.Burst(float(s), frame, amp, float(rng.uniform(0, 2 * np.pi)))
-        out.append(synth.burst_waveform(b, spc) + (frame,))
-    return out
+    iq, hexs, _ = synth.make_scene_device(cfg["rate"], n, seed=cfg["seed"] + channel, device=device,
+                                          noise_sigma=NOISE_SIGMA, out=out, **scene_args(cfg, n))
+    return iq, hexs
 
 
-def make_device_scene(n, seed, device):
+# ---- the checker: the reference's arithmetic on the very buffer that was timed (oracle/, test infrastructure) ----------
+def oracle_full(iq_np, rate, threads):
+    """Every detection and message the reference produces for this recording. Front end = the canonical restatement
+    (oracle/modes_oracle.c, fp64 ascending window sums) evaluated in parallel over cuts with 49*spc samples of
+    context (each output only depends on that many inputs); scan + slicer + CRC = oracle/_ref (the unmodified
+    preamble_impl.cc / slicer_impl.cc / modes_crc.cc) when it was built, else the C port."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import cpu_oracle as co
+    port = co.Port()
+    n = iq_np.size // 2
+    spc = int(rate / 2e6)
+    h = 49 * spc
+    bb = np.empty(n, np.float32)
+    avg = np.empty(n, np.float32)
+    chunk = 1 << 20
+
+    def work(a):
+        b = min(a + chunk, n)
+        a0 = max(0, a - h)
+        x, y = port.frontend(iq_np[2 * a0: 2 * b], rate, True, co.MA_CANONICAL)
+        bb[a:b] = x[a - a0:]
+        avg[a:b] = y[a - a0:]
+
+    with ThreadPoolExecutor(max(1, threads)) as ex:
+        list(ex.map(work, range(0, n, chunk)))
+    kind = "reference" if co.ref_available() else "port"
+    eng = co.Ref() if kind == "reference" else port
+    return eng.run_streams(bb, avg, rate, THRESHOLD_DB), kind
+
+
+def parity_check(rx, q, iq, rate, threads):
+    """Run the CUDA chain once more over `iq` (device tensor) collecting everything, D2H the recording, run the
+    oracle over it and compare every detection index and every message string."""
+    from collections import Counter
+    t0 = time.perf_counter()
+    rx.reset()
+    rx._slicer._first = True            # a fresh slicer's first message has 6 digits (slicer_impl.cc:192)
+    q.flush()
+    rx.process(iq, flush=True)
+    ours_idx = np.array([f.sample_index for f in rx.frames], dtype=np.uint64)
+    ours_msgs = q.strings()
+    q.flush()
+    host = iq.cpu().numpy()
+    want, kind = oracle_full(host, rate, threads)
+    del host
+    if ours_msgs == want.msgs:
+        m = dict(matched=len(ours_msgs), missing=0, extra=0)
+    else:
+        a, b = Counter(ours_msgs), Counter(want.msgs)
+        m = dict(matched=sum((a & b).values()), missing=sum((b - a).values()), extra=sum((a - b).values()))
+    wi = want.index.astype(np.uint64)
+    if ours_idx.size == wi.size and np.array_equal(ours_idx, wi):
+        d = dict(matched=int(wi.size), missing=0, extra=0)
+    else:
+        both = np.intersect1d(ours_idx, wi).size
+        d = dict(matched=int(both), missing=int(wi.size - both), extra=int(ours_idx.size - both))
+    return {"matched": m["matched"], "missing": m["missing"], "extra": m["extra"], "compared": "every message string "
+            "(payload, CRC syndrome, level, timestamp) and every detection index of the timed recording, full size",
+            "detections": d, "oracle": kind, "seconds": round(time.perf_counter() - t0, 1)}
+
+
+def run_config(key, n, args, rank, local_rank, world, device, fan=None, steps=None):
+    """Device-resident timing + full-size parity of one BASELINE config. Returns (result dict, iq, rx, q)."""
     import torch
-    g = torch.Generator(device=device); g.manual_seed(1000 + seed)
-    iq = torch.empty(2 * n, device=device, dtype=torch.float32)
-    step = 1 << 26
-    for a in range(0, 2 * n, step):
-        m = min(step, 2 * n - a)
-        iq[a:a + m] = torch.randn(m, device=device, generator=g) * NOISE_SIGMA
-    frames = []
-    for n0, w, frame in make_bursts(n, seed):
-        t = torch.from_numpy(np.ascontiguousarray(w).view(np.float32)).to(device)
-        iq[2 * n0: 2 * n0 + t.numel()] += t
-        frames.append(frame.hex())
-    return iq, frames
+    import torch.distributed as dist
+    import gr_air_modes_b200 as am
+    from gr_air_modes_b200 import shard
+    cfg = CONFIGS[key]
+    rate = cfg["rate"]
+    steps = steps or args.steps
+    t_f0 = time.perf_counter()
+    timing = {}
+    iq, sent = shard.fan_out(lambda ch: make_device_scene(cfg, n, ch, device), rank, world, device, 2 * n, timing)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_f0
+    q = am.msg_queue()
+    rx = am.rx_path(rate, THRESHOLD_DB, q, use_pmf=True, device=local_rank)
+    rx._ctx.use_stream(torch.cuda.current_stream().cuda_stream)
+    rx._ctx.call("amb_enable_timing", 1)
+
+    def step():
+        rx.reset()
+        rx.process(iq, flush=True, collect=False)
+
+    for _ in range(args.warmup):
+        step()
+    nmsg = rx.drain()
+    q.flush()
+    launches0 = rx.stats().kernel_launches
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    rx._ctx.join()                 # the sparse kernels of the last step run on the library's second stream
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    scan_ms = rx._ctx.scan_times_ms(min(steps, 64))
+    st = rx.stats()
+    launches = st.kernel_launches - launches0
+    rx.drain(); q.flush()
+    ms_max = shard.max_over_ranks(ms, world, device)
+    scan_avg = shard.max_over_ranks(float(np.mean(scan_ms)), world, device)
+    peak, peak_src = measured_peak_gbs()
+    res = {"config": key, "workload": cfg["what"], "rate_sps": rate, "samples_per_gpu": n,
+           "value": world * n * steps / (ms_max * 1e-3) / 1e6, "unit": "Msamples/s", "steps": steps,
+           "ms_per_step": ms_max / steps, "scan_ms": scan_avg,
+           "frac": 8.0 * n / (scan_avg * 1e-3) / 1e9 / peak, "step_frac": 8.0 * n / (ms_max / steps * 1e-3) / 1e9 / peak,
+           "msgs_per_step": nmsg, "candidates": int(st.candidates), "detections": int(st.detections),
+           "gpu_launches": int(launches), "setup_s": round(setup_s, 2)}
+    if sent is not None:
+        res["bursts_sent"] = len(sent)
+    if timing.get("bytes"):
+        res["fanout_gbps"] = timing["bytes"] / (timing["send_ms"] * 1e-3) / 1e9
+        res["fanout_ms"] = timing["send_ms"]
+    if not args.no_parity:
+        threads = max(1, len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+        par = parity_check(rx, q, iq, rate, threads)
+        if world > 1:       # sum over ranks
+            t = torch.tensor([par["matched"], par["missing"], par["extra"], par["detections"]["matched"],
+                              par["detections"]["missing"], par["detections"]["extra"]], dtype=torch.int64, device=device)
+            dist.all_reduce(t)
+            v = [int(x) for x in t.tolist()]
+            par.update(matched=v[0], missing=v[1], extra=v[2], detections=dict(matched=v[3], missing=v[4], extra=v[5]))
+        res["parity"] = par
+    return res, iq, rx, q
 
 
 def bind_near_gpu(index):
@@ -159,11 +287,8 @@ def _tame_malloc():
         pass
 
 
-def reference_arm(args, rank, world):
-    """The reference's own CPU implementation of the path, all host threads, bounded sample per step."""
-    if rank != 0:
-        return
-    from concurrent.futures import ThreadPoolExecutor
+def _cpu_arm_setup(cfg, log2n):
+    """Shared by the reference arm and the cpu_baseline leg: engine, thread count, one DISTINCT cut per thread."""
     from oracle import cpu_oracle as co
     from gr_air_modes_b200 import synth
     _tame_malloc()
@@ -172,14 +297,33 @@ def reference_arm(args, rank, world):
     ref = co.Ref() if kind == "reference" else None
     cores = max(1, min(len(os.sched_getaffinity(0)), 256))       # every host thread we are allowed to use
     n_slice = 1 << (23 if cores <= 64 else 22)
-    sc = synth.make_scene(RATE, n_slice, max(1, int(N_BURSTS * n_slice / (1 << args.log2n))), 7, noise_sigma=NOISE_SIGMA)
-    slices = [sc.iq] * cores                                     # read-only input shared by the threads
+    rate = cfg["rate"]
+    n_full = 1 << log2n
+    sa = scene_args(cfg, n_slice)
+    if not cfg["dense"]:
+        sa["n_bursts"] = max(1, int(N_BURSTS * n_slice / n_full))
+    sc = synth.make_scene(rate, n_slice, sa.pop("n_bursts"), 7, noise_sigma=NOISE_SIGMA, **sa)
+    # one private copy per thread: 128 threads re-reading ONE 32 MB cut would run out of the L3, a stream does not
+    slices = [sc.iq.copy() for _ in range(cores)]
 
     def work(iq):
-        bb, avg = port.frontend(iq, RATE, True, co.MA_GR_FLOAT, 4096)     # GNU Radio's fp32 running-sum schedule
-        r = (ref.run_streams(bb, avg, RATE, THRESHOLD_DB) if ref else port.run_streams(bb, avg, RATE, THRESHOLD_DB))
+        bb, avg = port.frontend(iq, rate, True, co.MA_GR_FLOAT, 4096)     # GNU Radio's fp32 running-sum schedule
+        r = (ref.run_streams(bb, avg, rate, THRESHOLD_DB) if ref else port.run_streams(bb, avg, rate, THRESHOLD_DB))
         return len(r.msgs)
 
+    what = "%d threads, each over its own 2^%d-sample cut of the same scene type (the full 2^%d-sample recording does " \
+           "not fit a bounded CPU step): GR fp32 moving averages + %s preamble/slicer/CRC" % (
+               cores, int(np.log2(n_slice)), log2n, "the unmodified reference's" if ref else "the oracle port's")
+    return work, slices, cores, n_slice, kind, what
+
+
+def reference_arm(args, rank, world, key):
+    """The reference's own CPU implementation of the path, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    cfg = CONFIGS[key]
+    work, slices, cores, n_slice, kind, what = _cpu_arm_setup(cfg, args.log2n)
     with ThreadPoolExecutor(cores) as ex:
         for _ in range(max(args.warmup, 2)):
             list(ex.map(work, slices))
@@ -189,48 +333,32 @@ def reference_arm(args, rank, world):
         dt = time.perf_counter() - t0
     total = args.steps * cores * n_slice
     val = total / dt / 1e6
-    sample = "%d threads x 2^%d-sample cuts of the 4 Msps scene per step (GR fp32 moving averages + %s scan/slice/CRC)" % (
-        cores, int(np.log2(n_slice)), "unmodified reference" if ref else "oracle port")
     line = {"impl": "reference", "metric": "Msamples/s IQ demod+slice+CRC", "value": val, "unit": "Msamples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "synthetic 1090 MHz IQ @ 4 Msps, DF11/DF17 bursts at mixed SNR (configs[1]), bounded CPU sample",
-                       "rate_sps": RATE, "threshold_db": THRESHOLD_DB, "use_pmf": True},
-            "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
+            "config": {"workload": cfg["what"] + "; CPU arm = bounded sample of that workload", "config_key": key,
+                       "rate_sps": cfg["rate"], "threshold_db": THRESHOLD_DB, "use_pmf": True,
+                       "same_config_note": "same scene type, rate, threshold and burst density as the GPU arm; per step "
+                                           "the CPU processes cores x 2^%d samples instead of 2^%d" % (int(np.log2(n_slice)), args.log2n)},
+            "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": what},
             "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "msgs_per_step": int(sum(msgs))}
     print(json.dumps(line))
 
 
-def cpu_baseline_leg(log2n):
+def cpu_baseline_leg(key, log2n):
     from concurrent.futures import ThreadPoolExecutor
-    from oracle import cpu_oracle as co
-    from gr_air_modes_b200 import synth
-    _tame_malloc()
-    port = co.Port()
-    kind = "reference" if co.ref_available() else "port"
-    ref = co.Ref() if kind == "reference" else None
-    cores = max(1, min(len(os.sched_getaffinity(0)), 256))       # every host thread we are allowed to use
-    n_slice = 1 << (23 if cores <= 64 else 22)
-    sc = synth.make_scene(RATE, n_slice, max(1, int(N_BURSTS * n_slice / (1 << log2n))), 7, noise_sigma=NOISE_SIGMA)
+    work, slices, cores, n_slice, kind, what = _cpu_arm_setup(CONFIGS[key], log2n)
     reps = max(1, int(round(2 * (1 << 29) / (cores * n_slice))))  # ~2^30 samples in total: 10-30 s of CPU work
-
-    def work(k):
-        bb, avg = port.frontend(sc.iq, RATE, True, co.MA_GR_FLOAT, 4096)
-        r = (ref.run_streams(bb, avg, RATE, THRESHOLD_DB) if ref else port.run_streams(bb, avg, RATE, THRESHOLD_DB))
-        return len(r.msgs)
-
     with ThreadPoolExecutor(cores) as ex:
-        list(ex.map(work, range(cores)))
-        list(ex.map(work, range(cores)))
+        list(ex.map(work, slices))
+        list(ex.map(work, slices))
         t0 = time.perf_counter()
         for _ in range(reps):
-            list(ex.map(work, range(cores)))
+            list(ex.map(work, slices))
         dt = time.perf_counter() - t0
     val = reps * cores * n_slice / dt / 1e6
-    return {"value": val, "unit": "Msamples/s", "cores": cores, "kind": kind,
-            "sample": "%d passes x %d threads over a 2^%d-sample cut of the same 4 Msps scene; GR fp32 moving averages + "
-                      "%s preamble/slicer/CRC" % (reps, cores, int(np.log2(n_slice)), "unmodified reference" if ref else "oracle port")}
+    return {"value": val, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": "%d passes x %s" % (reps, what)}
 
 
 def time_shard_arm(args, rank, local_rank, world, device):
@@ -247,7 +375,7 @@ def time_shard_arm(args, rank, local_rank, world, device):
     t_f0 = time.perf_counter()
     whole = sent = None
     if rank == 0:
-        whole, sent = make_device_scene(n, 0, device)
+        whole, sent = make_device_scene(CONFIGS['c1'], n, 0, device)
         for r in range(1, len(plan)):
             dist.send(whole[2 * plan[r].first_sample: 2 * plan[r].end].contiguous(), dst=r)
         iq = whole[: 2 * sp.end]
@@ -348,6 +476,55 @@ def time_shard_arm(args, rank, local_rank, world, device):
         dist.destroy_process_group()
 
 
+def e2e_legs(rx, q, iq, n, args, local_rank, world, device):
+    """End to end through the public API (rx_path.process): the step's IQ starts in HOST memory, the H2D copy, the
+    whole chain and the read-back of the frames are inside the timed region. Headline: pinned float32 (gr_complex,
+    the reference's boundary). Extras: pageable host memory, 16-bit IQ, small process() calls as GNU Radio makes them."""
+    import torch
+    import torch.distributed as dist
+    from gr_air_modes_b200 import shard
+    numa = bind_near_gpu(local_rank)          # the pinned buffer is first-touched on the GPU's NUMA node
+    host = torch.empty(2 * n, dtype=torch.float32, pin_memory=True)
+    host.copy_(iq)
+    torch.cuda.synchronize()
+
+    def timed(fn, reps):
+        fn()
+        q.flush()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.perf_counter() - t0) / reps
+        q.flush()
+        return shard.max_over_ranks(ms, world, device)
+
+    d2h = [0]
+
+    def pinned():
+        rx.reset()
+        rx.process(host, flush=True)          # H2D copy + kernels + frame read-back (drain) inside
+        d2h[0] = len(rx.frames) * 80 + 32
+
+    ms = timed(pinned, args.e2e_steps)
+    out = {"value": world * n / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 8 * n,
+           "d2h_bytes_per_step": d2h[0], "ms_per_step": ms, "h2d_gbps": 8 * n / (ms * 1e-3) / 1e9,
+           "host_numa_binding": numa, "input": "pinned host float32 I/Q (gr_complex)"}
+    extras = {}
+    if not args.no_e2e_extras:
+        extras = e2e_extra_legs(rx, q, host, n, args, world, timed)
+    del host
+    return out, extras
+
+
+def e2e_extra_legs(rx, q, host, n, args, world, timed):
+    """Filled in by the ingest pipeline of the library (pageable input, 16-bit IQ, small calls)."""
+    return {}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -356,7 +533,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=28)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="headline workload (default: c1 on one GPU, "
+                    "c2 = one 10 Msps channel per GPU on several)")
+    ap.add_argument("--rate", type=float, default=None, help="shorthand: 4e6 -> c1, 10e6 -> c2, 20e6 -> c3")
+    ap.add_argument("--dense", action="store_true", help="shorthand for --config c4")
+    ap.add_argument("--extra-configs", default=None, help="comma list of further configs measured into configs[] "
+                    "(default: the other three on one GPU, c1 on several; 'none' to skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-e2e-extras", action="store_true")
     ap.add_argument("--time-shard", action="store_true",
                     help="secondary mode: ONE 2^log2n-sample recording cut into --gpus spans (strong scaling)")
     ap.add_argument("--chain", action="store_true", help="--time-shard: plain hand-over chain instead of speculative resolution")
@@ -367,14 +552,22 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    key = args.config
+    if key is None and args.dense:
+        key = "c4"
+    if key is None and args.rate is not None:
+        key = {4e6: "c1", 10e6: "c2", 20e6: "c3"}.get(args.rate)
+        if key is None:
+            raise SystemExit("bench.py: --rate must be 4e6, 10e6 or 20e6 (the BASELINE configs)")
+    if key is None:
+        key = "c1" if max(world, args.gpus) == 1 else "c2"
+
     if args.impl == "reference":
-        reference_arm(args, rank, world)
+        reference_arm(args, rank, world, key)
         return
 
     import torch
     import torch.distributed as dist
-    import gr_air_modes_b200 as am
-    from gr_air_modes_b200 import shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - this framework has no CPU path (use --impl reference for the CPU arm)")
@@ -388,107 +581,90 @@ def main():
         time_shard_arm(args, rank, local_rank, world, device)
         return
 
-    # ---- input: rank 0 synthesises every channel and fans it out over NCCL (timed separately)
-    t_f0 = time.perf_counter()
-    iq, sent = shard.fan_out(lambda ch: make_device_scene(n, ch, device), rank, world, device, 2 * n)
-    torch.cuda.synchronize()
-    fanout_s = time.perf_counter() - t_f0
+    if args.extra_configs is None:
+        extra = [k for k in ("c2", "c3", "c4") if k != key] if world == 1 else [k for k in ("c1",) if k != key]
+        if world == 1 and key != "c1":
+            extra = ["c1"] + extra
+    else:
+        extra = [k for k in args.extra_configs.split(",") if k and k != "none"]
 
-    q = am.msg_queue()
-    rx = am.rx_path(RATE, THRESHOLD_DB, q, use_pmf=True, device=local_rank)
-    rx._ctx.use_stream(torch.cuda.current_stream().cuda_stream)
-    rx._ctx.call("amb_enable_timing", 1)
-
-    def step():
-        rx.reset()
-        rx.process(iq, flush=True, collect=False)
-
-    for _ in range(args.warmup):
-        step()
-    nmsg = rx.drain()
-    got = {m.split()[0] for m in q.strings()}
-    decoded = len(got & set(sent))
-    launches0 = rx.stats().kernel_launches
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    rx._ctx.join()                 # the sparse kernels of the last step run on the library's second stream
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    scan_ms = rx._ctx.scan_times_ms(min(args.steps, 64))
-    launches = rx.stats().kernel_launches - launches0
-    rx.drain(); q.flush()
-    ms_max = shard.max_over_ranks(ms, world, device)
-    scan_avg = shard.max_over_ranks(float(np.mean(scan_ms)), world, device)
-
-    # ---- end to end through the public API: pinned host IQ -> H2D -> chain -> frames D2H
     all_cpus = os.sched_getaffinity(0)
-    numa = bind_near_gpu(local_rank)          # the pinned buffer is first-touched on the GPU's NUMA node
-    host = torch.empty(2 * n, dtype=torch.float32, pin_memory=True)
-    host.copy_(iq)
-    torch.cuda.synchronize()
-    d2h = 0
-    for _ in range(1):
-        rx.reset(); rx.process(host, flush=True)
-    q.flush()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        rx.reset()
-        rx.process(host, flush=True)          # H2D copy + kernels + frame read-back (drain) inside
-        d2h = len(rx.frames) * 80 + 32
-    torch.cuda.synchronize()
-    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.e2e_steps
-    e2e_ms = shard.max_over_ranks(e2e_ms, world, device)
-    q.flush()
-    clocks = sampler.stop() if rank == 0 else None     # sampled across both timed regions (device + end to end)
-    os.sched_setaffinity(0, all_cpus)                  # the CPU baseline leg below gets every host thread back
+    head, iq, rx, q = run_config(key, n, args, rank, local_rank, world, device)
+    e2e, e2e_extras = e2e_legs(rx, q, iq, n, args, local_rank, world, device)
+    clocks = sampler.stop() if rank == 0 else None     # sampled across the headline's timed regions (device + end to end)
+    os.sched_setaffinity(0, all_cpus)                  # the CPU legs below get every host thread back
+    rx.close()
+    del iq, rx
+    torch.cuda.empty_cache()
+
+    others = []
+    for k in extra:
+        r, iq2, rx2, _ = run_config(k, n, args, rank, local_rank, world, device)
+        rx2.close()
+        del iq2, rx2
+        torch.cuda.empty_cache()
+        others.append(r)
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        ach = 8.0 * n / (scan_avg * 1e-3) / 1e9
+        cfg = CONFIGS[key]
+        ach = 8.0 * n / (head["scan_ms"] * 1e-3) / 1e9
+        scan_name = "amb_scan_kernel<%d,true,%d>" % (int(cfg["rate"] / 2e6), 2 if cfg["rate"] <= 6e6 else 1)
         line = {
-            "metric": "Msamples/s IQ demod+slice+CRC", "value": world * n * args.steps / (ms_max * 1e-3) / 1e6,
+            "metric": "Msamples/s IQ demod+slice+CRC", "value": head["value"],
             "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "synthetic 1090 MHz IQ @ 4 Msps, 2^%d complex samples per GPU, %d DF11/DF17 bursts at mixed SNR "
-                                   "(BASELINE configs[1]); one independent channel per GPU" % (args.log2n, N_BURSTS),
-                       "rate_sps": RATE, "threshold_db": THRESHOLD_DB, "use_pmf": True, "samples_per_gpu": n,
+            "config": {"workload": "%s; 2^%d complex samples per GPU; one independent channel per GPU" % (cfg["what"], args.log2n),
+                       "config_key": key, "rate_sps": cfg["rate"], "threshold_db": THRESHOLD_DB, "use_pmf": True,
+                       "samples_per_gpu": n,
                        "l2": "input (%.1f GiB per GPU) is larger than L2, no flush needed" % (8 * n / 2 ** 30),
-                       "parallelism": "channel-per-gpu x%d" % world, "fanout_s": round(fanout_s, 3),
-                       "e2e_steps": args.e2e_steps, "msgs_per_step": nmsg, "bursts_decoded": decoded},
+                       "parallelism": "channel-per-gpu x%d" % world, "setup_s": head["setup_s"],
+                       "e2e_steps": args.e2e_steps, "msgs_per_step": head["msgs_per_step"],
+                       "candidates_per_step": head["candidates"], "detections_per_step": head["detections"]},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "kernel": "amb_scan_kernel<2,true>", "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": 8 * n, "scan_ms": scan_avg},
-            "e2e": {"value": world * n / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 8 * n,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "h2d_gbps": 8 * n / (e2e_ms * 1e-3) / 1e9,
-                    "host_numa_binding": numa},
-            "gpu_launches": int(launches), "clocks": clocks,
+                         "traffic": None, "kernel": scan_name, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": 8 * n, "scan_ms": head["scan_ms"],
+                         "whole_step_frac": head["step_frac"]},
+            "e2e": e2e,
+            "gpu_launches": head["gpu_launches"], "clocks": clocks,
         }
-        tr = os.path.join(ROOT, "profiles", "scan_traffic.json")
-        if os.path.exists(tr):
-            try:
-                line["roofline"]["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch_2p%d" % args.log2n)
-            except Exception:
-                pass
+        if "fanout_gbps" in head:
+            line["config"]["fanout_gbps"] = head["fanout_gbps"]
+            line["config"]["fanout_ms"] = head["fanout_ms"]
+        if "parity" in head:
+            line["parity"] = head["parity"]
+        line.update(e2e_extras)
+        line["configs"] = others
+        line["roofline"].update(scan_traffic(key, args.log2n))
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline_leg(args.log2n)
+            line["cpu_baseline"] = cpu_baseline_leg(key, args.log2n)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def scan_traffic(key, log2n):
+    """dram bytes per scan launch from the committed ncu capture - only if that capture was taken of the kernel
+    source that is built now (profiles/scan_traffic.json records the sha256 of csrc/amb_kernels.cu)."""
+    import hashlib
+    tr = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    try:
+        rec = json.load(open(tr))
+        src = os.path.join(ROOT, "gr_air_modes_b200", "csrc", "amb_kernels.cu")
+        sha = hashlib.sha256(open(src, "rb").read()).hexdigest()
+        ent = rec.get("%s_2p%d" % (key, log2n))
+        if not ent:
+            return {"traffic": None, "traffic_note": "no ncu capture of this config committed"}
+        if ent.get("kernels_sha256") != sha:
+            return {"traffic": None, "traffic_note": "committed ncu capture is of another revision of amb_kernels.cu"}
+        return {"traffic": ent["dram_bytes_per_launch"], "traffic_source": ent.get("source")}
+    except Exception as e:      # noqa: BLE001
+        return {"traffic": None, "traffic_note": "profiles/scan_traffic.json unreadable (%s)" % type(e).__name__}
 
 
 if __name__ == "__main__":

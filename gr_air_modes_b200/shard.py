@@ -12,24 +12,41 @@ def channels_of(rank: int, world: int, n_channels: int):
     return [c for c in range(n_channels) if c % world == rank]
 
 
-def fan_out(make_channel, rank: int, world: int, device, numel: int):
+def fan_out(make_channel, rank: int, world: int, device, numel: int, timing: dict | None = None):
     """Rank 0 builds channel c with make_channel(c) -> (float32 tensor[numel], meta) and sends it to rank c.
-    Returns this rank's (tensor, meta)."""
+    Returns this rank's (tensor, meta). `timing` (optional dict) receives, on rank 0, the transfers ALONE:
+    "send_ms" (CUDA events around each dist.send on the current stream; host clock on CPU tensors) and "bytes"."""
     if world == 1:
         return make_channel(0)
+    import time
     import torch
     import torch.distributed as dist
     if rank == 0:
         metas = [None] * world
         mine = None
+        ms, nbytes = 0.0, 0
         for ch in range(world - 1, -1, -1):
             iq, meta = make_channel(ch)
             metas[ch] = meta
             if ch != 0:
-                dist.send(iq, dst=ch)
+                if iq.is_cuda:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    dist.send(iq, dst=ch)
+                    e1.record()
+                    e1.synchronize()
+                    ms += e0.elapsed_time(e1)
+                else:
+                    t0 = time.perf_counter()
+                    dist.send(iq, dst=ch)
+                    ms += 1e3 * (time.perf_counter() - t0)
+                nbytes += iq.numel() * iq.element_size()
                 del iq
             else:
                 mine = iq
+        if timing is not None:
+            timing["send_ms"] = timing.get("send_ms", 0.0) + ms
+            timing["bytes"] = timing.get("bytes", 0) + nbytes
     else:
         mine = torch.empty(numel, dtype=torch.float32, device=device)
         dist.recv(mine, src=0)
