@@ -63,6 +63,7 @@ struct AmbCounters {
     unsigned int npassed_call;
     unsigned int nreal_call;
     unsigned int ndet_list;    // entries of the detection list of this call (indices into the candidate arrays)
+    unsigned int frame_base;   // frames queued before this call's (set by the resolver; slot = frame_base + list position)
 };
 
 struct AmbScanArgs {

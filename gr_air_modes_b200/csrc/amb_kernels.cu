@@ -556,168 +556,252 @@ __device__ __forceinline__ float stream_at(const float* in, long long n, int H, 
 }
 
 
-// One warp per candidate. Writes info = late | real<<8 | valid<<9 and avg at the shifted index.
-// SPC > 0: integer samples/chip geometry known at compile time (loops unroll, offsets fold); SPC == 0: run-time values.
-template <bool STREAMS, int SPC>
+// ---- exact stage ----------------------------------------------------------------------------------
+// One THREAD per candidate. Writes info = late | real<<8 | valid<<9 and avg at the shifted index.
+//
+// A thread streams once through the m2 samples its candidate depends on, in ascending order, keeping the last FL of
+// them in a register ring (the pulse matched filter), and feeds every bb into
+//   * acc   - the fp64 ascending sum of bb[c-L+1 .. c]: LITERALLY the canonical noise-floor window of the start c,
+//   * fw[x] - bb[c+x], x = 0 .. maxlate+fwd+1, kept in a per-thread column of shared memory (conflict-free: element
+//             x of thread t lives at x*blockDim+t) for the pulse tests, the late gate and the quiet zones,
+//   * head[k] - bb[c-L+1+k], k < maxlate: what leaves the window when the late gate shifts the start.
+// After a late shift the window of c+i is acc - head[..] + fw[..] when every addend's exponent lies within 19 of the
+// others (then every partial sum of <= 1024 such floats is exact in fp64, 24+19+10 = 53 bits, so any association
+// gives the canonical bits); otherwise the window is summed again, literally ascending.
+// Neighbouring threads hold neighbouring candidates, so in dense traffic their spans overlap in L1; there are no
+// warp collectives: 32 candidates make progress per warp instruction (the previous revision spent a whole warp and
+// ~600 instructions with five dependent barriers on ONE candidate, which is what made dense traffic latency-bound).
+// SPC > 0: integer samples/chip geometry known at compile time (ring indices and loops fold); SPC == 0: run-time.
+template <int SPC, bool PMF>
 __global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a)
 {
-    AMB_DYN_SMEM(float, ex_smem, 4);                 // per warp: m2s[NMp] then bbs[NMp], sized by the launcher
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    AMB_DYN_SMEM(float, ex_smem, 4);
     const AmbParams& P = a.P;
     const int spc = SPC ? SPC : P.spc_i;
     const int L = 48 * spc, maxlate = SPC ? SPC : P.maxlate;
     const int po1 = SPC ? 2 * SPC : P.po1, po2 = SPC ? 7 * SPC : P.po2, po3 = SPC ? 9 * SPC : P.po3;
     const int qa0 = SPC ? 3 * SPC : P.qa0, qa1 = SPC ? 6 * SPC : P.qa1, qb0 = SPC ? 10 * SPC : P.qb0, qb1 = SPC ? 15 * SPC : P.qb1;
     const int fwd = SPC ? 15 * SPC + 2 : P.fwd;
-    const int fl = P.use_pmf ? spc : 1;
-    const int NB = STREAMS ? (maxlate + fwd + 1) : (L + maxlate + fwd + 1);
-    const int NM = NB + fl - 1;
-    const int NMp = (NM + 31) & ~31;
-    float* m2s = ex_smem + (size_t)warp * 2 * NMp;
-    float* bbs = m2s + NMp;
-    const int c0off = STREAMS ? 0 : (L - 1);       // bbs index of the candidate start
+    constexpr int FLC = (PMF && SPC > 1) ? SPC : 1;          // compile-time ring length (1 = no ring)
+    const int fl = PMF ? spc : 1;                            // pulse matched filter length
+    const int nf = maxlate + fwd + 2;                        // forward values kept
+    const int NB = L + nf - 1;                               // bb values streamed: bb[c-L+1 .. c+nf-1]
+    const int NM = NB + fl - 1;                              // m2 values behind them
+    const int T = blockDim.x;
+    float* fw = ex_smem + threadIdx.x;                       // fw[x * T]
+    float* head = fw + (size_t)nf * T;                       // head[k * T]
     const unsigned int ncand = a.ctr->ncand;
-    const int nwarps = gridDim.x * 4;
-    for (unsigned int ci = blockIdx.x * 4 + warp; ci < ncand; ci += nwarps) {
+    const float scale_p = P.scale_p, scale_a = P.scale_a;
+    for (unsigned int ci = blockIdx.x * T + threadIdx.x; ci < ncand; ci += gridDim.x * T) {
         const int c = a.cand_j[ci];
-        float avgk = 0.f;
-        if (STREAMS) {
-            for (int i = lane; i < NB; i += 32) bbs[i] = stream_at(a.in0, a.n_streams, P.H, (long long)c + i);
-            if (lane <= maxlate) avgk = stream_at(a.in1, a.n_streams, P.H, (long long)c + lane);
-            __syncwarp();
-        } else {
-            const int b_bb = c - L + 1;               // bbs[i] <-> bb[b_bb + i]
-            const int b_m2 = b_bb - (fl - 1);
-            const float2* span = seg_span(a.S, b_m2, NM);     // warp-uniform
-            if (span) {
-                for (int i0 = 0; i0 < NM; i0 += 256) {        // 8 independent loads in flight per lane
-                    float2 v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; v[u] = i < NM ? span[i] : make_float2(0.f, 0.f); }
-#pragma unroll
-                    for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; if (i < NM) m2s[i] = canon_m2_of(v[u]); }
-                }
-            } else {
-                for (int i = lane; i < NM; i += 32) m2s[i] = canon_m2(a.S, b_m2 + i);   // straddles a segment boundary
-            }
-            __syncwarp();
-            for (int i = lane; i < NB; i += 32) {
-                if (P.use_pmf) {
-                    double acc = 0.0;
-                    for (int t = 0; t < fl; t++) acc += (double)m2s[i + t];
-                    bbs[i] = __fmul_rn((float)acc, P.scale_p);
-                } else {
-                    bbs[i] = m2s[i];
-                }
-            }
-            __syncwarp();
-            // inavg at c+k, k <= maxlate: fp64 ascending sum of bb[c+k-L+1 .. c+k] (canonical definition).
-            // If every non-zero addend's exponent lies within 19 of the others, every partial sum of <= 1024 such
-            // floats is exactly representable in fp64 (24 + 19 + 10 = 53 bits), so ANY summation order - incl. a
-            // lane-parallel one and the sliding update - gives the canonical bits. Otherwise (huge dynamic range,
-            // Inf/NaN) fall back to the literal ascending loop.
-            unsigned emax = 0u, emin = 255u;
-            for (int i = lane; i < L + maxlate; i += 32) {
-                const unsigned bits = __float_as_uint(bbs[i]) & 0x7fffffffu;
+        const int b_m2 = c - L + 1 - (fl - 1);               // logical index of the first m2 sample
+        const float2* sp = seg_span(a.S, b_m2, NM);          // one segment (the common case) or nullptr
+        double acc = 0.0;
+        unsigned emax = 0u, emin = 255u;
+        auto m2_at = [&](int k) -> float {                    // m2 of logical sample b_m2 + k
+            if (sp) return canon_m2_of(__ldg(sp + k));
+            return canon_m2(a.S, b_m2 + k);
+        };
+        auto consume = [&](int i, float bb) {                 // bb = bb[c - L + 1 + i]
+            if (i < L + maxlate) {
+                const unsigned bits = __float_as_uint(bb) & 0x7fffffffu;
                 if (bits) { unsigned e = bits >> 23; e = e ? e : 1u; emax = max(emax, e); emin = min(emin, e); }
             }
+            if (i < maxlate) head[(size_t)i * T] = bb;
+            if (i <= L - 1) acc += (double)bb;
+            if (i >= L - 1) fw[(size_t)(i - (L - 1)) * T] = bb;
+        };
+        if (FLC > 1) {
+            float ring[FLC];                                  // slot of m2 sample k: k % FLC
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                emax = max(emax, __shfl_xor_sync(FULL, emax, d));
-                emin = min(emin, __shfl_xor_sync(FULL, emin, d));
-            }
-            if (emax < 255u && emax <= emin + 19u) {
-                double part = 0.0;
-                for (int i = lane; i < L; i += 32) part += (double)bbs[i];
+            for (int t = 0; t < FLC - 1; t++) ring[t] = m2_at(t);
+            ring[FLC - 1] = 0.f;
+            constexpr int U = FLC * ((8 + FLC - 1) / FLC);    // block of U outputs, a multiple of the ring length
+            for (int i0 = 0; i0 < NB; i0 += U) {
+                float mm[U];
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
-                double w = part;                                  // window of k = 0, identical in all lanes
-                if (lane == 0) avgk = __fmul_rn((float)w, P.scale_a);
-                for (int k = 1; k <= maxlate; k++) {
-                    w = (w - (double)bbs[k - 1]) + (double)bbs[k + L - 1];
-                    if (lane == k) avgk = __fmul_rn((float)w, P.scale_a);
+                for (int u = 0; u < U; u++) mm[u] = (i0 + u < NB) ? m2_at(i0 + u + FLC - 1) : 0.f;   // independent loads
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    ring[(FLC - 1 + u) % FLC] = mm[u];
+                    double sum = 0.0;                          // ascending: oldest sample first
+#pragma unroll
+                    for (int t = 0; t < FLC; t++) sum += (double)ring[(u + t) % FLC];
+                    if (i0 + u < NB) consume(i0 + u, __fmul_rn((float)sum, scale_p));
                 }
-            } else if (lane <= maxlate) {
-                double acc = 0.0;
-                for (int t = 0; t < L; t++) acc += (double)bbs[lane + t];
-                avgk = __fmul_rn((float)acc, P.scale_a);
+            }
+        } else if (fl > 1) {                                  // run-time filter length: re-sum from (L1-resident) loads
+            for (int i = 0; i < NB; i++) {
+                double sum = 0.0;
+                for (int t = 0; t < fl; t++) sum += (double)m2_at(i + t);
+                consume(i, __fmul_rn((float)sum, scale_p));
+            }
+        } else {
+            for (int i0 = 0; i0 < NB; i0 += 8) {
+                float mm[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) mm[u] = (i0 + u < NB) ? m2_at(i0 + u) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; u++) if (i0 + u < NB) consume(i0 + u, (PMF && SPC != 1) ? __fmul_rn((float)(double)mm[u], scale_p) : mm[u]);
             }
         }
-        // correlate_preamble (preamble_impl.cc:88-98) at c+k, k = lane-16 in [0, maxlate+1]
-        double corrk = 0.0;
-        if (lane >= 16 && lane - 16 <= maxlate + 1) {
-            const float* q = bbs + c0off + (lane - 16);
-            for (int t = 0; t < spc; t++) corrk += (double)q[t];
-            for (int t = 0; t < spc; t++) corrk += (double)q[2 * spc + t];
-            for (int t = 0; t < spc; t++) corrk += (double)q[7 * spc + t];
-            for (int t = 0; t < spc; t++) corrk += (double)q[9 * spc + t];
-        }
-        const float* in = bbs + c0off;                // in[x] == reference in[i+x] at the candidate start
-        const float avg0 = __shfl_sync(FULL, avgk, 0);
+        auto in = [&](int x) -> float { return fw[(size_t)x * T]; };   // in[x] == reference in[i+x] at the candidate start
+        const float avg0 = __fmul_rn((float)acc, scale_a);
         const float pulse_threshold = __fmul_rn(avg0, P.thr);                       // :173
-        bool real = in[0] > pulse_threshold;                                        // :174
-        if (real && (in[1] > in[0])) real = false;                                  // :175
-        if (real && (in[po1] < pulse_threshold)) real = false;                    // :177
-        if (real && (in[po2] < pulse_threshold)) real = false;                    // :178
-        if (real && (in[po3] < pulse_threshold)) real = false;                    // :179
+        const float in0 = in(0);
+        bool real = in0 > pulse_threshold;                                          // :174
+        if (real && (in(1) > in0)) real = false;                                    // :175
+        if (real && (in(po1) < pulse_threshold)) real = false;                      // :177
+        if (real && (in(po2) < pulse_threshold)) real = false;                      // :178
+        if (real && (in(po3) < pulse_threshold)) real = false;                      // :179
         uint32_t info = 0;
         float avg_fin = avg0;
         if (real) {
+            auto corr = [&](int k) -> double {                                      // correlate_preamble :88-98 at c+k
+                double v = 0.0;
+                for (int t = 0; t < spc; t++) v += (double)in(k + t);
+                for (int t = 0; t < spc; t++) v += (double)in(k + 2 * spc + t);
+                for (int t = 0; t < spc; t++) v += (double)in(k + 7 * spc + t);
+                for (int t = 0; t < spc; t++) v += (double)in(k + 9 * spc + t);
+                return v;
+            };
             int i = 0, how_late = 0;
             bool late;
+            double now_corr = corr(0);
             do {                                                                    // :184-192
-                const double now_corr = __shfl_sync(FULL, corrk, 16 + i);
-                const double late_corr = __shfl_sync(FULL, corrk, 16 + i + 1);
+                const double late_corr = corr(i + 1);
                 late = late_corr > now_corr;
-                if (late) { i++; how_late++; }
+                if (late) { i++; how_late++; now_corr = late_corr; }
             } while (late && (SPC ? how_late < SPC : (float)how_late < P.spc_f));
-            avg_fin = __shfl_sync(FULL, avgk, i);
-            const float* s = in + i;
-            const float sum4 = __fadd_rn(__fadd_rn(__fadd_rn(s[0], s[po1]), s[po2]), s[po3]);
+            if (i > 0) {
+                double w = 0.0;
+                if (emax < 255u && emax <= emin + 19u) {
+                    w = acc;
+                    for (int k = 1; k <= i; k++) w = (w - (double)head[(size_t)(k - 1) * T]) + (double)in(k);
+                } else {                                                            // literal ascending window of c+i
+                    const int j0 = c + i - L + 1;
+                    for (int t = 0; t < L; t++) {
+                        float bb;
+                        if (fl > 1) {
+                            double sum = 0.0;
+                            for (int u = 0; u < fl; u++) sum += (double)canon_m2(a.S, j0 + t - (fl - 1) + u);
+                            bb = __fmul_rn((float)sum, scale_p);
+                        } else {
+                            const float m = canon_m2(a.S, j0 + t);
+                            bb = (PMF && SPC != 1) ? __fmul_rn((float)(double)m, scale_p) : m;
+                        }
+                        w += (double)bb;
+                    }
+                }
+                avg_fin = __fmul_rn((float)w, scale_a);
+            }
+            const float sum4 = __fadd_rn(__fadd_rn(__fadd_rn(in(i), in(i + po1)), in(i + po2)), in(i + po3));
             const float avgpeak = (float)((double)sum4 / 4.0);                      // :198-201
             const float space_threshold =
                 __fadd_rn(avg_fin, __fdiv_rn(__fsub_rn(avgpeak, avg_fin), P.thr));  // :203
             bool viol = false;
-            for (int j = qa0 + lane; j <= qa1; j += 32) viol |= (s[j] > space_threshold);  // :205-206
-            for (int j = qb0 + lane; j <= qb1; j += 32) viol |= (s[j] > space_threshold);  // :207-208
-            const bool valid = !__any_sync(FULL, viol);
-            info = (uint32_t)i | (1u << 8) | (valid ? (1u << 9) : 0u);
+            for (int j = qa0; j <= qa1 && !viol; j++) viol = in(i + j) > space_threshold;   // :205-206
+            for (int j = qb0; j <= qb1 && !viol; j++) viol = in(i + j) > space_threshold;   // :207-208
+            info = (uint32_t)i | (1u << 8) | (!viol ? (1u << 9) : 0u);
         }
-        if (lane == 0) { a.cand_info[ci] = info; a.cand_avg[ci] = avg_fin; }
-        __syncwarp();
+        a.cand_info[ci] = info;
+        a.cand_avg[ci] = avg_fin;
+    }
+}
+
+// Split form (caller-supplied float streams): same decisions, in0/in1 play bb/avg; one thread per candidate.
+__global__ void __launch_bounds__(128) amb_exact_streams_kernel(const AmbExactArgs a)
+{
+    const AmbParams& P = a.P;
+    const int spc = P.spc_i, maxlate = P.maxlate;
+    const unsigned int ncand = a.ctr->ncand;
+    for (unsigned int ci = blockIdx.x * blockDim.x + threadIdx.x; ci < ncand; ci += gridDim.x * blockDim.x) {
+        const long long c = a.cand_j[ci];
+        auto in = [&](int x) -> float { return stream_at(a.in0, a.n_streams, P.H, c + x); };
+        const float avg0 = stream_at(a.in1, a.n_streams, P.H, c);
+        const float pulse_threshold = __fmul_rn(avg0, P.thr);                       // :173
+        const float in0 = in(0);
+        bool real = in0 > pulse_threshold;                                          // :174
+        if (real && (in(1) > in0)) real = false;                                    // :175
+        if (real && (in(P.po1) < pulse_threshold)) real = false;                    // :177
+        if (real && (in(P.po2) < pulse_threshold)) real = false;                    // :178
+        if (real && (in(P.po3) < pulse_threshold)) real = false;                    // :179
+        uint32_t info = 0;
+        float avg_fin = avg0;
+        if (real) {
+            auto corr = [&](int k) -> double {
+                double v = 0.0;
+                for (int t = 0; t < spc; t++) v += (double)in(k + t);
+                for (int t = 0; t < spc; t++) v += (double)in(k + 2 * spc + t);
+                for (int t = 0; t < spc; t++) v += (double)in(k + 7 * spc + t);
+                for (int t = 0; t < spc; t++) v += (double)in(k + 9 * spc + t);
+                return v;
+            };
+            int i = 0, how_late = 0;
+            bool late;
+            double now_corr = corr(0);
+            do {                                                                    // :184-192
+                const double late_corr = corr(i + 1);
+                late = late_corr > now_corr;
+                if (late) { i++; how_late++; now_corr = late_corr; }
+            } while (late && (float)how_late < P.spc_f);
+            (void)maxlate;
+            avg_fin = stream_at(a.in1, a.n_streams, P.H, c + i);
+            const float sum4 = __fadd_rn(__fadd_rn(__fadd_rn(in(i), in(i + P.po1)), in(i + P.po2)), in(i + P.po3));
+            const float avgpeak = (float)((double)sum4 / 4.0);                      // :198-201
+            const float space_threshold =
+                __fadd_rn(avg_fin, __fdiv_rn(__fsub_rn(avgpeak, avg_fin), P.thr));  // :203
+            bool viol = false;
+            for (int j = P.qa0; j <= P.qa1 && !viol; j++) viol = in(i + j) > space_threshold;   // :205-206
+            for (int j = P.qb0; j <= P.qb1 && !viol; j++) viol = in(i + j) > space_threshold;   // :207-208
+            info = (uint32_t)i | (1u << 8) | (!viol ? (1u << 9) : 0u);
+        }
+        a.cand_info[ci] = info;
+        a.cand_avg[ci] = avg_fin;
     }
 }
 
 template <int SPC>
-static cudaError_t launch_exact_t(const AmbExactArgs& a, int blocks, size_t smem, cudaStream_t s)
+static cudaError_t launch_exact_t(const AmbExactArgs& a, int blocks, int threads, size_t smem, cudaStream_t s)
 {
-    if (a.in0) AMB_LAUNCH((amb_exact_kernel<true, SPC>), blocks, 128, smem, s, a);
-    else AMB_LAUNCH((amb_exact_kernel<false, SPC>), blocks, 128, smem, s, a);
+    cudaError_t e;
+    if (a.P.use_pmf) {
+        e = cudaFuncSetAttribute(amb_exact_kernel<SPC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        AMB_LAUNCH((amb_exact_kernel<SPC, true>), blocks, threads, smem, s, a);
+    } else {
+        e = cudaFuncSetAttribute(amb_exact_kernel<SPC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        AMB_LAUNCH((amb_exact_kernel<SPC, false>), blocks, threads, smem, s, a);
+    }
     return cudaGetLastError();
 }
 
 cudaError_t amb_launch_exact(const AmbExactArgs& a, int sm_count, cudaStream_t s)
 {
     const AmbParams& P = a.P;
-    const int fl = P.use_pmf ? P.spc_i : 1;
+    if (a.in0) {
+        AMB_LAUNCH((amb_exact_streams_kernel), sm_count * 8, 128, 0, s, a);
+        return cudaGetLastError();
+    }
     // integer samples/chip: everything the kernel needs is a multiple of spc (see compute_params)
     const int k = P.spc_i;
     const bool integral = P.spc_f == (float)k && P.maxlate == k && P.po1 == 2 * k && P.po2 == 7 * k && P.po3 == 9 * k &&
                           P.qa0 == 3 * k && P.qa1 == 6 * k && P.qb0 == 10 * k && P.qb1 == 15 * k && P.fwd == 15 * k + 2;
-    const int NB = a.in0 ? (P.maxlate + P.fwd + 1) : (P.L + P.maxlate + P.fwd + 1);
-    const int NMp = (NB + fl - 1 + 31) & ~31;
-    const size_t smem = (size_t)4 * 2 * NMp * sizeof(float);            // <= 22 KiB at 20 Msps, ~1.3 KiB at 4 Msps
-    const int blocks = sm_count * 12;
+    const int rows = (P.maxlate + P.fwd + 2) + P.maxlate;                // fw + head, floats per thread
+    const int threads = rows * 128 * 4 <= 48 * 1024 ? 128 : 64;          // 174 rows at 20 Msps: 64 threads = 43.5 KiB
+    const size_t smem = (size_t)rows * threads * sizeof(float);
+    const int blocks = sm_count * (threads == 128 ? 8 : 10);
     if (integral) {
         switch (k) {
-            case 1: return launch_exact_t<1>(a, blocks, smem, s);
-            case 2: return launch_exact_t<2>(a, blocks, smem, s);
-            case 5: return launch_exact_t<5>(a, blocks, smem, s);
-            case 10: return launch_exact_t<10>(a, blocks, smem, s);
+            case 1: return launch_exact_t<1>(a, blocks, threads, smem, s);
+            case 2: return launch_exact_t<2>(a, blocks, threads, smem, s);
+            case 5: return launch_exact_t<5>(a, blocks, threads, smem, s);
+            case 10: return launch_exact_t<10>(a, blocks, threads, smem, s);
             default: break;
         }
     }
-    return launch_exact_t<0>(a, blocks, smem, s);
+    return launch_exact_t<0>(a, blocks, threads, smem, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -780,6 +864,7 @@ __global__ void amb_walk_seq_kernel(const AmbWalkArgs a)
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     AmbWalkState st = *a.st;
     const int n = (int)a.ctr->ncand;
+    a.ctr->ndet_list = 0;                       // (the compaction kernel does not run in front of a tiny closing call)
     unsigned int nreal = 0;
     for (int k = 0; k < n; k++) if (a.cand_info[k] & (1u << 8)) nreal++;
     const unsigned int ndet = seq_walk(a, st, 0, n);
@@ -787,6 +872,8 @@ __global__ void amb_walk_seq_kernel(const AmbWalkArgs a)
     *a.st = st;
     a.ctr->ndet_call = ndet;
     a.ctr->nreal_call = nreal;
+    a.ctr->frame_base = a.ctr->nframes;            // the slicer's frame slots: frame_base + position in det_list
+    a.ctr->nframes += a.ctr->ndet_list;
 }
 
 cudaError_t amb_launch_walk_seq(const AmbWalkArgs& a, cudaStream_t s)
@@ -956,6 +1043,8 @@ __global__ void amb_walk_finalize_kernel(const AmbWalkArgs a, AmbParScratch* sc)
         st.ndet += ndet; st.ncand_real += a.ctr->nreal_call;
         a.ctr->ndet_call = ndet;
         *a.st = st;
+        a.ctr->frame_base = a.ctr->nframes;
+        a.ctr->nframes += a.ctr->ndet_list;
         return;
     }
     st.fallback = 0;
@@ -971,6 +1060,8 @@ __global__ void amb_walk_finalize_kernel(const AmbWalkArgs a, AmbParScratch* sc)
     st.ndet += a.ctr->ndet_call + extra; st.ncand_real += a.ctr->nreal_call;
     a.ctr->ndet_call += extra;
     *a.st = st;
+    a.ctr->frame_base = a.ctr->nframes;            // the slicer's frame slots: frame_base + position in det_list
+    a.ctr->nframes += a.ctr->ndet_list;
 }
 
 size_t amb_walk_scratch_bytes(unsigned int cand_cap, long long n_samples)
@@ -1058,28 +1149,43 @@ __device__ __forceinline__ int llslice(float bit0, float bit1, float highlimit, 
     return (d ? 1 : 0) | (c ? 2 : 0);
 }
 
-// Packet rules of slicer_impl::work (slicer_impl.cc:117-182) on 240 chips held in shared memory.
-// Executed by a full warp; lane 0 fills *f (sample_index/secs/frac are the caller's business).
-__device__ bool slice_packet_warp(const float* chips, amb_frame* f, int lane, const unsigned int* crc_rem)
+// Packet rules of slicer_impl::work (slicer_impl.cc:117-182). Executed by a full warp; bit j of the packet belongs
+// to lane j % 32. `pair(j, b0, b1)` yields chips 16+2j and 17+2j (:133,:147); p0/p2/p7/p9 are the preamble chips of
+// the reference level. The second half of the packet is only fetched and sliced when the header says it is a long
+// one (:140), which is all the reference looks at, too. Lane 0..31 fill *f (sample_index/secs/frac are the caller's).
+template <class PairFn>
+__device__ __forceinline__ bool slice_packet_warp(float p0, float p2, float p7, float p9, PairFn pair, amb_frame* f,
+                                                  int lane, const unsigned int* crc_rem)
 {
-    const float ref = (float)((double)__fadd_rn(__fadd_rn(__fadd_rn(chips[0], chips[2]), chips[7]), chips[9]) / 4.0); // :128-131
+    const float ref = (float)((double)__fadd_rn(__fadd_rn(__fadd_rn(p0, p2), p7), p9) / 4.0);   // :128-131
     const float highlimit = (float)((double)ref * 1.414);                     // :71
     const float lowlimit = (float)((double)ref * 0.707);                      // :72
     const double lowhalf = (double)lowlimit * 0.5;
-    uint32_t dw[4], lw[4];
+    uint32_t dw[4] = {0u, 0u, 0u, 0u}, lw[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int k = 0; k < 4; k++) {                      // bit j = 32k + lane, chips 16+2j, 17+2j (:133,:147)
-        const int j = 32 * k + lane;
-        int r = 2;
-        if (j < 112) r = llslice(chips[16 + 2 * j], chips[17 + 2 * j], highlimit, lowlimit, lowhalf);
+    for (int k = 0; k < 2; k++) {                      // bits 0..63
+        float b0, b1;
+        pair(32 * k + lane, b0, b1);
+        const int r = llslice(b0, b1, highlimit, lowlimit, lowhalf);
         dw[k] = __brev(__ballot_sync(FULL, r & 1));    // MSB-first: bit 31 <-> j = 32k
         lw[k] = __ballot_sync(FULL, !(r & 2));         // bit lane <-> low confidence at j
     }
     const unsigned hdr = dw[0] >> 27;                                         // :135-139
     const bool is_long = (hdr == 16 || hdr == 17 || hdr == 20 || hdr == 21); // :140
     const int nbits = is_long ? 112 : 56;                                     // :142
-    if (!is_long) { dw[1] &= 0xFFFFFF00u; dw[2] = 0; dw[3] = 0; lw[1] &= 0x00FFFFFFu; lw[2] = 0; lw[3] = 0; }
-    else { dw[3] &= 0xFFFF0000u; lw[3] &= 0x0000FFFFu; }
+    if (is_long) {                                     // warp-uniform
+#pragma unroll
+        for (int k = 2; k < 4; k++) {
+            const int j = 32 * k + lane;
+            int r = 2;
+            if (j < 112) { float b0, b1; pair(j, b0, b1); r = llslice(b0, b1, highlimit, lowlimit, lowhalf); }
+            dw[k] = __brev(__ballot_sync(FULL, r & 1));
+            lw[k] = __ballot_sync(FULL, !(r & 2));
+        }
+        dw[3] &= 0xFFFF0000u; lw[3] &= 0x0000FFFFu;
+    } else {
+        dw[1] &= 0xFFFFFF00u; lw[1] &= 0x00FFFFFFu;
+    }
     // CRC over the first nbits-24 bits (modes_crc.cc:55-63) as an XOR fold of per-bit remainders
     uint32_t crc = 0;
     const int nmsg = nbits - 24;
@@ -1106,14 +1212,17 @@ __device__ bool slice_packet_warp(const float* chips, amb_frame* f, int lane, co
         if (syn && (df == 11 || df == 17)) passed = false;                    // :182
     }
     if (lane < 14) f->data[lane] = (uint8_t)(dw[lane >> 2] >> (24 - 8 * (lane & 3)));
-    if (lane < 24) {                                                          // :152-158: ascending j, first 24
-        uint8_t v = 0;
-        if ((unsigned)lane < numlow) {
-            unsigned need = (unsigned)lane, k = 0;
-            while (need >= (unsigned)__popc(lw[k])) { need -= __popc(lw[k]); k++; }
-            v = (uint8_t)(32 * k + __fns(lw[k], 0, (int)need + 1));
+    if (lane < 24 && (unsigned)lane >= numlow) f->lowconfbits[lane] = 0;      // :152-158: ascending j, first 24
+    if (lowtot) {
+        unsigned before = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if ((lw[k] >> lane) & 1u) {
+                const unsigned rank = before + __popc(lw[k] & ((1u << lane) - 1u));
+                if (rank < 24u) f->lowconfbits[rank] = (uint8_t)(32 * k + lane);
+            }
+            before += __popc(lw[k]);
         }
-        f->lowconfbits[lane] = v;
     }
     if (lane >= 24 && lane < 30) f->pad_[lane - 24] = 0;
     if (lane == 31) {
@@ -1127,104 +1236,82 @@ __device__ bool slice_packet_warp(const float* chips, amb_frame* f, int lane, co
     return passed;
 }
 
+// One warp per accepted preamble. Chip j of the packet is in[fin + int(j*spc)] - inavg[fin] (preamble_impl.cc:219-221);
+// every lane fetches the (at most) 2 x fl samples behind its own bit straight from global memory - neighbouring
+// lanes read neighbouring samples - and nothing is staged in shared memory, so a warp has all of its loads in flight
+// at once and 16 CTAs fit on an SM. The frame slot is frame_base + position in the work list (no atomics).
 template <bool STREAMS>
 __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
 {
-    __shared__ float s_chips[4][240];
     __shared__ unsigned int s_crc[96];
-    AMB_DYN_SMEM(float, sl_smem, 4);                         // per warp: m2 of the packet span (not in STREAMS mode)
     if (threadIdx.x < 96) s_crc[threadIdx.x] = c_crc_rem[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* chips = s_chips[warp];
     const AmbParams& P = a.P;
     const unsigned int ndet = a.ctr->ndet_list;                // accepted preambles of this call (any order)
+    const unsigned int base = a.ctr->frame_base;               // frames queued before this call
     const int nwarps = gridDim.x * 4;
     const int fl = P.use_pmf ? P.spc_i : 1;
     const int span = chip_off(239, P.spc_f) + fl;              // m2 samples a packet touches
-    const int spanp = (span + 31) & ~31;
+    unsigned int npassed = 0;
     for (unsigned int di = blockIdx.x * 4 + warp; di < ndet; di += nwarps) {
         const int ci = a.det_list[di];
         const uint32_t info = a.cand_info[ci];
         const int fin = a.cand_j[ci] + (int)(info & 0xffu);
         const float avg_fin = a.cand_avg[ci];
-        if (STREAMS) {
-            for (int j = lane; j < 240; j += 32)               // preamble_impl.cc:219-221
-                chips[j] = __fsub_rn(stream_at(a.in0, a.n_streams, P.H, (long long)fin + chip_off(j, P.spc_f)), avg_fin);
-        } else {
-            float* m2s = sl_smem + (size_t)warp * spanp;
-            const int b0 = fin - fl + 1;                       // m2s[i] <-> m2[b0 + i]; independent coalesced loads
-            const float2* src = seg_span(a.S, b0, span);       // warp-uniform
-            if (src) {
-                for (int i0 = 0; i0 < span; i0 += 256) {       // 8 independent loads in flight per lane
-                    float2 v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; v[u] = i < span ? src[i] : make_float2(0.f, 0.f); }
-#pragma unroll
-                    for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; if (i < span) m2s[i] = canon_m2_of(v[u]); }
-                }
+        const int b0 = fin - fl + 1;                           // m2 index behind chip offset 0
+        const float2* src = STREAMS ? nullptr : seg_span(a.S, b0, span);   // warp-uniform; nullptr: straddles a segment boundary
+        auto chip = [&](int j) -> float {
+            const int o = chip_off(j, P.spc_f);
+            if (STREAMS) return __fsub_rn(stream_at(a.in0, a.n_streams, P.H, (long long)fin + o), avg_fin);
+            float bb;
+            if (P.use_pmf) {                                   // bb[fin + o] = PMF over m2[fin+o-fl+1 .. fin+o]
+                double acc = 0.0;
+                for (int t = 0; t < fl; t++) acc += (double)(src ? canon_m2_of(__ldg(src + o + t)) : canon_m2(a.S, b0 + o + t));
+                bb = __fmul_rn((float)acc, P.scale_p);
             } else {
-                for (int i = lane; i < span; i += 32) m2s[i] = canon_m2(a.S, b0 + i);  // straddles a segment boundary
+                bb = src ? canon_m2_of(__ldg(src + o)) : canon_m2(a.S, b0 + o);
             }
-            __syncwarp();
-            for (int j = lane; j < 240; j += 32) {
-                const int o = chip_off(j, P.spc_f);            // bb[fin + o] = PMF over m2[fin+o-fl+1 .. fin+o]
-                float bb;
-                if (P.use_pmf) {
-                    double acc = 0.0;
-                    for (int t = 0; t < fl; t++) acc += (double)m2s[o + t];
-                    bb = __fmul_rn((float)acc, P.scale_p);
-                } else {
-                    bb = m2s[o];
-                }
-                chips[j] = __fsub_rn(bb, avg_fin);
-            }
-        }
-        __syncwarp();
-        unsigned int slot = 0;
-        if (lane == 0) slot = atomicAdd(&a.ctr->nframes, 1u);
-        slot = __shfl_sync(FULL, slot, 0);
+            return __fsub_rn(bb, avg_fin);
+        };
+        const unsigned int slot = base + di;
         if (slot < a.frame_cap) {
             amb_frame* f = a.frames + slot;
-            const bool passed = slice_packet_warp(chips, f, lane, s_crc);
+            const bool passed = slice_packet_warp(chip(0), chip(2), chip(7), chip(9),
+                                                  [&](int j, float& x0, float& x1) { x0 = chip(16 + 2 * j); x1 = chip(17 + 2 * j); },
+                                                  f, lane, s_crc);
             if (lane == 0) {
                 f->sample_index = (uint64_t)(a.org + fin);
                 f->secs = 0; f->frac = 0.0;
-                if (passed) atomicAdd(&a.ctr->npassed_call, 1u);
+                if (passed) npassed++;
             }
-            if (a.chips_out) for (int j = lane; j < 240; j += 32) a.chips_out[(size_t)slot * 240 + j] = chips[j];
+            if (a.chips_out) for (int j = lane; j < 240; j += 32) a.chips_out[(size_t)slot * 240 + j] = chip(j);
         } else if (lane == 0) {
             a.ctr->frame_overflow = 1;
         }
-        __syncwarp();
     }
+    if (lane == 0 && npassed) atomicAdd(&a.ctr->npassed_call, npassed);
 }
 
 cudaError_t amb_launch_slice(const AmbSliceArgs& a, int sm_count, cudaStream_t s)
 {
-    const int fl = a.P.use_pmf ? a.P.spc_i : 1;
-    const int spanp = ((int)(239 * a.P.spc_f) + fl + 31) & ~31;        // = int(239*spc) + fl, rounded
-    const size_t smem = a.in0 ? 0 : (size_t)4 * spanp * sizeof(float);  // 38 KiB at 20 Msps, 8 KiB at 4 Msps
-    const int blocks = sm_count * 8;
-    if (a.in0) AMB_LAUNCH((amb_slice_kernel<true>), blocks, 128, smem, s, a);
-    else AMB_LAUNCH((amb_slice_kernel<false>), blocks, 128, smem, s, a);
+    const int blocks = sm_count * 16;
+    if (a.in0) AMB_LAUNCH((amb_slice_kernel<true>), blocks, 128, 0, s, a);
+    else AMB_LAUNCH((amb_slice_kernel<false>), blocks, 128, 0, s, a);
     return cudaGetLastError();
 }
 
 // slicer only (split-form block): packets of 240 chips already in device memory
 __global__ void __launch_bounds__(128) amb_slice_chips_kernel(const float* __restrict__ chips_in, int ndet, amb_frame* frames)
 {
-    __shared__ float s_chips[4][240];
     __shared__ unsigned int s_crc[96];
     if (threadIdx.x < 96) s_crc[threadIdx.x] = c_crc_rem[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* chips = s_chips[warp];
     for (int d = blockIdx.x * 4 + warp; d < ndet; d += gridDim.x * 4) {
-        for (int j = lane; j < 240; j += 32) chips[j] = chips_in[(size_t)d * 240 + j];
-        __syncwarp();
-        slice_packet_warp(chips, frames + d, lane, s_crc);
-        __syncwarp();
+        const float* c = chips_in + (size_t)d * 240;
+        slice_packet_warp(c[0], c[2], c[7], c[9], [&](int j, float& x0, float& x1) { x0 = c[16 + 2 * j]; x1 = c[17 + 2 * j]; },
+                          frames + d, lane, s_crc);
     }
 }
 cudaError_t amb_launch_slice_chips(const float* chips, int ndet, amb_frame* frames, cudaStream_t s)
