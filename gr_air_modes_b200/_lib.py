@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libairmodes_b200.so")
 
 OK = 0
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_HOST_SC16, MEM_DEVICE_SC16 = 0, 1, 2, 3
 
 
 class Frame(C.Structure):
@@ -84,6 +84,9 @@ SYMBOLS = [
     ("amb_process", C.c_int, [_vp, _vp, C.c_size_t, C.c_int, C.c_int]),
     ("amb_poll_frames", C.c_int, [_vp, C.POINTER(Frame), C.c_int]),
     ("amb_pending_frames", C.c_int, [_vp]),
+    ("amb_poll_ready", C.c_int, [_vp, C.POINTER(Frame), C.c_int]),
+    ("amb_add_time_tag", C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_double]),
+    ("amb_wait_stream", C.c_int, [_vp, _vp]),
     ("amb_format_message", C.c_int, [C.POINTER(Frame), C.c_int, C.c_char_p, C.c_size_t]),
     ("amb_format_messages", C.c_int, [_vp, C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
     ("amb_modes_check_crc", C.c_uint32, [C.c_char_p, C.c_int]),

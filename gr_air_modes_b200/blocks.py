@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import collections
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -37,20 +38,31 @@ def message_from_string(s: str) -> message:
 
 
 class msg_queue:
+    """gr.msg_queue stand-in (gnuradio/msg_queue.h): handle / insert_tail, delete_head (BLOCKS until a message is
+    there, as gr.msg_queue.delete_head does - radio.py:84-87 relies on it), delete_head_nowait, empty_p, count, flush."""
+
     def __init__(self, limit: int = 0):
         self._q = collections.deque()
         self._limit = limit
+        self._cv = threading.Condition()
 
     def handle(self, msg) -> None:
-        self._q.append(msg)
+        with self._cv:
+            self._q.append(msg)
+            self._cv.notify()
 
     insert_tail = handle
 
     def delete_head_nowait(self):
-        return self._q.popleft() if self._q else None
+        with self._cv:
+            return self._q.popleft() if self._q else None
 
-    def delete_head(self):
-        return self.delete_head_nowait()
+    def delete_head(self, timeout: float | None = None):
+        """Blocks until a message arrives (timeout in seconds is an extension; None = wait for ever)."""
+        with self._cv:
+            if not self._cv.wait_for(lambda: len(self._q) > 0, timeout):
+                return None
+            return self._q.popleft()
 
     def empty_p(self) -> bool:
         return not self._q
@@ -59,10 +71,11 @@ class msg_queue:
         return len(self._q)
 
     def flush(self) -> None:
-        self._q.clear()
+        with self._cv:
+            self._q.clear()
 
     def strings(self):
-        return [m.to_string() for m in self._q]
+        return [m.to_string() for m in list(self._q)]
 
 
 def _make_gr_message(queue, text: str):
@@ -97,25 +110,38 @@ def query_geometry(rate, threshold_db=7.0, use_pmf=True) -> Geometry:
 
 
 def _as_iq(iq):
-    """Return (pointer, n_complex, mem_kind, keepalive) for numpy (host) or torch CUDA (device) input."""
+    """Return (pointer, n_complex, mem_kind, keepalive) for numpy (host) or torch (host / CUDA) input.
+
+    complex64 / interleaved float32 = gr_complex (rx_path.py:29); complex128 is narrowed to complex64; interleaved
+    int16 I,Q (full scale 32768, the receivers' wire format) is shipped as it is and widened on the device. Anything
+    else is refused: silently reinterpreting it would decode garbage."""
     try:
         import torch
         if isinstance(iq, torch.Tensor):
             t = iq
             if t.is_complex():
-                t = torch.view_as_real(t)
-            if t.dtype != torch.float32:
-                raise TypeError("IQ tensor must be complex64 or float32")
+                t = torch.view_as_real(t.to(torch.complex64))
+            if t.dtype == torch.int16:
+                kind = _lib.MEM_DEVICE_SC16 if t.is_cuda else _lib.MEM_HOST_SC16
+            elif t.dtype == torch.float32:
+                kind = _lib.MEM_DEVICE if t.is_cuda else _lib.MEM_HOST
+            else:
+                raise TypeError("IQ tensor must be complex64 / complex128, interleaved float32 or interleaved int16, not %s" % t.dtype)
             t = t.contiguous()
-            n = t.numel() // 2
-            kind = _lib.MEM_DEVICE if t.is_cuda else _lib.MEM_HOST
-            return C.c_void_p(t.data_ptr()), n, kind, t
+            return C.c_void_p(t.data_ptr()), t.numel() // 2, kind, t
     except ImportError:
         pass
     a = np.asarray(iq)
+    if a.dtype == np.complex128:
+        a = a.astype(np.complex64)
     if a.dtype == np.complex64:
-        a = a.view(np.float32)
-    a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+        a = np.ascontiguousarray(a).view(np.float32)
+    if a.dtype == np.int16:
+        a = np.ascontiguousarray(a).reshape(-1)
+        return C.c_void_p(a.ctypes.data), a.size // 2, _lib.MEM_HOST_SC16, a
+    if a.dtype != np.float32:
+        raise TypeError("IQ array must be complex64 / complex128, interleaved float32 or interleaved int16, not %s" % a.dtype)
+    a = np.ascontiguousarray(a).reshape(-1)
     return C.c_void_p(a.ctypes.data), a.size // 2, _lib.MEM_HOST, a
 
 
@@ -153,6 +179,16 @@ class _Context:
     def poll(self):
         buf, got = self.poll_array()
         return list(buf)[:got]
+
+    def poll_ready_array(self, max_frames: int = 4096):
+        """Non-blocking: (ctypes Frame array, count) of the frames whose calls have completed on the device."""
+        buf = (Frame * max_frames)()
+        got = self.call("amb_poll_ready", buf, max_frames)
+        return buf, got
+
+    def wait_stream(self, cuda_stream_ptr: int):
+        """Order the context's work after everything enqueued so far on another CUDA stream."""
+        self.call("amb_wait_stream", C.c_void_p(cuda_stream_ptr))
 
     def stats(self) -> Stats:
         s = Stats()
@@ -274,6 +310,7 @@ class rx_path:
         self._ctx = _Context(rate, threshold, use_pmf, use_dcblock, device)
         self._slicer = slicer(queue, device, _ctx=self._ctx)
         self.frames = []                            # every detection of the last process() call
+        self._keep = []                             # device inputs still being read
 
     # -- the reference's methods (rx_path.py:67-87)
     def set_rate(self, rate):
@@ -301,17 +338,51 @@ class rx_path:
     # -- data path
     def process(self, iq, flush: bool = False, collect: bool = True) -> int:
         """Consume a stretch of the stream; returns the number of messages queued (0 if collect=False:
-        results then stay on the device until drain())."""
+        results then stay on the device until drain() / poll_ready()).
+
+        Host arrays (numpy, CPU tensors; float32 / complex64 / int16 I,Q) are consumed before this returns. A torch
+        CUDA tensor is read in place: the call is ordered after the work already enqueued on torch's current stream,
+        and the tensor is kept alive until drain() (or a collecting process()) has synchronised."""
         ptr, n, kind, keep = _as_iq(iq)
+        if kind in (_lib.MEM_DEVICE, _lib.MEM_DEVICE_SC16):
+            try:
+                import torch
+                self._ctx.wait_stream(torch.cuda.current_stream(keep.device).cuda_stream)
+            except ImportError:
+                pass
+            self._keep.append(keep)
         self._ctx.call("amb_process", ptr, n, kind, int(flush))
-        self._keep = keep
         return self.drain() if collect else 0
 
     def drain(self) -> int:
+        """Wait for everything given so far and queue its messages."""
         buf, got = self._ctx.poll_array()
         self.frames = list(buf)[:got]
-        self._keep = None
+        self._keep.clear()
         return self._slicer.emit(buf, got)
+
+    def poll_ready(self, max_frames: int = 4096) -> int:
+        """Non-blocking drain: queue the messages of the calls that have already completed on the device (what a GNU
+        Radio work() function calls after handing over its items). Returns how many were queued."""
+        buf, got = self._ctx.poll_ready_array(max_frames)
+        self.frames = list(buf)[:got]
+        return self._slicer.emit(buf, got) if got else 0
+
+    def add_time_tag(self, offset: int, secs: int, frac: float):
+        """A later rx_time tag at absolute item `offset` (see amb_add_time_tag)."""
+        self._ctx.call("amb_add_time_tag", int(offset), int(secs), float(frac))
+
+    def use_stream(self, cuda_stream_ptr: int):
+        """Run the streaming pass on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._ctx.use_stream(cuda_stream_ptr)
+
+    def join(self):
+        """Make the caller-visible stream wait for everything enqueued so far (no host synchronisation)."""
+        self._ctx.join()
+
+    def set_option(self, name: str, value: int):
+        """Library options: "coalesce", "ingest_chunk", "copy_threads", "resolver", "overlap", "keep_chips"."""
+        self._ctx.call("amb_set_option", name.encode(), int(value))
 
     def reset(self):
         self._ctx.call("amb_reset")

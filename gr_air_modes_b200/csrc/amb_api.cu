@@ -9,7 +9,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #define AMB_VERSION "gr-air-modes_b200 0.1 (sm_100a)"
@@ -17,6 +21,18 @@
 typedef CUresult (*amb_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+#define AMB_ING_SLOTS 4
+#define AMB_SNAPS 8
+struct AmbIngestSlot {
+    float2* dev = nullptr;        // chunk of float32 I/Q the chain reads
+    void* dev_raw = nullptr;      // 16-bit chunk before widening (allocated on first use)
+    void* pin = nullptr;          // pinned host chunk (pageable / small input is gathered here)
+    cudaEvent_t e_h2d = nullptr;  // copy (+ widening) of this slot's chunk done
+    cudaEvent_t e_free_b = nullptr, e_free_c = nullptr;   // last readers of dev (sparse kernels, carry) done
+    bool used = false, h2d_pending = false;
+};
+struct amb_time_tag { uint64_t offset; uint64_t secs; double frac; };
 
 struct amb_ctx {
     int device = 0, sm_count = 0;
@@ -41,6 +57,18 @@ struct amb_ctx {
     float2* carry[3] = {nullptr, nullptr, nullptr};   // [2] stays all zero (sample history before the stream)
     float2* tail[2] = {nullptr, nullptr}; int tail_cap = 0;
     float2* staging = nullptr; size_t staging_cap = 0;
+    // host ingest pipeline (amb_process with host memory): ring of pinned + device chunk buffers, copy stream
+    cudaStream_t stream_h = nullptr;
+    size_t ing_chunk = (size_t)1 << 22;  // samples per chunk (32 MiB of float32 I/Q)
+    size_t coalesce = (size_t)1 << 18;   // small host calls are gathered until this many samples are pending
+    AmbIngestSlot ing[AMB_ING_SLOTS];
+    unsigned ing_next = 0;               // slot the next chunk uses
+    size_t pend_n = 0; int pend_kind = 0;  // samples gathered in ing[ing_next].pin, not dispatched yet
+    int copy_threads = 0;                // 0 = default
+    // non-blocking poll: counter snapshots of the calls in flight (pinned), frames already handed out
+    AmbCounters* ctr_snap = nullptr; cudaEvent_t snap_ev[AMB_SNAPS] = {}; unsigned long long snap_head = 0, snap_tail = 0;
+    unsigned polled = 0;                 // frames [0, polled) of the device frame buffer were returned by amb_poll_ready
+    std::vector<amb_time_tag> time_tags; // rx_time tags (absolute item offset -> time), ascending
     // optional DC blocker (rx_path.py:39-41)
     int use_dcblock = 0, dc_D = 0, dc_nc = 0, dc_cur = 0;
     float2* dc_carry[2] = {nullptr, nullptr}; float2* dc_out = nullptr; float2* dc_ma0 = nullptr; size_t dc_cap = 0;
@@ -75,6 +103,11 @@ struct amb_ctx {
     AmbWalkArgs def_wa{}; AmbSliceArgs def_sl{};
     std::string err;
 };
+
+extern "C" {
+static void ingest_free(amb_ctx* c);
+static int ingest_dispatch_pending(amb_ctx* ctx, int flush);
+}
 
 static int fail(amb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess)
 {
@@ -184,6 +217,9 @@ static int reset_stream(amb_ctx* ctx)
     ctx->frames_ub = 0;
     ctx->pending.clear();
     ctx->def_kind = 0; ctx->def_resolved = false;
+    ctx->pend_n = 0;                                   // samples gathered but not dispatched belong to the old stream
+    ctx->snap_tail = ctx->snap_head; ctx->polled = 0;
+    ctx->time_tags.clear();
     return AMB_OK;
 }
 
@@ -236,6 +272,10 @@ int amb_create(int device, float rate, float threshold_db, int use_pmf, int use_
                 cudaEventCreateWithFlags(&ctx->e_done[k], cudaEventDisableTiming) != cudaSuccess) rc = AMB_ERR_CUDA;
         if (rc != AMB_OK) break;
         if (cudaMalloc(&ctx->ctr, sizeof(AmbCounters)) != cudaSuccess || cudaMalloc(&ctx->st, sizeof(AmbWalkState)) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
+        if (cudaMallocHost(&ctx->ctr_snap, AMB_SNAPS * sizeof(AmbCounters)) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
+        for (int k = 0; k < AMB_SNAPS && rc == AMB_OK; k++)
+            if (cudaEventCreateWithFlags(&ctx->snap_ev[k], cudaEventDisableTiming) != cudaSuccess) rc = AMB_ERR_CUDA;
+        if (rc != AMB_OK) break;
         for (int k = 0; k < 4; k++) if (cudaEventCreate(&ctx->ev[k]) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
         for (int k = 0; k < 128 && rc == AMB_OK; k++) if (cudaEventCreate(&ctx->ring[k]) != cudaSuccess) rc = AMB_ERR_CUDA;
         if (rc != AMB_OK) break;
@@ -258,7 +298,12 @@ void amb_destroy(amb_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) sync_all(ctx);
+    if (ctx->stream_h) { cudaStreamSynchronize(ctx->stream_h); }
     free_dev(ctx);
+    ingest_free(ctx);
+    if (ctx->stream_h) cudaStreamDestroy(ctx->stream_h);
+    if (ctx->ctr_snap) cudaFreeHost(ctx->ctr_snap);
+    for (int k = 0; k < AMB_SNAPS; k++) if (ctx->snap_ev[k]) cudaEventDestroy(ctx->snap_ev[k]);
     for (int k = 0; k < 2; k++) {
         if (ctx->e_scan[k]) cudaEventDestroy(ctx->e_scan[k]);
         if (ctx->e_done[k]) cudaEventDestroy(ctx->e_done[k]);
@@ -349,6 +394,22 @@ int amb_set_option(amb_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "resolver")) { ctx->resolver = value; return AMB_OK; }
     if (!strcmp(name, "keep_chips")) { ctx->keep_chips = value != 0; return AMB_OK; }
     if (!strcmp(name, "overlap")) { ctx->overlap = value != 0; return AMB_OK; }
+    if (!strcmp(name, "coalesce")) {                       // samples of small host calls gathered before a dispatch
+        if (value < 1) return AMB_ERR_INVALID;
+        ctx->coalesce = std::min((size_t)value, ctx->ing_chunk); return AMB_OK;
+    }
+    if (!strcmp(name, "copy_threads")) { if (value < 0 || value > 64) return AMB_ERR_INVALID; ctx->copy_threads = value; return AMB_OK; }
+    if (!strcmp(name, "ingest_chunk")) {                   // samples per chunk of the host ingest ring (multiple of 512)
+        if (value < 4096 || (value & 511)) return AMB_ERR_INVALID;
+        CK(cudaSetDevice(ctx->device));
+        if (ctx->pend_n) { int rc = ingest_dispatch_pending(ctx, 0); if (rc) return rc; }
+        CK(sync_all(ctx));
+        if (ctx->stream_h) CK(cudaStreamSynchronize(ctx->stream_h));
+        ingest_free(ctx);
+        ctx->ing_chunk = (size_t)value;
+        if (ctx->coalesce > ctx->ing_chunk) ctx->coalesce = ctx->ing_chunk;
+        return AMB_OK;
+    }
     if (!strcmp(name, "defer_resolve")) {
         if (ctx->def_kind && !ctx->def_resolved) return fail(ctx, AMB_ERR_STATE, "amb_resolve pending");
         ctx->def_kind = 0; ctx->def_resolved = false;
@@ -361,6 +422,7 @@ int amb_synchronize(amb_ctx* ctx)
 {
     if (!ctx) return AMB_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->pend_n) { int rc = ingest_dispatch_pending(ctx, 0); if (rc) return rc; }
     CK(sync_all(ctx));
     return AMB_OK;
 }
@@ -426,15 +488,12 @@ static int ensure_call_buffers(amb_ctx* ctx, size_t rows_need, int n_spans, unsi
     return AMB_OK;
 }
 
-int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, int flush)
+// One call of the chain over n_complex samples that are in DEVICE memory (or, mem_kind == AMB_MEM_HOST, in host
+// memory that goes through the one-piece staging buffer: the deferred / time-sharded mode only).
+static int process_core(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, int flush)
 {
-    if (!ctx || (!iq && n_complex)) return AMB_ERR_INVALID;
-    if (ctx->flushed) return fail(ctx, AMB_ERR_STATE, "stream already flushed; amb_reset first");
-    if (n_complex > 0x60000000ull) return fail(ctx, AMB_ERR_INVALID, "at most 1.5 Gi samples per call");
-    if (ctx->def_kind && !ctx->def_resolved)
-        return fail(ctx, AMB_ERR_STATE, "amb_resolve pending (deferred mode allows one call per span)");
+    if (n_complex > 0x40000000ull) return fail(ctx, AMB_ERR_INVALID, "internal: at most 2^30 samples per pass");
     ctx->def_kind = 0; ctx->def_resolved = false;
-    CK(cudaSetDevice(ctx->device));
     cudaStream_t sa = ctx->stream, sb = ctx->stream_b, sc = ctx->stream_c;
     const AmbParams& P = ctx->P;
     const int kc = ctx->kc;
@@ -456,8 +515,9 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
             CK(cudaMalloc(&ctx->staging, ncap * sizeof(float2)));
             ctx->staging_cap = ncap;
         }
-        // the previous call's exact/slice kernels may still read the staging buffer
+        // the previous call's exact/slice kernels and its carry kernel may still read the staging buffer
         if (ctx->done_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_done[set ^ 1], 0));
+        if (ctx->aux_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_aux[set ^ 1], 0));
         if (n_complex)
             CK(cudaMemcpyAsync(ctx->staging, iq, n_complex * sizeof(float2),
                                mem_kind == AMB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, sa));
@@ -475,8 +535,9 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
             CK(cudaMalloc(&ctx->dc_ma0, ncap * sizeof(float2)));
             ctx->dc_cap = ncap;
         }
-        // the previous call's exact/slice kernels still read dc_out
+        // the previous call's exact/slice kernels and its carry kernel still read dc_out
         if (ctx->done_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_done[set ^ 1], 0));
+        if (ctx->aux_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_aux[set ^ 1], 0));
         CK(amb_launch_dcblock(ctx->dc_carry[ctx->dc_cur], ctx->dc_nc, src, (long long)n_complex, ctx->dc_D,
                               ctx->dc_ma0, ctx->dc_out, ctx->dc_carry[ctx->dc_cur ^ 1], sa));
         ctx->dc_cur ^= 1;
@@ -592,6 +653,13 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         }
         ctx->ev_valid = false;
     }
+    if (!ctx->defer && ctx->ctr_snap && ctx->snap_head - ctx->snap_tail < AMB_SNAPS) {
+        // where the frame counter stands once this call is through: read without blocking by amb_poll_ready
+        const unsigned k = (unsigned)(ctx->snap_head % AMB_SNAPS);
+        CK(cudaMemcpyAsync(&ctx->ctr_snap[k], ctx->ctr, sizeof(AmbCounters), cudaMemcpyDeviceToHost, sb));
+        CK(cudaEventRecord(ctx->snap_ev[k], sb));
+        ctx->snap_head++;
+    }
     CK(cudaEventRecord(ctx->e_done[set], sb));
     ctx->done_valid[set] = true;
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[3], sb));
@@ -612,6 +680,230 @@ int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, i
         CK(cudaStreamWaitEvent(sa, ctx->e_aux[set], 0));
     }
     return AMB_OK;
+}
+
+/* ---- host ingest pipeline ------------------------------------------------------------------------------------
+ * Host memory never reaches the chain as one monolithic copy. The stream is cut into chunks of ing_chunk samples
+ * that travel through a ring of AMB_ING_SLOTS device buffers on a copy stream of their own: the H2D copy (and, for
+ * 16-bit input, the widening kernel) of chunk k+1 runs under the scan of chunk k, the streaming carry makes the cut
+ * invisible in the results. Pinned caller memory is DMA'd from where it lies; pageable memory and small calls (what a
+ * GNU Radio scheduler hands over: <= 32 k items per work()) are first gathered in the ring's pinned host buffers by a
+ * few copy threads, and a partly filled chunk is only dispatched once `coalesce` samples are pending or somebody asks
+ * for results (poll / flush / synchronize). */
+namespace {
+struct CopyPool {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv, done_cv;
+    struct Task { char* d; const char* s; size_t n; };
+    std::deque<Task> q;
+    int outstanding = 0;
+    bool stop = false;
+    explicit CopyPool(int n)
+    {
+        for (int k = 0; k < n; k++) th.emplace_back([this] {
+            for (;;) {
+                Task t;
+                {
+                    std::unique_lock<std::mutex> lk(m);
+                    cv.wait(lk, [this] { return stop || !q.empty(); });
+                    if (stop && q.empty()) return;
+                    t = q.front(); q.pop_front();
+                }
+                memcpy(t.d, t.s, t.n);
+                { std::lock_guard<std::mutex> lk(m); if (--outstanding == 0) done_cv.notify_all(); }
+            }
+        });
+    }
+    ~CopyPool()
+    {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+    }
+    void copy(char* d, const char* s, size_t n)
+    {
+        const size_t piece = (size_t)1 << 20;
+        if (th.empty() || n < 2 * piece) { memcpy(d, s, n); return; }
+        size_t per = (n / (th.size() + 1) + 4095) & ~(size_t)4095;
+        if (per < piece) per = piece;
+        size_t off = per;                                   // the caller copies the first piece itself
+        {
+            std::lock_guard<std::mutex> lk(m);
+            for (; off < n; off += per) { q.push_back({d + off, s + off, std::min(per, n - off)}); outstanding++; }
+        }
+        cv.notify_all();
+        memcpy(d, s, std::min(per, n));
+        std::unique_lock<std::mutex> lk(m);
+        done_cv.wait(lk, [this] { return outstanding == 0; });
+    }
+};
+std::mutex g_pool_mutex;
+CopyPool* g_pool = nullptr; int g_pool_threads = -1;
+CopyPool* copy_pool(int want)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    if (want <= 0) {
+        const unsigned hc = std::thread::hardware_concurrency();
+        want = (int)std::min(12u, std::max(1u, hc / 8));    // enough to outrun a PCIe Gen5 x16 link, never the whole box
+    }
+    if (!g_pool || g_pool_threads != want) { delete g_pool; g_pool = new CopyPool(want - 1); g_pool_threads = want; }
+    return g_pool;
+}
+}  // namespace
+
+static int ingest_setup(amb_ctx* ctx, bool need_raw)
+{
+    if (!ctx->stream_h) CK(cudaStreamCreateWithFlags(&ctx->stream_h, cudaStreamNonBlocking));
+    for (int k = 0; k < AMB_ING_SLOTS; k++) {
+        AmbIngestSlot& sl = ctx->ing[k];
+        if (!sl.dev) {
+            CK(cudaMalloc(&sl.dev, ctx->ing_chunk * sizeof(float2)));
+            CK(cudaMallocHost(&sl.pin, ctx->ing_chunk * sizeof(float2)));
+            CK(cudaEventCreateWithFlags(&sl.e_h2d, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&sl.e_free_b, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&sl.e_free_c, cudaEventDisableTiming));
+        }
+        if (need_raw && !sl.dev_raw) CK(cudaMalloc(&sl.dev_raw, ctx->ing_chunk * 4));
+    }
+    return AMB_OK;
+}
+
+static void ingest_free(amb_ctx* c)
+{
+    for (int k = 0; k < AMB_ING_SLOTS; k++) {
+        AmbIngestSlot& sl = c->ing[k];
+        cudaFree(sl.dev); cudaFree(sl.dev_raw);
+        if (sl.pin) cudaFreeHost(sl.pin);
+        if (sl.e_h2d) cudaEventDestroy(sl.e_h2d);
+        if (sl.e_free_b) cudaEventDestroy(sl.e_free_b);
+        if (sl.e_free_c) cudaEventDestroy(sl.e_free_c);
+        sl = AmbIngestSlot();
+    }
+    c->pend_n = 0; c->ing_next = 0;
+}
+
+// One chunk: `src` (host or device memory, float32 I/Q or 16-bit I/Q) -> ring slot -> the chain.
+static int ingest_dispatch(amb_ctx* ctx, const void* src, size_t m, bool sc16, bool src_on_device, int flush)
+{
+    const unsigned s_idx = ctx->ing_next % AMB_ING_SLOTS;
+    AmbIngestSlot& sl = ctx->ing[s_idx];
+    cudaStream_t sh = ctx->stream_h;
+    if (sl.used) {        // the chunk that lived here before: its sparse kernels and its carry kernel must be through
+        CK(cudaStreamWaitEvent(sh, sl.e_free_b, 0));
+        CK(cudaStreamWaitEvent(sh, sl.e_free_c, 0));
+    }
+    if (m) {
+        const cudaMemcpyKind kind = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        if (sc16) {
+            CK(cudaMemcpyAsync(sl.dev_raw, src, m * 4, kind, sh));
+            CK(amb_launch_widen_sc16(sl.dev_raw, sl.dev, (long long)m, ctx->sm_count, sh));
+            ctx->stats.kernel_launches += 1;
+        } else {
+            CK(cudaMemcpyAsync(sl.dev, src, m * sizeof(float2), kind, sh));
+        }
+    }
+    CK(cudaEventRecord(sl.e_h2d, sh));
+    sl.h2d_pending = true;
+    CK(cudaStreamWaitEvent(ctx->stream, sl.e_h2d, 0));
+    int rc = process_core(ctx, reinterpret_cast<const float*>(sl.dev), m, AMB_MEM_DEVICE, flush);
+    if (rc != AMB_OK) return rc;
+    CK(cudaEventRecord(sl.e_free_b, ctx->stream_b));
+    CK(cudaEventRecord(sl.e_free_c, ctx->stream_c));
+    sl.used = true;
+    ctx->ing_next++;
+    return AMB_OK;
+}
+
+// The pinned buffer of the slot the next chunk will use, safe to write into (its last H2D has completed).
+static int ingest_pinned_slot(amb_ctx* ctx, char** out)
+{
+    AmbIngestSlot& sl = ctx->ing[ctx->ing_next % AMB_ING_SLOTS];
+    if (sl.h2d_pending) { CK(cudaEventSynchronize(sl.e_h2d)); sl.h2d_pending = false; }
+    *out = static_cast<char*>(sl.pin);
+    return AMB_OK;
+}
+
+static int ingest_dispatch_pending(amb_ctx* ctx, int flush)
+{
+    if (!ctx->pend_n && !flush) return AMB_OK;
+    const size_t m = ctx->pend_n;
+    ctx->pend_n = 0;
+    return ingest_dispatch(ctx, ctx->ing[ctx->ing_next % AMB_ING_SLOTS].pin, m, ctx->pend_kind == AMB_MEM_HOST_SC16, false, flush);
+}
+
+static bool is_pinned_host(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+static int ingest(amb_ctx* ctx, const void* data, size_t n, int mem_kind, int flush)
+{
+    const bool sc16 = mem_kind == AMB_MEM_HOST_SC16 || mem_kind == AMB_MEM_DEVICE_SC16;
+    const bool on_dev = mem_kind == AMB_MEM_DEVICE_SC16 || mem_kind == AMB_MEM_DEVICE;
+    const size_t esz = sc16 ? 4 : sizeof(float2);
+    { int rc = ingest_setup(ctx, sc16); if (rc) return rc; }
+    const size_t CH = ctx->ing_chunk;
+    if (ctx->pend_n && (on_dev || ctx->pend_kind != mem_kind)) { int rc = ingest_dispatch_pending(ctx, 0); if (rc) return rc; }
+    const char* p = static_cast<const char*>(data);
+    size_t left = n;
+    bool flushed = false;
+    const bool direct_ok = on_dev || is_pinned_host(p);
+    while (left) {
+        if (!ctx->pend_n && direct_ok && (on_dev || left >= ctx->coalesce)) {
+            const size_t m = std::min(left, CH);               // straight from the caller's memory
+            const int fl = flush && m == left;
+            int rc = ingest_dispatch(ctx, p, m, sc16, on_dev, fl); if (rc) return rc;
+            flushed = fl != 0;
+            p += m * esz; left -= m;
+            continue;
+        }
+        char* pin = nullptr;
+        { int rc = ingest_pinned_slot(ctx, &pin); if (rc) return rc; }
+        const size_t m = std::min(left, CH - ctx->pend_n);
+        copy_pool(ctx->copy_threads)->copy(pin + ctx->pend_n * esz, p, m * esz);
+        ctx->pend_n += m; ctx->pend_kind = mem_kind;
+        p += m * esz; left -= m;
+        if (ctx->pend_n == CH || (!left && (flush || ctx->pend_n >= ctx->coalesce))) {
+            const int fl = flush && !left;
+            int rc = ingest_dispatch_pending(ctx, fl); if (rc) return rc;
+            flushed = fl != 0;
+        }
+    }
+    if (flush && !flushed) { int rc = ingest_dispatch_pending(ctx, 1); if (rc) return rc; }   // also closes an empty stream
+    return AMB_OK;
+}
+
+int amb_process(amb_ctx* ctx, const float* iq, size_t n_complex, int mem_kind, int flush)
+{
+    if (!ctx || (!iq && n_complex)) return AMB_ERR_INVALID;
+    if (mem_kind < AMB_MEM_HOST || mem_kind > AMB_MEM_DEVICE_SC16) return AMB_ERR_INVALID;
+    if (ctx->flushed) return fail(ctx, AMB_ERR_STATE, "stream already flushed; amb_reset first");
+    if (ctx->def_kind && !ctx->def_resolved)
+        return fail(ctx, AMB_ERR_STATE, "amb_resolve pending (deferred mode allows one call per span)");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->defer) {     // time-sharded span: one pass, input stays where it is (or goes through the one-piece staging buffer)
+        if (mem_kind != AMB_MEM_HOST && mem_kind != AMB_MEM_DEVICE)
+            return fail(ctx, AMB_ERR_UNSUPPORTED, "16-bit input is not available in deferred (time-sharded) mode");
+        if (n_complex > 0x40000000ull) return fail(ctx, AMB_ERR_INVALID, "a time-sharded span holds at most 2^30 samples");
+        return process_core(ctx, iq, n_complex, mem_kind, flush);
+    }
+    if (mem_kind == AMB_MEM_DEVICE && !((uintptr_t)iq & 15u)) {
+        // device-resident float32 input is read in place; only very long buffers are cut (int indexing inside a pass)
+        if (ctx->pend_n) { int rc = ingest_dispatch_pending(ctx, 0); if (rc) return rc; }
+        const size_t piece = (size_t)1 << 30;
+        size_t done = 0;
+        do {
+            const size_t m = std::min(piece, n_complex - done);
+            int rc = process_core(ctx, iq + 2 * done, m, AMB_MEM_DEVICE, flush && done + m == n_complex);
+            if (rc) return rc;
+            done += m;
+        } while (done < n_complex);
+        return AMB_OK;
+    }
+    return ingest(ctx, iq, n_complex, mem_kind, flush);
 }
 
 /* ---- time-sharding: see the header ---------------------------------------------------------------------- */
@@ -700,6 +992,7 @@ int amb_join(amb_ctx* ctx)
 {
     if (!ctx) return AMB_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->pend_n) { int rc = ingest_dispatch_pending(ctx, 0); if (rc) return rc; }
     for (int k = 0; k < 2; k++) {
         if (ctx->done_valid[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->e_done[k], 0));
         if (ctx->aux_valid[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->e_aux[k], 0));
@@ -708,17 +1001,39 @@ int amb_join(amb_ctx* ctx)
 }
 
 // tag_to_timestamp with no rx_time tag (preamble_impl.cc:100-137)
-static void stamp(amb_frame* f, int rate_int, uint64_t t0_secs, double t0_frac)
+// tag_to_timestamp (preamble_impl.cc:100-137) against the rx_time tag in force at the frame: the most recent tag at or
+// before it (amb_add_time_tag), else the stream's start time (amb_set_start_time; (0, 0.0) = "no rx_time tag")
+static void stamp(const amb_ctx* ctx, amb_frame* f)
 {
-    const uint64_t cnt = f->sample_index;
-    f->secs = t0_secs + cnt / (uint64_t)rate_int;                                  // :122,:125
-    f->frac = t0_frac + (double)(cnt % (uint64_t)rate_int) / (double)rate_int;     // :123,:126
+    const uint64_t rate = (uint64_t)ctx->P.rate_int;
+    uint64_t off = 0, t_secs = ctx->t0_secs; double t_frac = ctx->t0_frac;
+    for (size_t k = ctx->time_tags.size(); k-- > 0;)
+        if (ctx->time_tags[k].offset <= f->sample_index) { off = ctx->time_tags[k].offset; t_secs = ctx->time_tags[k].secs; t_frac = ctx->time_tags[k].frac; break; }
+    const uint64_t cnt = f->sample_index - off;                                    // abs_sample_cnt - tstamp.offset
+    f->secs = t_secs + cnt / rate;                                                 // :122,:125
+    f->frac = t_frac + (double)(cnt % rate) / (double)rate;                        // :123,:126
     if (f->frac > 1.0f) { f->frac -= 1.0f; f->secs += 1; }                         // :127-130
+}
+
+// Frames [polled, upto) of the device frame buffer (complete by now) -> pending list, in stream order, stamped.
+static int fetch_frames(amb_ctx* ctx, unsigned upto)
+{
+    if (upto <= ctx->polled) return AMB_OK;
+    const size_t base = ctx->pending.size();
+    const unsigned cnt = upto - ctx->polled;
+    ctx->pending.resize(base + cnt);
+    CK(cudaMemcpy(ctx->pending.data() + base, ctx->frames + ctx->polled, (size_t)cnt * sizeof(amb_frame), cudaMemcpyDeviceToHost));
+    std::sort(ctx->pending.begin() + base, ctx->pending.end(),
+              [](const amb_frame& x, const amb_frame& y) { return x.sample_index < y.sample_index; });
+    for (size_t k = base; k < ctx->pending.size(); k++) stamp(ctx, &ctx->pending[k]);
+    ctx->polled = upto;
+    return AMB_OK;
 }
 
 static int collect(amb_ctx* ctx)
 {
     CK(cudaSetDevice(ctx->device));
+    if (ctx->pend_n) { int rc = ingest_dispatch_pending(ctx, 0); if (rc) return rc; }
     CK(sync_all(ctx));
     AmbCounters h;
     CK(cudaMemcpy(&h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost));
@@ -728,15 +1043,10 @@ static int collect(amb_ctx* ctx)
     ctx->stats.frames_passed = h.npassed_call;
     if (h.overflow) return fail(ctx, AMB_ERR_OVERFLOW, "candidate buffer overflow");
     if (h.frame_overflow) return fail(ctx, AMB_ERR_OVERFLOW, "frame buffer overflow");
-    if (h.nframes) {
-        const size_t base = ctx->pending.size();
-        ctx->pending.resize(base + h.nframes);
-        CK(cudaMemcpy(ctx->pending.data() + base, ctx->frames, (size_t)h.nframes * sizeof(amb_frame), cudaMemcpyDeviceToHost));
-        std::sort(ctx->pending.begin() + base, ctx->pending.end(),
-                  [](const amb_frame& x, const amb_frame& y) { return x.sample_index < y.sample_index; });
-        for (size_t k = base; k < ctx->pending.size(); k++) stamp(&ctx->pending[k], ctx->P.rate_int, ctx->t0_secs, ctx->t0_frac);
-        CK(cudaMemset(&ctx->ctr->nframes, 0, sizeof(unsigned)));
-    }
+    { int rc = fetch_frames(ctx, h.nframes); if (rc) return rc; }
+    if (h.nframes) CK(cudaMemset(&ctx->ctr->nframes, 0, sizeof(unsigned)));
+    ctx->polled = 0;
+    ctx->snap_tail = ctx->snap_head;
     ctx->frames_ub = 0;
     if (ctx->def_kind && ctx->def_resolved) { ctx->def_kind = 0; ctx->def_resolved = false; }   // frames read: span is final
     return AMB_OK;
@@ -761,10 +1071,56 @@ int amb_poll_frames(amb_ctx* ctx, amb_frame* out, int max)
     return n;
 }
 
+/* Non-blocking: frames of the calls that have already completed on the device; work in flight stays in flight. */
+int amb_poll_ready(amb_ctx* ctx, amb_frame* out, int max)
+{
+    if (!ctx || (!out && max > 0)) return AMB_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    bool have = false; AmbCounters last{};
+    while (ctx->snap_tail < ctx->snap_head) {
+        const unsigned k = (unsigned)(ctx->snap_tail % AMB_SNAPS);
+        const cudaError_t q = cudaEventQuery(ctx->snap_ev[k]);
+        if (q == cudaErrorNotReady) { cudaGetLastError(); break; }
+        if (q != cudaSuccess) return fail(ctx, AMB_ERR_CUDA, "cudaEventQuery", q);
+        last = ctx->ctr_snap[k]; have = true; ctx->snap_tail++;
+    }
+    if (have) {
+        if (last.overflow) return fail(ctx, AMB_ERR_OVERFLOW, "candidate buffer overflow");
+        if (last.frame_overflow) return fail(ctx, AMB_ERR_OVERFLOW, "frame buffer overflow");
+        int rc = fetch_frames(ctx, last.nframes); if (rc) return rc;
+    }
+    const int n = (int)std::min<size_t>(ctx->pending.size(), (size_t)std::max(max, 0));
+    if (n) memcpy(out, ctx->pending.data(), (size_t)n * sizeof(amb_frame));
+    ctx->pending.erase(ctx->pending.begin(), ctx->pending.begin() + n);
+    return n;
+}
+
+int amb_add_time_tag(amb_ctx* ctx, uint64_t offset, uint64_t secs, double frac)
+{
+    if (!ctx) return AMB_ERR_INVALID;
+    if (!ctx->time_tags.empty() && ctx->time_tags.back().offset >= offset)
+        return fail(ctx, AMB_ERR_INVALID, "rx_time tags must be added in ascending offset order");
+    ctx->time_tags.push_back({offset, secs, frac});
+    return AMB_OK;
+}
+
+/* Order the context's work after whatever has been enqueued so far on another CUDA stream (e.g. the stream that
+ * produces a device-resident input buffer). No host synchronisation. */
+int amb_wait_stream(amb_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return AMB_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if ((cudaStream_t)cuda_stream == ctx->stream) return AMB_OK;
+    CK(cudaEventRecord(ctx->e_in, (cudaStream_t)cuda_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->e_in, 0));
+    return AMB_OK;
+}
+
 int amb_get_stats(amb_ctx* ctx, amb_stats* out)
 {
     if (!ctx || !out) return AMB_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->pend_n) { int rc = ingest_dispatch_pending(ctx, 0); if (rc) return rc; }
     CK(sync_all(ctx));
     AmbCounters h; AmbWalkState st;
     CK(cudaMemcpy(&h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost));
@@ -788,6 +1144,7 @@ int amb_get_scan_times(amb_ctx* ctx, float* ms_out, int max)
 {
     if (!ctx || (!ms_out && max > 0)) return AMB_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->pend_n) { int rc = ingest_dispatch_pending(ctx, 0); if (rc) return rc; }
     CK(sync_all(ctx));
     const unsigned have = ctx->ring_n < 64u ? ctx->ring_n : 64u;
     const unsigned n = have < (unsigned)(max > 0 ? max : 0) ? have : (unsigned)(max > 0 ? max : 0);

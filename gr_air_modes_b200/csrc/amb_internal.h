@@ -131,3 +131,4 @@ cudaError_t amb_launch_dcblock(const float2* rawcarry, int nc, const float2* fre
 cudaError_t amb_launch_prologue(float2* tail, int tail_cap, const float2* src_rem, int n_rem,
                                 uint32_t* group_count, int n_groups, cudaStream_t s);
 size_t amb_scan_smem_bytes(int spc_i);
+cudaError_t amb_launch_widen_sc16(const void* in_sc16, float2* out, long long n, int sm_count, cudaStream_t s);

@@ -40,8 +40,10 @@ extern "C" {
 #define AMB_ERR_ALIGN (-7)        /* device IQ pointer not 16-byte aligned */
 #define AMB_ERR_STATE (-8)        /* call not valid in this state (e.g. process after flush without reset) */
 
-#define AMB_MEM_HOST 0
-#define AMB_MEM_DEVICE 1
+#define AMB_MEM_HOST 0          /* interleaved float32 I,Q in host memory (pinned or pageable) */
+#define AMB_MEM_DEVICE 1        /* ... in device memory (read in place when 16-byte aligned) */
+#define AMB_MEM_HOST_SC16 2     /* interleaved int16 I,Q in host memory, full scale 32768 (the receivers' wire format) */
+#define AMB_MEM_DEVICE_SC16 3   /* ... in device memory */
 
 typedef struct amb_ctx amb_ctx;
 
@@ -95,8 +97,16 @@ AMB_API float amb_get_threshold(const amb_ctx* ctx);            /* dB, as preamb
 AMB_API int amb_get_pmf(const amb_ctx* ctx);                    /* rx_path.get_pmf (rx_path.py:83-84) */
 /* The rx_time stream tag a UHD source attaches to item 0 (lib/preamble_impl.cc:104-116,164-170): frames are then
  * stamped tag + sample_index/rate with the reference's `frac > 1.0f` carry (:127-130). Default (0, 0.0) = no tag.
- * Applies to frames collected afterwards. Later rx_time tags (overflows) are not modelled. */
+ * Applies to frames collected afterwards. */
 AMB_API int amb_set_start_time(amb_ctx* ctx, uint64_t secs, double frac);
+/* A later rx_time tag (what a UHD source attaches after an overflow) at absolute item `offset` of the preamble
+ * block's input = the coordinate of amb_frame.sample_index. Frames at or after `offset` are stamped against it
+ * (tag_to_timestamp, preamble_impl.cc:100-137), earlier ones against the previous tag / the start time. This is what
+ * the reference computes whenever no general_work() window straddles the tag; when one does, the reference latches the
+ * tag at the START of that window (preamble_impl.cc:164-170) and stamps the window's earlier detections with a wrapped
+ * unsigned delay - an artefact of the scheduler's buffer boundaries that is not reproduced. Ascending offsets only;
+ * tags are forgotten by amb_reset. Applies to frames collected afterwards. */
+AMB_API int amb_add_time_tag(amb_ctx* ctx, uint64_t offset, uint64_t secs, double frac);
 
 /* Host-only (no GPU needed): the geometry preamble_impl derives from (rate, threshold) - preamble_impl.cc:56-68
  * (set_rate/set_threshold), :158-162 (pulse offsets), :205-208 (quiet-zone loop bounds), :184-192 (late-gate
@@ -121,12 +131,27 @@ AMB_API int amb_query_geometry(float rate, float threshold_db, int use_pmf, amb_
  * reference's end-of-input rules are applied and the stream must be reset before more input.
  * Work is enqueued on the ctx's CUDA stream; results are collected by amb_poll_frames. */
 AMB_API int amb_process(amb_ctx* ctx, const float* iq_interleaved, size_t n_complex, int mem_kind, int flush);
+/* Memory kinds. AMB_MEM_DEVICE (16-byte aligned) is read in place and must stay valid until amb_synchronize /
+ * amb_poll_frames / amb_join + a wait on the caller's side. Everything else is consumed before amb_process returns:
+ * host memory travels through a library-owned ring of pinned host + device chunk buffers (option "ingest_chunk",
+ * default 2^22 samples) on a copy stream, so the H2D copy of one chunk overlaps the kernels of the previous one;
+ * pinned caller memory is DMA'd from where it lies, pageable memory is first gathered into the ring by a few copy
+ * threads (option "copy_threads"). Calls smaller than option "coalesce" (default 2^18 samples) are gathered and only
+ * dispatched once that many samples are pending or when results are asked for (amb_poll_frames, amb_synchronize,
+ * flush) - GNU Radio hands a sink at most 32 k items per work() call. The *_SC16 kinds take interleaved int16 I,Q and
+ * widen them on the device with x * 2^-15 (exact): half the PCIe bytes of float32, bit-identical results to feeding
+ * the float32 the host-side conversion (radio.py:163-173, cpu_format "fc32") would have produced. `iq_interleaved`
+ * then points to int16 data. */
 
 /* Wait for enqueued work and copy out up to `max` frames in stream order (all detections; test
  * .passed for what slicer_impl.cc:193-194 would queue). Returns the count, or <0 on error.
  * amb_pending_frames() tells how many are waiting (also synchronises). */
 AMB_API int amb_poll_frames(amb_ctx* ctx, amb_frame* out, int max);
 AMB_API int amb_pending_frames(amb_ctx* ctx);
+/* Non-blocking variant for streaming callers (a GNU Radio work() function): returns the frames of the calls that
+ * have already completed on the device, in stream order, and leaves work in flight alone. Host input that is still
+ * being gathered (see amb_process) is not forced out. */
+AMB_API int amb_poll_ready(amb_ctx* ctx, amb_frame* out, int max);
 
 /* Message text exactly as slicer_impl.cc:186-192 builds it: "<hex payload> <crc %06x> <ref> <secs> <frac>".
  * `first` != 0 formats ref with the stream's default precision 6 (the first message a slicer instance
@@ -170,6 +195,9 @@ AMB_API int amb_synchronize(amb_ctx* ctx);
  * all of it without blocking the host; amb_synchronize / amb_poll_frames block. Input buffers must stay valid
  * until one of them. amb_set_option("overlap", 0) restores strictly stream-ordered behaviour. */
 AMB_API int amb_join(amb_ctx* ctx);
+/* The converse: make the context's streams wait for everything enqueued so far on `cuda_stream` (the stream that
+ * produces a device-resident input buffer) before the next amb_process reads it. No host synchronisation. */
+AMB_API int amb_wait_stream(amb_ctx* ctx, void* cuda_stream);
 /* Parity dumps of the last amb_process call: candidate start indices (reported coordinates) and their
  * exact-stage verdict: bits 0-7 late shift, bit 8 passes preamble_impl.cc:174-179, bit 9 valid preamble
  * (:205-209), bit 10 visited-and-accepted. Returns count. */

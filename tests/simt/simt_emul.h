@@ -129,6 +129,7 @@ static inline int __double2hiint(double d) { uint64_t b; memcpy(&b, &d, 8); retu
 
 // ---- vector types, runtime stand-ins, launch macros (amb_internal.h skips the CUDA headers under AMB_SIMT_EMUL) ----
 struct float2 { float x, y; };
+struct short2 { short x, y; };
 struct double2 { double x, y; };
 static inline float2 make_float2(float x, float y) { float2 v = {x, y}; return v; }
 static inline double2 make_double2(double x, double y) { double2 v = {x, y}; return v; }

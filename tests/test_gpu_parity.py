@@ -1,6 +1,7 @@
 """Parity tests proper: the CUDA path through the C ABI vs the CPU oracle / reference goldens. Need a B200."""
 import ctypes as C
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -14,12 +15,34 @@ from helpers import first_four, load_golden, parse_msg
 pytestmark = pytest.mark.gpu
 
 
-def run_cuda(iq, rate, thr, pmf, chunks=None, resolver=0, keep=False):
+def device_resident(iq):
+    """The recording as ONE device-resident buffer (read in place, one pass of the chain). Under the emulated build of
+    tests/test_emulated_gpu_suite.py "device" memory is host memory, so the numpy buffer itself plays that part."""
+    if os.environ.get("AMB_TEST_EMULATED_LIB"):
+        class _Dev:                                             # what blocks._as_iq needs from a CUDA tensor
+            def __init__(self, a):
+                self.a = np.ascontiguousarray(a, dtype=np.float32)
+        return _Dev(iq)
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(iq, dtype=np.float32)).cuda()
+
+
+def run_cuda(iq, rate, thr, pmf, chunks=None, resolver=0, keep=False, one_pass=False):
     q = am.msg_queue()
     rx = am.rx_path(rate, thr, q, use_pmf=pmf)
     rx._ctx.call("amb_set_option", b"resolver", resolver)
     frames = []
-    if chunks is None:
+    if one_pass:
+        d = device_resident(iq)
+        if hasattr(d, "a"):
+            import ctypes as C
+            from gr_air_modes_b200 import _lib
+            rx._ctx.call("amb_process", C.c_void_p(d.a.ctypes.data), d.a.size // 2, _lib.MEM_DEVICE, 1)
+            rx.drain()
+        else:
+            rx.process(d, flush=True)
+        frames += rx.frames
+    elif chunks is None:
         rx.process(iq, flush=True)
         frames += rx.frames
     else:
@@ -140,10 +163,15 @@ def test_long_gap_float_rounding_falls_back_to_sequential(port):
     sc = synth.make_scene(rate, (1 << 25) + 5_000_001, 0, 3,
                           starts=[1_000_000.4, 1_000_000.4 + (1 << 24) + 4_000_001, 33_000_000.2], amplitude=0.3)
     want = port.run_iq(sc.iq, rate, 7.0, True, co.MA_SLIDING64)
-    msgs, frames, rx = run_cuda(sc.iq, rate, 7.0, True)
+    msgs, frames, rx = run_cuda(sc.iq, rate, 7.0, True, one_pass=True)     # one device-resident pass over the whole gap
     assert [f.sample_index for f in frames] == [int(x) for x in want.index] and len(frames) == 3
     assert [m.split()[:2] for m in msgs] == [m.split()[:2] for m in want.msgs]
     assert rx.stats().resolver_fallback == 1
+    # host memory goes through the ingest ring in 2^22-sample chunks: the packet behind the gap is then the first
+    # cluster of its chunk, whose entry state is known exactly - same frames, no fallback needed
+    msgs, frames, rx = run_cuda(sc.iq, rate, 7.0, True)
+    assert [f.sample_index for f in frames] == [int(x) for x in want.index] and len(frames) == 3
+    assert [m.split()[:2] for m in msgs] == [m.split()[:2] for m in want.msgs]
 
 
 def test_device_crc_and_slicer_block(port):

@@ -350,3 +350,96 @@ def test_candidate_flood_does_not_overflow(port):
     assert st.candidates > n // 8                         # the flood is real ...
     assert q.strings() == want.msgs and len(want.msgs) > 20   # ... and harmless
     rx.close()
+
+
+# ---- host ingest pipeline (amb_process with host memory): chunk ring, gathering of small calls, 16-bit IQ, polls ----
+def test_ingest_ring_small_calls_and_nonblocking_poll(port):
+    """GNU Radio-sized calls are gathered in the ring's pinned buffer and dispatched every `coalesce` samples; a tiny
+    chunk size forces many ring wrap-arounds. Results = one shot = oracle, whichever way they are collected."""
+    rate = 4e6
+    sc = synth.make_scene(rate, 120_000, 24, 901)
+    want = port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL)
+    assert len(want.msgs) >= 10
+    for chunk, coalesce, call in ((4096, 1024, 700), (8192, 8192, 3001), (1 << 22, 1 << 18, 8192)):
+        q = am.msg_queue()
+        rx = am.rx_path(rate, 7.0, q, use_pmf=True)
+        rx.set_option("ingest_chunk", chunk)
+        rx.set_option("coalesce", coalesce)
+        n, pos, early = sc.iq.size // 2, 0, 0
+        while pos < n:
+            c = min(call, n - pos)
+            rx.process(sc.iq[2 * pos: 2 * (pos + c)], flush=False, collect=False)
+            early += rx.poll_ready()                       # non-blocking: whatever has completed
+            pos += c
+        rx.process(sc.iq[:0], flush=True, collect=True)    # closes the stream, forces the rest out
+        assert q.strings() == want.msgs, (chunk, coalesce, call)
+        assert rx.stats().samples_in == n
+        if coalesce < 100_000:
+            assert early > 0                               # messages did arrive through the non-blocking poll
+        rx.close()
+
+
+def test_ingest_large_pageable_call_is_cut_into_chunks(port):
+    rate = 10e6
+    sc = synth.make_scene(rate, 200_000, 16, 902)
+    want = port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL)
+    q = am.msg_queue()
+    rx = am.rx_path(rate, 7.0, q, use_pmf=True)
+    rx.set_option("ingest_chunk", 16384)                   # 13 chunks, ring of 4
+    rx.process(sc.iq, flush=True)
+    assert q.strings() == want.msgs and [f.sample_index for f in rx.frames] == [int(x) for x in want.index]
+    # and again on the same context after a reset, now complex64 and in two uneven calls
+    q.flush(); rx.reset(); rx._slicer._first = True
+    c = sc.iq.view(np.complex64)
+    rx.process(c[:77_777], collect=False)
+    rx.process(c[77_777:], flush=True)
+    assert q.strings() == want.msgs
+    rx.close()
+
+
+def test_sc16_input_equals_its_float32_widening(port):
+    """16-bit IQ is widened on the device with x * 2^-15: identical to feeding the float32 a host-side conversion
+    (radio.py:163-173, cpu_format fc32) would have produced - every message, bit for bit."""
+    rate = 4e6
+    sc = synth.make_scene(rate, 100_000, 20, 903, noise_sigma=0.01)
+    i16 = np.clip(np.rint(sc.iq * 32768.0), -32768, 32767).astype(np.int16)
+    f32 = i16.astype(np.float32) * np.float32(1.0 / 32768.0)
+    want = port.run_iq(f32, rate, 7.0, True, co.MA_CANONICAL)
+    assert len(want.msgs) >= 8
+    for chunk in (8192, 1 << 22):
+        q = am.msg_queue()
+        rx = am.rx_path(rate, 7.0, q, use_pmf=True)
+        rx.set_option("ingest_chunk", chunk)
+        rx.process(i16[:60_002], collect=False)
+        rx.process(i16[60_002:], flush=True)
+        assert q.strings() == want.msgs, chunk
+        rx.close()
+    with pytest.raises(TypeError):
+        am.rx_path(rate, 7.0, am.msg_queue()).process(np.zeros(64, np.float64))
+    q = am.msg_queue()
+    rx = am.rx_path(rate, 7.0, q, use_pmf=True)
+    rx.process(f32.view(np.complex64).astype(np.complex128), flush=True)   # complex128 is narrowed, not reinterpreted
+    assert q.strings() == want.msgs
+
+
+def test_mid_stream_rx_time_tag(port):
+    rate = 4e6
+    sc = synth.make_scene(rate, 80_000, 16, 904)
+    plain = port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL)
+    T = 40_000
+    q = am.msg_queue()
+    rx = am.rx_path(rate, 7.0, q, use_pmf=True)
+    rx.set_start_time(100, 0.25)
+    rx.add_time_tag(T, 200, 0.5)
+    rx.process(sc.iq, flush=True)
+    assert [f.sample_index for f in rx.frames] == [int(x) for x in plain.index]
+    ri = int(rate)
+    for f in rx.frames:
+        i = int(f.sample_index)
+        base, off = ((200, 0.5), T) if i >= T else ((100, 0.25), 0)
+        secs, frac = base[0] + (i - off) // ri, base[1] + ((i - off) % ri) / float(ri)
+        if frac > 1.0:
+            frac -= 1.0; secs += 1
+        assert (f.secs, f.frac) == (secs, frac)
+    with pytest.raises(RuntimeError):
+        rx.add_time_tag(T - 1, 1, 0.0)                      # ascending offsets only
