@@ -521,8 +521,64 @@ def e2e_legs(rx, q, iq, n, args, local_rank, world, device):
 
 
 def e2e_extra_legs(rx, q, host, n, args, world, timed):
-    """Filled in by the ingest pipeline of the library (pageable input, 16-bit IQ, small calls)."""
-    return {}
+    """Further end-to-end figures through the same public call (not the headline):
+      e2e_pageable    the recording in ordinary pageable memory (np.fromfile, GNU Radio buffers): the library gathers it
+                      into its pinned ring with a few copy threads while earlier chunks are in flight
+      e2e_sc16        16-bit IQ (the receivers' wire format) from pinned memory, widened on the device: half the bytes
+      e2e_small_call  process() calls of 8 k / 32 k / 256 k samples + a non-blocking poll each, the way a GNU Radio
+                      sink block's work() drives the library; x real time at the config's sample rate"""
+    import torch
+    out = {}
+    rate = rx._rate
+    # ---- pageable
+    page = np.empty(2 * n, dtype=np.float32)
+    page[:] = host.numpy()
+
+    def pageable():
+        rx.reset()
+        rx.process(page, flush=True)
+
+    ms = timed(pageable, max(1, args.e2e_steps - 1))
+    out["e2e_pageable"] = {"value": world * n / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms,
+                           "h2d_bytes_per_step": 8 * n, "input": "pageable host float32 I/Q"}
+    del page
+    # ---- 16-bit IQ
+    i16 = torch.empty(2 * n, dtype=torch.int16, pin_memory=True)
+    step = 1 << 26
+    for a in range(0, 2 * n, step):
+        i16[a:a + step] = torch.clamp(torch.round(host[a:a + step] * 32768.0), -32768, 32767).to(torch.int16)
+
+    def sc16():
+        rx.reset()
+        rx.process(i16, flush=True)
+
+    ms = timed(sc16, args.e2e_steps)
+    out["e2e_sc16"] = {"value": world * n / (ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms,
+                       "h2d_bytes_per_step": 4 * n, "input": "pinned host int16 I/Q, widened x*2^-15 on the device",
+                       "msgs_per_step": len([f for f in rx.frames if f.passed])}
+    del i16
+    # ---- small calls (bounded stretch of the stream)
+    small = {}
+    hv = host.numpy()
+    for call in (8192, 32768, 262144):
+        total = min(n, call * 512)
+
+        def run():
+            rx.reset()
+            got = 0
+            for a in range(0, total, call):
+                rx.process(hv[2 * a: 2 * (a + call)], flush=False, collect=False)
+                got += rx.poll_ready()
+            rx.process(hv[:0], flush=True)
+            return got
+
+        ms = timed(run, 2)
+        small[str(call)] = {"Msamples/s": total / (ms * 1e-3) / 1e6, "x_real_time": total / (ms * 1e-3) / rate,
+                            "us_per_call": 1e3 * ms / (total // call)}
+    out["e2e_small_call"] = {"calls_of_samples": small, "how": "rx_path.process(chunk, collect=False) + rx_path.poll_ready() per "
+                             "call over 512 calls of pinned-host float32, then a closing flush; input gathered by the library "
+                             "(option coalesce = 2^18 samples)"}
+    return out
 
 
 def main():

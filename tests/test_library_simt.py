@@ -443,3 +443,98 @@ def test_mid_stream_rx_time_tag(port):
         assert (f.secs, f.frac) == (secs, frac)
     with pytest.raises(RuntimeError):
         rx.add_time_tag(T - 1, 1, 0.0)                      # ascending offsets only
+
+
+# ---- GNU Radio adapters (gr_adapter.py) against a stand-in gnuradio.gr: the test is the scheduler ---------------------
+def _import_gr_adapter():
+    stubs = os.path.join(ROOT, "tests", "stubs")
+    if stubs not in sys.path:
+        sys.path.insert(0, stubs)
+    import importlib
+    import gr_air_modes_b200.gr_adapter as ga
+    return importlib.reload(ga)
+
+
+def _drive_sink(blk, items, cuts, tags=()):
+    """Hand `items` to a sink block's work() in ragged pieces; honours partial consumption."""
+    from gnuradio import gr
+    blk._in_tags[0] = [gr.tag_t(o, k, v) for (o, k, v) in tags]
+    pos, n, k = 0, len(items), 0
+    blk._nread[0] = 0
+    blk.start()
+    while pos < n:
+        c = min(int(cuts[k % len(cuts)]), n - pos); k += 1
+        c -= c % blk.output_multiple if c >= blk.output_multiple and pos + c < n else 0
+        used = blk.work([items[pos:pos + c]], [])
+        assert 0 <= used <= c
+        if used == 0 and pos + c >= n:
+            break
+        if used == 0:
+            cuts = [x + 240 for x in cuts]                      # give it more next time, as a scheduler would
+        blk._nread[0] += used
+        pos += used
+    blk.stop()
+
+
+def test_gr_adapter_rx_path_sink_with_ragged_work_calls_and_restart(port):
+    ga = _import_gr_adapter()
+    rate = 4e6
+    sc = synth.make_scene(rate, 150_000, 30, 905)
+    want = port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL)
+    q = am.msg_queue()
+    blk = ga.rx_path(rate, 7.0, q, use_pmf=True)
+    blk._impl.set_option("coalesce", 20_000)
+    c64 = sc.iq.view(np.complex64)
+    _drive_sink(blk, c64, [8191, 4096, 1, 32768, 777])
+    assert q.strings() == want.msgs
+    assert blk.get_threshold() == 7.0 and blk.get_pmf() is True
+    q.flush()
+    _drive_sink(blk, c64, [32768])                              # stop() + start(): the flowgraph was restarted
+    assert q.strings() == want.msgs                             # a new stream incl. the first-message precision quirk
+    # rx_time tags from a UHD source: item 0 = start time, a later one = after an overflow
+    import pmt
+    q.flush()
+    key = pmt.string_to_symbol("rx_time")
+    tags = [(0, key, pmt.make_tuple(pmt.from_uint64(1000), pmt.from_double(0.5))),
+            (70_000, key, pmt.make_tuple(pmt.from_uint64(2000), pmt.from_double(0.125)))]
+    _drive_sink(blk, c64, [30_000], tags)
+    secs = [int(m.split()[3]) for m in q.strings()]
+    idx = [int(f) for f in want.index[[i for i, f in enumerate(want.frames) if f.passed]]]
+    assert len(secs) == len(idx) and all((s >= 2000) == (i >= 70_000) for s, i in zip(secs, idx)) and min(secs) >= 1000
+
+
+def test_gr_adapter_split_blocks_preamble_then_slicer(port, ref):
+    """The reference's own wiring of the two blocks (rx_path.py:57-65) with the adapters in their place: float streams
+    -> preamble adapter (240 items + preamble_found tag per detection) -> slicer adapter -> queue."""
+    ga = _import_gr_adapter()
+    from gnuradio import gr
+    rate = 4e6
+    sc = synth.make_scene(rate, 120_000, 24, 906)
+    bb, avg = port.frontend(sc.iq, rate, True, co.MA_CANONICAL)
+    want = ref.run_streams(bb, avg, rate, 7.0)
+    pre = ga.preamble(rate, 7.0)
+    assert pre.get_rate() == 4e6 and pre.get_threshold() == 7.0
+    stream, pos, cuts, k = [], 0, [4096, 9999, 1, 30000], 0
+    while pos < bb.size:
+        c = min(cuts[k % len(cuts)], bb.size - pos); k += 1
+        out = np.zeros(240 * 3, np.float32)                      # deliberately small: packets must queue up inside
+        pre._consumed = [0, 0]
+        produced = pre.general_work([bb[pos:pos + c], avg[pos:pos + c]], [out])
+        assert pre._consumed == [c, c] and produced % 240 == 0
+        stream.append(out[:produced].copy()); pre._nwritten[0] += produced
+        pos += c
+        while pre._out:                                          # the scheduler keeps calling while forecast() says 0 inputs
+            need = [1, 1]; pre.forecast(240, need); assert need == [0, 0]
+            produced = pre.general_work([bb[:0], avg[:0]], [out])
+            stream.append(out[:produced].copy()); pre._nwritten[0] += produced
+    pre.stop()
+    out = np.zeros(240 * max(1, len(pre._out)), np.float32)
+    produced = pre._emit(out); stream.append(out[:produced].copy())
+    items = np.concatenate(stream)
+    assert items.size == 240 * len(want.index)
+    assert np.array_equal(items.reshape(-1, 240), want.chips)
+    assert [t.offset for t in pre.out_tags] == [240 * i for i in range(len(want.index))]
+    q = am.msg_queue()
+    sl = ga.slicer(q)
+    _drive_sink(sl, items, [240 * 5, 240, 240 * 17 + 100], [(t.offset, t.key, t.value) for t in pre.out_tags])
+    assert q.strings() == want.msgs
