@@ -181,8 +181,11 @@ class _Context:
         return list(buf)[:got]
 
     def poll_ready_array(self, max_frames: int = 4096):
-        """Non-blocking: (ctypes Frame array, count) of the frames whose calls have completed on the device."""
-        buf = (Frame * max_frames)()
+        """Non-blocking: (ctypes Frame array, count) of the frames whose calls have completed on the device. The
+        array is reused from call to call."""
+        buf = getattr(self, "_ready_buf", None)
+        if buf is None or len(buf) < max_frames:
+            buf = self._ready_buf = (Frame * max_frames)()
         got = self.call("amb_poll_ready", buf, max_frames)
         return buf, got
 
@@ -357,7 +360,7 @@ class rx_path:
     def drain(self) -> int:
         """Wait for everything given so far and queue its messages."""
         buf, got = self._ctx.poll_array()
-        self.frames = list(buf)[:got]
+        self.frames = list(buf)[:got] if got else []
         self._keep.clear()
         return self._slicer.emit(buf, got)
 
@@ -365,8 +368,12 @@ class rx_path:
         """Non-blocking drain: queue the messages of the calls that have already completed on the device (what a GNU
         Radio work() function calls after handing over its items). Returns how many were queued."""
         buf, got = self._ctx.poll_ready_array(max_frames)
-        self.frames = list(buf)[:got]
-        return self._slicer.emit(buf, got) if got else 0
+        if not got:
+            self.frames = []
+            return 0
+        arr = (Frame * got).from_buffer_copy(buf)            # own copy: the poll buffer is reused
+        self.frames = list(arr)
+        return self._slicer.emit(arr, got)
 
     def add_time_tag(self, offset: int, secs: int, frac: float):
         """A later rx_time tag at absolute item `offset` (see amb_add_time_tag)."""

@@ -744,13 +744,16 @@ CopyPool* copy_pool(int want)
 {
     std::lock_guard<std::mutex> lk(g_pool_mutex);
     if (want <= 0) {
-        const unsigned hc = std::thread::hardware_concurrency();
-        want = (int)std::min(12u, std::max(1u, hc / 8));    // enough to outrun a PCIe Gen5 x16 link, never the whole box
+        static const int dflt = (int)std::min(12u, std::max(1u, std::thread::hardware_concurrency() / 8));
+        want = dflt;                                        // enough to outrun a PCIe Gen5 x16 link, never the whole box
     }
     if (!g_pool || g_pool_threads != want) { delete g_pool; g_pool = new CopyPool(want - 1); g_pool_threads = want; }
     return g_pool;
 }
 }  // namespace
+
+// also used by the decoder's staging (amb_decode.cu)
+void amb_parallel_memcpy(void* dst, const void* src, size_t n) { copy_pool(0)->copy(static_cast<char*>(dst), static_cast<const char*>(src), n); }
 
 static int ingest_setup(amb_ctx* ctx, bool need_raw)
 {

@@ -13,6 +13,11 @@
 //                       (2^26 x 16 B: one slot per (ICAO, surface, even/odd), so no probing, no collisions, no locks -
 //                       a slot has exactly one owner warp).
 //   amb_resolve_kernel  one thread per frame: global CPR decode, range/bearing.
+// The pairing stage is the bucket-partition version (amb_decode_v3.cuh: O(n) traffic, one warp per owner bucket);
+// -DAMB_PAIR_V1 / -DAMB_PAIR_V2 select the two earlier experiments (every warp walks the whole report list).
+#if !defined(AMB_PAIR_V1) && !defined(AMB_PAIR_V2) && !defined(AMB_PAIR_V3)
+#define AMB_PAIR_V3 1
+#endif
 #include "amb_launch.h"
 #include "amb_decode_core.h"
 #include "amb_decode_kernels.cuh"
@@ -32,6 +37,9 @@ struct amb_decoder {
     double* nl_T = nullptr;              // device copy of the NL transition table
     amb_frame* d_frames = nullptr; amb_fields* d_fields = nullptr; AmbPosRec* d_pos = nullptr; AmbPair* d_pair = nullptr;
     int cap = 0;
+    // host <-> device staging: pageable caller arrays go through two pinned bounce buffers per direction so that the
+    // copies run at PCIe speed and overlap the memcpy of the next piece
+    void* pin[2] = {nullptr, nullptr}; cudaEvent_t pin_ev[2] = {nullptr, nullptr}; size_t pin_bytes = 0;
 #ifdef AMB_PAIR_V2
     uint32_t* d_keys = nullptr;
 #endif
@@ -58,6 +66,56 @@ static int dfail(amb_decoder* d, int code, const char* what, cudaError_t e = cud
     do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return dfail(d, AMB_ERR_CUDA, #call, e_); } while (0)
 
 // ---- host ---------------------------------------------------------------------------------------------------------
+extern "C" void amb_parallel_memcpy(void* dst, const void* src, size_t n);      // amb_api.cu (the ingest copy threads)
+#define AMB_DEC_PIECE ((size_t)8 << 20)
+
+static int ensure_pinned(amb_decoder* d)
+{
+    if (d->pin[0]) return AMB_OK;
+    for (int k = 0; k < 2; k++) {
+        DCK(cudaMallocHost(&d->pin[k], AMB_DEC_PIECE));
+        DCK(cudaEventCreateWithFlags(&d->pin_ev[k], cudaEventDisableTiming));
+    }
+    d->pin_bytes = AMB_DEC_PIECE;
+    return AMB_OK;
+}
+
+// pageable host -> device through the pinned pieces (memcpy of piece k+1 overlaps the DMA of piece k)
+static int staged_h2d(amb_decoder* d, void* dst, const void* src, size_t bytes, cudaStream_t s)
+{
+    int rc = ensure_pinned(d); if (rc) return rc;
+    size_t off = 0; int k = 0;
+    while (off < bytes) {
+        const size_t m = bytes - off < AMB_DEC_PIECE ? bytes - off : AMB_DEC_PIECE;
+        DCK(cudaEventSynchronize(d->pin_ev[k]));
+        amb_parallel_memcpy(d->pin[k], static_cast<const char*>(src) + off, m);
+        DCK(cudaMemcpyAsync(static_cast<char*>(dst) + off, d->pin[k], m, cudaMemcpyHostToDevice, s));
+        DCK(cudaEventRecord(d->pin_ev[k], s));
+        off += m; k ^= 1;
+    }
+    return AMB_OK;
+}
+
+// device -> pageable host: the DMA of piece i overlaps the memcpy of piece i-1 out of its pinned buffer
+static int staged_d2h(amb_decoder* d, void* dst, const void* src, size_t bytes, cudaStream_t s)
+{
+    int rc = ensure_pinned(d); if (rc) return rc;
+    const size_t np = (bytes + AMB_DEC_PIECE - 1) / AMB_DEC_PIECE;
+    for (size_t i = 0; i <= np; i++) {
+        if (i < np) {
+            const size_t off = i * AMB_DEC_PIECE, m = bytes - off < AMB_DEC_PIECE ? bytes - off : AMB_DEC_PIECE;
+            DCK(cudaMemcpyAsync(d->pin[i & 1], static_cast<const char*>(src) + off, m, cudaMemcpyDeviceToHost, s));
+            DCK(cudaEventRecord(d->pin_ev[i & 1], s));
+        }
+        if (i >= 1) {
+            const size_t off = (i - 1) * AMB_DEC_PIECE, m = bytes - off < AMB_DEC_PIECE ? bytes - off : AMB_DEC_PIECE;
+            DCK(cudaEventSynchronize(d->pin_ev[(i - 1) & 1]));
+            amb_parallel_memcpy(static_cast<char*>(dst) + off, d->pin[(i - 1) & 1], m);
+        }
+    }
+    return AMB_OK;
+}
+
 static void free_bufs(amb_decoder* d)
 {
     if (d->d_frames) cudaFree(d->d_frames);
@@ -134,6 +192,7 @@ void amb_decoder_destroy(amb_decoder* d)
 #ifdef AMB_PAIR_V3
     amb_v3_free(&d->v3);
 #endif
+    for (int k = 0; k < 2; k++) { if (d->pin[k]) cudaFreeHost(d->pin[k]); if (d->pin_ev[k]) cudaEventDestroy(d->pin_ev[k]); }
     if (d->table) cudaFree(d->table);
     if (d->nl_T) cudaFree(d->nl_T);
     if (d->e0) cudaEventDestroy(d->e0);
@@ -170,7 +229,8 @@ int amb_decode_frames(amb_decoder* d, const amb_frame* frames, int n, int mem_ki
     DCK(cudaEventRecord(d->e0, s));
     const amb_frame* src = frames;
     if (mem_kind == AMB_MEM_HOST) {
-        DCK(cudaMemcpyAsync(d->d_frames, frames, (size_t)n * sizeof(amb_frame), cudaMemcpyHostToDevice, s));
+        rc = staged_h2d(d, d->d_frames, frames, (size_t)n * sizeof(amb_frame), s);
+        if (rc != AMB_OK) return rc;
         src = d->d_frames;
     }
     const int nb = (n + 127) / 128;
@@ -210,7 +270,8 @@ int amb_decode_frames(amb_decoder* d, const amb_frame* frames, int n, int mem_ki
     AMB_LAUNCH((amb_resolve_kernel), nb, 128, 0, s, d->d_fields, d->d_pos, d->d_pair, n, d->have_loc, d->lat, d->lon, d->nl_T);
     DCK(cudaGetLastError());
     d->launches += 3;
-    DCK(cudaMemcpyAsync(out, d->d_fields, (size_t)n * sizeof(amb_fields), cudaMemcpyDeviceToHost, s));
+    rc = staged_d2h(d, out, d->d_fields, (size_t)n * sizeof(amb_fields), s);
+    if (rc != AMB_OK) return rc;
     DCK(cudaEventRecord(d->e1, s));
     DCK(cudaStreamSynchronize(s));
     float ms = 0.f;

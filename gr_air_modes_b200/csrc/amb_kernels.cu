@@ -557,155 +557,177 @@ __device__ __forceinline__ float stream_at(const float* in, long long n, int H, 
 
 
 // ---- exact stage ----------------------------------------------------------------------------------
-// One THREAD per candidate. Writes info = late | real<<8 | valid<<9 and avg at the shifted index.
-//
-// A thread streams once through the m2 samples its candidate depends on, in ascending order, keeping the last FL of
-// them in a register ring (the pulse matched filter), and feeds every bb into
-//   * acc   - the fp64 ascending sum of bb[c-L+1 .. c]: LITERALLY the canonical noise-floor window of the start c,
-//   * fw[x] - bb[c+x], x = 0 .. maxlate+fwd+1, kept in a per-thread column of shared memory (conflict-free: element
-//             x of thread t lives at x*blockDim+t) for the pulse tests, the late gate and the quiet zones,
-//   * head[k] - bb[c-L+1+k], k < maxlate: what leaves the window when the late gate shifts the start.
-// After a late shift the window of c+i is acc - head[..] + fw[..] when every addend's exponent lies within 19 of the
+// A warp takes G consecutive candidates (G = 32 / 16 / 8 by samples per chip) in two phases:
+//   gather    all 32 lanes copy every candidate's span of the recording - the L + maxlate + fwd + fl samples its
+//             verdict depends on - into that candidate's ROW of shared memory as m2 = |x|^2: 16-byte loads from
+//             even sample positions, neighbouring lanes read neighbouring addresses, 16 loads in flight per lane, so
+//             a group costs a handful of memory round trips whatever its size;
+//   evaluate  lane t owns candidate t and walks its row alone: pulse matched filter in place (row[i] <- bb), the fp64
+//             ascending sum of bb[c-L+1 .. c] = LITERALLY the canonical noise-floor window of the start c, then the
+//             pulse tests, the late gate and the quiet zones from the row. Rows have an odd stride, so 32 lanes
+//             walking 32 rows in step never collide on a bank. No shuffles, no votes: 32 candidates advance per warp
+//             instruction (the round-1 kernel spent a whole warp, ~560 instructions and five barriers on ONE
+//             candidate and was instruction-bound in dense traffic - profiles/r2_dense_sparse_before.txt).
+// After a late shift the window of c+i is acc - head + tail when every addend's exponent lies within 19 of the
 // others (then every partial sum of <= 1024 such floats is exact in fp64, 24+19+10 = 53 bits, so any association
-// gives the canonical bits); otherwise the window is summed again, literally ascending.
-// Neighbouring threads hold neighbouring candidates, so in dense traffic their spans overlap in L1; there are no
-// warp collectives: 32 candidates make progress per warp instruction (the previous revision spent a whole warp and
-// ~600 instructions with five dependent barriers on ONE candidate, which is what made dense traffic latency-bound).
-// SPC > 0: integer samples/chip geometry known at compile time (ring indices and loops fold); SPC == 0: run-time.
+// gives the canonical bits); otherwise that window is summed again, literally ascending.
+// Writes info = late | real<<8 | valid<<9 and avg at the shifted index.
+// SPC > 0: integer samples/chip geometry known at compile time (loops fold); SPC == 0: run-time values.
 template <int SPC, bool PMF>
-__global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a)
+__global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a, const int G, const int ROW)
 {
-    AMB_DYN_SMEM(float, ex_smem, 4);
+    AMB_DYN_SMEM(float, ex_smem, 16);
     const AmbParams& P = a.P;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int spc = SPC ? SPC : P.spc_i;
     const int L = 48 * spc, maxlate = SPC ? SPC : P.maxlate;
     const int po1 = SPC ? 2 * SPC : P.po1, po2 = SPC ? 7 * SPC : P.po2, po3 = SPC ? 9 * SPC : P.po3;
     const int qa0 = SPC ? 3 * SPC : P.qa0, qa1 = SPC ? 6 * SPC : P.qa1, qb0 = SPC ? 10 * SPC : P.qb0, qb1 = SPC ? 15 * SPC : P.qb1;
     const int fwd = SPC ? 15 * SPC + 2 : P.fwd;
-    constexpr int FLC = (PMF && SPC > 1) ? SPC : 1;          // compile-time ring length (1 = no ring)
+    constexpr int FLC = (PMF && SPC > 1) ? SPC : 1;          // compile-time filter length (1 = none / run-time)
     const int fl = PMF ? spc : 1;                            // pulse matched filter length
-    const int nf = maxlate + fwd + 2;                        // forward values kept
-    const int NB = L + nf - 1;                               // bb values streamed: bb[c-L+1 .. c+nf-1]
+    const int nf = maxlate + fwd + 2;                        // forward values: bb[c .. c+nf-1]
+    const int NB = L + nf - 1;                               // bb values per candidate: bb[c-L+1 .. c+nf-1]
     const int NM = NB + fl - 1;                              // m2 values behind them
-    const int T = blockDim.x;
-    float* fw = ex_smem + threadIdx.x;                       // fw[x * T]
-    float* head = fw + (size_t)nf * T;                       // head[k * T]
+    const int P2 = (NM + 2) / 2;                             // 16-byte pairs per row (rows start at an even sample)
+    float* rows = ex_smem + (size_t)warp * ((size_t)G * ROW + 64);
+    const float4** ptrs = reinterpret_cast<const float4**>(rows + (size_t)G * ROW);   // G span pointers (8 B each, <= 32)
     const unsigned int ncand = a.ctr->ncand;
     const float scale_p = P.scale_p, scale_a = P.scale_a;
-    for (unsigned int ci = blockIdx.x * T + threadIdx.x; ci < ncand; ci += gridDim.x * T) {
-        const int c = a.cand_j[ci];
+    const unsigned int ngroups = (ncand + G - 1) / G;
+    for (unsigned int grp = blockIdx.x * 4 + warp; grp < ngroups; grp += gridDim.x * 4) {
+        const unsigned int ci = grp * G + lane;
+        const bool valid = lane < G && ci < ncand;
+        const int c = valid ? a.cand_j[ci] : 0;
         const int b_m2 = c - L + 1 - (fl - 1);               // logical index of the first m2 sample
-        const float2* sp = seg_span(a.S, b_m2, NM);          // one segment (the common case) or nullptr
-        double acc = 0.0;
-        unsigned emax = 0u, emin = 255u;
-        auto m2_at = [&](int k) -> float {                    // m2 of logical sample b_m2 + k
-            if (sp) return canon_m2_of(__ldg(sp + k));
-            return canon_m2(a.S, b_m2 + k);
-        };
-        auto consume = [&](int i, float bb) {                 // bb = bb[c - L + 1 + i]
-            if (i < L + maxlate) {
-                const unsigned bits = __float_as_uint(bb) & 0x7fffffffu;
-                if (bits) { unsigned e = bits >> 23; e = e ? e : 1u; emax = max(emax, e); emin = min(emin, e); }
-            }
-            if (i < maxlate) head[(size_t)i * T] = bb;
-            if (i <= L - 1) acc += (double)bb;
-            if (i >= L - 1) fw[(size_t)(i - (L - 1)) * T] = bb;
-        };
-        if (FLC > 1) {
-            float ring[FLC];                                  // slot of m2 sample k: k % FLC
+        const int be = b_m2 & ~1;                            // even start (also for negative indices)
+        if (lane < G) {
+            const float2* sp = valid ? seg_span(a.S, be, 2 * P2) : nullptr;
+            ptrs[lane] = reinterpret_cast<const float4*>(sp);      // 16-byte aligned: segment bases are, `be` is even
+        }
+        __syncwarp();
+        // ---- gather: element e of the group = pair p of row q
+        const int total = G * P2;
+        for (int e0 = 0; e0 < total; e0 += 32 * 16) {
+            float4 v[16];
 #pragma unroll
-            for (int t = 0; t < FLC - 1; t++) ring[t] = m2_at(t);
-            ring[FLC - 1] = 0.f;
-            constexpr int U = FLC * ((8 + FLC - 1) / FLC);    // block of U outputs, a multiple of the ring length
-            for (int i0 = 0; i0 < NB; i0 += U) {
-                float mm[U];
-#pragma unroll
-                for (int u = 0; u < U; u++) mm[u] = (i0 + u < NB) ? m2_at(i0 + u + FLC - 1) : 0.f;   // independent loads
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    ring[(FLC - 1 + u) % FLC] = mm[u];
-                    double sum = 0.0;                          // ascending: oldest sample first
-#pragma unroll
-                    for (int t = 0; t < FLC; t++) sum += (double)ring[(u + t) % FLC];
-                    if (i0 + u < NB) consume(i0 + u, __fmul_rn((float)sum, scale_p));
+            for (int u = 0; u < 16; u++) {
+                const int e = e0 + 32 * u + lane;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e < total) {
+                    const int q = e / P2, p = e - q * P2;
+                    const float4* sp = ptrs[q];
+                    if (sp) v[u] = __ldg(sp + p);
                 }
             }
-        } else if (fl > 1) {                                  // run-time filter length: re-sum from (L1-resident) loads
-            for (int i = 0; i < NB; i++) {
-                double sum = 0.0;
-                for (int t = 0; t < fl; t++) sum += (double)m2_at(i + t);
-                consume(i, __fmul_rn((float)sum, scale_p));
-            }
-        } else {
-            for (int i0 = 0; i0 < NB; i0 += 8) {
-                float mm[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) mm[u] = (i0 + u < NB) ? m2_at(i0 + u) : 0.f;
-#pragma unroll
-                for (int u = 0; u < 8; u++) if (i0 + u < NB) consume(i0 + u, (PMF && SPC != 1) ? __fmul_rn((float)(double)mm[u], scale_p) : mm[u]);
-            }
-        }
-        auto in = [&](int x) -> float { return fw[(size_t)x * T]; };   // in[x] == reference in[i+x] at the candidate start
-        const float avg0 = __fmul_rn((float)acc, scale_a);
-        const float pulse_threshold = __fmul_rn(avg0, P.thr);                       // :173
-        const float in0 = in(0);
-        bool real = in0 > pulse_threshold;                                          // :174
-        if (real && (in(1) > in0)) real = false;                                    // :175
-        if (real && (in(po1) < pulse_threshold)) real = false;                      // :177
-        if (real && (in(po2) < pulse_threshold)) real = false;                      // :178
-        if (real && (in(po3) < pulse_threshold)) real = false;                      // :179
-        uint32_t info = 0;
-        float avg_fin = avg0;
-        if (real) {
-            auto corr = [&](int k) -> double {                                      // correlate_preamble :88-98 at c+k
-                double v = 0.0;
-                for (int t = 0; t < spc; t++) v += (double)in(k + t);
-                for (int t = 0; t < spc; t++) v += (double)in(k + 2 * spc + t);
-                for (int t = 0; t < spc; t++) v += (double)in(k + 7 * spc + t);
-                for (int t = 0; t < spc; t++) v += (double)in(k + 9 * spc + t);
-                return v;
-            };
-            int i = 0, how_late = 0;
-            bool late;
-            double now_corr = corr(0);
-            do {                                                                    // :184-192
-                const double late_corr = corr(i + 1);
-                late = late_corr > now_corr;
-                if (late) { i++; how_late++; now_corr = late_corr; }
-            } while (late && (SPC ? how_late < SPC : (float)how_late < P.spc_f));
-            if (i > 0) {
-                double w = 0.0;
-                if (emax < 255u && emax <= emin + 19u) {
-                    w = acc;
-                    for (int k = 1; k <= i; k++) w = (w - (double)head[(size_t)(k - 1) * T]) + (double)in(k);
-                } else {                                                            // literal ascending window of c+i
-                    const int j0 = c + i - L + 1;
-                    for (int t = 0; t < L; t++) {
-                        float bb;
-                        if (fl > 1) {
-                            double sum = 0.0;
-                            for (int u = 0; u < fl; u++) sum += (double)canon_m2(a.S, j0 + t - (fl - 1) + u);
-                            bb = __fmul_rn((float)sum, scale_p);
-                        } else {
-                            const float m = canon_m2(a.S, j0 + t);
-                            bb = (PMF && SPC != 1) ? __fmul_rn((float)(double)m, scale_p) : m;
-                        }
-                        w += (double)bb;
+            for (int u = 0; u < 16; u++) {
+                const int e = e0 + 32 * u + lane;
+                if (e < total) {
+                    const int q = e / P2, p = e - q * P2;
+                    float* r = rows + (size_t)q * ROW + 2 * p;
+                    if (ptrs[q]) {                            // else: filled below (span straddles a segment boundary)
+                        r[0] = __fadd_rn(__fmul_rn(v[u].x, v[u].x), __fmul_rn(v[u].y, v[u].y));
+                        r[1] = __fadd_rn(__fmul_rn(v[u].z, v[u].z), __fmul_rn(v[u].w, v[u].w));
                     }
                 }
-                avg_fin = __fmul_rn((float)w, scale_a);
             }
-            const float sum4 = __fadd_rn(__fadd_rn(__fadd_rn(in(i), in(i + po1)), in(i + po2)), in(i + po3));
-            const float avgpeak = (float)((double)sum4 / 4.0);                      // :198-201
-            const float space_threshold =
-                __fadd_rn(avg_fin, __fdiv_rn(__fsub_rn(avgpeak, avg_fin), P.thr));  // :203
-            bool viol = false;
-            for (int j = qa0; j <= qa1 && !viol; j++) viol = in(i + j) > space_threshold;   // :205-206
-            for (int j = qb0; j <= qb1 && !viol; j++) viol = in(i + j) > space_threshold;   // :207-208
-            info = (uint32_t)i | (1u << 8) | (!viol ? (1u << 9) : 0u);
         }
-        a.cand_info[ci] = info;
-        a.cand_avg[ci] = avg_fin;
+        __syncwarp();
+        // rows whose span is not inside one segment (first / last samples of a call): filled sample by sample
+        for (int q = 0; q < G; q++) {
+            const int bq = __shfl_sync(FULL, be, q);
+            const bool vq = __shfl_sync(FULL, valid ? 1 : 0, q) != 0;
+            if (vq && !ptrs[q]) {
+                float* r = rows + (size_t)q * ROW;
+                for (int k = lane; k < 2 * P2; k += 32) r[k] = canon_m2(a.S, bq + k);
+            }
+        }
+        __syncwarp();
+        // ---- evaluate: lane t, candidate t
+        if (valid) {
+            float* r = rows + (size_t)lane * ROW + (b_m2 - be);     // r[k] = m2[b_m2 + k]; becomes bb[c-L+1+k] in place
+            double acc = 0.0;
+            unsigned emax = 0u, emin = 255u;
+            auto consume = [&](int i, float bb) {             // bb = bb[c - L + 1 + i]
+                if (i < L + maxlate) {
+                    const unsigned bits = __float_as_uint(bb) & 0x7fffffffu;
+                    if (bits) { unsigned e = bits >> 23; e = e ? e : 1u; emax = max(emax, e); emin = min(emin, e); }
+                }
+                if (i <= L - 1) acc += (double)bb;
+            };
+            if (PMF && (FLC > 1 || (SPC == 0 && fl > 1))) {
+#pragma unroll 4
+                for (int i = 0; i < NB; i++) {
+                    double sum = 0.0;                          // ascending: oldest sample first
+                    if (FLC > 1) {
+#pragma unroll
+                        for (int t = 0; t < FLC; t++) sum += (double)r[i + t];
+                    } else {
+                        for (int t = 0; t < fl; t++) sum += (double)r[i + t];
+                    }
+                    const float bb = __fmul_rn((float)sum, scale_p);
+                    r[i] = bb;                                 // m2[i] is not needed again
+                    consume(i, bb);
+                }
+            } else {
+#pragma unroll 4
+                for (int i = 0; i < NB; i++) {
+                    const float bb = PMF ? __fmul_rn((float)(double)r[i], scale_p) : r[i];   // filter length 1: scale 1.0
+                    if (PMF) r[i] = bb;
+                    consume(i, bb);
+                }
+            }
+            const float* in = r + (L - 1);                    // in[x] == reference in[i+x] at the candidate start
+            const float avg0 = __fmul_rn((float)acc, scale_a);
+            const float pulse_threshold = __fmul_rn(avg0, P.thr);                       // :173
+            bool real = in[0] > pulse_threshold;                                        // :174
+            if (real && (in[1] > in[0])) real = false;                                  // :175
+            if (real && (in[po1] < pulse_threshold)) real = false;                      // :177
+            if (real && (in[po2] < pulse_threshold)) real = false;                      // :178
+            if (real && (in[po3] < pulse_threshold)) real = false;                      // :179
+            uint32_t info = 0;
+            float avg_fin = avg0;
+            if (real) {
+                auto corr = [&](int k) -> double {                                      // correlate_preamble :88-98 at c+k
+                    double v = 0.0;
+                    for (int t = 0; t < spc; t++) v += (double)in[k + t];
+                    for (int t = 0; t < spc; t++) v += (double)in[k + 2 * spc + t];
+                    for (int t = 0; t < spc; t++) v += (double)in[k + 7 * spc + t];
+                    for (int t = 0; t < spc; t++) v += (double)in[k + 9 * spc + t];
+                    return v;
+                };
+                int i = 0, how_late = 0;
+                bool late;
+                double now_corr = corr(0);
+                do {                                                                    // :184-192
+                    const double late_corr = corr(i + 1);
+                    late = late_corr > now_corr;
+                    if (late) { i++; how_late++; now_corr = late_corr; }
+                } while (late && (SPC ? how_late < SPC : (float)how_late < P.spc_f));
+                if (i > 0) {
+                    double w = 0.0;
+                    if (emax < 255u && emax <= emin + 19u) {
+                        w = acc;
+                        for (int k = 1; k <= i; k++) w = (w - (double)r[k - 1]) + (double)in[k];
+                    } else {                                                            // literal ascending window of c+i
+                        for (int t = 0; t < L; t++) w += (double)r[i + t];
+                    }
+                    avg_fin = __fmul_rn((float)w, scale_a);
+                }
+                const float sum4 = __fadd_rn(__fadd_rn(__fadd_rn(in[i], in[i + po1]), in[i + po2]), in[i + po3]);
+                const float avgpeak = (float)((double)sum4 / 4.0);                      // :198-201
+                const float space_threshold =
+                    __fadd_rn(avg_fin, __fdiv_rn(__fsub_rn(avgpeak, avg_fin), P.thr));  // :203
+                bool viol = false;
+                for (int j = qa0; j <= qa1 && !viol; j++) viol = in[i + j] > space_threshold;   // :205-206
+                for (int j = qb0; j <= qb1 && !viol; j++) viol = in[i + j] > space_threshold;   // :207-208
+                info = (uint32_t)i | (1u << 8) | (!viol ? (1u << 9) : 0u);
+            }
+            a.cand_info[ci] = info;
+            a.cand_avg[ci] = avg_fin;
+        }
+        __syncwarp();
     }
 }
 
@@ -762,17 +784,17 @@ __global__ void __launch_bounds__(128) amb_exact_streams_kernel(const AmbExactAr
 }
 
 template <int SPC>
-static cudaError_t launch_exact_t(const AmbExactArgs& a, int blocks, int threads, size_t smem, cudaStream_t s)
+static cudaError_t launch_exact_t(const AmbExactArgs& a, int blocks, int G, int ROW, size_t smem, cudaStream_t s)
 {
     cudaError_t e;
     if (a.P.use_pmf) {
         e = cudaFuncSetAttribute(amb_exact_kernel<SPC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        AMB_LAUNCH((amb_exact_kernel<SPC, true>), blocks, threads, smem, s, a);
+        AMB_LAUNCH((amb_exact_kernel<SPC, true>), blocks, 128, smem, s, a, G, ROW);
     } else {
         e = cudaFuncSetAttribute(amb_exact_kernel<SPC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        AMB_LAUNCH((amb_exact_kernel<SPC, false>), blocks, threads, smem, s, a);
+        AMB_LAUNCH((amb_exact_kernel<SPC, false>), blocks, 128, smem, s, a, G, ROW);
     }
     return cudaGetLastError();
 }
@@ -788,20 +810,23 @@ cudaError_t amb_launch_exact(const AmbExactArgs& a, int sm_count, cudaStream_t s
     const int k = P.spc_i;
     const bool integral = P.spc_f == (float)k && P.maxlate == k && P.po1 == 2 * k && P.po2 == 7 * k && P.po3 == 9 * k &&
                           P.qa0 == 3 * k && P.qa1 == 6 * k && P.qb0 == 10 * k && P.qb1 == 15 * k && P.fwd == 15 * k + 2;
-    const int rows = (P.maxlate + P.fwd + 2) + P.maxlate;                // fw + head, floats per thread
-    const int threads = rows * 128 * 4 <= 48 * 1024 ? 128 : 64;          // 174 rows at 20 Msps: 64 threads = 43.5 KiB
-    const size_t smem = (size_t)rows * threads * sizeof(float);
-    const int blocks = sm_count * (threads == 128 ? 8 : 10);
+    const int fl = P.use_pmf ? k : 1;
+    const int NM = P.L + (P.maxlate + P.fwd + 2) - 1 + fl - 1;
+    const int ROW = (2 * ((NM + 2) / 2)) | 1;                        // floats per row: whole 16-byte pairs, odd stride
+    const int G = ROW <= 160 ? 32 : ROW <= 340 ? 16 : 8;              // candidates per warp: <= ~21 KiB of rows per warp
+    const size_t smem = (size_t)4 * ((size_t)G * ROW + 64) * sizeof(float);
+    const int per_sm = smem <= 72 * 1024 ? 3 : 2;
+    const int blocks = sm_count * per_sm;
     if (integral) {
         switch (k) {
-            case 1: return launch_exact_t<1>(a, blocks, threads, smem, s);
-            case 2: return launch_exact_t<2>(a, blocks, threads, smem, s);
-            case 5: return launch_exact_t<5>(a, blocks, threads, smem, s);
-            case 10: return launch_exact_t<10>(a, blocks, threads, smem, s);
+            case 1: return launch_exact_t<1>(a, blocks, G, ROW, smem, s);
+            case 2: return launch_exact_t<2>(a, blocks, G, ROW, smem, s);
+            case 5: return launch_exact_t<5>(a, blocks, G, ROW, smem, s);
+            case 10: return launch_exact_t<10>(a, blocks, G, ROW, smem, s);
             default: break;
         }
     }
-    return launch_exact_t<0>(a, blocks, threads, smem, s);
+    return launch_exact_t<0>(a, blocks, G, ROW, smem, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1272,41 +1297,71 @@ __device__ __forceinline__ bool slice_packet_warp(float p0, float p2, float p7, 
     return passed;
 }
 
-// One warp per accepted preamble. Chip j of the packet is in[fin + int(j*spc)] - inavg[fin] (preamble_impl.cc:219-221);
-// every lane fetches the (at most) 2 x fl samples behind its own bit straight from global memory - neighbouring
-// lanes read neighbouring samples - and nothing is staged in shared memory, so a warp has all of its loads in flight
-// at once and 16 CTAs fit on an SM. The frame slot is frame_base + position in the work list (no atomics).
+// One warp per accepted preamble. Chip j of the packet is in[fin + int(j*spc)] - inavg[fin] (preamble_impl.cc:219-221).
+// The packet's span of the recording (240*spc + fl samples) is copied into shared memory as m2 by ONE batch of
+// 16-byte loads per lane; the work-list entry and candidate record of the NEXT packet are fetched while the current
+// one is sliced, so a packet costs one memory round trip. The frame slot is frame_base + position in the work list
+// (no atomics), bits are sliced straight from the staged samples (no chip array unless the caller asked for chips).
 template <bool STREAMS>
-__global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
+__global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a, const int spanp)
 {
     __shared__ unsigned int s_crc[96];
+    AMB_DYN_SMEM(float, sl_smem, 16);                        // per warp: m2 of the packet span (not in STREAMS mode)
     if (threadIdx.x < 96) s_crc[threadIdx.x] = c_crc_rem[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const AmbParams& P = a.P;
     const unsigned int ndet = a.ctr->ndet_list;                // accepted preambles of this call (any order)
     const unsigned int base = a.ctr->frame_base;               // frames queued before this call
-    const int nwarps = gridDim.x * 4;
+    const unsigned int nwarps = gridDim.x * 4;
     const int fl = P.use_pmf ? P.spc_i : 1;
     const int span = chip_off(239, P.spc_f) + fl;              // m2 samples a packet touches
+    float* m2s = sl_smem + (size_t)warp * spanp;
     unsigned int npassed = 0;
-    for (unsigned int di = blockIdx.x * 4 + warp; di < ndet; di += nwarps) {
-        const int ci = a.det_list[di];
-        const uint32_t info = a.cand_info[ci];
-        const int fin = a.cand_j[ci] + (int)(info & 0xffu);
-        const float avg_fin = a.cand_avg[ci];
+    unsigned int di = blockIdx.x * 4 + warp;
+    int n_j = 0; uint32_t n_info = 0; float n_avg = 0.f;       // record of the packet about to be processed
+    if (di < ndet) { const int ci = a.det_list[di]; n_j = a.cand_j[ci]; n_info = a.cand_info[ci]; n_avg = a.cand_avg[ci]; }
+    for (; di < ndet; di += nwarps) {
+        const int fin = n_j + (int)(n_info & 0xffu);
+        const float avg_fin = n_avg;
+        if (di + nwarps < ndet) {                              // prefetch the next record (independent of the work below)
+            const int ci = a.det_list[di + nwarps]; n_j = a.cand_j[ci]; n_info = a.cand_info[ci]; n_avg = a.cand_avg[ci];
+        }
         const int b0 = fin - fl + 1;                           // m2 index behind chip offset 0
-        const float2* src = STREAMS ? nullptr : seg_span(a.S, b0, span);   // warp-uniform; nullptr: straddles a segment boundary
+        const int be = b0 & ~1;                                // even start: 16-byte loads
+        const int sh = b0 - be;
+        if (!STREAMS) {
+            const int pairs = (span + sh + 1) / 2;
+            const float4* src = reinterpret_cast<const float4*>(seg_span(a.S, be, 2 * pairs));   // warp-uniform
+            if (src) {
+                for (int p0 = 0; p0 < pairs; p0 += 256) {      // 8 independent loads in flight per lane
+                    float4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { const int p = p0 + 32 * u + lane; v[u] = p < pairs ? __ldg(src + p) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int p = p0 + 32 * u + lane;
+                        if (p < pairs) {
+                            m2s[2 * p] = __fadd_rn(__fmul_rn(v[u].x, v[u].x), __fmul_rn(v[u].y, v[u].y));
+                            m2s[2 * p + 1] = __fadd_rn(__fmul_rn(v[u].z, v[u].z), __fmul_rn(v[u].w, v[u].w));
+                        }
+                    }
+                }
+            } else {
+                for (int i = lane; i < 2 * pairs; i += 32) m2s[i] = canon_m2(a.S, be + i);   // straddles a segment boundary
+            }
+            __syncwarp();
+        }
         auto chip = [&](int j) -> float {
             const int o = chip_off(j, P.spc_f);
             if (STREAMS) return __fsub_rn(stream_at(a.in0, a.n_streams, P.H, (long long)fin + o), avg_fin);
             float bb;
             if (P.use_pmf) {                                   // bb[fin + o] = PMF over m2[fin+o-fl+1 .. fin+o]
                 double acc = 0.0;
-                for (int t = 0; t < fl; t++) acc += (double)(src ? canon_m2_of(__ldg(src + o + t)) : canon_m2(a.S, b0 + o + t));
+                for (int t = 0; t < fl; t++) acc += (double)m2s[sh + o + t];
                 bb = __fmul_rn((float)acc, P.scale_p);
             } else {
-                bb = src ? canon_m2_of(__ldg(src + o)) : canon_m2(a.S, b0 + o);
+                bb = m2s[sh + o];
             }
             return __fsub_rn(bb, avg_fin);
         };
@@ -1325,15 +1380,27 @@ __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a)
         } else if (lane == 0) {
             a.ctr->frame_overflow = 1;
         }
+        __syncwarp();
     }
     if (lane == 0 && npassed) atomicAdd(&a.ctr->npassed_call, npassed);
 }
 
 cudaError_t amb_launch_slice(const AmbSliceArgs& a, int sm_count, cudaStream_t s)
 {
-    const int blocks = sm_count * 16;
-    if (a.in0) AMB_LAUNCH((amb_slice_kernel<true>), blocks, 128, 0, s, a);
-    else AMB_LAUNCH((amb_slice_kernel<false>), blocks, 128, 0, s, a);
+    const int fl = a.P.use_pmf ? a.P.spc_i : 1;
+    const int spanp = ((int)(239 * a.P.spc_f) + fl + 3 + 31) & ~31;     // span + the alignment sample(s), rounded
+    const size_t smem = a.in0 ? 0 : (size_t)4 * spanp * sizeof(float);  // 38 KiB at 20 Msps, 8 KiB at 4 Msps
+    int per_sm = smem ? (int)((200 * 1024) / smem) : 16;
+    if (per_sm > 16) per_sm = 16;
+    if (per_sm < 1) per_sm = 1;
+    const int blocks = sm_count * per_sm;
+    cudaError_t e;
+    if (a.in0) { AMB_LAUNCH((amb_slice_kernel<true>), blocks, 128, smem, s, a, spanp); }
+    else {
+        e = cudaFuncSetAttribute(amb_slice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        AMB_LAUNCH((amb_slice_kernel<false>), blocks, 128, smem, s, a, spanp);
+    }
     return cudaGetLastError();
 }
 

@@ -40,7 +40,7 @@ def test_decode_matches_reference_golden(dec_mod):
     for ci, case in enumerate(load_decode_golden()):
         d = dec_mod.batch_decoder(case["location"])
         recs = _dicts(dec_mod, d.decode_messages([tuple(m) for m in case["msgs"]]))
-        assert d.stats()[0] == 3                       # three kernels per batch
+        assert d.stats()[0] == 7                       # fields + five pairing kernels (bucket partition) + resolve
         d.close()
         assert len(recs) == len(case["ref"])
         for k, (rec, ref) in enumerate(zip(recs, case["ref"])):
