@@ -598,6 +598,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-e2e-extras", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end legs (the line then has no e2e)")
     ap.add_argument("--time-shard", action="store_true",
                     help="secondary mode: ONE 2^log2n-sample recording cut into --gpus spans (strong scaling)")
     ap.add_argument("--chain", action="store_true", help="--time-shard: plain hand-over chain instead of speculative resolution")
@@ -649,7 +650,7 @@ def main():
         sampler.start()
     all_cpus = os.sched_getaffinity(0)
     head, iq, rx, q = run_config(key, n, args, rank, local_rank, world, device)
-    e2e, e2e_extras = e2e_legs(rx, q, iq, n, args, local_rank, world, device)
+    e2e, e2e_extras = (None, {}) if args.no_e2e else e2e_legs(rx, q, iq, n, args, local_rank, world, device)
     clocks = sampler.stop() if rank == 0 else None     # sampled across the headline's timed regions (device + end to end)
     os.sched_setaffinity(0, all_cpus)                  # the CPU legs below get every host thread back
     rx.close()

@@ -20,6 +20,12 @@
 #ifndef AMB_PROXY_FENCE
 #define AMB_PROXY_FENCE 0
 #endif
+// Register cap of the scan kernel. Four of its CTAs are resident per SM for the whole pass (one wave); at 112 registers
+// they leave 8 K registers (and ~60 KiB of shared memory) per SM free, which is what lets the sparse kernels of the
+// previous call (<= 128 threads x 64 registers, or 64 x 128) run UNDER the scan instead of after it.
+#ifndef AMB_SCAN_REGS
+#define AMB_SCAN_REGS 112
+#endif
 
 __constant__ unsigned int c_crc_rem[96]; // x^(t+24) mod 0xFFF409, t = distance of a message bit from the parity field
 
@@ -343,7 +349,7 @@ struct ScanWarp {
 };
 
 template <int SPC, bool PMF, int PREF>
-__global__ void __launch_bounds__(128) amb_scan_kernel(const __grid_constant__ AmbScanArgs a)
+__global__ void __maxnreg__(AMB_SCAN_REGS) amb_scan_kernel(const __grid_constant__ AmbScanArgs a)
 {
     using C = ScanCfg<SPC, PMF, PREF>;
     AMB_DYN_SMEM(unsigned char, smem, 1024);
@@ -574,7 +580,7 @@ __device__ __forceinline__ float stream_at(const float* in, long long n, int H, 
 // Writes info = late | real<<8 | valid<<9 and avg at the shifted index.
 // SPC > 0: integer samples/chip geometry known at compile time (loops fold); SPC == 0: run-time values.
 template <int SPC, bool PMF>
-__global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a, const int G, const int ROW)
+__global__ void __launch_bounds__(64) amb_exact_kernel(const AmbExactArgs a, const int G, const int ROW)
 {
     AMB_DYN_SMEM(float, ex_smem, 16);
     const AmbParams& P = a.P;
@@ -595,7 +601,7 @@ __global__ void __launch_bounds__(128) amb_exact_kernel(const AmbExactArgs a, co
     const unsigned int ncand = a.ctr->ncand;
     const float scale_p = P.scale_p, scale_a = P.scale_a;
     const unsigned int ngroups = (ncand + G - 1) / G;
-    for (unsigned int grp = blockIdx.x * 4 + warp; grp < ngroups; grp += gridDim.x * 4) {
+    for (unsigned int grp = blockIdx.x * 2 + warp; grp < ngroups; grp += gridDim.x * 2) {
         const unsigned int ci = grp * G + lane;
         const bool valid = lane < G && ci < ncand;
         const int c = valid ? a.cand_j[ci] : 0;
@@ -790,11 +796,11 @@ static cudaError_t launch_exact_t(const AmbExactArgs& a, int blocks, int G, int 
     if (a.P.use_pmf) {
         e = cudaFuncSetAttribute(amb_exact_kernel<SPC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        AMB_LAUNCH((amb_exact_kernel<SPC, true>), blocks, 128, smem, s, a, G, ROW);
+        AMB_LAUNCH((amb_exact_kernel<SPC, true>), blocks, 64, smem, s, a, G, ROW);
     } else {
         e = cudaFuncSetAttribute(amb_exact_kernel<SPC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        AMB_LAUNCH((amb_exact_kernel<SPC, false>), blocks, 128, smem, s, a, G, ROW);
+        AMB_LAUNCH((amb_exact_kernel<SPC, false>), blocks, 64, smem, s, a, G, ROW);
     }
     return cudaGetLastError();
 }
@@ -814,8 +820,11 @@ cudaError_t amb_launch_exact(const AmbExactArgs& a, int sm_count, cudaStream_t s
     const int NM = P.L + (P.maxlate + P.fwd + 2) - 1 + fl - 1;
     const int ROW = (2 * ((NM + 2) / 2)) | 1;                        // floats per row: whole 16-byte pairs, odd stride
     const int G = ROW <= 160 ? 32 : ROW <= 340 ? 16 : 8;              // candidates per warp: <= ~21 KiB of rows per warp
-    const size_t smem = (size_t)4 * ((size_t)G * ROW + 64) * sizeof(float);
-    const int per_sm = smem <= 72 * 1024 ? 3 : 2;
+    // two warps per CTA: <= 43 KiB of rows and <= 8 K registers, so that a CTA fits beside the four resident scan CTAs
+    const size_t smem = (size_t)2 * ((size_t)G * ROW + 64) * sizeof(float);
+    int per_sm = (int)((200 * 1024) / smem);
+    if (per_sm > 6) per_sm = 6;
+    if (per_sm < 1) per_sm = 1;
     const int blocks = sm_count * per_sm;
     if (integral) {
         switch (k) {
@@ -972,7 +981,7 @@ struct AmbParScratch {
 // Pass 1 keeps everything that would be a same-address atomic per packet or per cluster in registers and folds it
 // once per warp at the end (with 236 k packets and 224 k clusters per call in dense traffic those atomics WERE the
 // kernel: 0.3 ms at 9 % issue utilisation); the slicer's work list is built by pass 2 from the verdict bits.
-__global__ void __launch_bounds__(256) amb_walk_par1_kernel(const AmbWalkArgs a, AmbParScratch* sc, long long* first_fin,
+__global__ void __launch_bounds__(128) amb_walk_par1_kernel(const AmbWalkArgs a, AmbParScratch* sc, long long* first_fin,
                                                             unsigned long long* buckets, long long zone)
 {
     const AmbParams& P = a.P;
@@ -1140,7 +1149,7 @@ cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, unsigned in
     cudaError_t e;                                          // scratch header + buckets were zeroed by the prologue kernel
     const long long guard = (long long)a.P.maxlate + a.P.skip0 + 2 * a.P.spc_i + 8;
     const long long zone = a.flush ? (a.ntot - guard) : a.r_safe;
-    AMB_LAUNCH((amb_walk_par1_kernel), 296, 256, 0, s, a, sc, first_fin, buckets, zone);
+    AMB_LAUNCH((amb_walk_par1_kernel), 592, 128, 0, s, a, sc, first_fin, buckets, zone);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     AMB_LAUNCH((amb_walk_par2_kernel), 296, 256, 0, s, a, sc, first_fin, buckets);

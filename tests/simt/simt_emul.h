@@ -49,6 +49,7 @@ static unsigned long long simt_shuffle_state = [] { const char* e = getenv("SIMT
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __shared__ static
 #define AMB_SIMT_EMUL 1
 

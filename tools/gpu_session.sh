@@ -23,6 +23,13 @@ if has launches; then   # launch list of the bench command: shares of the step, 
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --no-parity --extra-configs none --no-e2e-extras > gpurun_out/bench_under_ncu.log 2>&1
   echo "launch list exit $?"
 fi
+if has launchcfg; then   # per-kernel durations of a device-resident step for each BASELINE config (serialised under ncu)
+  for c in c1 c2 c3 c4; do
+    timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$c.csv \
+        python bench.py --config $c --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-parity --extra-configs none > /dev/null 2>&1
+    python tools/launch_list.py gpurun_out/launches_$c.csv 9 > gpurun_out/launches_$c.txt 2>&1; tail -11 gpurun_out/launches_$c.txt
+  done
+fi
 if has scan; then       # one full capture of the dominant kernel per rate
   for r in 4 10 20; do
     timeout 300 $NCU_FULL -k regex:amb_scan -s 1 -c 1 -o gpurun_out/scan_${r}msps \
@@ -52,7 +59,6 @@ if has decode; then     # row f4: parity + timings of the batch decoder, then it
       --log-file gpurun_out/decode_launches.csv python tests/tools/prof_decode.py 16 20 > /dev/null 2>&1
 fi
 if has variants; then   # experiment builds (python tools/variants.py build on the CPU box first)
-  timeout 300 python tools/variants.py run-decode 16 20 > gpurun_out/variants_decode.log 2>&1; cat gpurun_out/variants_decode.log
-  timeout 300 python tools/variants.py run 28 20e6 > gpurun_out/variants_scan20.log 2>&1; cat gpurun_out/variants_scan20.log
+  for r in 4e6 10e6 20e6; do timeout 300 python tools/variants.py run 28 $r > gpurun_out/variants_scan_$r.log 2>&1; cat gpurun_out/variants_scan_$r.log; done
 fi
 echo "gpu_session done: $STAGES"

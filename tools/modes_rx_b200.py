@@ -55,6 +55,7 @@ def open_udp(ip, port, idle_s):
         pass
     sock.bind((ip, port))
     sock.settimeout(idle_s)
+    print("UDP receive buffer %d bytes" % sock.getsockopt(socket.SOL_SOCKET, socket.SO_RCVBUF), file=sys.stderr, flush=True)
     return sock
 
 

@@ -6,11 +6,8 @@ import os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "gr_air_modes_b200", "variants")
-VARIANTS = {"nst2": ["AMB_NST=2"], "nst3": ["AMB_NST=3"], "nst2_noeval": ["AMB_NST=2", "AMB_DBG_NOEVAL"], "nst2_loadonly": ["AMB_NST=2", "AMB_DBG_LOADONLY"],
-            # decoder experiment (row f4): pairing kernel with a key array + 8 steps in flight; time with tests/tools/prof_decode.py --check
-            "pair_v2": ["AMB_PAIR_V2"],
-            # ... and with a stable partition of the reports by owner bucket + one warp per bucket (O(n) traffic)
-            "pair_v3": ["AMB_PAIR_V3"]}
+VARIANTS = {"regs128": ["AMB_SCAN_REGS=128"], "regs112": ["AMB_SCAN_REGS=112"], "regs104": ["AMB_SCAN_REGS=104"], "regs96": ["AMB_SCAN_REGS=96"],
+            }
 if sys.argv[1] == "build":
     from gr_air_modes_b200 import build
     os.makedirs(VDIR, exist_ok=True)
