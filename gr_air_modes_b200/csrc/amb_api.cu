@@ -65,6 +65,7 @@ struct amb_ctx {
     unsigned ing_next = 0;               // slot the next chunk uses
     size_t pend_n = 0; int pend_kind = 0;  // samples gathered in ing[ing_next].pin, not dispatched yet
     int copy_threads = 0;                // 0 = default
+    int scan_ctas = 0;                   // CTAs of the scan kernel (0 = 4 per SM: one full wave)
     // non-blocking poll: counter snapshots of the calls in flight (pinned), frames already handed out
     AmbCounters* ctr_snap = nullptr; cudaEvent_t snap_ev[AMB_SNAPS] = {}; unsigned long long snap_head = 0, snap_tail = 0;
     unsigned polled = 0;                 // frames [0, polled) of the device frame buffer were returned by amb_poll_ready
@@ -398,6 +399,7 @@ int amb_set_option(amb_ctx* ctx, const char* name, int value)
         if (value < 1) return AMB_ERR_INVALID;
         ctx->coalesce = std::min((size_t)value, ctx->ing_chunk); return AMB_OK;
     }
+    if (!strcmp(name, "scan_ctas")) { if (value < 0 || value > 65536) return AMB_ERR_INVALID; ctx->scan_ctas = value; return AMB_OK; }
     if (!strcmp(name, "copy_threads")) { if (value < 0 || value > 64) return AMB_ERR_INVALID; ctx->copy_threads = value; return AMB_OK; }
     if (!strcmp(name, "ingest_chunk")) {                   // samples per chunk of the host ingest ring (multiple of 512)
         if (value < 4096 || (value & 511)) return AMB_ERR_INVALID;
@@ -575,7 +577,7 @@ static int process_core(amb_ctx* ctx, const float* iq, size_t n_complex, int mem
         a.row_lo = (int)(j_lo / AMB_ROW) & ~(AMB_SPAN_ROWS_ALIGN - 1);
         a.row_hi = (int)((j_hi + AMB_ROW - 1) / AMB_ROW);
         const int rows = a.row_hi - a.row_lo;
-        const int target = ctx->sm_count * 16;
+        const int target = (ctx->scan_ctas > 0 ? ctx->scan_ctas : ctx->sm_count * 4) * 4;    // one warp per span, 4 warps per CTA
         int rps = (rows + target - 1) / target;
         rps = (rps + AMB_SPAN_ROWS_ALIGN - 1) / AMB_SPAN_ROWS_ALIGN * AMB_SPAN_ROWS_ALIGN;
         if (rps < AMB_SPAN_ROWS_ALIGN) rps = AMB_SPAN_ROWS_ALIGN;

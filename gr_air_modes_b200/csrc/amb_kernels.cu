@@ -26,6 +26,9 @@
 #ifndef AMB_SCAN_REGS
 #define AMB_SCAN_REGS 112
 #endif
+// ... applied where it costs nothing (spc <= 2: no spills, same speed); the long filters keep all 128 registers
+// (capped at 112 the 20 Msps kernel runs 13 % slower - profiles/r2_scan_register_caps.txt).
+#define AMB_SCAN_REGS_FOR(SPC) ((SPC) <= 2 ? AMB_SCAN_REGS : 128)
 
 __constant__ unsigned int c_crc_rem[96]; // x^(t+24) mod 0xFFF409, t = distance of a message bit from the parity field
 
@@ -349,7 +352,7 @@ struct ScanWarp {
 };
 
 template <int SPC, bool PMF, int PREF>
-__global__ void __maxnreg__(AMB_SCAN_REGS) amb_scan_kernel(const __grid_constant__ AmbScanArgs a)
+__global__ void __maxnreg__(AMB_SCAN_REGS_FOR(SPC)) amb_scan_kernel(const __grid_constant__ AmbScanArgs a)
 {
     using C = ScanCfg<SPC, PMF, PREF>;
     AMB_DYN_SMEM(unsigned char, smem, 1024);
@@ -444,6 +447,10 @@ static cudaError_t launch_scan_t(const AmbScanArgs& a, cudaStream_t s)
 {
     const size_t smem = (size_t)ScanCfg<SPC, PMF, PREF>::CTA_BYTES;
     cudaError_t e = cudaFuncSetAttribute(amb_scan_kernel<SPC, PMF, PREF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // whole L1 as shared memory: the scan does not use L1 (TMA), and the ~60 KiB its four CTAs leave over are what the
+    // sparse kernels of the previous call need to be resident beside them (the split is only reconfigured on an idle SM)
+    e = cudaFuncSetAttribute(amb_scan_kernel<SPC, PMF, PREF>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
     const int blocks = (a.n_spans + 3) / 4;
     AMB_LAUNCH((amb_scan_kernel<SPC, PMF, PREF>), blocks, 128, smem, s, a);
@@ -566,7 +573,7 @@ __device__ __forceinline__ float stream_at(const float* in, long long n, int H, 
 // A warp takes G consecutive candidates (G = 32 / 16 / 8 by samples per chip) in two phases:
 //   gather    all 32 lanes copy every candidate's span of the recording - the L + maxlate + fwd + fl samples its
 //             verdict depends on - into that candidate's ROW of shared memory as m2 = |x|^2: 16-byte loads from
-//             even sample positions, neighbouring lanes read neighbouring addresses, 16 loads in flight per lane, so
+//             even sample positions, neighbouring lanes read neighbouring addresses, 8 loads in flight per lane (and up to 12 warps per SM), so
 //             a group costs a handful of memory round trips whatever its size;
 //   evaluate  lane t owns candidate t and walks its row alone: pulse matched filter in place (row[i] <- bb), the fp64
 //             ascending sum of bb[c-L+1 .. c] = LITERALLY the canonical noise-floor window of the start c, then the
@@ -612,68 +619,76 @@ __global__ void __launch_bounds__(64) amb_exact_kernel(const AmbExactArgs a, con
             ptrs[lane] = reinterpret_cast<const float4*>(sp);      // 16-byte aligned: segment bases are, `be` is even
         }
         __syncwarp();
-        // ---- gather: element e of the group = pair p of row q
+        // ---- gather: element e of the group = pair p of row q; a lane's elements are e = lane, lane + 32, ...
         const int total = G * P2;
-        for (int e0 = 0; e0 < total; e0 += 32 * 16) {
-            float4 v[16];
+        int gq = lane / P2, gp = lane - gq * P2;               // P2 >= 34: at most one row change per step of 32
+        for (int e0 = 0; e0 < total; e0 += 32 * 8) {
+            float4 v[8];
+            int q = gq, p = gp;
 #pragma unroll
-            for (int u = 0; u < 16; u++) {
-                const int e = e0 + 32 * u + lane;
+            for (int u = 0; u < 8; u++) {
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (e < total) {
-                    const int q = e / P2, p = e - q * P2;
+                if (e0 + 32 * u + lane < total) {
                     const float4* sp = ptrs[q];
                     if (sp) v[u] = __ldg(sp + p);
                 }
+                p += 32; if (p >= P2) { p -= P2; q++; }
             }
+            q = gq; p = gp;
 #pragma unroll
-            for (int u = 0; u < 16; u++) {
-                const int e = e0 + 32 * u + lane;
-                if (e < total) {
-                    const int q = e / P2, p = e - q * P2;
+            for (int u = 0; u < 8; u++) {
+                if (e0 + 32 * u + lane < total && ptrs[q]) {   // rows without a pointer are filled below
                     float* r = rows + (size_t)q * ROW + 2 * p;
-                    if (ptrs[q]) {                            // else: filled below (span straddles a segment boundary)
-                        r[0] = __fadd_rn(__fmul_rn(v[u].x, v[u].x), __fmul_rn(v[u].y, v[u].y));
-                        r[1] = __fadd_rn(__fmul_rn(v[u].z, v[u].z), __fmul_rn(v[u].w, v[u].w));
-                    }
+                    r[0] = __fadd_rn(__fmul_rn(v[u].x, v[u].x), __fmul_rn(v[u].y, v[u].y));
+                    r[1] = __fadd_rn(__fmul_rn(v[u].z, v[u].z), __fmul_rn(v[u].w, v[u].w));
                 }
+                p += 32; if (p >= P2) { p -= P2; q++; }
             }
+            gq = q; gp = p;
         }
         __syncwarp();
         // rows whose span is not inside one segment (first / last samples of a call): filled sample by sample
-        for (int q = 0; q < G; q++) {
+        for (unsigned todo = __ballot_sync(FULL, valid && lane < G && !ptrs[lane < G ? lane : 0]); todo; todo &= todo - 1) {
+            const int q = __ffs(todo) - 1;
             const int bq = __shfl_sync(FULL, be, q);
-            const bool vq = __shfl_sync(FULL, valid ? 1 : 0, q) != 0;
-            if (vq && !ptrs[q]) {
-                float* r = rows + (size_t)q * ROW;
-                for (int k = lane; k < 2 * P2; k += 32) r[k] = canon_m2(a.S, bq + k);
-            }
+            float* r = rows + (size_t)q * ROW;
+            for (int k = lane; k < 2 * P2; k += 32) r[k] = canon_m2(a.S, bq + k);
         }
         __syncwarp();
         // ---- evaluate: lane t, candidate t
         if (valid) {
             float* r = rows + (size_t)lane * ROW + (b_m2 - be);     // r[k] = m2[b_m2 + k]; becomes bb[c-L+1+k] in place
             double acc = 0.0;
-            unsigned emax = 0u, emin = 255u;
-            auto consume = [&](int i, float bb) {             // bb = bb[c - L + 1 + i]
-                if (i < L + maxlate) {
-                    const unsigned bits = __float_as_uint(bb) & 0x7fffffffu;
-                    if (bits) { unsigned e = bits >> 23; e = e ? e : 1u; emax = max(emax, e); emin = min(emin, e); }
-                }
-                if (i <= L - 1) acc += (double)bb;
+            float mx = 0.f, mn = 3.0e38f;                     // largest / smallest non-zero bb that can enter a window
+            auto consume = [&](int i, float bb) {             // bb = bb[c - L + 1 + i] (never negative)
+                if (i < L + maxlate) { mx = fmaxf(mx, bb); mn = bb > 0.f ? fminf(mn, bb) : mn; }
+                if (i < L) acc += (double)bb;
             };
-            if (PMF && (FLC > 1 || (SPC == 0 && fl > 1))) {
-#pragma unroll 4
-                for (int i = 0; i < NB; i++) {
-                    double sum = 0.0;                          // ascending: oldest sample first
-                    if (FLC > 1) {
+            if (FLC > 1) {
+                float w[FLC];                                  // the last FLC m2 values; slot of m2 sample k: k % FLC
 #pragma unroll
-                        for (int t = 0; t < FLC; t++) sum += (double)r[i + t];
-                    } else {
-                        for (int t = 0; t < fl; t++) sum += (double)r[i + t];
+                for (int t = 0; t < FLC - 1; t++) w[t] = r[t];
+                for (int i0 = 0; i0 < NB; i0 += FLC) {         // FLC outputs per round: ring positions are static
+#pragma unroll
+                    for (int u = 0; u < FLC; u++) {
+                        const int i = i0 + u;
+                        if (i < NB) {
+                            w[(u + FLC - 1) % FLC] = r[i + FLC - 1];
+                            double sum = 0.0;                  // ascending: oldest sample first
+#pragma unroll
+                            for (int t = 0; t < FLC; t++) sum += (double)w[(u + t) % FLC];
+                            const float bb = __fmul_rn((float)sum, scale_p);
+                            r[i] = bb;                         // m2[i] is not needed again
+                            consume(i, bb);
+                        }
                     }
+                }
+            } else if (PMF && fl > 1) {                       // run-time filter length
+                for (int i = 0; i < NB; i++) {
+                    double sum = 0.0;
+                    for (int t = 0; t < fl; t++) sum += (double)r[i + t];
                     const float bb = __fmul_rn((float)sum, scale_p);
-                    r[i] = bb;                                 // m2[i] is not needed again
+                    r[i] = bb;
                     consume(i, bb);
                 }
             } else {
@@ -684,6 +699,9 @@ __global__ void __launch_bounds__(64) amb_exact_kernel(const AmbExactArgs a, con
                     consume(i, bb);
                 }
             }
+            unsigned emax = __float_as_uint(mx) >> 23, emin = __float_as_uint(mn) >> 23;
+            emax = emax ? emax : 1u; emin = emin ? emin : 1u;  // denormals share the quantum of exponent field 1
+            if (mx == 0.f) { emax = 1u; emin = 1u; }           // all zero: trivially exact
             const float* in = r + (L - 1);                    // in[x] == reference in[i+x] at the candidate start
             const float avg0 = __fmul_rn((float)acc, scale_a);
             const float pulse_threshold = __fmul_rn(avg0, P.thr);                       // :173
@@ -795,10 +813,12 @@ static cudaError_t launch_exact_t(const AmbExactArgs& a, int blocks, int G, int 
     cudaError_t e;
     if (a.P.use_pmf) {
         e = cudaFuncSetAttribute(amb_exact_kernel<SPC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(amb_exact_kernel<SPC, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return e;
         AMB_LAUNCH((amb_exact_kernel<SPC, true>), blocks, 64, smem, s, a, G, ROW);
     } else {
         e = cudaFuncSetAttribute(amb_exact_kernel<SPC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(amb_exact_kernel<SPC, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return e;
         AMB_LAUNCH((amb_exact_kernel<SPC, false>), blocks, 64, smem, s, a, G, ROW);
     }
@@ -1407,6 +1427,7 @@ cudaError_t amb_launch_slice(const AmbSliceArgs& a, int sm_count, cudaStream_t s
     if (a.in0) { AMB_LAUNCH((amb_slice_kernel<true>), blocks, 128, smem, s, a, spanp); }
     else {
         e = cudaFuncSetAttribute(amb_slice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(amb_slice_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return e;
         AMB_LAUNCH((amb_slice_kernel<false>), blocks, 128, smem, s, a, spanp);
     }

@@ -143,6 +143,7 @@ struct CUtensorMap { alignas(64) unsigned long long opaque[16]; };
 #define __align__(n) __attribute__((aligned(n)))
 #define cudaGetLastError() (cudaSuccess)
 #define cudaFuncSetAttribute(...) (cudaSuccess)
+#define cudaFuncAttributePreferredSharedMemoryCarveout 0
 #define cudaMemcpyToSymbol(sym, src, n) (memcpy((void*)&(sym), (src), (n)), cudaSuccess)
 
 static unsigned char* simt_dyn_smem = nullptr;       // dynamic shared memory of the running block
