@@ -97,6 +97,7 @@ SYMBOLS = [
     ("amb_enable_timing", C.c_int, [_vp, C.c_int]),
     ("amb_get_stats", C.c_int, [_vp, C.POINTER(Stats)]),
     ("amb_get_scan_times", C.c_int, [_vp, _f32p, C.c_int]),
+    ("amb_get_timeline", C.c_int, [_vp, _f32p, C.c_int]),
     ("amb_synchronize", C.c_int, [_vp]),
     ("amb_join", C.c_int, [_vp]),
     ("amb_debug_candidates", C.c_int, [_vp, _u64p, C.POINTER(C.c_uint32), C.c_int]),

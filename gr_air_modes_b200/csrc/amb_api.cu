@@ -66,6 +66,7 @@ struct amb_ctx {
     size_t pend_n = 0; int pend_kind = 0;  // samples gathered in ing[ing_next].pin, not dispatched yet
     int copy_threads = 0;                // 0 = default
     int scan_ctas = 0;                   // CTAs of the scan kernel (0 = 4 per SM: one full wave)
+    unsigned exact_dense = 65536;        // candidates per call beyond which the row-based exact kernel takes over
     // non-blocking poll: counter snapshots of the calls in flight (pinned), frames already handed out
     AmbCounters* ctr_snap = nullptr; cudaEvent_t snap_ev[AMB_SNAPS] = {}; unsigned long long snap_head = 0, snap_tail = 0;
     unsigned polled = 0;                 // frames [0, polled) of the device frame buffer were returned by amb_poll_ready
@@ -94,6 +95,7 @@ struct amb_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
     cudaEvent_t ring[128] = {};          // 64 (start, stop) pairs around the scan kernel of the last calls
+    cudaEvent_t ring_done[64] = {};      // ... and the end of the same calls' sparse stages (stream B)
     unsigned ring_n = 0;
     int resolver = 0;
     // time-sharded operation (amb_seek / amb_resolve): a call whose walk + slice stages are still to run
@@ -279,6 +281,7 @@ int amb_create(int device, float rate, float threshold_db, int use_pmf, int use_
         if (rc != AMB_OK) break;
         for (int k = 0; k < 4; k++) if (cudaEventCreate(&ctx->ev[k]) != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
         for (int k = 0; k < 128 && rc == AMB_OK; k++) if (cudaEventCreate(&ctx->ring[k]) != cudaSuccess) rc = AMB_ERR_CUDA;
+        for (int k = 0; k < 64 && rc == AMB_OK; k++) if (cudaEventCreate(&ctx->ring_done[k]) != cudaSuccess) rc = AMB_ERR_CUDA;
         if (rc != AMB_OK) break;
         {   // driver entry point for tensor-map encoding (no link-time dependency on libcuda)
             void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
@@ -315,6 +318,7 @@ void amb_destroy(amb_ctx* ctx)
     if (ctx->stream_c) cudaStreamDestroy(ctx->stream_c);
     for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < 128; k++) if (ctx->ring[k]) cudaEventDestroy(ctx->ring[k]);
+    for (int k = 0; k < 64; k++) if (ctx->ring_done[k]) cudaEventDestroy(ctx->ring_done[k]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -399,6 +403,7 @@ int amb_set_option(amb_ctx* ctx, const char* name, int value)
         if (value < 1) return AMB_ERR_INVALID;
         ctx->coalesce = std::min((size_t)value, ctx->ing_chunk); return AMB_OK;
     }
+    if (!strcmp(name, "exact_dense")) { if (value < 0) return AMB_ERR_INVALID; ctx->exact_dense = (unsigned)value; return AMB_OK; }
     if (!strcmp(name, "scan_ctas")) { if (value < 0 || value > 65536) return AMB_ERR_INVALID; ctx->scan_ctas = value; return AMB_OK; }
     if (!strcmp(name, "copy_threads")) { if (value < 0 || value > 64) return AMB_ERR_INVALID; ctx->copy_threads = value; return AMB_OK; }
     if (!strcmp(name, "ingest_chunk")) {                   // samples per chunk of the host ingest ring (multiple of 512)
@@ -612,7 +617,9 @@ static int process_core(amb_ctx* ctx, const float* iq, size_t n_complex, int mem
                               (long long)S.n_carry + S.n_main + S.n_tail, sb));
         AmbExactArgs ea{};
         ea.P = P; ea.S = S; ea.cand_j = ctx->cand_j; ea.cand_info = ctx->cand_info; ea.cand_avg = ctx->cand_avg; ea.ctr = ctx->ctr;
+        ea.dense_threshold = ctx->exact_dense;
         CK(amb_launch_exact(ea, ctx->sm_count, sb));
+        ctx->stats.kernel_launches += 1;      // the exact stage is two launches (sparse / dense regime)
         wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info; wa.det_list = ctx->det_list;
         AmbSliceArgs sl{};
         sl.P = P; sl.S = S; sl.cand_j = ctx->cand_j; sl.cand_info = ctx->cand_info; sl.cand_avg = ctx->cand_avg;
@@ -664,7 +671,10 @@ static int process_core(amb_ctx* ctx, const float* iq, size_t n_complex, int mem
     }
     CK(cudaEventRecord(ctx->e_done[set], sb));
     ctx->done_valid[set] = true;
-    if (ctx->timing) CK(cudaEventRecord(ctx->ev[3], sb));
+    if (ctx->timing) {
+        CK(cudaEventRecord(ctx->ev[3], sb));
+        if (ctx->ev_valid) CK(cudaEventRecord(ctx->ring_done[(ctx->ring_n - 1) & 63u], sb));
+    }
     // ---- carry the tail of the stream into the next call (stream C, concurrently with this call's scan).
     // The buffer written here is the one the PREVIOUS call's scan and sparse kernels read as their carry.
     if (ctx->done_valid[set ^ 1]) CK(cudaStreamWaitEvent(sc, ctx->e_done[set ^ 1], 0));
@@ -1158,6 +1168,28 @@ int amb_get_scan_times(amb_ctx* ctx, float* ms_out, int max)
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, ctx->ring[(call & 63u) * 2], ctx->ring[(call & 63u) * 2 + 1]));
         ms_out[k] = ms;
+    }
+    return (int)n;
+}
+
+/* Per call, oldest first: [0] idle time of the scan stream in front of this call's scan (previous scan end -> this
+ * scan start), [1] the scan kernel, [2] scan end -> end of the call's sparse stages. Timing must be on. */
+int amb_get_timeline(amb_ctx* ctx, float* ms_out, int max_calls)
+{
+    if (!ctx || (!ms_out && max_calls > 0)) return AMB_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->pend_n) { int rc = ingest_dispatch_pending(ctx, 0); if (rc) return rc; }
+    CK(sync_all(ctx));
+    const unsigned have = ctx->ring_n < 63u ? ctx->ring_n : 63u;
+    const unsigned n = have < (unsigned)(max_calls > 0 ? max_calls : 0) ? have : (unsigned)(max_calls > 0 ? max_calls : 0);
+    for (unsigned k = 0; k < n; k++) {
+        const unsigned call = ctx->ring_n - n + k;
+        float gap = 0.f, sc = 0.f, tail = 0.f;
+        if (call > 0 && ctx->ring_n - (call - 1) <= 64u)
+            if (cudaEventElapsedTime(&gap, ctx->ring[((call - 1) & 63u) * 2 + 1], ctx->ring[(call & 63u) * 2]) != cudaSuccess) { gap = 0.f; cudaGetLastError(); }
+        CK(cudaEventElapsedTime(&sc, ctx->ring[(call & 63u) * 2], ctx->ring[(call & 63u) * 2 + 1]));
+        if (cudaEventElapsedTime(&tail, ctx->ring[(call & 63u) * 2 + 1], ctx->ring_done[call & 63u]) != cudaSuccess) { tail = 0.f; cudaGetLastError(); }
+        ms_out[3 * k] = gap; ms_out[3 * k + 1] = sc; ms_out[3 * k + 2] = tail;
     }
     return (int)n;
 }

@@ -82,6 +82,7 @@ struct AmbExactArgs {
     AmbParams P; AmbSegs S;
     const int* cand_j; uint32_t* cand_info; float* cand_avg;
     const AmbCounters* ctr;
+    unsigned int dense_threshold;   // candidates per call beyond which the row-based kernel decides instead of the warp-per-candidate one
     // split-form (float streams instead of IQ): if in0 != nullptr the exact stage reads these
     const float* in0; const float* in1; long long n_streams;
 };

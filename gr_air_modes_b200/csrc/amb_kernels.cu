@@ -14,6 +14,9 @@
 #include "amb_internal.h"
 
 #define FULL 0xffffffffu
+#ifndef AMB_EXACT_DENSE
+#define AMB_EXACT_DENSE 65536u     // candidates per call beyond which the row-based exact kernel takes over
+#endif
 #ifndef AMB_NST
 #define AMB_NST 2
 #endif
@@ -606,6 +609,7 @@ __global__ void __launch_bounds__(64) amb_exact_kernel(const AmbExactArgs a, con
     float* rows = ex_smem + (size_t)warp * ((size_t)G * ROW + 64);
     const float4** ptrs = reinterpret_cast<const float4**>(rows + (size_t)G * ROW);   // G span pointers (8 B each, <= 32)
     const unsigned int ncand = a.ctr->ncand;
+    if (ncand <= a.dense_threshold) return;                  // sparse traffic: amb_exact_warp_kernel's regime
     const float scale_p = P.scale_p, scale_a = P.scale_a;
     const unsigned int ngroups = (ncand + G - 1) / G;
     for (unsigned int grp = blockIdx.x * 2 + warp; grp < ngroups; grp += gridDim.x * 2) {
@@ -755,6 +759,142 @@ __global__ void __launch_bounds__(64) amb_exact_kernel(const AmbExactArgs a, con
     }
 }
 
+// ---- exact stage, sparse traffic: one WARP per candidate (round-1 kernel) -----------------------------------------
+// With a few thousand candidates per call what counts is the latency of ONE candidate, not throughput: here the 32
+// lanes share a candidate's window sums (order-independent when every addend's exponent lies within 19 of the others,
+// else the literal ascending loop), so a candidate is decided in one memory round trip and ~10 us. It needs ~560 warp
+// instructions per candidate, though, which is what made dense traffic instruction-bound: beyond dense_threshold
+// candidates per call amb_exact_kernel (rows + one lane per candidate) takes over. Both kernels are launched; the one
+// whose regime it is not returns at once. Writes info = late | real<<8 | valid<<9 and avg at the shifted index.
+// SPC > 0: integer samples/chip geometry known at compile time (loops unroll, offsets fold); SPC == 0: run-time values.
+template <int SPC>
+__global__ void __launch_bounds__(128) amb_exact_warp_kernel(const AmbExactArgs a)
+{
+    AMB_DYN_SMEM(float, ex_smem, 4);                 // per warp: m2s[NMp] then bbs[NMp], sized by the launcher
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const AmbParams& P = a.P;
+    const int spc = SPC ? SPC : P.spc_i;
+    const int L = 48 * spc, maxlate = SPC ? SPC : P.maxlate;
+    const int po1 = SPC ? 2 * SPC : P.po1, po2 = SPC ? 7 * SPC : P.po2, po3 = SPC ? 9 * SPC : P.po3;
+    const int qa0 = SPC ? 3 * SPC : P.qa0, qa1 = SPC ? 6 * SPC : P.qa1, qb0 = SPC ? 10 * SPC : P.qb0, qb1 = SPC ? 15 * SPC : P.qb1;
+    const int fwd = SPC ? 15 * SPC + 2 : P.fwd;
+    const int fl = P.use_pmf ? spc : 1;
+    const int NB = L + maxlate + fwd + 1;
+    const int NM = NB + fl - 1;
+    const int NMp = (NM + 31) & ~31;
+    float* m2s = ex_smem + (size_t)warp * 2 * NMp;
+    float* bbs = m2s + NMp;
+    const int c0off = L - 1;                        // bbs index of the candidate start
+    const unsigned int ncand = a.ctr->ncand;
+    if (ncand > a.dense_threshold) return;
+    const int nwarps = gridDim.x * 4;
+    for (unsigned int ci = blockIdx.x * 4 + warp; ci < ncand; ci += nwarps) {
+        const int c = a.cand_j[ci];
+        float avgk = 0.f;
+        {
+            const int b_bb = c - L + 1;               // bbs[i] <-> bb[b_bb + i]
+            const int b_m2 = b_bb - (fl - 1);
+            const float2* span = seg_span(a.S, b_m2, NM);     // warp-uniform
+            if (span) {
+                for (int i0 = 0; i0 < NM; i0 += 256) {        // 8 independent loads in flight per lane
+                    float2 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; v[u] = i < NM ? span[i] : make_float2(0.f, 0.f); }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { const int i = i0 + 32 * u + lane; if (i < NM) m2s[i] = canon_m2_of(v[u]); }
+                }
+            } else {
+                for (int i = lane; i < NM; i += 32) m2s[i] = canon_m2(a.S, b_m2 + i);   // straddles a segment boundary
+            }
+            __syncwarp();
+            for (int i = lane; i < NB; i += 32) {
+                if (P.use_pmf) {
+                    double acc = 0.0;
+                    for (int t = 0; t < fl; t++) acc += (double)m2s[i + t];
+                    bbs[i] = __fmul_rn((float)acc, P.scale_p);
+                } else {
+                    bbs[i] = m2s[i];
+                }
+            }
+            __syncwarp();
+            // inavg at c+k, k <= maxlate: fp64 ascending sum of bb[c+k-L+1 .. c+k] (canonical definition).
+            // If every non-zero addend's exponent lies within 19 of the others, every partial sum of <= 1024 such
+            // floats is exactly representable in fp64 (24 + 19 + 10 = 53 bits), so ANY summation order - incl. a
+            // lane-parallel one and the sliding update - gives the canonical bits. Otherwise (huge dynamic range,
+            // Inf/NaN) fall back to the literal ascending loop.
+            unsigned emax = 0u, emin = 255u;
+            for (int i = lane; i < L + maxlate; i += 32) {
+                const unsigned bits = __float_as_uint(bbs[i]) & 0x7fffffffu;
+                if (bits) { unsigned e = bits >> 23; e = e ? e : 1u; emax = max(emax, e); emin = min(emin, e); }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                emax = max(emax, __shfl_xor_sync(FULL, emax, d));
+                emin = min(emin, __shfl_xor_sync(FULL, emin, d));
+            }
+            if (emax < 255u && emax <= emin + 19u) {
+                double part = 0.0;
+                for (int i = lane; i < L; i += 32) part += (double)bbs[i];
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
+                double w = part;                                  // window of k = 0, identical in all lanes
+                if (lane == 0) avgk = __fmul_rn((float)w, P.scale_a);
+                for (int k = 1; k <= maxlate; k++) {
+                    w = (w - (double)bbs[k - 1]) + (double)bbs[k + L - 1];
+                    if (lane == k) avgk = __fmul_rn((float)w, P.scale_a);
+                }
+            } else if (lane <= maxlate) {
+                double acc = 0.0;
+                for (int t = 0; t < L; t++) acc += (double)bbs[lane + t];
+                avgk = __fmul_rn((float)acc, P.scale_a);
+            }
+        }
+        // correlate_preamble (preamble_impl.cc:88-98) at c+k, k = lane-16 in [0, maxlate+1]
+        double corrk = 0.0;
+        if (lane >= 16 && lane - 16 <= maxlate + 1) {
+            const float* q = bbs + c0off + (lane - 16);
+            for (int t = 0; t < spc; t++) corrk += (double)q[t];
+            for (int t = 0; t < spc; t++) corrk += (double)q[2 * spc + t];
+            for (int t = 0; t < spc; t++) corrk += (double)q[7 * spc + t];
+            for (int t = 0; t < spc; t++) corrk += (double)q[9 * spc + t];
+        }
+        const float* in = bbs + c0off;                // in[x] == reference in[i+x] at the candidate start
+        const float avg0 = __shfl_sync(FULL, avgk, 0);
+        const float pulse_threshold = __fmul_rn(avg0, P.thr);                       // :173
+        bool real = in[0] > pulse_threshold;                                        // :174
+        if (real && (in[1] > in[0])) real = false;                                  // :175
+        if (real && (in[po1] < pulse_threshold)) real = false;                    // :177
+        if (real && (in[po2] < pulse_threshold)) real = false;                    // :178
+        if (real && (in[po3] < pulse_threshold)) real = false;                    // :179
+        uint32_t info = 0;
+        float avg_fin = avg0;
+        if (real) {
+            int i = 0, how_late = 0;
+            bool late;
+            do {                                                                    // :184-192
+                const double now_corr = __shfl_sync(FULL, corrk, 16 + i);
+                const double late_corr = __shfl_sync(FULL, corrk, 16 + i + 1);
+                late = late_corr > now_corr;
+                if (late) { i++; how_late++; }
+            } while (late && (SPC ? how_late < SPC : (float)how_late < P.spc_f));
+            avg_fin = __shfl_sync(FULL, avgk, i);
+            const float* s = in + i;
+            const float sum4 = __fadd_rn(__fadd_rn(__fadd_rn(s[0], s[po1]), s[po2]), s[po3]);
+            const float avgpeak = (float)((double)sum4 / 4.0);                      // :198-201
+            const float space_threshold =
+                __fadd_rn(avg_fin, __fdiv_rn(__fsub_rn(avgpeak, avg_fin), P.thr));  // :203
+            bool viol = false;
+            for (int j = qa0 + lane; j <= qa1; j += 32) viol |= (s[j] > space_threshold);  // :205-206
+            for (int j = qb0 + lane; j <= qb1; j += 32) viol |= (s[j] > space_threshold);  // :207-208
+            const bool valid = !__any_sync(FULL, viol);
+            info = (uint32_t)i | (1u << 8) | (valid ? (1u << 9) : 0u);
+        }
+        if (lane == 0) { a.cand_info[ci] = info; a.cand_avg[ci] = avg_fin; }
+        __syncwarp();
+    }
+}
+
+
 // Split form (caller-supplied float streams): same decisions, in0/in1 play bb/avg; one thread per candidate.
 __global__ void __launch_bounds__(128) amb_exact_streams_kernel(const AmbExactArgs a)
 {
@@ -846,16 +986,28 @@ cudaError_t amb_launch_exact(const AmbExactArgs& a, int sm_count, cudaStream_t s
     if (per_sm > 6) per_sm = 6;
     if (per_sm < 1) per_sm = 1;
     const int blocks = sm_count * per_sm;
+    // the warp-per-candidate kernel (sparse traffic): per warp m2s[NMp] + bbs[NMp]
+    const int NBw = P.L + P.maxlate + P.fwd + 1;
+    const int NMpw = (NBw + fl - 1 + 31) & ~31;
+    const size_t smem_w = (size_t)4 * 2 * NMpw * sizeof(float);          // <= 22 KiB at 20 Msps, ~1.3 KiB at 4 Msps
+    const int blocks_w = sm_count * 12;
+    cudaError_t e;
+#define AMB_EXACT_BOTH(N)                                                                         \
+    AMB_LAUNCH((amb_exact_warp_kernel<N>), blocks_w, 128, smem_w, s, a);                          \
+    e = cudaGetLastError();                                                                       \
+    if (e != cudaSuccess) return e;                                                               \
+    return launch_exact_t<N>(a, blocks, G, ROW, smem, s);
     if (integral) {
         switch (k) {
-            case 1: return launch_exact_t<1>(a, blocks, G, ROW, smem, s);
-            case 2: return launch_exact_t<2>(a, blocks, G, ROW, smem, s);
-            case 5: return launch_exact_t<5>(a, blocks, G, ROW, smem, s);
-            case 10: return launch_exact_t<10>(a, blocks, G, ROW, smem, s);
+            case 1: { AMB_EXACT_BOTH(1) }
+            case 2: { AMB_EXACT_BOTH(2) }
+            case 5: { AMB_EXACT_BOTH(5) }
+            case 10: { AMB_EXACT_BOTH(10) }
             default: break;
         }
     }
-    return launch_exact_t<0>(a, blocks, G, ROW, smem, s);
+    { AMB_EXACT_BOTH(0) }
+#undef AMB_EXACT_BOTH
 }
 
 // ------------------------------------------------------------------------------------------------

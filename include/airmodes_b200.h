@@ -189,6 +189,10 @@ AMB_API int amb_get_stats(amb_ctx* ctx, amb_stats* out);       /* synchronises *
 /* Device time (ms) of the streaming scan kernel for the most recent calls made with timing on (oldest
  * first, at most 64). Returns how many were written. Synchronises. */
 AMB_API int amb_get_scan_times(amb_ctx* ctx, float* ms_out, int max);
+/* Timeline of the most recent calls made with timing on (oldest first, at most 63), three floats per call in ms:
+ * idle time of the scan stream in front of the call's scan, the scan kernel, and scan end -> end of the call's sparse
+ * stages (which run on a second stream under the next call's scan). Returns the number of calls. Synchronises. */
+AMB_API int amb_get_timeline(amb_ctx* ctx, float* ms_out, int max_calls);
 AMB_API int amb_synchronize(amb_ctx* ctx);
 /* amb_process returns with work pending on the caller-visible stream AND on an internal stream (the sparse
  * kernels of call k overlap the streaming pass of call k+1). amb_join makes the caller-visible stream wait for

@@ -155,6 +155,9 @@ extern "C" int emul_process_iq(const float* iq, int n, const float* bb, const fl
     if (amb_launch_compact(a, cand_j.data(), cand_cap, &ctr, par ? walk_scratch.data() : nullptr, n_samples, s) != cudaSuccess) return -3;
     AmbExactArgs ea{};
     ea.P = P; ea.S = S; ea.cand_j = cand_j.data(); ea.cand_info = cand_info.data(); ea.cand_avg = cand_avg.data(); ea.ctr = &ctr;
+    // both regimes of the exact stage are exercised: the row-based kernel (threshold 0) unless the test asks for the
+    // warp-per-candidate one (AMB_TEST_EXACT_DENSE = a large number)
+    { const char* t = getenv("AMB_TEST_EXACT_DENSE"); ea.dense_threshold = t ? (unsigned)strtoul(t, nullptr, 10) : 0u; }
     if (amb_launch_exact(ea, sm_count, s) != cudaSuccess) return -4;
     AmbWalkArgs wa{};
     wa.P = P; wa.org = org; wa.ntot = ntot; wa.r_safe = 0; wa.flush = 1; wa.ctr = &ctr; wa.st = &st;

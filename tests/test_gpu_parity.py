@@ -27,10 +27,12 @@ def device_resident(iq):
     return torch.from_numpy(np.ascontiguousarray(iq, dtype=np.float32)).cuda()
 
 
-def run_cuda(iq, rate, thr, pmf, chunks=None, resolver=0, keep=False, one_pass=False):
+def run_cuda(iq, rate, thr, pmf, chunks=None, resolver=0, keep=False, one_pass=False, exact_dense=None):
     q = am.msg_queue()
     rx = am.rx_path(rate, thr, q, use_pmf=pmf)
     rx._ctx.call("amb_set_option", b"resolver", resolver)
+    if exact_dense is not None:        # 0: the row-based exact kernel decides every call (dense-traffic regime)
+        rx.set_option("exact_dense", exact_dense)
     frames = []
     if one_pass:
         d = device_resident(iq)
@@ -79,9 +81,11 @@ def test_frames_bit_exact_vs_oracle(port, rate, n, nb, pmf, thr, seed):
         assert bytes(f.data) == bytes(g.data) and f.crc == g.crc and f.nbits == g.nbits
         assert f.numlowconf == g.numlowconf and bytes(f.lowconfbits) == bytes(g.lowconfbits)
         assert f.passed == g.passed and f.ref_level == g.ref_level and f.secs == g.secs and f.frac == g.frac
-    # both resolvers agree
+    # both resolvers agree, and so do both kernels of the exact stage (row-based for dense traffic forced here)
     msgs1, _, _ = run_cuda(sc.iq, rate, thr, pmf, resolver=1)
     assert msgs1 == want.msgs
+    msgs2, frames2, _ = run_cuda(sc.iq, rate, thr, pmf, exact_dense=0)
+    assert msgs2 == want.msgs and [f.sample_index for f in frames2] == [int(x) for x in want.index]
 
 
 def test_golden_fixtures_from_unmodified_reference():
@@ -291,6 +295,8 @@ def test_dense_traffic_threshold_sweep_matches_reference(port):
     # streaming over the same dense scene
     want = port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL)
     msgs, _, _ = run_cuda(sc.iq, rate, 7.0, True, chunks=[123_457] * 40)
+    assert msgs == want.msgs
+    msgs, _, _ = run_cuda(sc.iq, rate, 7.0, True, chunks=[123_457] * 40, exact_dense=0)
     assert msgs == want.msgs
 
 

@@ -84,6 +84,12 @@ def test_fused_iq_chain_under_the_emulator_matches_the_oracle(emul, port, rate, 
     # (resolver, bitmap source): the REAL scan kernel (TMA tile copies with the 128-byte swizzle and mbarriers emulated,
     # kernel source unchanged) with the parallel resolver, and the stream-candidate stand-in with both resolvers
     for resolver, use_scan in ((2, True), (1, False), (2, False)):
+        # the exact stage has two kernels: rows + one lane per candidate (dense traffic; the harness default) and one
+        # warp per candidate (sparse traffic); the middle pass runs the latter
+        if resolver == 1:
+            os.environ["AMB_TEST_EXACT_DENSE"] = "1000000000"
+        else:
+            os.environ.pop("AMB_TEST_EXACT_DENSE", None)
         chips = np.zeros((md, 240), np.float32)
         idx = np.zeros(md, np.uint64)
         frames = (_lib.Frame * md)()

@@ -37,10 +37,12 @@ def emulated_library(tmp_path_factory):
         _lib.LIB_PATH, _lib._lib = saved
 
 
-def run(iq, rate, thr, pmf, chunks=None, resolver=0, dcblock=False):
+def run(iq, rate, thr, pmf, chunks=None, resolver=0, dcblock=False, exact_dense=None):
     q = am.msg_queue()
     rx = am.rx_path(rate, thr, q, use_pmf=pmf, use_dcblock=dcblock)
     rx._ctx.call("amb_set_option", b"resolver", resolver)
+    if exact_dense is not None:        # 0: every call is decided by the row-based exact kernel (dense-traffic regime)
+        rx.set_option("exact_dense", exact_dense)
     frames, pos, n = [], 0, iq.size // 2
     for c in (chunks or []) + [n]:
         c = int(min(c, n - pos))
@@ -67,7 +69,7 @@ def test_streaming_equals_one_shot_equals_oracle(port, rate, n, nb, pmf, thr):
     rng = np.random.default_rng(1)
     for resolver in (0, 1):
         chunks = [int(x) for x in rng.integers(1, n // 3, 3)] + [1, 511, 513]
-        msgs2, frames2, _ = run(sc.iq, rate, thr, pmf, chunks=chunks, resolver=resolver)
+        msgs2, frames2, _ = run(sc.iq, rate, thr, pmf, chunks=chunks, resolver=resolver, exact_dense=0 if resolver else None)
         assert msgs2 == want.msgs and [f.sample_index for f in frames2] == [int(x) for x in want.index], resolver
     for f, g in zip(frames, want.frames):
         assert bytes(f.data) == bytes(g.data) and f.ref_level == g.ref_level and f.crc == g.crc and f.numlowconf == g.numlowconf

@@ -13,7 +13,7 @@ dev = torch.device("cuda")
 iq, _ = bench.make_device_scene(cfg, n, 0, dev)
 torch.cuda.synchronize()
 sm = torch.cuda.get_device_properties(0).multi_processor_count
-for ctas in (4 * sm, 4 * sm - 4, 4 * sm - 8, 4 * sm - 16, 4 * sm - 32, 4 * sm - 64, 5 * sm):
+for ctas in (4 * sm,):
     q = am.msg_queue(); rx = am.rx_path(cfg["rate"], 7.0, q, use_pmf=True)
     rx.set_option("scan_ctas", ctas)
     rx._ctx.call("amb_enable_timing", 1)
@@ -29,6 +29,11 @@ for ctas in (4 * sm, 4 * sm - 4, 4 * sm - 8, 4 * sm - 16, 4 * sm - 32, 4 * sm - 
     rx.join(); e1.record(); torch.cuda.synchronize()
     b2b = e0.elapsed_time(e1) / K
     sc = float(np.mean(rx._ctx.scan_times_ms(K)))
+    import ctypes as C
+    buf = (C.c_float * (3 * 20))()
+    k = rx._ctx.call("amb_get_timeline", buf, 20)
+    tl = np.array(buf[:3 * k]).reshape(k, 3)[3:]
     nm = rx.drain()
+    print("   timeline (mean over calls): scan-stream idle before scan %.4f ms, scan %.4f ms, scan end -> sparse done %.4f ms" % tuple(tl.mean(0)))
     print("%s scan_ctas %4d: step %.4f ms (%.1f GS/s)  scan under overlap %.4f ms  msgs %d" % (key, ctas, b2b, n / b2b / 1e6, sc, nm))
     rx.close()
