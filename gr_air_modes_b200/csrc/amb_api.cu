@@ -288,6 +288,7 @@ int amb_create(int device, float rate, float threshold_db, int use_pmf, int use_
             if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) { rc = AMB_ERR_CUDA; break; }
             ctx->encode = (amb_encode_fn)fn;
         }
+        if (amb_prefer_max_shared() != cudaSuccess) { rc = AMB_ERR_CUDA; break; }
         rc = setup_rate(ctx);
         if (rc != AMB_OK) break;
         rc = reset_stream(ctx);

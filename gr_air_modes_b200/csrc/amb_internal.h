@@ -127,6 +127,7 @@ cudaError_t amb_launch_stream_candidates(const AmbScanArgs& a, const float* in0,
 cudaError_t amb_launch_slice_chips(const float* chips, int ndet, amb_frame* frames, cudaStream_t s);
 cudaError_t amb_launch_crc(const uint8_t* data, int n, int length, uint32_t* out, cudaStream_t s);
 cudaError_t amb_upload_tables(const int* chip_off);
+cudaError_t amb_prefer_max_shared();
 cudaError_t amb_launch_dcblock(const float2* rawcarry, int nc, const float2* fresh, long long n_new, int D,
                                float2* ma0_tmp, float2* out, float2* rawcarry_next, cudaStream_t s);
 cudaError_t amb_launch_prologue(float2* tail, int tail_cap, const float2* src_rem, int n_rem,

@@ -31,7 +31,10 @@
 #endif
 // ... applied where it costs nothing (spc <= 2: no spills, same speed); the long filters keep all 128 registers
 // (capped at 112 the 20 Msps kernel runs 13 % slower - profiles/r2_scan_register_caps.txt).
-#define AMB_SCAN_REGS_FOR(SPC) ((SPC) <= 2 ? AMB_SCAN_REGS : 128)
+#ifndef AMB_SCAN_REGS_HI
+#define AMB_SCAN_REGS_HI 120
+#endif
+#define AMB_SCAN_REGS_FOR(SPC) ((SPC) <= 2 ? AMB_SCAN_REGS : AMB_SCAN_REGS_HI)
 
 __constant__ unsigned int c_crc_rem[96]; // x^(t+24) mod 0xFFF409, t = distance of a message bit from the parity field
 
@@ -1153,7 +1156,7 @@ struct AmbParScratch {
 // Pass 1 keeps everything that would be a same-address atomic per packet or per cluster in registers and folds it
 // once per warp at the end (with 236 k packets and 224 k clusters per call in dense traffic those atomics WERE the
 // kernel: 0.3 ms at 9 % issue utilisation); the slicer's work list is built by pass 2 from the verdict bits.
-__global__ void __launch_bounds__(128) amb_walk_par1_kernel(const AmbWalkArgs a, AmbParScratch* sc, long long* first_fin,
+__global__ void __launch_bounds__(64) amb_walk_par1_kernel(const AmbWalkArgs a, AmbParScratch* sc, long long* first_fin,
                                                             unsigned long long* buckets, long long zone)
 {
     const AmbParams& P = a.P;
@@ -1231,10 +1234,10 @@ __global__ void __launch_bounds__(128) amb_walk_par1_kernel(const AmbWalkArgs a,
 
 // Pass 2: (a) the float-rounding check described above; (b) the slicer's work list = every candidate pass 1 accepted
 // (verdict bit 10), appended with one atomic per block and iteration.
-__global__ void __launch_bounds__(256) amb_walk_par2_kernel(const AmbWalkArgs a, AmbParScratch* sc, const long long* first_fin,
+__global__ void __launch_bounds__(128) amb_walk_par2_kernel(const AmbWalkArgs a, AmbParScratch* sc, const long long* first_fin,
                                                             const unsigned long long* buckets)
 {
-    __shared__ unsigned int s_cnt[8], s_base;
+    __shared__ unsigned int s_cnt[4], s_base;
     const AmbParams& P = a.P;
     const int n = (int)a.ctr->ncand;
     const int back = (int)(P.i_exact >> AMB_BUCKET_SHIFT) - 1;     // buckets wholly inside the exact range
@@ -1262,7 +1265,7 @@ __global__ void __launch_bounds__(256) amb_walk_par2_kernel(const AmbWalkArgs a,
         if (threadIdx.x == 0) {
             unsigned int tot = 0;
 #pragma unroll
-            for (int w = 0; w < 8; w++) { const unsigned int v = s_cnt[w]; s_cnt[w] = tot; tot += v; }
+            for (int w = 0; w < 4; w++) { const unsigned int v = s_cnt[w]; s_cnt[w] = tot; tot += v; }
             s_base = tot ? atomicAdd(&a.ctr->ndet_list, tot) : 0u;
         }
         __syncthreads();
@@ -1321,10 +1324,10 @@ cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, unsigned in
     cudaError_t e;                                          // scratch header + buckets were zeroed by the prologue kernel
     const long long guard = (long long)a.P.maxlate + a.P.skip0 + 2 * a.P.spc_i + 8;
     const long long zone = a.flush ? (a.ntot - guard) : a.r_safe;
-    AMB_LAUNCH((amb_walk_par1_kernel), 592, 128, 0, s, a, sc, first_fin, buckets, zone);
+    AMB_LAUNCH((amb_walk_par1_kernel), 1184, 64, 0, s, a, sc, first_fin, buckets, zone);    // <= 4 K registers per CTA
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    AMB_LAUNCH((amb_walk_par2_kernel), 296, 256, 0, s, a, sc, first_fin, buckets);
+    AMB_LAUNCH((amb_walk_par2_kernel), 592, 128, 0, s, a, sc, first_fin, buckets);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     AMB_LAUNCH((amb_walk_finalize_kernel), 1, 32, 0, s, a, sc);
@@ -1484,7 +1487,7 @@ __device__ __forceinline__ bool slice_packet_warp(float p0, float p2, float p7, 
 // one is sliced, so a packet costs one memory round trip. The frame slot is frame_base + position in the work list
 // (no atomics), bits are sliced straight from the staged samples (no chip array unless the caller asked for chips).
 template <bool STREAMS>
-__global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a, const int spanp)
+__global__ void __launch_bounds__(64) amb_slice_kernel(const AmbSliceArgs a, const int spanp)
 {
     __shared__ unsigned int s_crc[96];
     AMB_DYN_SMEM(float, sl_smem, 16);                        // per warp: m2 of the packet span (not in STREAMS mode)
@@ -1494,12 +1497,12 @@ __global__ void __launch_bounds__(128) amb_slice_kernel(const AmbSliceArgs a, co
     const AmbParams& P = a.P;
     const unsigned int ndet = a.ctr->ndet_list;                // accepted preambles of this call (any order)
     const unsigned int base = a.ctr->frame_base;               // frames queued before this call
-    const unsigned int nwarps = gridDim.x * 4;
+    const unsigned int nwarps = gridDim.x * 2;
     const int fl = P.use_pmf ? P.spc_i : 1;
     const int span = chip_off(239, P.spc_f) + fl;              // m2 samples a packet touches
     float* m2s = sl_smem + (size_t)warp * spanp;
     unsigned int npassed = 0;
-    unsigned int di = blockIdx.x * 4 + warp;
+    unsigned int di = blockIdx.x * 2 + warp;
     int n_j = 0; uint32_t n_info = 0; float n_avg = 0.f;       // record of the packet about to be processed
     if (di < ndet) { const int ci = a.det_list[di]; n_j = a.cand_j[ci]; n_info = a.cand_info[ci]; n_avg = a.cand_avg[ci]; }
     for (; di < ndet; di += nwarps) {
@@ -1570,18 +1573,18 @@ cudaError_t amb_launch_slice(const AmbSliceArgs& a, int sm_count, cudaStream_t s
 {
     const int fl = a.P.use_pmf ? a.P.spc_i : 1;
     const int spanp = ((int)(239 * a.P.spc_f) + fl + 3 + 31) & ~31;     // span + the alignment sample(s), rounded
-    const size_t smem = a.in0 ? 0 : (size_t)4 * spanp * sizeof(float);  // 38 KiB at 20 Msps, 8 KiB at 4 Msps
-    int per_sm = smem ? (int)((200 * 1024) / smem) : 16;
-    if (per_sm > 16) per_sm = 16;
+    const size_t smem = a.in0 ? 0 : (size_t)2 * spanp * sizeof(float);  // two warps per CTA (<= 4 K registers): 19 KiB at 20 Msps, 4 KiB at 4 Msps
+    int per_sm = smem ? (int)((200 * 1024) / smem) : 32;
+    if (per_sm > 32) per_sm = 32;
     if (per_sm < 1) per_sm = 1;
     const int blocks = sm_count * per_sm;
     cudaError_t e;
-    if (a.in0) { AMB_LAUNCH((amb_slice_kernel<true>), blocks, 128, smem, s, a, spanp); }
+    if (a.in0) { AMB_LAUNCH((amb_slice_kernel<true>), blocks, 64, smem, s, a, spanp); }
     else {
         e = cudaFuncSetAttribute(amb_slice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(amb_slice_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return e;
-        AMB_LAUNCH((amb_slice_kernel<false>), blocks, 128, smem, s, a, spanp);
+        AMB_LAUNCH((amb_slice_kernel<false>), blocks, 64, smem, s, a, spanp);
     }
     return cudaGetLastError();
 }
@@ -1880,6 +1883,47 @@ cudaError_t amb_launch_dcblock(const float2* rawcarry, int nc, const float2* fre
     AmbSegs S; S.carry = rawcarry; S.main_ = fresh; S.tail = fresh; S.n_carry = nc; S.n_main = (int)n_new; S.n_tail = 0;
     S.n_valid = nc + (int)n_new;
     return amb_launch_carry(S, rawcarry_next, nc, s);
+}
+
+// Every kernel of the library asks for the same L1 / shared-memory split (all shared). An SM's split is only changed
+// while the SM is idle, so a kernel that prefers another split than the one the resident scan CTAs run with is NOT
+// co-scheduled with them - it waits for the scan to drain. With one common preference the sparse kernels of call k
+// really do run under the scan of call k+1.
+template <class K> static cudaError_t prefer_shared(K kernel)
+{
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
+template <int SPC> static cudaError_t prefer_shared_spc()
+{
+    cudaError_t e = prefer_shared(amb_exact_warp_kernel<SPC>);
+    if (e == cudaSuccess) e = prefer_shared(amb_exact_kernel<SPC, true>);
+    if (e == cudaSuccess) e = prefer_shared(amb_exact_kernel<SPC, false>);
+    return e;
+}
+cudaError_t amb_prefer_max_shared()
+{
+    cudaError_t e = prefer_shared(amb_compact_kernel);
+    if (e == cudaSuccess) e = prefer_shared_spc<0>();
+    if (e == cudaSuccess) e = prefer_shared_spc<1>();
+    if (e == cudaSuccess) e = prefer_shared_spc<2>();
+    if (e == cudaSuccess) e = prefer_shared_spc<5>();
+    if (e == cudaSuccess) e = prefer_shared_spc<10>();
+    if (e == cudaSuccess) e = prefer_shared(amb_exact_streams_kernel);
+    if (e == cudaSuccess) e = prefer_shared(amb_walk_seq_kernel);
+    if (e == cudaSuccess) e = prefer_shared(amb_walk_par1_kernel);
+    if (e == cudaSuccess) e = prefer_shared(amb_walk_par2_kernel);
+    if (e == cudaSuccess) e = prefer_shared(amb_walk_finalize_kernel);
+    if (e == cudaSuccess) e = prefer_shared(amb_walk_reset_kernel);
+    if (e == cudaSuccess) e = prefer_shared(amb_walk_summary_kernel);
+    if (e == cudaSuccess) e = prefer_shared(amb_set_state_kernel);
+    if (e == cudaSuccess) e = prefer_shared(amb_slice_kernel<false>);
+    if (e == cudaSuccess) e = prefer_shared(amb_slice_kernel<true>);
+    if (e == cudaSuccess) e = prefer_shared(amb_slice_chips_kernel);
+    if (e == cudaSuccess) e = prefer_shared(amb_carry_kernel);
+    if (e == cudaSuccess) e = prefer_shared(amb_prologue_kernel);
+    if (e == cudaSuccess) e = prefer_shared(amb_widen_sc16_kernel);
+    if (e == cudaSuccess) e = prefer_shared(amb_stream_cand_kernel);
+    return e;
 }
 
 cudaError_t amb_upload_tables(const int*)

@@ -6,7 +6,7 @@ import os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "gr_air_modes_b200", "variants")
-VARIANTS = {"regs128": ["AMB_SCAN_REGS=128"], "regs112": ["AMB_SCAN_REGS=112"], "regs104": ["AMB_SCAN_REGS=104"], "regs96": ["AMB_SCAN_REGS=96"],
+VARIANTS = {"hi128": ["AMB_SCAN_REGS_HI=128"], "hi120": ["AMB_SCAN_REGS_HI=120"], "hi112": ["AMB_SCAN_REGS_HI=112"],
             }
 if sys.argv[1] == "build":
     from gr_air_modes_b200 import build
@@ -25,6 +25,10 @@ else:
                 if not name.startswith("pair"): continue
                 out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "prof_decode.py"), "--check"] + sys.argv[2:], capture_output=True, text=True)
                 print(name, out.stdout.strip() if out.stdout.strip() else out.stderr[-300:])
+                continue
+            if sys.argv[1] == "run-holes":
+                out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "prof_holes.py")] + sys.argv[2:], capture_output=True, text=True)
+                print(name, "\n".join(out.stdout.strip().splitlines()[-2:]) if out.stdout.strip() else out.stderr[-300:])
                 continue
             out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "prof_time.py")] + sys.argv[2:], capture_output=True, text=True)
             print(name, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:])
