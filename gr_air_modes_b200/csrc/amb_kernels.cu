@@ -34,7 +34,10 @@
 #ifndef AMB_SCAN_REGS_HI
 #define AMB_SCAN_REGS_HI 120
 #endif
-#define AMB_SCAN_REGS_FOR(SPC) ((SPC) <= 2 ? AMB_SCAN_REGS : AMB_SCAN_REGS_HI)
+// spc 3..5: 120 registers leave 4 K registers (and 25 KiB of shared memory) for the sparse kernels: the 10 Msps step
+// drops from 0.40 to 0.36 ms although the scan alone is 1 % slower. spc >= 6: the prefix ring leaves too little shared
+// memory for anything to be resident beside the scan, so it keeps every register (profiles/r2_scan_register_caps.txt).
+#define AMB_SCAN_REGS_FOR(SPC) ((SPC) <= 2 ? AMB_SCAN_REGS : (SPC) <= 5 ? AMB_SCAN_REGS_HI : 128)
 
 __constant__ unsigned int c_crc_rem[96]; // x^(t+24) mod 0xFFF409, t = distance of a message bit from the parity field
 
@@ -1491,7 +1494,7 @@ __global__ void __launch_bounds__(64) amb_slice_kernel(const AmbSliceArgs a, con
 {
     __shared__ unsigned int s_crc[96];
     AMB_DYN_SMEM(float, sl_smem, 16);                        // per warp: m2 of the packet span (not in STREAMS mode)
-    if (threadIdx.x < 96) s_crc[threadIdx.x] = c_crc_rem[threadIdx.x];
+    for (int i = threadIdx.x; i < 96; i += blockDim.x) s_crc[i] = c_crc_rem[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const AmbParams& P = a.P;
