@@ -149,6 +149,7 @@ struct ScanWarp {
     float lastm[8];         // previous row's m2 of this lane (PMF look-back across the row boundary)
     uint32_t cw, cnt;
     int ra, rb;
+    int ppos;               // slot of the current row in the prefix ring = row index mod PRR
 
     // tile t = rows 2t, 2t+1 = 512 samples = 32 lines of 128 B. Three separate issues so that each uses a
     // compile-time descriptor address (a run-time selected pointer makes ptxas emit a uniformisation loop).
@@ -193,7 +194,23 @@ struct ScanWarp {
                 const float src = (lane > 31 - d) ? lastm[ridx] : m[ridx];
                 v[C::FL - 1 - t] = __shfl_sync(FULL, src, (lane - d) & 31);
             }
-            if (C::FL >= 4) {
+            if (C::FL >= 8) {
+                // the 8 windows v[r .. r+FL-1] share the core v[7 .. FL-1]; what differs is a suffix of v[0..6] and a
+                // prefix of v[FL .. FL+6]: FL + 18 all-positive adds instead of 4 FL + 8 (same error bound: <= FL roundings)
+                float core = v[7];
+#pragma unroll
+                for (int i = 8; i < C::FL; i++) core += v[i];
+                float lft[8], rgt[8];
+                lft[7] = 0.f; lft[6] = v[6];
+#pragma unroll
+                for (int i = 5; i >= 0; i--) lft[i] = v[i] + lft[i + 1];
+                rgt[0] = 0.f; rgt[1] = v[C::FL];
+#pragma unroll
+                for (int i = 2; i < 8; i++) rgt[i] = rgt[i - 1] + v[C::FL + i - 1];
+                b[0] = lft[0] + core; b[7] = core + rgt[7];
+#pragma unroll
+                for (int r = 1; r < 7; r++) b[r] = (lft[r] + core) + rgt[r];
+            } else if (C::FL >= 4) {
                 // pair sums shared between neighbouring outputs: s2[i] = v[i] + v[i+1]; all-positive, same bound
                 float s2[C::FL - 1 + 8 - 1];
 #pragma unroll
@@ -241,7 +258,7 @@ struct ScanWarp {
 #pragma unroll
         for (int r = 0; r < 8; r++) p[r] = fmaf(cT, p[r], cexc);
         float* bslot = bbr + (k & 1) * 256;
-        float* pslot = prr + (k % C::PRR) * 256;
+        float* pslot = prr + ppos * 256;                       // ppos == k % PRR, carried (no division in the loop)
         if (PREF != 2) {
             *reinterpret_cast<float4*>(bslot + own) = make_float4(b[0], b[1], b[2], b[3]);
             *reinterpret_cast<float4*>(bslot + (own ^ 4)) = make_float4(b[4], b[5], b[6], b[7]);
@@ -254,7 +271,9 @@ struct ScanWarp {
 #pragma unroll
         for (int mm = 0; mm < C::RB; mm++) A += rth[mm];
         if (hi) A += rth[C::RB];
-        const float* dslot = prr + ((k + C::PRR - rows_back) % C::PRR) * 256;
+        int dpos = ppos - rows_back; dpos += dpos < 0 ? C::PRR : 0;
+        const float* dslot = prr + dpos * 256;
+        ppos = ppos + 1 == C::PRR ? 0 : ppos + 1;
         const float4 d0 = *reinterpret_cast<const float4*>(dslot + ownd);
         const float4 d1 = *reinterpret_cast<const float4*>(dslot + (ownd ^ 4));
         // t = cT*W - G with cT*W = (cT*A - q_kd[posd]) + q_k[pos]; every term is a product of cT and a partial sum
@@ -280,6 +299,15 @@ struct ScanWarp {
             float u[8];
 #pragma unroll
             for (int r = 0; r < 8; r++) u[r] = prev.b[r];
+            bool first = true;
+            if (PREF == 1) {       // long filters: noise rarely crosses the threshold, so most rows end here (8 compares, 1 vote)
+                bool h0 = false;
+#pragma unroll
+                for (int r = 0; r < 8; r++) h0 = h0 || !(u[r] < prev.t[r]);
+                first = __any_sync(FULL, h0);
+            }
+            if (!first) {
+            } else
             if (PREF == 2) {
 #pragma unroll
                 for (int r = 0; r < 8; r++)
@@ -292,7 +320,7 @@ struct ScanWarp {
             bool hot = false;
 #pragma unroll
             for (int r = 0; r < 8; r++) hot = hot || !(u[r] < prev.t[r]);   // negated '<': a NaN/Inf-contaminated threshold must not hide candidates
-            if (__any_sync(FULL, hot)) {
+            if (first && __any_sync(FULL, hot)) {
                 const float nx = ahead<1>(7, prev.b, b);       // first sample of the next lane / row
                 uint32_t msk = 0;
                 if (hot) {
@@ -395,6 +423,7 @@ __global__ void __maxnreg__(AMB_SCAN_REGS_FOR(SPC)) amb_scan_kernel(const __grid
     w.rb = min(w.ra + a.rows_per_span, a.row_hi);
     const int rs = max(w.ra - C::WARM, 0);                 // first row computed (even; window warm-up)
     const int t0 = rs >> 1;
+    w.ppos = (2 * t0) % C::PRR;
     const int ntiles = (w.rb >> 1) - t0 + 1;               // row rb is computed as look-ahead only
 
     for (int i = lane; i < C::BB_FLOATS; i += 32) w.bbr[i] = 0.f;
