@@ -575,7 +575,7 @@ static int process_core(amb_ctx* ctx, const float* iq, size_t n_complex, int mem
 
     AmbWalkArgs wa{};
     wa.P = P; wa.org = org; wa.ntot = ntot; wa.r_safe = r_safe; wa.flush = flush ? 1 : 0;
-    wa.ctr = ctx->ctr; wa.st = ctx->st;
+    wa.ctr = ctx->ctr; wa.st = ctx->st; wa.sm_count = ctx->sm_count;
 
     if (j_hi > j_lo) {
         AmbScanArgs a{};
@@ -1408,7 +1408,7 @@ int amb_preamble_process(amb_ctx* ctx, const float* in0, const float* in1, size_
         ea.in0 = d0; ea.in1 = d1; ea.n_streams = (long long)m;
         if (e == cudaSuccess) e = amb_launch_exact(ea, ctx->sm_count, s);
         AmbWalkArgs wa{};
-        wa.P = P; wa.org = b0; wa.ntot = ntot; wa.r_safe = r_safe; wa.flush = flush ? 1 : 0; wa.ctr = ctx->ctr; wa.st = ctx->st;
+        wa.P = P; wa.org = b0; wa.ntot = ntot; wa.r_safe = r_safe; wa.flush = flush ? 1 : 0; wa.ctr = ctx->ctr; wa.st = ctx->st; wa.sm_count = ctx->sm_count;
         wa.cand_j = ctx->cand_j; wa.cand_info = ctx->cand_info; wa.det_list = ctx->det_list;
         if (e == cudaSuccess) e = (ctx->resolver == 1) ? amb_launch_walk_seq(wa, s)
                                                        : amb_launch_walk_par(wa, ctx->walk_scratch, ctx->cand_cap, (long long)m + P.H + 4096, s);

@@ -96,6 +96,7 @@ struct AmbWalkArgs {
     long long ntot;       // flush: total items incl. history (N + H); else unused
     long long r_safe;     // !flush: first reported index that may not be decided yet
     int flush;
+    int sm_count;         // grid sizing of the cluster walk (0: a small default)
 };
 
 struct AmbSliceArgs {

@@ -300,7 +300,8 @@ struct ScanWarp {
 #pragma unroll
             for (int r = 0; r < 8; r++) u[r] = prev.b[r];
             bool first = true;
-            if (PREF == 1) {       // long filters: noise rarely crosses the threshold, so most rows end here (8 compares, 1 vote)
+            if (PREF == 1 && C::FL >= 8) {   // long filters: noise rarely crosses the threshold (1.5e-3 per sample at 10 samples/chip,
+                                             // 1.3e-2 at 5), so two rows in three end here after 8 compares and a vote
                 bool h0 = false;
 #pragma unroll
                 for (int r = 0; r < 8; r++) h0 = h0 || !(u[r] < prev.t[r]);
@@ -1356,10 +1357,13 @@ cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, unsigned in
     cudaError_t e;                                          // scratch header + buckets were zeroed by the prologue kernel
     const long long guard = (long long)a.P.maxlate + a.P.skip0 + 2 * a.P.spc_i + 8;
     const long long zone = a.flush ? (a.ntot - guard) : a.r_safe;
-    AMB_LAUNCH((amb_walk_par1_kernel), 1184, 64, 0, s, a, sc, first_fin, buckets, zone);    // <= 4 K registers per CTA
+    // latency-bound (dependent loads per candidate): many small CTAs (<= 4 K registers each) so that dense traffic has
+    // ~300 k threads in flight; with a few thousand candidates almost all of them exit at once
+    const int sms = a.sm_count > 0 ? a.sm_count : 8;
+    AMB_LAUNCH((amb_walk_par1_kernel), sms * 32, 64, 0, s, a, sc, first_fin, buckets, zone);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    AMB_LAUNCH((amb_walk_par2_kernel), 592, 128, 0, s, a, sc, first_fin, buckets);
+    AMB_LAUNCH((amb_walk_par2_kernel), sms * 16, 128, 0, s, a, sc, first_fin, buckets);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     AMB_LAUNCH((amb_walk_finalize_kernel), 1, 32, 0, s, a, sc);
@@ -1518,7 +1522,8 @@ __device__ __forceinline__ bool slice_packet_warp(float p0, float p2, float p7, 
 // 16-byte loads per lane; the work-list entry and candidate record of the NEXT packet are fetched while the current
 // one is sliced, so a packet costs one memory round trip. The frame slot is frame_base + position in the work list
 // (no atomics), bits are sliced straight from the staged samples (no chip array unless the caller asked for chips).
-template <bool STREAMS>
+// SPC > 0: integer samples/chip (chip offsets j*SPC and the filter loop fold at compile time); SPC == 0: run-time values.
+template <bool STREAMS, int SPC, bool PMF>
 __global__ void __launch_bounds__(64) amb_slice_kernel(const AmbSliceArgs a, const int spanp)
 {
     __shared__ unsigned int s_crc[96];
@@ -1530,8 +1535,10 @@ __global__ void __launch_bounds__(64) amb_slice_kernel(const AmbSliceArgs a, con
     const unsigned int ndet = a.ctr->ndet_list;                // accepted preambles of this call (any order)
     const unsigned int base = a.ctr->frame_base;               // frames queued before this call
     const unsigned int nwarps = gridDim.x * 2;
-    const int fl = P.use_pmf ? P.spc_i : 1;
-    const int span = chip_off(239, P.spc_f) + fl;              // m2 samples a packet touches
+    constexpr int FLC = (PMF && SPC > 0) ? SPC : 1;            // compile-time filter length (SPC == 0: run-time `fl`)
+    const int fl = PMF ? (SPC ? SPC : P.spc_i) : 1;
+    auto off = [&](int j) -> int { return SPC ? j * SPC : chip_off(j, P.spc_f); };   // int(j * spc) of preamble_impl.cc:220
+    const int span = off(239) + fl;                            // m2 samples a packet touches
     float* m2s = sl_smem + (size_t)warp * spanp;
     unsigned int npassed = 0;
     unsigned int di = blockIdx.x * 2 + warp;
@@ -1569,12 +1576,17 @@ __global__ void __launch_bounds__(64) amb_slice_kernel(const AmbSliceArgs a, con
             __syncwarp();
         }
         auto chip = [&](int j) -> float {
-            const int o = chip_off(j, P.spc_f);
+            const int o = off(j);
             if (STREAMS) return __fsub_rn(stream_at(a.in0, a.n_streams, P.H, (long long)fin + o), avg_fin);
             float bb;
-            if (P.use_pmf) {                                   // bb[fin + o] = PMF over m2[fin+o-fl+1 .. fin+o]
+            if (PMF) {                                         // bb[fin + o] = PMF over m2[fin+o-fl+1 .. fin+o]
                 double acc = 0.0;
-                for (int t = 0; t < fl; t++) acc += (double)m2s[sh + o + t];
+                if (SPC) {
+#pragma unroll
+                    for (int t = 0; t < FLC; t++) acc += (double)m2s[sh + o + t];
+                } else {
+                    for (int t = 0; t < fl; t++) acc += (double)m2s[sh + o + t];
+                }
                 bb = __fmul_rn((float)acc, P.scale_p);
             } else {
                 bb = m2s[sh + o];
@@ -1601,24 +1613,40 @@ __global__ void __launch_bounds__(64) amb_slice_kernel(const AmbSliceArgs a, con
     if (lane == 0 && npassed) atomicAdd(&a.ctr->npassed_call, npassed);
 }
 
+template <int SPC, bool PMF>
+static cudaError_t launch_slice_t(const AmbSliceArgs& a, int blocks, size_t smem, int spanp, cudaStream_t s)
+{
+    cudaError_t e = cudaFuncSetAttribute(amb_slice_kernel<false, SPC, PMF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(amb_slice_kernel<false, SPC, PMF>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e != cudaSuccess) return e;
+    AMB_LAUNCH((amb_slice_kernel<false, SPC, PMF>), blocks, 64, smem, s, a, spanp);
+    return cudaGetLastError();
+}
+
 cudaError_t amb_launch_slice(const AmbSliceArgs& a, int sm_count, cudaStream_t s)
 {
-    const int fl = a.P.use_pmf ? a.P.spc_i : 1;
-    const int spanp = ((int)(239 * a.P.spc_f) + fl + 3 + 31) & ~31;     // span + the alignment sample(s), rounded
+    const AmbParams& P = a.P;
+    const int fl = P.use_pmf ? P.spc_i : 1;
+    const int spanp = ((int)(239 * P.spc_f) + fl + 3 + 31) & ~31;       // span + the alignment sample(s), rounded
     const size_t smem = a.in0 ? 0 : (size_t)2 * spanp * sizeof(float);  // two warps per CTA (<= 4 K registers): 19 KiB at 20 Msps, 4 KiB at 4 Msps
     int per_sm = smem ? (int)((200 * 1024) / smem) : 32;
     if (per_sm > 32) per_sm = 32;
     if (per_sm < 1) per_sm = 1;
     const int blocks = sm_count * per_sm;
-    cudaError_t e;
-    if (a.in0) { AMB_LAUNCH((amb_slice_kernel<true>), blocks, 64, smem, s, a, spanp); }
-    else {
-        e = cudaFuncSetAttribute(amb_slice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(amb_slice_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        if (e != cudaSuccess) return e;
-        AMB_LAUNCH((amb_slice_kernel<false>), blocks, 64, smem, s, a, spanp);
+    if (a.in0) {
+        AMB_LAUNCH((amb_slice_kernel<true, 0, false>), blocks, 64, smem, s, a, spanp);
+        return cudaGetLastError();
     }
-    return cudaGetLastError();
+    const int k = P.spc_i;
+    if (P.spc_f == (float)k) {                                           // integer samples/chip: int(j * spc) == j * k
+        switch (k) {
+#define CASE(N) case N: return P.use_pmf ? launch_slice_t<N, true>(a, blocks, smem, spanp, s) : launch_slice_t<N, false>(a, blocks, smem, spanp, s);
+            CASE(1) CASE(2) CASE(5) CASE(10)
+#undef CASE
+            default: break;
+        }
+    }
+    return P.use_pmf ? launch_slice_t<0, true>(a, blocks, smem, spanp, s) : launch_slice_t<0, false>(a, blocks, smem, spanp, s);
 }
 
 // slicer only (split-form block): packets of 240 chips already in device memory
@@ -1948,8 +1976,7 @@ cudaError_t amb_prefer_max_shared()
     if (e == cudaSuccess) e = prefer_shared(amb_walk_reset_kernel);
     if (e == cudaSuccess) e = prefer_shared(amb_walk_summary_kernel);
     if (e == cudaSuccess) e = prefer_shared(amb_set_state_kernel);
-    if (e == cudaSuccess) e = prefer_shared(amb_slice_kernel<false>);
-    if (e == cudaSuccess) e = prefer_shared(amb_slice_kernel<true>);
+    if (e == cudaSuccess) e = prefer_shared(amb_slice_kernel<true, 0, false>);
     if (e == cudaSuccess) e = prefer_shared(amb_slice_chips_kernel);
     if (e == cudaSuccess) e = prefer_shared(amb_carry_kernel);
     if (e == cudaSuccess) e = prefer_shared(amb_prologue_kernel);
