@@ -537,10 +537,9 @@ static int process_core(amb_ctx* ctx, const float* iq, size_t n_complex, int mem
         // ---- DC blocker: x -> out[n] = x[n-D+1] - MA(MA(x))[n] into a ctx-owned buffer that then plays the input
         if (ctx->dc_cap < n_complex + (size_t)ctx->dc_D) {
             CK(sync_all(ctx));
-            cudaFree(ctx->dc_out); cudaFree(ctx->dc_ma0); ctx->dc_out = ctx->dc_ma0 = nullptr;
+            cudaFree(ctx->dc_out); ctx->dc_out = nullptr;
             const size_t ncap = n_complex + (size_t)ctx->dc_D + 1024;
             CK(cudaMalloc(&ctx->dc_out, ncap * sizeof(float2)));
-            CK(cudaMalloc(&ctx->dc_ma0, ncap * sizeof(float2)));
             ctx->dc_cap = ncap;
         }
         // the previous call's exact/slice kernels and its carry kernel still read dc_out
@@ -549,7 +548,7 @@ static int process_core(amb_ctx* ctx, const float* iq, size_t n_complex, int mem
         CK(amb_launch_dcblock(ctx->dc_carry[ctx->dc_cur], ctx->dc_nc, src, (long long)n_complex, ctx->dc_D,
                               ctx->dc_ma0, ctx->dc_out, ctx->dc_carry[ctx->dc_cur ^ 1], sa));
         ctx->dc_cur ^= 1;
-        ctx->stats.kernel_launches += n_complex ? 3 : 1;
+        ctx->stats.kernel_launches += n_complex ? 2 : 1;
         src = ctx->dc_out;
         CK(cudaEventRecord(ctx->e_in, sa));
         CK(cudaStreamWaitEvent(sc, ctx->e_in, 0));
@@ -1298,7 +1297,6 @@ int amb_dump_stage(amb_ctx* ctx, int stage, const float* iq, size_t n_complex, f
         const int D = 100 * ctx->P.spc_i, nc = 2 * D - 2;                       // rx_path.py:40
         float2 *d = nullptr, *t = nullptr, *o = nullptr, *c0 = nullptr, *c1 = nullptr;
         cudaError_t e = cudaMalloc(&d, n_complex * sizeof(float2));
-        if (e == cudaSuccess) e = cudaMalloc(&t, (n_complex + D) * sizeof(float2));
         if (e == cudaSuccess) e = cudaMalloc(&o, n_complex * sizeof(float2));
         if (e == cudaSuccess) e = cudaMalloc(&c0, (size_t)nc * sizeof(float2));
         if (e == cudaSuccess) e = cudaMalloc(&c1, (size_t)nc * sizeof(float2));
@@ -1308,7 +1306,7 @@ int amb_dump_stage(amb_ctx* ctx, int stage, const float* iq, size_t n_complex, f
         if (e == cudaSuccess) e = cudaMemcpyAsync(out, o, n_complex * sizeof(float2), cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         cudaFree(d); cudaFree(t); cudaFree(o); cudaFree(c0); cudaFree(c1);
-        ctx->stats.kernel_launches += 3;
+        ctx->stats.kernel_launches += 2;
         if (e != cudaSuccess) return fail(ctx, AMB_ERR_CUDA, "amb_dump_stage", e);
         return AMB_OK;
     }

@@ -1814,129 +1814,159 @@ __device__ __forceinline__ double shfl_up_f64(double v, int d)
     return __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(v), d), __shfl_up_sync(0xffffffffu, __double2loint(v), d));
 }
 
-// pass 0: ma0[i] = MA_D(x) at raw index (D-1)+i, i in [0, n_new + D - 1);  pass 1: out[m] for the n_new new samples.
-// CH = elements per thread in the prefix phase, ceil(W / 256) rounded up to an ODD number: a thread's chunk is
+// ONE pass (round 2): a CTA produces DC_T outputs from W2 = DC_T + 2D - 2 raw samples held in shared memory:
+//   raw (W2)  --MA_D-->  ma0 (W1 = DC_T + D - 1)  --MA_D-->  m1 (DC_T);   out[t] = raw[t + D - 1] - m1[t]
+// Each moving average is evaluated as P[i+D] - P[i] from a block-wide fp64 prefix sum when the exactness test above
+// holds for its input (raw for the first, ma0 for the second), else literally. Traffic: 8 B read + 8 B written per
+// sample (the two-pass version moved 40 B: x, ma0 out, ma0 in, x again, out); the 2D-2 halo re-reads hit L2.
+// CH = elements per thread in the prefix phase, ceil(W2 / 256) rounded up to an ODD number: a thread's chunk is
 // contiguous, so with an odd CH the 8-byte source reads and the 16-byte prefix writes of a warp are bank-conflict free.
-template <int PASS, int CH>
-__global__ void __launch_bounds__(256) amb_dcblock_kernel(const float2* __restrict__ carry, int nc, const float2* __restrict__ fresh,
-                                                          const float2* __restrict__ ma0, float2* __restrict__ dst,
-                                                          long long n_out, int D, int lim)
+struct DcRange { unsigned mxr, mnr, mxi, mni; };          // largest |bits|, smallest non-zero |bits| - 1, per component
+__device__ __forceinline__ void dc_range_add(DcRange& g, float2 v)
 {
-    AMB_DYN_SMEM(unsigned char, dc_smem, 16);
-    const int W = DC_T + D - 1;
-    float2* src = reinterpret_cast<float2*>(dc_smem);                                               // W source elements
-    double2* P = reinterpret_cast<double2*>(dc_smem + (size_t)((W + 1) & ~1) * sizeof(float2));     // W + 1 prefix sums (re, im)
-    __shared__ unsigned int s_rng[8][4];
-    __shared__ double2 s_tot[8];
-    const long long base = (long long)blockIdx.x * DC_T;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // window of output base+t covers source elements base+t .. base+t+D-1
-    const long long src_end = PASS == 0 ? (long long)nc + (n_out - (D - 1)) : n_out + D - 1;       // raw / ma0 index space
-    unsigned int mxr = 0, mnr = ~0u, mxi = 0, mni = ~0u;         // largest |bits|, smallest non-zero |bits| - 1
-    // interior tiles read one contiguous run of one array; only the first and last tiles need the general form
-    const float2* run = nullptr;
-    if (PASS == 0) { if (base >= nc && base + W <= src_end) run = fresh + (base - nc); }
-    else if (base + W <= src_end) run = ma0 + base;
-    for (int i = tid; i < W; i += 256) {
-        float2 v = make_float2(0.f, 0.f);
-        if (run) v = run[i];
-        else {
-            const long long q = base + i;
-            if (q < src_end) v = PASS == 0 ? dc_raw(carry, nc, fresh, q) : ma0[q];
-        }
-        src[i] = v;
-        const unsigned int ux = __float_as_uint(v.x) & 0x7fffffffu, uy = __float_as_uint(v.y) & 0x7fffffffu;
-        mxr = max(mxr, ux); mnr = min(mnr, ux - 1u);             // zero wraps to 0xffffffff and drops out of the minimum
-        mxi = max(mxi, uy); mni = min(mni, uy - 1u);
-    }
-    mxr = __reduce_max_sync(0xffffffffu, mxr); mnr = __reduce_min_sync(0xffffffffu, mnr);
-    mxi = __reduce_max_sync(0xffffffffu, mxi); mni = __reduce_min_sync(0xffffffffu, mni);
-    if (lane == 0) { s_rng[warp][0] = mxr; s_rng[warp][1] = mnr; s_rng[warp][2] = mxi; s_rng[warp][3] = mni; }
+    const unsigned int ux = __float_as_uint(v.x) & 0x7fffffffu, uy = __float_as_uint(v.y) & 0x7fffffffu;
+    g.mxr = max(g.mxr, ux); g.mnr = min(g.mnr, ux - 1u);     // zero wraps to 0xffffffff and drops out of the minimum
+    g.mxi = max(g.mxi, uy); g.mni = min(g.mni, uy - 1u);
+}
+// block-wide verdict: every sum of these values is exact in fp64 (see above). s_rng: 8 x 4 words of scratch.
+__device__ __forceinline__ bool dc_range_exact(DcRange g, unsigned int (*s_rng)[4], int lim)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    g.mxr = __reduce_max_sync(0xffffffffu, g.mxr); g.mnr = __reduce_min_sync(0xffffffffu, g.mnr);
+    g.mxi = __reduce_max_sync(0xffffffffu, g.mxi); g.mni = __reduce_min_sync(0xffffffffu, g.mni);
+    __syncthreads();                                         // previous users of s_rng are done
+    if (lane == 0) { s_rng[warp][0] = g.mxr; s_rng[warp][1] = g.mnr; s_rng[warp][2] = g.mxi; s_rng[warp][3] = g.mni; }
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < 8; w++) { mxr = max(mxr, s_rng[w][0]); mnr = min(mnr, s_rng[w][1]); mxi = max(mxi, s_rng[w][2]); mni = min(mni, s_rng[w][3]); }
+    for (int w = 0; w < 8; w++) { g.mxr = max(g.mxr, s_rng[w][0]); g.mnr = min(g.mnr, s_rng[w][1]); g.mxi = max(g.mxi, s_rng[w][2]); g.mni = min(g.mni, s_rng[w][3]); }
     // exponent fields; denormals share the quantum of exponent field 1
-    const int er1 = (int)max(mxr >> 23, 1u), er0 = (int)max((mnr + 1u) >> 23, 1u);
-    const int ei1 = (int)max(mxi >> 23, 1u), ei0 = (int)max((mni + 1u) >> 23, 1u);
-    const bool exact = (mxr == 0 || (er1 < 255 && er1 - er0 <= lim)) && (mxi == 0 || (ei1 < 255 && ei1 - ei0 <= lim));
-    const float fD = (float)D;
-    if (exact) {
-        // block-wide inclusive prefix sums in fp64 (every addition exact, so the association is free)
-        const int k0 = tid * CH;
-        double xr[CH], xi[CH];
-        double sr = 0.0, si = 0.0;
+    const int er1 = (int)max(g.mxr >> 23, 1u), er0 = (int)max((g.mnr + 1u) >> 23, 1u);
+    const int ei1 = (int)max(g.mxi >> 23, 1u), ei0 = (int)max((g.mni + 1u) >> 23, 1u);
+    return (g.mxr == 0 || (er1 < 255 && er1 - er0 <= lim)) && (g.mxi == 0 || (ei1 < 255 && ei1 - ei0 <= lim));
+}
+// block-wide inclusive fp64 prefix sums of v[0 .. W) into P[1 .. W], P[0] = 0 (every addition exact: association is free)
+template <int CH>
+__device__ __forceinline__ void dc_prefix(const float2* v, int W, double2* P, double2* s_tot)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k0 = tid * CH;
+    double xr[CH], xi[CH];
+    double sr = 0.0, si = 0.0;
 #pragma unroll
-        for (int j = 0; j < CH; j++) {
-            const float2 v = (k0 + j < W) ? src[k0 + j] : make_float2(0.f, 0.f);
-            xr[j] = (double)v.x; xi[j] = (double)v.y;
-            sr += xr[j]; si += xi[j];
-        }
-        double ar = sr, ai = si;                              // inclusive scan of the per-thread totals within the warp
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const double tr = shfl_up_f64(ar, d), ti = shfl_up_f64(ai, d);
-            if (lane >= d) { ar += tr; ai += ti; }
-        }
-        if (lane == 31) s_tot[warp] = make_double2(ar, ai);
-        __syncthreads();
-        double offr = ar - sr, offi = ai - si;                // exclusive offset of this thread
-#pragma unroll
-        for (int w = 0; w < 7; w++) if (w < warp) { offr += s_tot[w].x; offi += s_tot[w].y; }
-        if (tid == 0) P[0] = make_double2(0.0, 0.0);
-#pragma unroll
-        for (int j = 0; j < CH; j++) {
-            offr += xr[j]; offi += xi[j];
-            if (k0 + j < W) P[k0 + j + 1] = make_double2(offr, offi);
-        }
-        __syncthreads();
+    for (int j = 0; j < CH; j++) {
+        const float2 e = (k0 + j < W) ? v[k0 + j] : make_float2(0.f, 0.f);
+        xr[j] = (double)e.x; xi[j] = (double)e.y;
+        sr += xr[j]; si += xi[j];
     }
+    double ar = sr, ai = si;                              // inclusive scan of the per-thread totals within the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double tr = shfl_up_f64(ar, d), ti = shfl_up_f64(ai, d);
+        if (lane >= d) { ar += tr; ai += ti; }
+    }
+    __syncthreads();                                      // previous users of s_tot / P are done
+    if (lane == 31) s_tot[warp] = make_double2(ar, ai);
+    __syncthreads();
+    double offr = ar - sr, offi = ai - si;                // exclusive offset of this thread
+#pragma unroll
+    for (int w = 0; w < 7; w++) if (w < warp) { offr += s_tot[w].x; offi += s_tot[w].y; }
+    if (tid == 0) P[0] = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int j = 0; j < CH; j++) {
+        offr += xr[j]; offi += xi[j];
+        if (k0 + j < W) P[k0 + j + 1] = make_double2(offr, offi);
+    }
+    __syncthreads();
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) amb_dcblock_kernel(const float2* __restrict__ carry, int nc, const float2* __restrict__ fresh,
+                                                          float2* __restrict__ dst, long long n_out, int D, int lim1, int lim2)
+{
+    AMB_DYN_SMEM(unsigned char, dc_smem, 16);
+    const int W1 = DC_T + D - 1, W2 = DC_T + 2 * D - 2;
+    float2* src = reinterpret_cast<float2*>(dc_smem);                                               // W2 raw samples
+    float2* ma0 = src + ((W2 + 1) & ~1);                                                            // W1 first averages
+    double2* P = reinterpret_cast<double2*>(ma0 + ((W1 + 1) & ~1));                                 // W2 + 1 prefix sums (re, im)
+    __shared__ unsigned int s_rng[8][4];
+    __shared__ double2 s_tot[8];
+    const long long base = (long long)blockIdx.x * DC_T;          // first output of the tile = raw index base
+    const int tid = threadIdx.x;
+    const long long raw_end = (long long)nc + n_out;              // raw = carry ++ fresh
+    const float fD = (float)D;
+    // ---- raw samples of the tile (interior tiles: one contiguous run of `fresh`)
+    DcRange g = {0u, ~0u, 0u, ~0u};
+    const float2* run = (base >= nc && base + W2 <= raw_end) ? fresh + (base - nc) : nullptr;
+    for (int i = tid; i < W2; i += 256) {
+        float2 v = make_float2(0.f, 0.f);
+        if (run) v = run[i];
+        else { const long long q = base + i; if (q < raw_end) v = dc_raw(carry, nc, fresh, q); }
+        src[i] = v;
+        dc_range_add(g, v);
+    }
+    const bool exact1 = dc_range_exact(g, s_rng, lim2);           // also orders the src[] stores before their readers
+    // ---- first moving average: ma0[i] covers raw[base+i .. base+i+D-1]
+    if (exact1) dc_prefix<CH>(src, W2, P, s_tot);
+    g = {0u, ~0u, 0u, ~0u};
+    for (int i = tid; i < W1; i += 256) {
+        double ar = 0.0, ai = 0.0;
+        if (exact1) { const double2 hi = P[i + D], lo = P[i]; ar = hi.x - lo.x; ai = hi.y - lo.y; }
+        else for (int k = 0; k < D; k++) { ar += (double)src[i + k].x; ai += (double)src[i + k].y; }
+        const float2 m = make_float2(__fdiv_rn((float)ar, fD), __fdiv_rn((float)ai, fD));
+        ma0[i] = m;
+        dc_range_add(g, m);
+    }
+    const bool exact2 = dc_range_exact(g, s_rng, lim1);           // (its barriers also retire the readers of P)
+    // ---- second moving average and the output
+    if (exact2) dc_prefix<CH>(ma0, W1, P, s_tot);
 #pragma unroll
     for (int u = 0; u < DC_T / 256; u++) {
         const int t = tid + 256 * u;
         const long long m = base + t;
         if (m >= n_out) break;
         double ar = 0.0, ai = 0.0;
-        if (exact) { const double2 hi = P[t + D], lo = P[t]; ar = hi.x - lo.x; ai = hi.y - lo.y; }
-        else for (int k = 0; k < D; k++) { ar += (double)src[t + k].x; ai += (double)src[t + k].y; }
+        if (exact2) { const double2 hi = P[t + D], lo = P[t]; ar = hi.x - lo.x; ai = hi.y - lo.y; }
+        else for (int k = 0; k < D; k++) { ar += (double)ma0[t + k].x; ai += (double)ma0[t + k].y; }
         const float mr = __fdiv_rn((float)ar, fD), mi = __fdiv_rn((float)ai, fD);
-        if (PASS == 0) dst[m] = make_float2(mr, mi);
-        else {
-            const float2 d = dc_raw(carry, nc, fresh, m + D - 1);        // x[n-D+1]: raw index of new sample m is nc+m
-            dst[m] = make_float2(__fsub_rn(d.x, mr), __fsub_rn(d.y, mi));
-        }
+        const float2 d = src[t + D - 1];                              // x[n-D+1]: raw index of new sample m is nc + m = base + t + 2D-2 ... - (D-1)
+        dst[m] = make_float2(__fsub_rn(d.x, mr), __fsub_rn(d.y, mi));
     }
 }
 
 template <int CH>
-static cudaError_t launch_dcblock_t(const float2* rawcarry, int nc, const float2* fresh, long long n_new, int D, int lim,
-                                    size_t smem, float2* ma0_tmp, float2* out, cudaStream_t s)
+static cudaError_t launch_dcblock_t(const float2* rawcarry, int nc, const float2* fresh, long long n_new, int D, int lim1, int lim2,
+                                    size_t smem, float2* out, cudaStream_t s)
 {
     // per device, like the scan kernel: set on every launch (a host-side table write)
-    cudaError_t e = cudaFuncSetAttribute(amb_dcblock_kernel<0, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(amb_dcblock_kernel<1, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(amb_dcblock_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(amb_dcblock_kernel<CH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
-    const long long n0 = n_new + D - 1;
-    AMB_LAUNCH((amb_dcblock_kernel<0, CH>), (unsigned)((n0 + DC_T - 1) / DC_T), 256, smem, s, rawcarry, nc, fresh, nullptr, ma0_tmp, n0, D, lim);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    AMB_LAUNCH((amb_dcblock_kernel<1, CH>), (unsigned)((n_new + DC_T - 1) / DC_T), 256, smem, s, rawcarry, nc, fresh, ma0_tmp, out, n_new, D, lim);
+    AMB_LAUNCH((amb_dcblock_kernel<CH>), (unsigned)((n_new + DC_T - 1) / DC_T), 256, smem, s, rawcarry, nc, fresh, out, n_new, D, lim1, lim2);
     return cudaGetLastError();
+}
+
+static int dc_lim(int W)
+{
+    int c = 0;
+    while ((1 << c) < W) c++;
+    return 29 - c;                                       // see the exactness argument above
 }
 
 cudaError_t amb_launch_dcblock(const float2* rawcarry, int nc, const float2* fresh, long long n_new, int D,
                                float2* ma0_tmp, float2* out, float2* rawcarry_next, cudaStream_t s)
 {
-    const int W = DC_T + D - 1;
-    const size_t smem = (size_t)((W + 1) & ~1) * sizeof(float2) + (size_t)(W + 1) * sizeof(double2);
-    int c = 0;
-    while ((1 << c) < W) c++;
-    const int lim = 29 - c;                              // see the exactness argument above
-    if (smem > 96 * 1024 || W > 9 * 256) return cudaErrorInvalidValue;
+    (void)ma0_tmp;                                       // the two-pass version's intermediate: not needed any more
+    const int W1 = DC_T + D - 1, W2 = DC_T + 2 * D - 2;
+    const size_t smem = (size_t)(((W2 + 1) & ~1) + ((W1 + 1) & ~1)) * sizeof(float2) + (size_t)(W2 + 1) * sizeof(double2);
+    if (smem > 160 * 1024 || W2 > 13 * 256) return cudaErrorInvalidValue;
     if (n_new > 0) {
         cudaError_t e;
-        if (W <= 5 * 256) e = launch_dcblock_t<5>(rawcarry, nc, fresh, n_new, D, lim, smem, ma0_tmp, out, s);
-        else if (W <= 7 * 256) e = launch_dcblock_t<7>(rawcarry, nc, fresh, n_new, D, lim, smem, ma0_tmp, out, s);
-        else e = launch_dcblock_t<9>(rawcarry, nc, fresh, n_new, D, lim, smem, ma0_tmp, out, s);
+        const int l1 = dc_lim(W1), l2 = dc_lim(W2);
+        if (W2 <= 5 * 256) e = launch_dcblock_t<5>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
+        else if (W2 <= 7 * 256) e = launch_dcblock_t<7>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
+        else if (W2 <= 9 * 256) e = launch_dcblock_t<9>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
+        else if (W2 <= 11 * 256) e = launch_dcblock_t<11>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
+        else e = launch_dcblock_t<13>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
         if (e != cudaSuccess) return e;
     }
     // next raw carry = last nc samples of rawcarry ++ fresh
