@@ -599,10 +599,11 @@ static int process_core(amb_ctx* ctx, const float* iq, size_t n_complex, int mem
         if (n_main) { int rc2 = make_tmap(ctx, &a.tm_main, src, (size_t)n_main); if (rc2) return rc2; }
         else a.tm_main = ctx->tm_tail[set];
 
-        // ---- stream C: stage the tail, reset the group counts; stream A: stream over the IQ
-        CK(amb_launch_prologue(ctx->tail[set], ctx->tail_cap, src + n_main, n_tv, a.group_count, 128, sc));
-        CK(cudaEventRecord(ctx->e_aux[set], sc));
-        CK(cudaStreamWaitEvent(sa, ctx->e_aux[set], 0));
+        // ---- stream A: stage the tail + reset the group counts (2 us, in front of the scan: a hop over to stream C and
+        // back cost ~14 us of idle scan stream per call), then stream over the IQ. Stream C's carry kernel reads the tail.
+        CK(amb_launch_prologue(ctx->tail[set], ctx->tail_cap, src + n_main, n_tv, a.group_count, 128, sa));
+        CK(cudaEventRecord(ctx->e_in, sa));
+        CK(cudaStreamWaitEvent(sc, ctx->e_in, 0));
         if (ctx->aux_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_aux[set ^ 1], 0));   // carry written by the previous call
         const unsigned slot = (ctx->ring_n & 63u) * 2;
         if (ctx->timing) { CK(cudaEventRecord(ctx->ev[0], sa)); CK(cudaEventRecord(ctx->ring[slot], sa)); }
@@ -640,9 +641,9 @@ static int process_core(amb_ctx* ctx, const float* iq, size_t n_complex, int mem
     } else {
         // nothing can be decided yet (tiny call): keep it simple and serial
         if (ctx->done_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_done[set ^ 1], 0));
-        CK(amb_launch_prologue(ctx->tail[set], ctx->tail_cap, src + n_main, n_tv, nullptr, 0, sc));
-        CK(cudaEventRecord(ctx->e_aux[set], sc));
-        CK(cudaStreamWaitEvent(sa, ctx->e_aux[set], 0));
+        CK(amb_launch_prologue(ctx->tail[set], ctx->tail_cap, src + n_main, n_tv, nullptr, 0, sa));
+        CK(cudaEventRecord(ctx->e_in, sa));
+        CK(cudaStreamWaitEvent(sc, ctx->e_in, 0));
         if (ctx->aux_valid[set ^ 1]) CK(cudaStreamWaitEvent(sa, ctx->e_aux[set ^ 1], 0));
         CK(cudaEventRecord(ctx->e_scan[set], sa));
         CK(cudaStreamWaitEvent(sb, ctx->e_scan[set], 0));

@@ -1884,18 +1884,19 @@ __device__ __forceinline__ void dc_prefix(const float2* v, int W, double2* P, do
     __syncthreads();
 }
 
-template <int CH>
+// TILE = outputs per CTA: 1024 for D <= 256, 2048 beyond (the 2D-2 halo is recomputed by every tile).
+template <int CH, int TILE>
 __global__ void __launch_bounds__(256) amb_dcblock_kernel(const float2* __restrict__ carry, int nc, const float2* __restrict__ fresh,
                                                           float2* __restrict__ dst, long long n_out, int D, int lim1, int lim2)
 {
     AMB_DYN_SMEM(unsigned char, dc_smem, 16);
-    const int W1 = DC_T + D - 1, W2 = DC_T + 2 * D - 2;
+    const int W1 = TILE + D - 1, W2 = TILE + 2 * D - 2;
     float2* src = reinterpret_cast<float2*>(dc_smem);                                               // W2 raw samples
     float2* ma0 = src + ((W2 + 1) & ~1);                                                            // W1 first averages
     double2* P = reinterpret_cast<double2*>(ma0 + ((W1 + 1) & ~1));                                 // W2 + 1 prefix sums (re, im)
     __shared__ unsigned int s_rng[8][4];
     __shared__ double2 s_tot[8];
-    const long long base = (long long)blockIdx.x * DC_T;          // first output of the tile = raw index base
+    const long long base = (long long)blockIdx.x * TILE;          // first output of the tile = raw index base
     const int tid = threadIdx.x;
     const long long raw_end = (long long)nc + n_out;              // raw = carry ++ fresh
     const float fD = (float)D;
@@ -1925,7 +1926,7 @@ __global__ void __launch_bounds__(256) amb_dcblock_kernel(const float2* __restri
     // ---- second moving average and the output
     if (exact2) dc_prefix<CH>(ma0, W1, P, s_tot);
 #pragma unroll
-    for (int u = 0; u < DC_T / 256; u++) {
+    for (int u = 0; u < TILE / 256; u++) {
         const int t = tid + 256 * u;
         const long long m = base + t;
         if (m >= n_out) break;
@@ -1938,15 +1939,15 @@ __global__ void __launch_bounds__(256) amb_dcblock_kernel(const float2* __restri
     }
 }
 
-template <int CH>
+template <int CH, int TILE>
 static cudaError_t launch_dcblock_t(const float2* rawcarry, int nc, const float2* fresh, long long n_new, int D, int lim1, int lim2,
                                     size_t smem, float2* out, cudaStream_t s)
 {
     // per device, like the scan kernel: set on every launch (a host-side table write)
-    cudaError_t e = cudaFuncSetAttribute(amb_dcblock_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(amb_dcblock_kernel<CH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaError_t e = cudaFuncSetAttribute(amb_dcblock_kernel<CH, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(amb_dcblock_kernel<CH, TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
-    AMB_LAUNCH((amb_dcblock_kernel<CH>), (unsigned)((n_new + DC_T - 1) / DC_T), 256, smem, s, rawcarry, nc, fresh, out, n_new, D, lim1, lim2);
+    AMB_LAUNCH((amb_dcblock_kernel<CH, TILE>), (unsigned)((n_new + TILE - 1) / TILE), 256, smem, s, rawcarry, nc, fresh, out, n_new, D, lim1, lim2);
     return cudaGetLastError();
 }
 
@@ -1961,17 +1962,22 @@ cudaError_t amb_launch_dcblock(const float2* rawcarry, int nc, const float2* fre
                                float2* ma0_tmp, float2* out, float2* rawcarry_next, cudaStream_t s)
 {
     (void)ma0_tmp;                                       // the two-pass version's intermediate: not needed any more
-    const int W1 = DC_T + D - 1, W2 = DC_T + 2 * D - 2;
+    const int T = D <= 256 ? 1024 : 2048;
+    const int W1 = T + D - 1, W2 = T + 2 * D - 2;
     const size_t smem = (size_t)(((W2 + 1) & ~1) + ((W1 + 1) & ~1)) * sizeof(float2) + (size_t)(W2 + 1) * sizeof(double2);
-    if (smem > 160 * 1024 || W2 > 13 * 256) return cudaErrorInvalidValue;
+    if (smem > 200 * 1024 || W2 > 17 * 256) return cudaErrorInvalidValue;
     if (n_new > 0) {
         cudaError_t e;
         const int l1 = dc_lim(W1), l2 = dc_lim(W2);
-        if (W2 <= 5 * 256) e = launch_dcblock_t<5>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
-        else if (W2 <= 7 * 256) e = launch_dcblock_t<7>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
-        else if (W2 <= 9 * 256) e = launch_dcblock_t<9>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
-        else if (W2 <= 11 * 256) e = launch_dcblock_t<11>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
-        else e = launch_dcblock_t<13>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
+        if (T == 1024) {
+            if (W2 <= 5 * 256) e = launch_dcblock_t<5, 1024>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
+            else e = launch_dcblock_t<7, 1024>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
+        } else {
+            if (W2 <= 11 * 256) e = launch_dcblock_t<11, 2048>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
+            else if (W2 <= 13 * 256) e = launch_dcblock_t<13, 2048>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
+            else if (W2 <= 15 * 256) e = launch_dcblock_t<15, 2048>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
+            else e = launch_dcblock_t<17, 2048>(rawcarry, nc, fresh, n_new, D, l1, l2, smem, out, s);
+        }
         if (e != cudaSuccess) return e;
     }
     // next raw carry = last nc samples of rawcarry ++ fresh

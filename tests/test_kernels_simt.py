@@ -196,10 +196,12 @@ def test_scan_kernel_under_the_emulator_on_pathological_inputs(emul, port):
 
 
 def test_dc_blocker_kernels_under_the_emulator(emul, port):
-    """amb_dcblock_kernel<0/1> (exact fp64 prefix sums per tile, literal sums where the exponent spread forbids them):
-    output bit-identical to the CPU restatement, on ordinary samples and on tiles that force the literal path."""
+    """amb_dcblock_kernel (one pass: raw tile -> MA -> MA -> output; exact fp64 prefix sums per tile, literal sums where
+    the exponent spread forbids them; 1024-output tiles up to D = 256, 2048 beyond): output bit-identical to the CPU
+    restatement, on ordinary samples and on tiles that force the literal path in the first or the second average."""
     rng = np.random.default_rng(9)
-    for D, n, kind in ((200, 5000, "plain"), (500, 6000, "plain"), (200, 4000, "spread"), (200, 3000, "naninf")):
+    for D, n, kind in ((200, 5000, "plain"), (500, 6000, "plain"), (1000, 7000, "plain"), (200, 4000, "spread"),
+                       (500, 5000, "spread"), (200, 3000, "naninf")):
         iq = (rng.standard_normal(2 * n) * 0.01).astype(np.float32)
         iq[0::2] += np.float32(0.05)
         if kind == "spread":
