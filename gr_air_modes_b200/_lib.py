@@ -112,6 +112,7 @@ SYMBOLS = [
     ("amb_decoder_set_location", C.c_int, [_vp, C.c_int, C.c_double, C.c_double]),
     ("amb_decoder_reset", C.c_int, [_vp]),
     ("amb_decode_frames", C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
+    ("amb_decode_frames_device", C.c_int, [_vp, _vp, C.c_int, _vp]),
     ("amb_decoder_stats", C.c_int, [_vp, _u64p, _f32p]),
     ("amb_decoder_last_error", C.c_char_p, [_vp]),
     ("amb_frame_bits", C.c_uint64, [C.POINTER(Frame), C.c_int, C.c_int]),

@@ -757,7 +757,7 @@ CopyPool* copy_pool(int want)
 {
     std::lock_guard<std::mutex> lk(g_pool_mutex);
     if (want <= 0) {
-        static const int dflt = (int)std::min(12u, std::max(1u, std::thread::hardware_concurrency() / 8));
+        static const int dflt = (int)std::min(24u, std::max(1u, std::thread::hardware_concurrency() / 6));
         want = dflt;                                        // enough to outrun a PCIe Gen5 x16 link, never the whole box
     }
     if (!g_pool || g_pool_threads != want) { delete g_pool; g_pool = new CopyPool(want - 1); g_pool_threads = want; }

@@ -217,7 +217,21 @@ int amb_decoder_reset(amb_decoder* d)
     return AMB_OK;
 }
 
+static int decode_impl(amb_decoder* d, const amb_frame* frames, int n, int mem_kind, amb_fields* out, bool out_on_device);
+
 int amb_decode_frames(amb_decoder* d, const amb_frame* frames, int n, int mem_kind, amb_fields* out)
+{
+    return decode_impl(d, frames, n, mem_kind, out, false);
+}
+
+/* Frames AND records in device memory (e.g. the frames of a poll copied to the device once, or produced there): no
+ * host copy at all; the records stay on the device for whatever consumes them next. Synchronises the decoder's stream. */
+int amb_decode_frames_device(amb_decoder* d, const amb_frame* frames_dev, int n, amb_fields* out_dev)
+{
+    return decode_impl(d, frames_dev, n, AMB_MEM_DEVICE, out_dev, true);
+}
+
+static int decode_impl(amb_decoder* d, const amb_frame* frames, int n, int mem_kind, amb_fields* out, bool out_on_device)
 {
     if (!d || n < 0 || (n > 0 && (!frames || !out)) || (mem_kind != AMB_MEM_HOST && mem_kind != AMB_MEM_DEVICE))
         return dfail(d, AMB_ERR_INVALID, "amb_decode_frames: bad argument");
@@ -226,6 +240,7 @@ int amb_decode_frames(amb_decoder* d, const amb_frame* frames, int n, int mem_ki
     int rc = ensure_cap(d, n);
     if (rc != AMB_OK) return rc;
     cudaStream_t s = d->stream;
+    amb_fields* const fields = out_on_device ? out : d->d_fields;
     DCK(cudaEventRecord(d->e0, s));
     const amb_frame* src = frames;
     if (mem_kind == AMB_MEM_HOST) {
@@ -234,7 +249,7 @@ int amb_decode_frames(amb_decoder* d, const amb_frame* frames, int n, int mem_ki
         src = d->d_frames;
     }
     const int nb = (n + 127) / 128;
-    AMB_LAUNCH((amb_fields_kernel), nb, 128, 0, s, src, n, d->d_fields, d->d_pos, d->d_pair);
+    AMB_LAUNCH((amb_fields_kernel), nb, 128, 0, s, src, n, fields, d->d_pos, d->d_pair);
     DCK(cudaGetLastError());
     // one warp per ~256 frames, at most 8 CTAs per SM: every warp reads the whole key list (L2-resident) but only
     // touches the table for its own aircraft
@@ -267,11 +282,13 @@ int amb_decode_frames(amb_decoder* d, const amb_frame* frames, int n, int mem_ki
     AMB_LAUNCH((amb_pair_kernel), pair_ctas, 32 * AMB_PAIR_WARPS_PER_CTA, 0, s, d->d_pos, n, d->table, d->d_pair);
 #endif
     DCK(cudaGetLastError());
-    AMB_LAUNCH((amb_resolve_kernel), nb, 128, 0, s, d->d_fields, d->d_pos, d->d_pair, n, d->have_loc, d->lat, d->lon, d->nl_T);
+    AMB_LAUNCH((amb_resolve_kernel), nb, 128, 0, s, fields, d->d_pos, d->d_pair, n, d->have_loc, d->lat, d->lon, d->nl_T);
     DCK(cudaGetLastError());
     d->launches += 3;
-    rc = staged_d2h(d, out, d->d_fields, (size_t)n * sizeof(amb_fields), s);
-    if (rc != AMB_OK) return rc;
+    if (!out_on_device) {
+        rc = staged_d2h(d, out, d->d_fields, (size_t)n * sizeof(amb_fields), s);
+        if (rc != AMB_OK) return rc;
+    }
     DCK(cudaEventRecord(d->e1, s));
     DCK(cudaStreamSynchronize(s));
     float ms = 0.f;

@@ -102,6 +102,19 @@ class batch_decoder:
         del keep
         return out
 
+    def decode_device(self, frames_dev, out_dev=None):
+        """frames_dev: torch CUDA uint8 tensor holding n amb_frame records (80 bytes each) in stream order; returns (or
+        fills) a CUDA uint8 tensor of n amb_fields records (144 bytes each). Nothing crosses PCIe."""
+        import torch
+        n = frames_dev.numel() // 80
+        if out_dev is None:
+            out_dev = torch.empty(n * 144, dtype=torch.uint8, device=frames_dev.device)
+        if n:
+            torch.cuda.current_stream(frames_dev.device).synchronize()      # the decoder runs on its own stream
+            self._check(self._lib.amb_decode_frames_device(self._h, C.c_void_p(frames_dev.data_ptr()), int(n),
+                                                           C.c_void_p(out_dev.data_ptr())))
+        return out_dev
+
     def decode_messages(self, msgs) -> np.ndarray:
         arr, n = frames_from_messages(msgs)
         return self.decode(arr, n)

@@ -21,6 +21,14 @@ def fan_out(make_channel, rank: int, world: int, device, numel: int, timing: dic
     import time
     import torch
     import torch.distributed as dist
+    if timing is not None and not timing.get("warm"):      # NCCL sets a peer connection up on first use: not part of the transfer
+        timing["warm"] = True
+        w = torch.zeros(4, dtype=torch.float32, device=device)
+        if rank == 0:
+            for ch in range(1, world):
+                dist.send(w, dst=ch)
+        else:
+            dist.recv(w, src=0)
     if rank == 0:
         metas = [None] * world
         mine = None

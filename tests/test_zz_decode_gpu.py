@@ -320,3 +320,18 @@ def test_cpr_decoder_dropin_class(dec_mod):
                 ok += 1
     ours.close()
     assert ok >= 290
+
+
+def test_device_resident_decode_equals_the_host_path(dec_mod):
+    """amb_decode_frames_device: frames and records stay in device memory; byte-identical to the host-array path."""
+    import torch
+    import decode_cases
+    loc, msgs = decode_cases.make_case(907, location=(48.1, 11.5), seconds=60.0, surface_share=0.3, n_random=900, n_aircraft=40)
+    arr, n = dec_mod.frames_from_messages(msgs)
+    d1, d2 = dec_mod.batch_decoder(loc), dec_mod.batch_decoder(loc)
+    want = d1.decode(arr, n)
+    raw = np.frombuffer(bytes(arr), dtype=np.uint8)[: n * 80].copy()
+    out = d2.decode_device(torch.from_numpy(raw).cuda())
+    got = out.cpu().numpy().view(dec_mod.FIELDS_DTYPE)
+    assert got.size == n and got.tobytes() == want.tobytes()
+    d1.close(); d2.close()

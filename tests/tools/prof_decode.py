@@ -72,6 +72,18 @@ def main():
         npos = int(((out["status"] & decode.FS_HAS_POS) != 0).sum())
         print("n=2^%d frames: device %.3f ms (%.1f M frames/s), wall %.1f ms incl. numpy; %d positions, %d straddles/no-pair"
               % (lg, ms, n / ms / 1e3, 1e3 * wall, npos, n - npos))
+        try:                                            # the same batch with frames and records resident on the device
+            import torch
+            fd = torch.from_numpy(f.view(np.uint8).reshape(-1).copy()).cuda()
+            od = torch.empty(n * 144, dtype=torch.uint8, device="cuda")
+            d.reset(); d.decode_device(fd, od)
+            d.reset(); d.decode_device(fd, od)
+            ms2 = d.stats()[1]
+            same = np.array_equal(od.cpu().numpy().view(decode.FIELDS_DTYPE), out)
+            print("n=2^%d frames, device-resident frames and records: %.3f ms (%.0f M frames/s), records identical: %s"
+                  % (lg, ms2, n / ms2 / 1e3, same))
+        except ImportError:
+            pass
     d.close()
 
 
