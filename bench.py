@@ -393,7 +393,15 @@ def time_shard_arm(args, rank, local_rank, world, device):
     last = len(plan) - 1
     fallbacks = [0]
 
+    scratch = (shard.AsyncPass(world, len(plan), device, steps=args.warmup + args.steps + 1)
+               if args.ts_mode == "async" and not args.chain else None)
+    counter = [0]
+
     def step():
+        if scratch is not None:                          # device-side hand-over: a fixed sequence of enqueues
+            shard.time_shard_pass_async(rx, iq if active else None, plan, rank, scratch, counter[0])
+            counter[0] += 1
+            return
         if args.chain:
             if not active:
                 return
@@ -440,6 +448,8 @@ def time_shard_arm(args, rank, local_rank, world, device):
     launches = rx.stats().kernel_launches - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_max = shard.max_over_ranks(ms, world, device)
+    if scratch is not None:                              # passes whose speculation did not hold would have to be redone
+        fallbacks[0] = int((scratch.out[args.warmup: args.warmup + args.steps, 0] < last).sum().item())
     # ---- check: the spans' messages, concatenated in rank order, are the one-shot run's
     if args.chain:
         mine = shard.process_time_sharded(rx, iq, sp, recv, send) if active else 0
@@ -462,7 +472,7 @@ def time_shard_arm(args, rank, local_rank, world, device):
         line = {"metric": "Msamples/s IQ demod+slice+CRC", "value": n * args.steps / (ms_max * 1e-3) / 1e6,
                 "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "mode": "time-shard/" + ("chain" if args.chain else "speculative"),
+                "dtype": "f32", "data": "synthetic", "mode": "time-shard/" + ("async (device-side hand-over)" if scratch is not None else "chain" if args.chain else "speculative (host-driven)"),
                 "fallback_steps": fallbacks[0],
                 "config": {"workload": "ONE synthetic 4 Msps recording of 2^%d samples cut into %d time spans with halos"
                                        % (args.log2n, len(plan)), "parallelism": "time-shard x%d" % len(plan),
@@ -602,6 +612,8 @@ def main():
     ap.add_argument("--time-shard", action="store_true",
                     help="secondary mode: ONE 2^log2n-sample recording cut into --gpus spans (strong scaling)")
     ap.add_argument("--chain", action="store_true", help="--time-shard: plain hand-over chain instead of speculative resolution")
+    ap.add_argument("--ts-mode", default="async", choices=["async", "host"], help="--time-shard: speculative resolution with the "
+                    "device-side hand-over (default) or driven by the host (round 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

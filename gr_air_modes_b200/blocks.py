@@ -418,6 +418,16 @@ class rx_path:
         self._ctx.call("amb_get_walk_summary", C.byref(s))
         return s
 
+    # -- the same hand-over with nothing waiting on the host (amb_walk_summary_async and friends): device pointers
+    def walk_summary_async(self, dev_ptr: int):
+        self._ctx.call("amb_walk_summary_async", C.c_void_p(dev_ptr))
+
+    def compose_entries_async(self, gathered_ptr: int, n_spans: int, out_ptr: int):
+        self._ctx.call("amb_compose_entries_async", C.c_void_p(gathered_ptr), int(n_spans), C.c_void_p(out_ptr))
+
+    def resolve_device(self, entry_ptr: int):
+        self._ctx.call("amb_resolve_device", C.c_void_p(entry_ptr))
+
     def dump_stage(self, stage: str, iq) -> np.ndarray:
         """Parity dump: "m2" | "bb" | "avg" | "dc" of a short host buffer taken as a whole stream (amb_dump_stage)."""
         iq = np.ascontiguousarray(np.asarray(iq).view(np.float32).reshape(-1))

@@ -1003,6 +1003,68 @@ int amb_get_walk_summary(amb_ctx* ctx, amb_walk_summary* out)
     return AMB_OK;
 }
 
+/* The same summary, written as six int64 to DEVICE memory by a kernel on the context's second stream: no host
+ * synchronisation (amb_join then orders the caller's stream, e.g. an NCCL all-gather, after it). */
+int amb_walk_summary_async(amb_ctx* ctx, int64_t* dev_out6)
+{
+    if (!ctx || !dev_out6) return AMB_ERR_INVALID;
+    if (!ctx->def_kind || !ctx->def_resolved) return fail(ctx, AMB_ERR_STATE, "no resolved deferred span");
+    CK(cudaSetDevice(ctx->device));
+    const bool have = ctx->def_kind == 1;
+    if (have) { CK(amb_launch_walk_summary(ctx->def_wa, ctx->stream_b)); ctx->stats.kernel_launches += 1; }
+    AmbWalkArgs wa = ctx->def_wa; wa.st = ctx->st; wa.ctr = ctx->ctr;
+    CK(amb_launch_pack_summary(wa, ctx->P.i_exact, have ? 1 : 0, reinterpret_cast<long long*>(dev_out6), ctx->stream_b));
+    CK(cudaEventRecord(ctx->e_done[ctx->def_set], ctx->stream_b));
+    ctx->stats.kernel_launches += 1;
+    return AMB_OK;
+}
+
+/* gathered_dev: n_spans x 6 int64 (every span's summary, device memory, ready on the caller-visible stream);
+ * out_dev: 1 + 3 n_spans int64: [0] first span whose speculation fails (n_spans - 1: none), [1 + 2k .. 2 + 2k] the true
+ * entry (pos, p) of span k, [1 + 2 n_spans + k] messages queued before span k. One tiny kernel on the caller-visible
+ * stream; shard.compose_entries is the same computation on the host. */
+int amb_compose_entries_async(amb_ctx* ctx, const int64_t* gathered_dev, int n_spans, int64_t* out_dev)
+{
+    if (!ctx || !gathered_dev || !out_dev || n_spans < 1 || n_spans > 4096) return AMB_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(amb_launch_compose(reinterpret_cast<const long long*>(gathered_dev), n_spans, reinterpret_cast<long long*>(out_dev), ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    return AMB_OK;
+}
+
+/* amb_resolve with the entry state (pos, p) read from device memory at execution time (e.g. a row of
+ * amb_compose_entries_async's output): the walk + slice of the deferred span are enqueued behind whatever produced
+ * entry_dev on the caller-visible stream; nothing waits on the host. */
+int amb_resolve_device(amb_ctx* ctx, const int64_t* entry_dev)
+{
+    if (!ctx || !entry_dev) return AMB_ERR_INVALID;
+    if (!ctx->def_kind) return fail(ctx, AMB_ERR_STATE, "no deferred call to resolve");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t sb = ctx->stream_b;
+    CK(cudaEventRecord(ctx->e_in, ctx->stream));
+    CK(cudaStreamWaitEvent(sb, ctx->e_in, 0));
+    if (ctx->def_resolved && ctx->def_kind == 1) {
+        CK(amb_launch_walk_reset(ctx->def_wa, ctx->def_par ? ctx->walk_scratch : nullptr, ctx->def_nsamp, sb));
+        ctx->stats.kernel_launches += 1;
+    }
+    CK(amb_launch_set_state_dev(ctx->st, reinterpret_cast<const long long*>(entry_dev), sb));
+    if (ctx->def_kind == 1) {
+        if (!ctx->def_par) { CK(amb_launch_walk_seq(ctx->def_wa, sb)); ctx->stats.kernel_launches += 1; }
+        else { CK(amb_launch_walk_par(ctx->def_wa, ctx->walk_scratch, ctx->cand_cap, ctx->def_nsamp, sb)); ctx->stats.kernel_launches += 3; }
+        CK(amb_launch_slice(ctx->def_sl, ctx->sm_count, sb));
+        ctx->stats.kernel_launches += 1;
+    } else if (ctx->def_kind == 2) {
+        CK(amb_launch_walk_seq(ctx->def_wa, sb));
+        ctx->stats.kernel_launches += 1;
+    }
+    CK(cudaEventRecord(ctx->e_done[ctx->def_set], sb));
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[3], sb));
+    if (!ctx->overlap) CK(cudaStreamWaitEvent(ctx->stream, ctx->e_done[ctx->def_set], 0));
+    ctx->stats.kernel_launches += 1;
+    ctx->def_resolved = true;
+    return AMB_OK;
+}
+
 /* Make the caller-visible stream wait for everything enqueued so far (no host synchronisation). */
 int amb_join(amb_ctx* ctx)
 {

@@ -119,6 +119,9 @@ cudaError_t amb_launch_dump(const float2* iq, long long n, const AmbParams& P, i
 cudaError_t amb_launch_walk_reset(const AmbWalkArgs& a, void* scratch, long long n_samples, cudaStream_t s);
 cudaError_t amb_launch_walk_summary(const AmbWalkArgs& a, cudaStream_t s);
 cudaError_t amb_launch_set_state(AmbWalkState* st, long long pos, long long p, cudaStream_t s);
+cudaError_t amb_launch_pack_summary(const AmbWalkArgs& a, long long i_exact, int have, long long* out, cudaStream_t s);
+cudaError_t amb_launch_compose(const long long* gathered, int n_spans, long long* out, cudaStream_t s);
+cudaError_t amb_launch_set_state_dev(AmbWalkState* st, const long long* entry, cudaStream_t s);
 cudaError_t amb_launch_walk_seq(const AmbWalkArgs& a, cudaStream_t s);
 cudaError_t amb_launch_walk_par(const AmbWalkArgs& a, void* scratch, unsigned int cand_cap, long long n_samples, cudaStream_t s);
 size_t amb_walk_scratch_bytes(unsigned int cand_cap, long long n_samples);

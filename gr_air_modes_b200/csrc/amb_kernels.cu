@@ -1417,6 +1417,62 @@ cudaError_t amb_launch_walk_summary(const AmbWalkArgs& a, cudaStream_t s)
     return cudaGetLastError();
 }
 
+// ---- time-sharded spans, hand-over without the host (amb_walk_summary_async / amb_compose_entries_async /
+// amb_resolve_device): the six numbers of a span's speculative resolution go to device memory, every rank composes the
+// true entries of all spans from the all-gathered table in a one-thread kernel, and the last span (never speculated on)
+// takes its entry state straight from that kernel's output.
+__global__ void amb_pack_summary_kernel(const AmbWalkState* st, const AmbCounters* ctr, long long i_exact, int have, long long* out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    out[0] = st->pos; out[1] = st->p;
+    out[2] = (have && st->first_real != ~0ull) ? (long long)st->first_real : -1;
+    out[3] = (have && st->first_packet != ~0ull) ? (long long)st->first_packet : -1;
+    out[4] = i_exact;
+    out[5] = have ? (long long)ctr->npassed_call : 0;
+}
+// out[0] = first span whose speculation does not hold (n_spans - 1 if all hold); out[1 + 2k], out[2 + 2k] = true entry
+// (pos, p) of span k; out[1 + 2 n_spans + k] = messages queued before span k - all valid for k <= out[0].
+__global__ void amb_compose_kernel(const long long* g, int n_spans, long long* out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int last = n_spans - 1;
+    long long pos_in = 0, p_in = 0, queued = 0;
+    long long* ent = out + 1; long long* qd = out + 1 + 2 * n_spans;
+    ent[0] = 0; ent[1] = 0; qd[0] = 0;
+    int bad = last;
+    for (int k = 0; k < last; k++) {
+        const long long pos = g[6 * k], p = g[6 * k + 1], first_real = g[6 * k + 2], first_packet = g[6 * k + 3];
+        const long long exact_span = g[6 * k + 4], passed = g[6 * k + 5];
+        const bool ok = (first_real < 0 || p_in <= first_real) && (first_packet < 0 || first_packet - pos_in < exact_span);
+        if (!ok) { bad = k; break; }
+        pos_in = first_packet >= 0 ? pos : pos_in;
+        p_in = p > p_in ? p : p_in;
+        queued += passed;
+        ent[2 * (k + 1)] = pos_in; ent[2 * (k + 1) + 1] = p_in; qd[k + 1] = queued;
+    }
+    out[0] = bad;
+}
+__global__ void amb_set_state_dev_kernel(AmbWalkState* st, const long long* entry)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    st->pos = entry[0]; st->p = entry[1]; st->done = 0;
+}
+cudaError_t amb_launch_pack_summary(const AmbWalkArgs& a, long long i_exact, int have, long long* out, cudaStream_t s)
+{
+    AMB_LAUNCH((amb_pack_summary_kernel), 1, 32, 0, s, a.st, a.ctr, i_exact, have, out);
+    return cudaGetLastError();
+}
+cudaError_t amb_launch_compose(const long long* gathered, int n_spans, long long* out, cudaStream_t s)
+{
+    AMB_LAUNCH((amb_compose_kernel), 1, 32, 0, s, gathered, n_spans, out);
+    return cudaGetLastError();
+}
+cudaError_t amb_launch_set_state_dev(AmbWalkState* st, const long long* entry, cudaStream_t s)
+{
+    AMB_LAUNCH((amb_set_state_dev_kernel), 1, 32, 0, s, st, entry);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // slicer: one warp per accepted preamble
 // ------------------------------------------------------------------------------------------------
@@ -2017,6 +2073,9 @@ cudaError_t amb_prefer_max_shared()
     if (e == cudaSuccess) e = prefer_shared(amb_walk_reset_kernel);
     if (e == cudaSuccess) e = prefer_shared(amb_walk_summary_kernel);
     if (e == cudaSuccess) e = prefer_shared(amb_set_state_kernel);
+    if (e == cudaSuccess) e = prefer_shared(amb_pack_summary_kernel);
+    if (e == cudaSuccess) e = prefer_shared(amb_compose_kernel);
+    if (e == cudaSuccess) e = prefer_shared(amb_set_state_dev_kernel);
     if (e == cudaSuccess) e = prefer_shared(amb_slice_kernel<true, 0, false>);
     if (e == cudaSuccess) e = prefer_shared(amb_slice_chips_kernel);
     if (e == cudaSuccess) e = prefer_shared(amb_carry_kernel);

@@ -256,6 +256,19 @@ typedef struct amb_walk_summary {
     int64_t frames_passed;           /* messages this span would queue (slicer_impl.cc:193-194) */
 } amb_walk_summary;
 AMB_API int amb_get_walk_summary(amb_ctx* ctx, amb_walk_summary* out);   /* synchronises */
+/* The same exchange WITHOUT the host in the loop (one NCCL all-gather of 48 bytes per span between two tiny kernels):
+ *   amb_walk_summary_async     the six int64 of amb_walk_summary {pos, p, first_real, first_packet, exact_span,
+ *                              frames_passed}, written to device memory by a kernel on the context's second stream;
+ *   amb_join + all-gather      (the caller's collective, ordered on the caller-visible stream);
+ *   amb_compose_entries_async  every rank composes all spans' true entries from the gathered n_spans x 6 table:
+ *                              out[0] = first span whose speculation fails (n_spans - 1: none), out[1 + 2k], out[2 + 2k] =
+ *                              entry (pos, p) of span k, out[1 + 2 n_spans + k] = messages queued before span k;
+ *   amb_resolve_device         the last span (never speculated on) takes its entry from that output on the device.
+ * A pass is then a fixed sequence of enqueues; the host only reads out[0] afterwards, and re-resolves the rare pass whose
+ * speculation failed with amb_resolve as before. */
+AMB_API int amb_walk_summary_async(amb_ctx* ctx, int64_t* dev_out6);
+AMB_API int amb_compose_entries_async(amb_ctx* ctx, const int64_t* gathered_dev, int n_spans, int64_t* out_dev);
+AMB_API int amb_resolve_device(amb_ctx* ctx, const int64_t* entry_dev);
 /* ---- batch field decode of queued frames ---------------------------------------
  * What the reference does per message in Python after the slicer: modes_reply field extraction
  * (python/parse.py:27-231), decode_alt (python/altitude.py:28-108), decode_id (parse.py:233-254), the BDS0,5 / 0,6 /

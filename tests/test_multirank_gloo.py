@@ -239,7 +239,22 @@ def _emul_worker(rank, world, port_no, lib_path, ret):
         out[mode] = q.strings()
         rx.close()
         dist.barrier()
-    ret[rank] = (counts, out["chain"], out["speculative"], want)
+    # (3) the speculative pass with nothing waiting on the host: summary kernel -> all-gather on the "device" -> compose
+    # kernel on every rank -> the last span resolves from that kernel's output
+    q = am.msg_queue()
+    rx = am.rx_path(rate, 7.0, q, use_pmf=True)
+    rx.defer_resolve(True)
+    scratch = shard.AsyncPass(world, len(plan), dev, steps=2)
+    for step in range(2):                                     # twice: a pass leaves nothing behind
+        row = shard.time_shard_pass_async(rx, span_iq, plan, rank, scratch, step)
+    rx._ctx.call("amb_synchronize")
+    verdict = int(row[0])
+    rx._slicer._first = int(row[1 + 2 * len(plan) + rank]) == 0
+    rx.drain()
+    out["async"] = (verdict, len(plan) - 1, q.strings())
+    rx.close()
+    dist.barrier()
+    ret[rank] = (counts, out["chain"], out["speculative"], want, out["async"])
     dist.barrier()
     dist.destroy_process_group()
 
@@ -258,3 +273,5 @@ def test_both_multi_gpu_modes_world2_with_the_emulated_library(tmp_path):
     assert len(want) >= 15
     assert ret[0][1] + ret[1][1] == want                 # the spans' messages, in rank order, are the one-shot run's
     assert ret[0][2] + ret[1][2] == want
+    assert ret[0][4][0] == ret[0][4][1] == ret[1][4][0]       # the speculation held on every span (same verdict on both ranks)
+    assert ret[0][4][2] + ret[1][4][2] == want                # ... and the device-side hand-over gives the same messages
