@@ -393,7 +393,7 @@ def time_shard_arm(args, rank, local_rank, world, device):
     last = len(plan) - 1
     fallbacks = [0]
 
-    scratch = (shard.AsyncPass(world, len(plan), device, steps=args.warmup + args.steps + 1)
+    scratch = (shard.AsyncPass(world, len(plan), device, steps=args.warmup + args.steps + 1, side=torch.cuda.Stream(device))
                if args.ts_mode == "async" and not args.chain else None)
     counter = [0]
 

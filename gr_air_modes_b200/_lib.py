@@ -108,8 +108,9 @@ SYMBOLS = [
     ("amb_get_walk_state", C.c_int, [_vp, C.POINTER(WalkState)]),
     ("amb_get_walk_summary", C.c_int, [_vp, C.POINTER(WalkSummary)]),
     ("amb_walk_summary_async", C.c_int, [_vp, _vp]),
-    ("amb_compose_entries_async", C.c_int, [_vp, _vp, C.c_int, _vp]),
-    ("amb_resolve_device", C.c_int, [_vp, _vp]),
+    ("amb_compose_entries_async", C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    ("amb_resolve_device", C.c_int, [_vp, _vp, _vp]),
+    ("amb_join_stream", C.c_int, [_vp, _vp]),
     ("amb_decoder_create", C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(_vp)]),
     ("amb_decoder_destroy", None, [_vp]),
     ("amb_decoder_set_location", C.c_int, [_vp, C.c_int, C.c_double, C.c_double]),

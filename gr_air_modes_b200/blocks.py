@@ -422,11 +422,15 @@ class rx_path:
     def walk_summary_async(self, dev_ptr: int):
         self._ctx.call("amb_walk_summary_async", C.c_void_p(dev_ptr))
 
-    def compose_entries_async(self, gathered_ptr: int, n_spans: int, out_ptr: int):
-        self._ctx.call("amb_compose_entries_async", C.c_void_p(gathered_ptr), int(n_spans), C.c_void_p(out_ptr))
+    def compose_entries_async(self, gathered_ptr: int, n_spans: int, out_ptr: int, stream_ptr: int = 0):
+        self._ctx.call("amb_compose_entries_async", C.c_void_p(gathered_ptr), int(n_spans), C.c_void_p(out_ptr), C.c_void_p(stream_ptr))
 
-    def resolve_device(self, entry_ptr: int):
-        self._ctx.call("amb_resolve_device", C.c_void_p(entry_ptr))
+    def resolve_device(self, entry_ptr: int, after_stream_ptr: int = 0):
+        self._ctx.call("amb_resolve_device", C.c_void_p(entry_ptr), C.c_void_p(after_stream_ptr))
+
+    def join_stream(self, stream_ptr: int = 0):
+        """Make another CUDA stream of the caller's wait for everything enqueued so far (0: the caller-visible one)."""
+        self._ctx.call("amb_join_stream", C.c_void_p(stream_ptr))
 
     def dump_stage(self, stage: str, iq) -> np.ndarray:
         """Parity dump: "m2" | "bb" | "avg" | "dc" of a short host buffer taken as a whole stream (amb_dump_stage)."""

@@ -1023,11 +1023,12 @@ int amb_walk_summary_async(amb_ctx* ctx, int64_t* dev_out6)
  * out_dev: 1 + 3 n_spans int64: [0] first span whose speculation fails (n_spans - 1: none), [1 + 2k .. 2 + 2k] the true
  * entry (pos, p) of span k, [1 + 2 n_spans + k] messages queued before span k. One tiny kernel on the caller-visible
  * stream; shard.compose_entries is the same computation on the host. */
-int amb_compose_entries_async(amb_ctx* ctx, const int64_t* gathered_dev, int n_spans, int64_t* out_dev)
+int amb_compose_entries_async(amb_ctx* ctx, const int64_t* gathered_dev, int n_spans, int64_t* out_dev, void* cuda_stream)
 {
     if (!ctx || !gathered_dev || !out_dev || n_spans < 1 || n_spans > 4096) return AMB_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    CK(amb_launch_compose(reinterpret_cast<const long long*>(gathered_dev), n_spans, reinterpret_cast<long long*>(out_dev), ctx->stream));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    CK(amb_launch_compose(reinterpret_cast<const long long*>(gathered_dev), n_spans, reinterpret_cast<long long*>(out_dev), st));
     ctx->stats.kernel_launches += 1;
     return AMB_OK;
 }
@@ -1035,13 +1036,13 @@ int amb_compose_entries_async(amb_ctx* ctx, const int64_t* gathered_dev, int n_s
 /* amb_resolve with the entry state (pos, p) read from device memory at execution time (e.g. a row of
  * amb_compose_entries_async's output): the walk + slice of the deferred span are enqueued behind whatever produced
  * entry_dev on the caller-visible stream; nothing waits on the host. */
-int amb_resolve_device(amb_ctx* ctx, const int64_t* entry_dev)
+int amb_resolve_device(amb_ctx* ctx, const int64_t* entry_dev, void* after_stream)
 {
     if (!ctx || !entry_dev) return AMB_ERR_INVALID;
     if (!ctx->def_kind) return fail(ctx, AMB_ERR_STATE, "no deferred call to resolve");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t sb = ctx->stream_b;
-    CK(cudaEventRecord(ctx->e_in, ctx->stream));
+    CK(cudaEventRecord(ctx->e_in, after_stream ? (cudaStream_t)after_stream : ctx->stream));
     CK(cudaStreamWaitEvent(sb, ctx->e_in, 0));
     if (ctx->def_resolved && ctx->def_kind == 1) {
         CK(amb_launch_walk_reset(ctx->def_wa, ctx->def_par ? ctx->walk_scratch : nullptr, ctx->def_nsamp, sb));
@@ -1065,18 +1066,23 @@ int amb_resolve_device(amb_ctx* ctx, const int64_t* entry_dev)
     return AMB_OK;
 }
 
-/* Make the caller-visible stream wait for everything enqueued so far (no host synchronisation). */
-int amb_join(amb_ctx* ctx)
+/* Make a stream wait for everything enqueued so far (no host synchronisation): amb_join = the caller-visible stream,
+ * amb_join_stream = any other stream of the caller's (e.g. the one a collective runs on, so that the scan stream is
+ * not held up by it). */
+int amb_join_stream(amb_ctx* ctx, void* cuda_stream)
 {
     if (!ctx) return AMB_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     if (ctx->pend_n) { int rc = ingest_dispatch_pending(ctx, 0); if (rc) return rc; }
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
     for (int k = 0; k < 2; k++) {
-        if (ctx->done_valid[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->e_done[k], 0));
-        if (ctx->aux_valid[k]) CK(cudaStreamWaitEvent(ctx->stream, ctx->e_aux[k], 0));
+        if (ctx->done_valid[k]) CK(cudaStreamWaitEvent(st, ctx->e_done[k], 0));
+        if (ctx->aux_valid[k]) CK(cudaStreamWaitEvent(st, ctx->e_aux[k], 0));
     }
     return AMB_OK;
 }
+
+int amb_join(amb_ctx* ctx) { return amb_join_stream(ctx, nullptr); }
 
 // tag_to_timestamp with no rx_time tag (preamble_impl.cc:100-137)
 // tag_to_timestamp (preamble_impl.cc:100-137) against the rx_time tag in force at the frame: the most recent tag at or

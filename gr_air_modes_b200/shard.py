@@ -244,37 +244,43 @@ def dist_all_gather6(world: int, device):
 # looks at the verdict (out[0]) only after the passes it wants have been enqueued; a pass whose speculation failed
 # (out[0] < len(plan) - 1: rare, a packet straddling a cut in an unlucky way) is redone with the functions above.
 class AsyncPass:
-    """Device scratch of one rank for time_shard_pass_async."""
+    """Device scratch of one rank for time_shard_pass_async: one row per pass, so that passes in flight never share a
+    buffer. `side`: a CUDA stream of the caller's on which the exchange runs (None: the current stream / CPU tensors)."""
 
-    def __init__(self, world: int, n_spans: int, device, steps: int = 1):
+    def __init__(self, world: int, n_spans: int, device, steps: int = 1, side=None):
         import torch
-        self.mine = torch.zeros(6, dtype=torch.int64, device=device)
-        self.all = torch.zeros(world * 6, dtype=torch.int64, device=device)
+        self.mine = torch.zeros(steps, 6, dtype=torch.int64, device=device)
+        self.all = torch.zeros(steps, world * 6, dtype=torch.int64, device=device)
         self.out = torch.zeros(steps, 1 + 3 * n_spans, dtype=torch.int64, device=device)
-        self.n_spans, self.world = n_spans, world
+        self.n_spans, self.world, self.side = n_spans, world, side
 
 
 def time_shard_pass_async(rx, span_iq, plan, rank, scratch: "AsyncPass", step: int = 0):
     """Enqueue one time-sharded pass of this rank (rx in deferred mode). Nothing here blocks on the device. The caller
     later checks scratch.out[step, 0] == len(plan) - 1 (every speculation held) before trusting the frames."""
+    import contextlib
+    import torch
     import torch.distributed as dist
     last = len(plan) - 1
     active = rank < len(plan)
+    side = scratch.side
+    sptr = side.cuda_stream if side is not None else 0
+    mine, gathered, row = scratch.mine[step], scratch.all[step], scratch.out[step]
     if active:
         sp = plan[rank]
         rx.seek(sp.first_sample, sp.first_decision)
         rx.process(span_iq, flush=sp.flush, collect=False)
         if rank < last:
             rx.resolve(None)                               # speculative: fresh entry at first_decision
-            rx.walk_summary_async(scratch.mine.data_ptr())
-        rx.join()                                          # the caller's stream (where the collective runs) waits for it
-    if scratch.world > 1:
-        dist.all_gather_into_tensor(scratch.all, scratch.mine)
-    else:
-        scratch.all.copy_(scratch.mine)
-    row = scratch.out[step]
+            rx.walk_summary_async(mine.data_ptr())
+        rx.join_stream(sptr)                               # the stream the collective runs on waits for the summary
+    with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+        if scratch.world > 1:
+            dist.all_gather_into_tensor(gathered, mine)
+        else:
+            gathered.copy_(mine)
     if active:
-        rx.compose_entries_async(scratch.all.data_ptr(), len(plan), row.data_ptr())
+        rx.compose_entries_async(gathered.data_ptr(), len(plan), row.data_ptr(), sptr)
         if rank == last:
-            rx.resolve_device(row.data_ptr() + 8 * (1 + 2 * rank))
+            rx.resolve_device(row.data_ptr() + 8 * (1 + 2 * rank), sptr)
     return row

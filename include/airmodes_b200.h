@@ -267,8 +267,11 @@ AMB_API int amb_get_walk_summary(amb_ctx* ctx, amb_walk_summary* out);   /* sync
  * A pass is then a fixed sequence of enqueues; the host only reads out[0] afterwards, and re-resolves the rare pass whose
  * speculation failed with amb_resolve as before. */
 AMB_API int amb_walk_summary_async(amb_ctx* ctx, int64_t* dev_out6);
-AMB_API int amb_compose_entries_async(amb_ctx* ctx, const int64_t* gathered_dev, int n_spans, int64_t* out_dev);
-AMB_API int amb_resolve_device(amb_ctx* ctx, const int64_t* entry_dev);
+AMB_API int amb_compose_entries_async(amb_ctx* ctx, const int64_t* gathered_dev, int n_spans, int64_t* out_dev, void* cuda_stream);
+AMB_API int amb_resolve_device(amb_ctx* ctx, const int64_t* entry_dev, void* after_stream);
+/* cuda_stream / after_stream: the caller's stream the exchange runs on (NULL: the caller-visible stream). Running the
+ * collective on a side stream (amb_join_stream) keeps the scan stream free for the next pass. */
+AMB_API int amb_join_stream(amb_ctx* ctx, void* cuda_stream);
 /* ---- batch field decode of queued frames ---------------------------------------
  * What the reference does per message in Python after the slicer: modes_reply field extraction
  * (python/parse.py:27-231), decode_alt (python/altitude.py:28-108), decode_id (parse.py:233-254), the BDS0,5 / 0,6 /
