@@ -355,7 +355,10 @@ AMB_HD void amb_resolve_position(amb_fields* r, const AmbPair& pr, int have_loc,
 
 // Latest-report bookkeeping of cpr_decoder.decode for ONE message given the table state before it (cpr.py:214-229):
 // used by the pairing kernel lane by lane and, sequentially, by the host shim.
-AMB_HD int amb_report_alive(double now, double t, int surface) { return !((now - t) > (surface ? 25.0 : 10.0)); }
+// A stored report stamped LATER than the current message can only stem from an earlier stream (frame timestamps restart
+// after amb_reset / a new recording, while a decoder keeps its table): the reference's wall clock would have expired it
+// long ago, so it counts as expired here too instead of being paired with.
+AMB_HD int amb_report_alive(double now, double t, int surface) { const double age = now - t; return age >= 0.0 && !(age > (surface ? 25.0 : 10.0)); }
 
 // `me` has just been stored as the latest report of its format; (o_*) is the latest stored report of the other
 // format, if any. -> what cpr_decoder.decode hands to cpr_resolve_global (cpr.py:226-229), or have = 0 (:231).

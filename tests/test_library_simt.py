@@ -307,6 +307,23 @@ def test_two_contexts_and_device_crc(port):
     ra.close(); rb.close()
 
 
+def test_decoder_does_not_pair_with_reports_of_an_earlier_stream():
+    """A persistent decoder, a new recording whose timestamps restart at 0: a stored report that is LATER than the
+    current message belongs to the earlier stream and must count as expired (the reference's wall clock would have
+    weeded it long ago, cpr.py:196-204) instead of producing a position out of two unrelated reports."""
+    from gr_air_modes_b200 import decode
+    even, odd = "8d40621d58c382d690c8ac2863a7", "8d40621d58c386435cc412692ad6"
+    d = decode.batch_decoder(None)
+    a = d.decode_messages([(even, 0, 100, 0.0), (odd, 0, 101, 0.0)])
+    assert (a["status"][0] & decode.FS_CPR_NO_POS) and (a["status"][1] & decode.FS_HAS_POS)
+    assert abs(a["lat"][1] - 52.26) < 0.02 and abs(a["lon"][1] - 3.93) < 0.03         # the textbook pair (odd frame latest)
+    b = d.decode_messages([(odd, 0, 1, 0.0)])                 # new stream: t restarts; the even report of t = 100 is "later"
+    assert (b["status"][0] & decode.FS_CPR_NO_POS) and not (b["status"][0] & decode.FS_HAS_POS)
+    c = d.decode_messages([(even, 0, 2, 0.0)])                # ... and pairs normally within the new stream
+    assert c["status"][0] & decode.FS_HAS_POS
+    d.close()
+
+
 def test_decoder_through_its_c_abi():
     from gr_air_modes_b200 import decode, report
     from helpers import compare_decode, load_decode_golden
