@@ -708,9 +708,8 @@ struct CopyPool {
     std::vector<std::thread> th;
     std::mutex m;
     std::condition_variable cv, done_cv;
-    struct Task { char* d; const char* s; size_t n; };
+    struct Task { char* d; const char* s; size_t n; int* left; };   // left: the submitting call's count of unfinished pieces
     std::deque<Task> q;
-    int outstanding = 0;
     bool stop = false;
     explicit CopyPool(int n)
     {
@@ -724,7 +723,7 @@ struct CopyPool {
                     t = q.front(); q.pop_front();
                 }
                 memcpy(t.d, t.s, t.n);
-                { std::lock_guard<std::mutex> lk(m); if (--outstanding == 0) done_cv.notify_all(); }
+                { std::lock_guard<std::mutex> lk(m); if (--*t.left == 0) done_cv.notify_all(); }
             }
         });
     }
@@ -741,14 +740,15 @@ struct CopyPool {
         size_t per = (n / (th.size() + 1) + 4095) & ~(size_t)4095;
         if (per < piece) per = piece;
         size_t off = per;                                   // the caller copies the first piece itself
+        int left = 0;                                       // several contexts / threads may share the pool: each call counts its own pieces
         {
             std::lock_guard<std::mutex> lk(m);
-            for (; off < n; off += per) { q.push_back({d + off, s + off, std::min(per, n - off)}); outstanding++; }
+            for (; off < n; off += per) { q.push_back({d + off, s + off, std::min(per, n - off), &left}); left++; }
         }
         cv.notify_all();
         memcpy(d, s, std::min(per, n));
         std::unique_lock<std::mutex> lk(m);
-        done_cv.wait(lk, [this] { return outstanding == 0; });
+        done_cv.wait(lk, [&left] { return left == 0; });
     }
 };
 std::mutex g_pool_mutex;
@@ -867,10 +867,12 @@ static int ingest(amb_ctx* ctx, const void* data, size_t n, int mem_kind, int fl
     size_t left = n;
     bool flushed = false;
     const bool direct_ok = on_dev || is_pinned_host(p);
+    cudaEvent_t last_direct = nullptr;                         // last DMA out of the caller's own (pinned) host memory
     while (left) {
         if (!ctx->pend_n && direct_ok && (on_dev || left >= ctx->coalesce)) {
             const size_t m = std::min(left, CH);               // straight from the caller's memory
             const int fl = flush && m == left;
+            if (!on_dev) last_direct = ctx->ing[ctx->ing_next % AMB_ING_SLOTS].e_h2d;
             int rc = ingest_dispatch(ctx, p, m, sc16, on_dev, fl); if (rc) return rc;
             flushed = fl != 0;
             p += m * esz; left -= m;
@@ -889,6 +891,9 @@ static int ingest(amb_ctx* ctx, const void* data, size_t n, int mem_kind, int fl
         }
     }
     if (flush && !flushed) { int rc = ingest_dispatch_pending(ctx, 1); if (rc) return rc; }   // also closes an empty stream
+    // host memory is consumed when the call returns: the copies out of a pinned caller buffer are asynchronous, so wait
+    // for the last of them (the kernels behind it stay asynchronous)
+    if (last_direct) CK(cudaEventSynchronize(last_direct));
     return AMB_OK;
 }
 

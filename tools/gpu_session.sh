@@ -2,7 +2,7 @@
 # One gpurun call that re-establishes the evidence set on a fresh B200:
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'
 # Everything lands in gpurun_out/ (merged back by gpurun); copy what should be judged into profiles/.
-# Stages can be selected: bash tools/gpu_session.sh tests bench launches scan dense dc decode variants
+# Stages can be selected: bash tools/gpu_session.sh tests bench launches launchcfg scan dense dc decode sanitize e2e variants
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -57,6 +57,21 @@ if has decode; then     # row f4: parity + timings of the batch decoder, then it
   timeout 120 python tests/tools/prof_decode.py --check 16 20 > gpurun_out/decode_time.log 2>&1; cat gpurun_out/decode_time.log
   timeout 120 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
       --log-file gpurun_out/decode_launches.csv python tests/tools/prof_decode.py 16 20 > /dev/null 2>&1
+fi
+if has sanitize; then   # compute-sanitizer over every kernel and host path (both exact regimes, ingest ring, sc16, DC blocker)
+  timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python tests/tools/sanitize_run.py > gpurun_out/sanitize_memcheck.log 2>&1
+  echo "memcheck rc $?"; tail -4 gpurun_out/sanitize_memcheck.log
+  timeout 600 compute-sanitizer --tool racecheck --racecheck-report all --error-exitcode 9 python tests/tools/sanitize_run.py > gpurun_out/sanitize_racecheck.log 2>&1
+  echo "racecheck rc $?"; tail -3 gpurun_out/sanitize_racecheck.log
+fi
+if has e2e; then        # quick look at the end-to-end legs only
+  timeout 600 python bench.py --steps 10 --warmup 3 --extra-configs none --no-parity --no-cpu-baseline > gpurun_out/bench_e2e.json 2>/dev/null
+  python - <<'PY'
+import json
+l = json.loads([x for x in open("gpurun_out/bench_e2e.json") if x.startswith("{")][-1])
+print("value", l["value"], "step", l["ms_per_step"], "e2e", l["e2e"]["value"], "pageable", l["e2e_pageable"]["value"], "sc16", l["e2e_sc16"]["value"])
+print(json.dumps(l["e2e_small_call"]["calls_of_samples"]))
+PY
 fi
 if has variants; then   # experiment builds (python tools/variants.py build on the CPU box first)
   for r in 4e6 10e6 20e6; do timeout 300 python tools/variants.py run 28 $r > gpurun_out/variants_scan_$r.log 2>&1; cat gpurun_out/variants_scan_$r.log; done
