@@ -2,11 +2,11 @@
 # One gpurun call that re-establishes the evidence set on a fresh B200:
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'
 # Everything lands in gpurun_out/ (merged back by gpurun); copy what should be judged into profiles/.
-# Stages can be selected: bash tools/gpu_session.sh tests bench launches launchcfg scan dense dc decode sanitize e2e variants
+# Stages can be selected: bash tools/gpu_session.sh tests bench launches launchcfg scan dense dc decode timeline sanitize e2e variants
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-STAGES="${*:-tests bench launches scan dense dc decode}"
+STAGES="${*:-tests bench launchcfg scan dense dc decode timeline}"
 has() { [[ " $STAGES " == *" $1 "* ]]; }
 NCU_FULL="ncu --set full --clock-control none --import-source on -f"
 
@@ -57,6 +57,9 @@ if has decode; then     # row f4: parity + timings of the batch decoder, then it
   timeout 120 python tests/tools/prof_decode.py --check 16 20 > gpurun_out/decode_time.log 2>&1; cat gpurun_out/decode_time.log
   timeout 120 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
       --log-file gpurun_out/decode_launches.csv python tests/tools/prof_decode.py 16 20 > /dev/null 2>&1
+fi
+if has timeline; then   # per call: idle scan stream / scan / scan end -> sparse stages done (amb_get_timeline)
+  for c in c1 c2 c3 c4; do timeout 200 python tools/prof_holes.py $c 2>&1 | tail -2; done > gpurun_out/timeline.txt; cat gpurun_out/timeline.txt
 fi
 if has sanitize; then   # compute-sanitizer over every kernel and host path (both exact regimes, ingest ring, sc16, DC blocker)
   timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python tests/tools/sanitize_run.py > gpurun_out/sanitize_memcheck.log 2>&1
