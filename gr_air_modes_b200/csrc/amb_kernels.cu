@@ -616,8 +616,7 @@ __device__ __forceinline__ float stream_at(const float* in, long long n, int H, 
 //             a group costs a handful of memory round trips whatever its size;
 //   evaluate  lane t owns candidate t and walks its row alone: pulse matched filter in place (row[i] <- bb), the fp64
 //             ascending sum of bb[c-L+1 .. c] = LITERALLY the canonical noise-floor window of the start c, then the
-//             pulse tests, the late gate and the quiet zones from the row. Rows have an odd stride (and start at the
-//             candidate's own first sample whatever its parity), so 32 lanes
+//             pulse tests, the late gate and the quiet zones from the row. Rows have an odd stride, so 32 lanes
 //             walking 32 rows in step never collide on a bank. No shuffles, no votes: 32 candidates advance per warp
 //             instruction (the round-1 kernel spent a whole warp, ~560 instructions and five barriers on ONE
 //             candidate and was instruction-bound in dense traffic - profiles/r2_dense_sparse_before.txt).
@@ -659,9 +658,6 @@ __global__ void __launch_bounds__(64) amb_exact_kernel(const AmbExactArgs a, con
             const float2* sp = valid ? seg_span(a.S, be, 2 * P2) : nullptr;
             ptrs[lane] = reinterpret_cast<const float4*>(sp);      // 16-byte aligned: segment bases are, `be` is even
         }
-        // Row q holds m2[b_m2(q) + k] at rows[q * ROW + 1 + k] whatever the parity of b_m2(q) (an odd start puts the
-        // one extra leading sample into the pad slot): 32 lanes walking their rows in step then hit 32 different banks.
-        const unsigned odd = __ballot_sync(FULL, (b_m2 & 1) != 0);
         __syncwarp();
         // ---- gather: element e of the group = pair p of row q; a lane's elements are e = lane, lane + 32, ...
         const int total = G * P2;
@@ -682,7 +678,7 @@ __global__ void __launch_bounds__(64) amb_exact_kernel(const AmbExactArgs a, con
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 if (e0 + 32 * u + lane < total && ptrs[q]) {   // rows without a pointer are filled below
-                    float* r = rows + (size_t)q * ROW + 1 + 2 * p - (int)((odd >> q) & 1u);
+                    float* r = rows + (size_t)q * ROW + 2 * p;
                     r[0] = __fadd_rn(__fmul_rn(v[u].x, v[u].x), __fmul_rn(v[u].y, v[u].y));
                     r[1] = __fadd_rn(__fmul_rn(v[u].z, v[u].z), __fmul_rn(v[u].w, v[u].w));
                 }
@@ -695,13 +691,13 @@ __global__ void __launch_bounds__(64) amb_exact_kernel(const AmbExactArgs a, con
         for (unsigned todo = __ballot_sync(FULL, valid && lane < G && !ptrs[lane < G ? lane : 0]); todo; todo &= todo - 1) {
             const int q = __ffs(todo) - 1;
             const int bq = __shfl_sync(FULL, be, q);
-            float* r = rows + (size_t)q * ROW + 1 - (int)((odd >> q) & 1u);
+            float* r = rows + (size_t)q * ROW;
             for (int k = lane; k < 2 * P2; k += 32) r[k] = canon_m2(a.S, bq + k);
         }
         __syncwarp();
         // ---- evaluate: lane t, candidate t
         if (valid) {
-            float* r = rows + (size_t)lane * ROW + 1;               // r[k] = m2[b_m2 + k]; becomes bb[c-L+1+k] in place
+            float* r = rows + (size_t)lane * ROW + (b_m2 - be);     // r[k] = m2[b_m2 + k]; becomes bb[c-L+1+k] in place
             double acc = 0.0;
             float mx = 0.f, mn = 3.0e38f;                     // largest / smallest non-zero bb that can enter a window
             auto consume = [&](int i, float bb) {             // bb = bb[c - L + 1 + i] (never negative)
@@ -712,7 +708,6 @@ __global__ void __launch_bounds__(64) amb_exact_kernel(const AmbExactArgs a, con
                 float w[FLC];                                  // the last FLC m2 values; slot of m2 sample k: k % FLC
 #pragma unroll
                 for (int t = 0; t < FLC - 1; t++) w[t] = r[t];
-#pragma unroll 4
                 for (int i0 = 0; i0 < NB; i0 += FLC) {         // FLC outputs per round: ring positions are static
 #pragma unroll
                     for (int u = 0; u < FLC; u++) {
@@ -1019,7 +1014,7 @@ cudaError_t amb_launch_exact(const AmbExactArgs& a, int sm_count, cudaStream_t s
                           P.qa0 == 3 * k && P.qa1 == 6 * k && P.qb0 == 10 * k && P.qb1 == 15 * k && P.fwd == 15 * k + 2;
     const int fl = P.use_pmf ? k : 1;
     const int NM = P.L + (P.maxlate + P.fwd + 2) - 1 + fl - 1;
-    const int ROW = 2 * ((NM + 2) / 2) + 1;                          // floats per row: one pad + whole 16-byte pairs = odd stride
+    const int ROW = (2 * ((NM + 2) / 2)) | 1;                        // floats per row: whole 16-byte pairs, odd stride
     const int G = ROW <= 160 ? 32 : ROW <= 340 ? 16 : 8;              // candidates per warp: <= ~21 KiB of rows per warp
     // two warps per CTA: <= 43 KiB of rows and <= 8 K registers, so that a CTA fits beside the four resident scan CTAs
     const size_t smem = (size_t)2 * ((size_t)G * ROW + 64) * sizeof(float);
