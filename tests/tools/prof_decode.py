@@ -79,7 +79,7 @@ def main():
             d.reset(); d.decode_device(fd, od)
             d.reset(); d.decode_device(fd, od)
             ms2 = d.stats()[1]
-            same = np.array_equal(od.cpu().numpy().view(decode.FIELDS_DTYPE), out)
+            same = od.cpu().numpy().tobytes() == out.tobytes()        # bytes: the records hold NaN for "no position"
             print("n=2^%d frames, device-resident frames and records: %.3f ms (%.0f M frames/s), records identical: %s"
                   % (lg, ms2, n / ms2 / 1e3, same))
         except ImportError:

@@ -42,7 +42,7 @@ if has dense; then      # BASELINE configs[4]: the sparse stages under dense tra
   timeout 300 python tools/prof_dense.py 28 4e6 3 time > gpurun_out/dense_time_2p28.log 2>&1; tail -5 gpurun_out/dense_time_2p28.log
   timeout 300 python tools/prof_dense.py 24 4e6 3 time > gpurun_out/dense_time_2p24.log 2>&1; tail -2 gpurun_out/dense_time_2p24.log
   # second process() call only: skip the first call's launches of the matched kernels
-  timeout 400 $NCU_FULL -k regex:'amb_(compact|exact|walk|slice)' -s 6 -c 6 -o gpurun_out/dense_sparse_2p26 \
+  timeout 400 $NCU_FULL -k regex:'amb_(compact|exact|walk|slice)' -s 7 -c 7 -o gpurun_out/dense_sparse_2p26 \
       python tools/prof_dense.py 26 4e6 2 > gpurun_out/dense_sparse_ncu.log 2>&1
   timeout 300 $NCU_FULL -k regex:amb_scan -s 1 -c 1 -o gpurun_out/dense_scan_2p26 \
       python tools/prof_dense.py 26 4e6 2 > gpurun_out/dense_scan_ncu.log 2>&1
