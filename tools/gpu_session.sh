@@ -2,7 +2,7 @@
 # One gpurun call that re-establishes the evidence set on a fresh B200:
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'
 # Everything lands in gpurun_out/ (merged back by gpurun); copy what should be judged into profiles/.
-# Stages can be selected: bash tools/gpu_session.sh tests bench launches launchcfg scan dense dc decode timeline sanitize e2e variants
+# Stages can be selected: bash tools/gpu_session.sh tests bench launches launchcfg scan dense dc decode decodefull sc16 timeline sanitize e2e variants
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -57,6 +57,14 @@ if has decode; then     # row f4: parity + timings of the batch decoder, then it
   timeout 120 python tests/tools/prof_decode.py --check 16 20 > gpurun_out/decode_time.log 2>&1; cat gpurun_out/decode_time.log
   timeout 120 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
       --log-file gpurun_out/decode_launches.csv python tests/tools/prof_decode.py 16 20 > /dev/null 2>&1
+fi
+if has decodefull; then # full ncu sections of the seven decoder kernels (the 2^20-frame batch: skip the warm-up batch's launches)
+  timeout 300 $NCU_FULL -k regex:'amb_(fields|v3|resolve)' -s 7 -c 7 -o gpurun_out/decode_2p20 \
+      python tests/tools/prof_decode.py 20 > gpurun_out/decode_ncu.log 2>&1; tail -2 gpurun_out/decode_ncu.log
+fi
+if has sc16; then       # the widening kernel of the 16-bit ingest path (second process() call)
+  timeout 200 $NCU_FULL -k regex:amb_widen -s 17 -c 1 -o gpurun_out/widen_sc16 python tools/prof_run_sc16.py 26 > gpurun_out/widen_ncu.log 2>&1
+  tail -2 gpurun_out/widen_ncu.log
 fi
 if has timeline; then   # per call: idle scan stream / scan / scan end -> sparse stages done (amb_get_timeline)
   for c in c1 c2 c3 c4; do timeout 200 python tools/prof_holes.py $c 2>&1 | tail -2; done > gpurun_out/timeline.txt; cat gpurun_out/timeline.txt
