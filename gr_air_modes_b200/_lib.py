@@ -85,6 +85,7 @@ SYMBOLS = [
     ("amb_poll_frames", C.c_int, [_vp, C.POINTER(Frame), C.c_int]),
     ("amb_pending_frames", C.c_int, [_vp]),
     ("amb_poll_ready", C.c_int, [_vp, C.POINTER(Frame), C.c_int]),
+    ("amb_drain_device", C.c_int, [_vp, _vp, C.c_int]),
     ("amb_add_time_tag", C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_double]),
     ("amb_wait_stream", C.c_int, [_vp, _vp]),
     ("amb_format_message", C.c_int, [C.POINTER(Frame), C.c_int, C.c_char_p, C.c_size_t]),

@@ -154,6 +154,7 @@ class _Context:
         check(self._lib.amb_create(int(device), float(rate), float(threshold_db), int(bool(use_pmf)),
                                    int(bool(use_dcblock)), C.byref(h)))
         self._h = h
+        self.device = int(device)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -364,6 +365,22 @@ class rx_path:
         self._keep.clear()
         return self._slicer.emit(buf, got)
 
+    def drain_device(self, out=None):
+        """The device-side drain(): waits for everything given so far and returns its frames as a torch CUDA uint8 tensor
+        of n * 80 bytes (amb_frame records in stream order, stamped) WITHOUT copying them to the host - the input of
+        batch_decoder.decode_device(). No messages are queued for these frames (that needs them on the host: drain())."""
+        import torch
+        n = self._ctx.call("amb_drain_device", None, 0)
+        dev = torch.device("cuda", self._ctx.device)
+        if out is None:
+            out = torch.empty(n * 80, dtype=torch.uint8, device=dev)
+        elif out.numel() < n * 80:
+            raise ValueError("drain_device: out holds %d bytes, %d needed" % (out.numel(), n * 80))
+        got = self._ctx.call("amb_drain_device", C.c_void_p(out.data_ptr()), int(out.numel() // 80)) if n else 0
+        self.frames = []
+        self._keep.clear()
+        return out[:got * 80]
+
     def poll_ready(self, max_frames: int = 4096) -> int:
         """Non-blocking drain: queue the messages of the calls that have already completed on the device (what a GNU
         Radio work() function calls after handing over its items). Returns how many were queued."""
@@ -388,7 +405,8 @@ class rx_path:
         self._ctx.join()
 
     def set_option(self, name: str, value: int):
-        """Library options: "coalesce", "ingest_chunk", "copy_threads", "resolver", "overlap", "keep_chips"."""
+        """Library options: "coalesce", "ingest_chunk", "copy_threads", "resolver", "overlap", "keep_chips", "exact_dense",
+        "scan_ctas", "order_tile"."""
         self._ctx.call("amb_set_option", name.encode(), int(value))
 
     def reset(self):

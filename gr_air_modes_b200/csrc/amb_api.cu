@@ -3,6 +3,7 @@
 // launches the kernels in amb_kernels.cu or fails. Citations are file:line under gr-air-modes.
 #include "amb_internal.h"
 #include "amb_params.h"
+#include "amb_order_kernels.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -71,6 +72,9 @@ struct amb_ctx {
     AmbCounters* ctr_snap = nullptr; cudaEvent_t snap_ev[AMB_SNAPS] = {}; unsigned long long snap_head = 0, snap_tail = 0;
     unsigned polled = 0;                 // frames [0, polled) of the device frame buffer were returned by amb_poll_ready
     std::vector<amb_time_tag> time_tags; // rx_time tags (absolute item offset -> time), ascending
+    // device-side drain (amb_drain_device): sort scratch, device copy of the tags
+    unsigned long long* ord_key = nullptr; unsigned* ord_val = nullptr; unsigned ord_cap = 0; unsigned order_tile = 2048;
+    AmbTagDev* tags_dev = nullptr; int tags_dev_cap = 0;
     // optional DC blocker (rx_path.py:39-41)
     int use_dcblock = 0, dc_D = 0, dc_nc = 0, dc_cur = 0;
     float2* dc_carry[2] = {nullptr, nullptr}; float2* dc_out = nullptr; float2* dc_ma0 = nullptr; size_t dc_cap = 0;
@@ -306,6 +310,7 @@ void amb_destroy(amb_ctx* ctx)
     if (ctx->stream_h) { cudaStreamSynchronize(ctx->stream_h); }
     free_dev(ctx);
     ingest_free(ctx);
+    cudaFree(ctx->ord_key); cudaFree(ctx->ord_val); cudaFree(ctx->tags_dev);
     if (ctx->stream_h) cudaStreamDestroy(ctx->stream_h);
     if (ctx->ctr_snap) cudaFreeHost(ctx->ctr_snap);
     for (int k = 0; k < AMB_SNAPS; k++) if (ctx->snap_ev[k]) cudaEventDestroy(ctx->snap_ev[k]);
@@ -406,6 +411,10 @@ int amb_set_option(amb_ctx* ctx, const char* name, int value)
     }
     if (!strcmp(name, "exact_dense")) { if (value < 0) return AMB_ERR_INVALID; ctx->exact_dense = (unsigned)value; return AMB_OK; }
     if (!strcmp(name, "scan_ctas")) { if (value < 0 || value > 65536) return AMB_ERR_INVALID; ctx->scan_ctas = value; return AMB_OK; }
+    if (!strcmp(name, "order_tile")) {                     // elements per CTA of the device-side drain's sorting network
+        if (value < 2 || value > 2048 || (value & (value - 1))) return AMB_ERR_INVALID;
+        ctx->order_tile = (unsigned)value; return AMB_OK;
+    }
     if (!strcmp(name, "copy_threads")) { if (value < 0 || value > 64) return AMB_ERR_INVALID; ctx->copy_threads = value; return AMB_OK; }
     if (!strcmp(name, "ingest_chunk")) {                   // samples per chunk of the host ingest ring (multiple of 512)
         if (value < 4096 || (value & 511)) return AMB_ERR_INVALID;
@@ -1119,19 +1128,26 @@ static int fetch_frames(amb_ctx* ctx, unsigned upto)
     return AMB_OK;
 }
 
-static int collect(amb_ctx* ctx)
+// Everything enqueued so far is through; counters of the last call read back.
+static int collect_sync(amb_ctx* ctx, AmbCounters* h)
 {
     CK(cudaSetDevice(ctx->device));
     if (ctx->pend_n) { int rc = ingest_dispatch_pending(ctx, 0); if (rc) return rc; }
     CK(sync_all(ctx));
+    CK(cudaMemcpy(h, ctx->ctr, sizeof *h, cudaMemcpyDeviceToHost));
+    ctx->stats.candidates = h->ncand;
+    ctx->stats.candidates_real = h->nreal_call;
+    ctx->stats.detections = h->ndet_call;
+    ctx->stats.frames_passed = h->npassed_call;
+    if (h->overflow) return fail(ctx, AMB_ERR_OVERFLOW, "candidate buffer overflow");
+    if (h->frame_overflow) return fail(ctx, AMB_ERR_OVERFLOW, "frame buffer overflow");
+    return AMB_OK;
+}
+
+static int collect(amb_ctx* ctx)
+{
     AmbCounters h;
-    CK(cudaMemcpy(&h, ctx->ctr, sizeof h, cudaMemcpyDeviceToHost));
-    ctx->stats.candidates = h.ncand;
-    ctx->stats.candidates_real = h.nreal_call;
-    ctx->stats.detections = h.ndet_call;
-    ctx->stats.frames_passed = h.npassed_call;
-    if (h.overflow) return fail(ctx, AMB_ERR_OVERFLOW, "candidate buffer overflow");
-    if (h.frame_overflow) return fail(ctx, AMB_ERR_OVERFLOW, "frame buffer overflow");
+    { int rc = collect_sync(ctx, &h); if (rc) return rc; }
     { int rc = fetch_frames(ctx, h.nframes); if (rc) return rc; }
     if (h.nframes) CK(cudaMemset(&ctx->ctr->nframes, 0, sizeof(unsigned)));
     ctx->polled = 0;
@@ -1182,6 +1198,52 @@ int amb_poll_ready(amb_ctx* ctx, amb_frame* out, int max)
     if (n) memcpy(out, ctx->pending.data(), (size_t)n * sizeof(amb_frame));
     ctx->pending.erase(ctx->pending.begin(), ctx->pending.begin() + n);
     return n;
+}
+
+/* The device-side amb_poll_frames: every frame not handed out yet, in stream order and stamped, written to DEVICE memory.
+ * out_dev == NULL: only report how many there are. Frames that an earlier amb_poll_ready already moved to the host's
+ * pending list are not included (they come out of amb_poll_frames / amb_poll_ready). */
+int amb_drain_device(amb_ctx* ctx, amb_frame* out_dev, int cap)
+{
+    if (!ctx || cap < 0) return AMB_ERR_INVALID;
+    AmbCounters h;
+    { int rc = collect_sync(ctx, &h); if (rc) return rc; }
+    const unsigned n = h.nframes > ctx->polled ? h.nframes - ctx->polled : 0u;
+    if (!out_dev) return (int)n;
+    if ((unsigned)cap < n) return fail(ctx, AMB_ERR_OVERFLOW, "amb_drain_device: output buffer too small");
+    if (n) {
+        unsigned npad = 1; while (npad < n) npad <<= 1;
+        if (ctx->ord_cap < npad) {
+            cudaFree(ctx->ord_key); cudaFree(ctx->ord_val); ctx->ord_key = nullptr; ctx->ord_val = nullptr; ctx->ord_cap = 0;
+            CK(cudaMalloc(&ctx->ord_key, (size_t)npad * sizeof(unsigned long long)));
+            CK(cudaMalloc(&ctx->ord_val, (size_t)npad * sizeof(unsigned)));
+            ctx->ord_cap = npad;
+        }
+        const int ntags = (int)ctx->time_tags.size();
+        if (ntags) {
+            if (ctx->tags_dev_cap < ntags) {
+                cudaFree(ctx->tags_dev); ctx->tags_dev = nullptr; ctx->tags_dev_cap = 0;
+                CK(cudaMalloc(&ctx->tags_dev, (size_t)ntags * 2 * sizeof(AmbTagDev)));
+                ctx->tags_dev_cap = ntags * 2;
+            }
+            std::vector<AmbTagDev> t((size_t)ntags);
+            for (int k = 0; k < ntags; k++) t[(size_t)k] = {ctx->time_tags[(size_t)k].offset, ctx->time_tags[(size_t)k].secs, ctx->time_tags[(size_t)k].frac};
+            CK(cudaMemcpy(ctx->tags_dev, t.data(), (size_t)ntags * sizeof(AmbTagDev), cudaMemcpyHostToDevice));
+        }
+        cudaError_t e = cudaSuccess;
+        const int launched = amb_launch_order(ctx->frames + ctx->polled, n, npad, ctx->order_tile, ctx->ord_key, ctx->ord_val, out_dev,
+                                              (unsigned long long)ctx->P.rate_int, ctx->t0_secs, ctx->t0_frac, ctx->tags_dev, ntags,
+                                              ctx->stream_b, &e);
+        if (e != cudaSuccess) return fail(ctx, AMB_ERR_CUDA, "amb_drain_device launch", e);
+        ctx->stats.kernel_launches += (uint64_t)launched;
+        CK(cudaStreamSynchronize(ctx->stream_b));
+    }
+    if (h.nframes) CK(cudaMemset(&ctx->ctr->nframes, 0, sizeof(unsigned)));
+    ctx->polled = 0;
+    ctx->snap_tail = ctx->snap_head;
+    ctx->frames_ub = 0;
+    if (ctx->def_kind && ctx->def_resolved) { ctx->def_kind = 0; ctx->def_resolved = false; }
+    return (int)n;
 }
 
 int amb_add_time_tag(amb_ctx* ctx, uint64_t offset, uint64_t secs, double frac)

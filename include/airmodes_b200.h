@@ -152,6 +152,14 @@ AMB_API int amb_pending_frames(amb_ctx* ctx);
  * have already completed on the device, in stream order, and leaves work in flight alone. Host input that is still
  * being gathered (see amb_process) is not forced out. */
 AMB_API int amb_poll_ready(amb_ctx* ctx, amb_frame* out, int max);
+/* The device-side amb_poll_frames: waits for enqueued work, then writes every frame that has not been handed out yet to
+ * DEVICE memory - in stream order and stamped (tag_to_timestamp, preamble_impl.cc:100-137), i.e. byte for byte what
+ * amb_poll_frames would have copied to the host - so that a consumer on the same GPU (amb_decode_frames_device) reads
+ * them without a PCIe round trip. Only the count crosses to the host. out_dev == NULL: report the count, consume
+ * nothing. Returns the count, AMB_ERR_OVERFLOW (nothing consumed) if cap is too small. Frames that an earlier
+ * amb_poll_ready moved to the host side stay there. Option "order_tile" (power of two <= 2048, default 2048) sizes the
+ * shared-memory tile of the ordering network. */
+AMB_API int amb_drain_device(amb_ctx* ctx, amb_frame* out_dev, int cap);
 
 /* Message text exactly as slicer_impl.cc:186-192 builds it: "<hex payload> <crc %06x> <ref> <secs> <frac>".
  * `first` != 0 formats ref with the stream's default precision 6 (the first message a slicer instance

@@ -15,7 +15,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXCLUDE = ("full_size or config0 or c_abi_example or cli_ or randomised_stress or time_sharded_speculative or "
-           "host_ingest_paths or sc16_input or torch_input or device_resident_decode")   # the last three need pinned / CUDA tensors; test_library_simt.py has their emulated twins
+           "host_ingest_paths or sc16_input or torch_input or device_resident_decode or device_side_drain or "
+           "without_leaving_the_device")   # the last six need pinned / CUDA tensors; test_library_simt.py has their emulated twins
 
 
 def test_gpu_parity_tests_pass_against_the_emulated_library(tmp_path):

@@ -300,6 +300,45 @@ def test_dense_traffic_threshold_sweep_matches_reference(port):
     assert msgs == want.msgs
 
 
+def test_device_side_drain_equals_host_poll(port):
+    """amb_drain_device (rx_path.drain_device): the frames of several calls, put into stream order and stamped ON THE
+    DEVICE, are byte for byte the records amb_poll_frames copies to the host - on dense traffic (thousands of frames:
+    the ordering network needs its global stages) and on a sparse 10 Msps scene, with a start time and a later rx_time
+    tag in force."""
+    import torch
+    cases = [(4e6, 2_000_000, 5000, 99, dict(garble_frac=0.2, fruit=2000, snr_db=(4.0, 30.0))), (10e6, 1_200_000, 40, 4, {})]
+    for rate, n, nb, seed, kw in cases:
+        sc = synth.make_scene(rate, n, nb, seed, **kw)
+        cuts = [0, 300_000, 300_000 + 123_456, n]
+
+        def ctx():
+            rx = am.rx_path(rate, 7.0, am.msg_queue(), use_pmf=True)
+            rx.set_start_time(77, 0.5)
+            rx.add_time_tag(n // 2, 9000, 0.25)
+            return rx
+
+        rx = ctx()
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            rx.process(sc.iq[2 * a: 2 * b], flush=(b == n), collect=False)
+        buf, got = rx._ctx.poll_array()
+        want = bytes(buf)[:got * 80]
+        idx = [int(buf[k].sample_index) for k in range(got)]
+        assert idx == [int(x) for x in port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL).index]
+        rx.close()
+        if nb == 5000:
+            assert got > 2048
+
+        rx = ctx()
+        dev = torch.from_numpy(sc.iq).cuda()
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            rx.process(dev[2 * a: 2 * b], flush=(b == n), collect=False)
+        fr = rx.drain_device()
+        assert fr.is_cuda and fr.numel() == got * 80
+        assert fr.cpu().numpy().tobytes() == want
+        assert rx.drain_device().numel() == 0
+        rx.close()
+
+
 def test_overlap_off_is_identical(port):
     sc = synth.make_scene(4e6, 700_000, 50, 17)
     want = port.run_iq(sc.iq, 4e6, 7.0, True, co.MA_CANONICAL).msgs

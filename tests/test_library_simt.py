@@ -557,3 +557,103 @@ def test_gr_adapter_split_blocks_preamble_then_slicer(port, ref):
     sl = ga.slicer(q)
     _drive_sink(sl, items, [240 * 5, 240, 240 * 17 + 100], [(t.offset, t.key, t.value) for t in pre.out_tags])
     assert q.strings() == want.msgs
+
+
+# ---- device-side drain (amb_drain_device): stream order + stamps without the host -------------------------------------
+def _feed(rx, iq, cuts):
+    pos, n = 0, iq.size // 2
+    for c in list(cuts) + [n]:
+        c = int(min(c, n - pos))
+        last = pos + c >= n
+        rx.process(iq[2 * pos: 2 * (pos + c)], flush=last, collect=False)
+        pos += c
+        if last:
+            break
+
+
+@pytest.mark.parametrize("tile", [2048, 16, 2])
+def test_device_side_drain_equals_host_poll(port, tile):
+    """amb_drain_device hands out, in device memory, byte for byte the records amb_poll_frames copies to the host: same
+    order (sorting network over the work-list order of several calls; small tiles force its global stages), same stamps
+    (start time + a later rx_time tag)."""
+    import ctypes as C
+    rate = 4e6
+    sc = synth.make_scene(rate, 260_000, 150, 907, garble_frac=0.2)
+    cuts = [70_000, 33_333, 90_001]
+
+    def ctx():
+        q = am.msg_queue()
+        rx = am.rx_path(rate, 7.0, q, use_pmf=True)
+        rx.set_option("order_tile", tile)
+        rx.set_start_time(1000, 0.75)
+        rx.add_time_tag(120_000, 5000, 0.999)
+        return rx
+
+    rx = ctx()
+    _feed(rx, sc.iq, cuts)
+    buf, got = rx._ctx.poll_array()
+    want = bytes(buf)[:got * 80]
+    rx.close()
+    assert got > 64                                   # several tiles of 16: the global stages run
+    idx = [int(buf[k].sample_index) for k in range(got)]
+    assert idx == sorted(idx) and idx == [int(x) for x in port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL).index]
+
+    rx = ctx()
+    _feed(rx, sc.iq, cuts)
+    n = rx._ctx.call("amb_drain_device", None, 0)
+    assert n == got
+    with pytest.raises(RuntimeError):
+        rx._ctx.call("amb_drain_device", (am.Frame * n)(), n - 1)      # too small: nothing consumed
+    out = (am.Frame * n)()
+    assert rx._ctx.call("amb_drain_device", out, n) == n
+    assert bytes(out) == want
+    assert rx._ctx.call("amb_drain_device", None, 0) == 0 and rx._ctx.call("amb_pending_frames") == 0
+    rx.close()
+
+    # frames that a non-blocking poll already moved to the host stay there; the device drain hands out the rest
+    rx = ctx()
+    rx.set_option("coalesce", 4096)                   # dispatch the first call at once instead of gathering 2^18 samples
+    rx.process(sc.iq[: 2 * 100_000], flush=False, collect=False)
+    hb, hgot = rx._ctx.poll_ready_array(4096)
+    head = bytes(hb)[:hgot * 80]
+    rx.process(sc.iq[2 * 100_000:], flush=True, collect=False)
+    n2 = rx._ctx.call("amb_drain_device", None, 0)
+    out2 = (am.Frame * max(n2, 1))()
+    assert rx._ctx.call("amb_drain_device", out2, n2) == n2
+    assert hgot > 0 and n2 > 0 and head + bytes(out2)[:n2 * 80] == want
+    rx.close()
+
+
+def test_frames_go_from_the_slicer_to_the_decoder_in_device_memory():
+    """amb_drain_device -> amb_decode_frames_device (the whole chain without a host copy of the frames) gives the records
+    of the host-driven chain (amb_poll_frames -> amb_decode_frames), byte for byte."""
+    import ctypes as C
+    from gr_air_modes_b200 import decode
+    rate = 4e6
+    sc = synth.make_scene(rate, 200_000, 110, 911)
+
+    def ctx():
+        rx = am.rx_path(rate, 7.0, am.msg_queue(), use_pmf=True)
+        rx.set_start_time(500, 0.5)
+        return rx
+
+    rx = ctx()
+    rx.process(sc.iq, flush=True)
+    frames = list(rx.frames)
+    rx.close()
+    d = decode.batch_decoder([45.0, 9.0])
+    want = d.decode(frames).tobytes()
+    d.close()
+
+    rx = ctx()
+    _feed(rx, sc.iq, [90_000, 50_000])
+    n = rx._ctx.call("amb_drain_device", None, 0)
+    assert n == len(frames) > 50
+    fr = (am.Frame * n)()
+    assert rx._ctx.call("amb_drain_device", fr, n) == n
+    rx.close()
+    d = decode.batch_decoder([45.0, 9.0])
+    rec = (C.c_uint8 * (144 * n))()
+    d._check(d._lib.amb_decode_frames_device(d._h, fr, n, rec))
+    d.close()
+    assert bytes(rec) == want

@@ -335,3 +335,40 @@ def test_device_resident_decode_equals_the_host_path(dec_mod):
     got = out.cpu().numpy().view(dec_mod.FIELDS_DTYPE)
     assert got.size == n and got.tobytes() == want.tobytes()
     d1.close(); d2.close()
+
+
+def test_iq_to_positions_without_leaving_the_device(dec_mod):
+    """The whole chain on the GPU: IQ (device) -> rx_path -> drain_device (frames ordered and stamped on the device) ->
+    batch_decoder.decode_device -> records on the device. Byte-identical to the host-driven chain (drain() ->
+    decode())."""
+    import torch
+    import gr_air_modes_b200 as am
+    rate, n = 4e6, 1 << 22
+    iq, sent = _position_scene(rate, n, 33)
+    loc = [50.0, 8.5]
+    q = am.msg_queue()
+    rx = am.rx_path(rate, 7.0, q, use_pmf=True)
+    rx.set_start_time(1_600_000_000, 0.125)
+    rx.process(iq, flush=True)
+    frames = list(rx.frames)
+    rx.close()
+    assert len(frames) >= sent
+    d1 = dec_mod.batch_decoder(loc)
+    want = d1.decode(frames)
+    d1.close()
+    assert int(((want["status"] & dec_mod.FS_HAS_POS) != 0).sum()) >= sent // 2
+
+    q2 = am.msg_queue()
+    rx2 = am.rx_path(rate, 7.0, q2, use_pmf=True)
+    rx2.set_start_time(1_600_000_000, 0.125)
+    dev = torch.from_numpy(iq).cuda()
+    cuts = [0, 1_000_000, 1_000_000 + 777_776, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        rx2.process(dev[2 * a: 2 * b], flush=(b == n), collect=False)
+    fr = rx2.drain_device()
+    assert fr.numel() == 80 * len(frames) and fr.cpu().numpy().tobytes() == b"".join(bytes(f) for f in frames)
+    d2 = dec_mod.batch_decoder(loc)
+    out = d2.decode_device(fr)
+    assert out.is_cuda and out.cpu().numpy().tobytes() == want.tobytes()
+    assert q2.strings() == []                       # nothing was formatted on the host for these frames
+    d2.close(); rx2.close()

@@ -31,3 +31,14 @@ rx.process(i16[:0], flush=True)
 print("sc16 small calls", q.strings() == want, len(want)); rx.close()
 bb, avg = port.frontend(sc.iq, 4e6, True, co.MA_CANONICAL)
 pre = am.preamble(4e6, 7.0); chips, tags = pre.process(bb, avg); print("split", len(tags))
+# device-side drain (ordering network incl. its global stages: tile 16) -> decoder on device memory
+import torch
+from gr_air_modes_b200 import decode
+sc = synth.make_scene(4e6, 300_000, 160, 7, garble_frac=0.2)
+q = am.msg_queue(); rx = am.rx_path(4e6, 7.0, q, use_pmf=True)
+rx.set_option("order_tile", 16); rx.add_time_tag(100_000, 50, 0.5)
+dev = torch.from_numpy(sc.iq).cuda()
+for k in range(0, 300_000, 100_000):
+    rx.process(dev[2 * k: 2 * (k + 100_000)], flush=(k + 100_000 >= 300_000), collect=False)
+fr = rx.drain_device(); d = decode.batch_decoder([40.0, -3.0]); out = d.decode_device(fr); torch.cuda.synchronize()
+print("device drain + decode", fr.numel() // 80, out.numel() // 144); d.close(); rx.close()
