@@ -302,8 +302,9 @@ def test_dense_traffic_threshold_sweep_matches_reference(port):
 
 def test_device_side_drain_equals_host_poll(port):
     """amb_drain_device (rx_path.drain_device): the frames of several calls, put into stream order and stamped ON THE
-    DEVICE, are byte for byte the records amb_poll_frames copies to the host - on dense traffic (thousands of frames:
-    the ordering network needs its global stages) and on a sparse 10 Msps scene, with a start time and a later rx_time
+    DEVICE, are byte for byte the records amb_poll_frames copies to the host - on dense traffic (1.7 k frames over
+    tiles of 256: the ordering network needs its global stages; tools/prof_chain.py checks 2.4 x 10^5 frames with the
+    default tile) and on a sparse 10 Msps scene, with a start time and a later rx_time
     tag in force."""
     import torch
     cases = [(4e6, 2_000_000, 5000, 99, dict(garble_frac=0.2, fruit=2000, snr_db=(4.0, 30.0))), (10e6, 1_200_000, 40, 4, {})]
@@ -315,6 +316,8 @@ def test_device_side_drain_equals_host_poll(port):
             rx = am.rx_path(rate, 7.0, am.msg_queue(), use_pmf=True)
             rx.set_start_time(77, 0.5)
             rx.add_time_tag(n // 2, 9000, 0.25)
+            if nb == 5000:
+                rx.set_option("order_tile", 256)      # 1.7 k frames: several tiles, so the network's global stages run too
             return rx
 
         rx = ctx()
@@ -326,7 +329,7 @@ def test_device_side_drain_equals_host_poll(port):
         assert idx == [int(x) for x in port.run_iq(sc.iq, rate, 7.0, True, co.MA_CANONICAL).index]
         rx.close()
         if nb == 5000:
-            assert got > 2048
+            assert got > 1024
 
         rx = ctx()
         dev = torch.from_numpy(sc.iq).cuda()
