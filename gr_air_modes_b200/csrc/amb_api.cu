@@ -761,16 +761,17 @@ struct CopyPool {
     }
 };
 std::mutex g_pool_mutex;
-CopyPool* g_pool = nullptr; int g_pool_threads = -1;
-CopyPool* copy_pool(int want)
+CopyPool* g_pools[65] = {};                                 // one pool per thread count, created on first use, never torn down:
+CopyPool* copy_pool(int want)                               // a context of another thread may be inside copy() of any of them
 {
     std::lock_guard<std::mutex> lk(g_pool_mutex);
     if (want <= 0) {
         static const int dflt = (int)std::min(24u, std::max(1u, std::thread::hardware_concurrency() / 6));
         want = dflt;                                        // enough to outrun a PCIe Gen5 x16 link, never the whole box
     }
-    if (!g_pool || g_pool_threads != want) { delete g_pool; g_pool = new CopyPool(want - 1); g_pool_threads = want; }
-    return g_pool;
+    if (want > 64) want = 64;
+    if (!g_pools[want]) g_pools[want] = new CopyPool(want - 1);
+    return g_pools[want];
 }
 }  // namespace
 
