@@ -374,10 +374,11 @@ class rx_path:
         dev = torch.device("cuda", self._ctx.device)
         if out is None:
             out = torch.empty(n * 80, dtype=torch.uint8, device=dev)
-            # the block may be one torch has just recycled: whatever torch's stream still does with it comes first
-            torch.cuda.current_stream(dev).synchronize()
         elif out.numel() < n * 80:
             raise ValueError("drain_device: out holds %d bytes, %d needed" % (out.numel(), n * 80))
+        # the library writes `out` on its own stream: whatever torch's stream still does with that memory (a recycled
+        # block, a producer of a caller-supplied tensor) comes first
+        torch.cuda.current_stream(dev).synchronize()
         got = self._ctx.call("amb_drain_device", C.c_void_p(out.data_ptr()), int(out.numel() // 80)) if n else 0
         self.frames = []
         self._keep.clear()
